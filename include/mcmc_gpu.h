@@ -1,0 +1,415 @@
+/* mcmc_gpu.h -- C ABI of the B200-native sampling-and-evidence path.
+ *
+ * Every entry point replaces one piece of the OCaml interface of
+ * farr/mcmc-ocaml (citations are file:line in the reference tree).  The
+ * reference has no FFI at all; this header is the boundary a
+ * maintainer binds from OCaml with thin C stubs over float64 Bigarrays
+ * (see INTEGRATION.md and ocaml/).  Plain C: opaque handles, plain pointers
+ * and sizes, int status codes.  No torch / C++ types cross this boundary.
+ *
+ * Conventions
+ *   - all reals are IEEE float64, all arrays C layout, caller allocated.
+ *   - "host" entry points take host pointers (pinned or pageable) and do the
+ *     H2D / D2H copies themselves; "*_dev" entry points take device pointers
+ *     on the context's device and never touch host memory.
+ *   - status: MG_OK or an error; mg_last_error(ctx) gives the message.
+ *     MG_EINVAL <-> Invalid_argument, MG_EFAIL <-> Failure,
+ *     MG_ECUDA <-> Failure "cuda: ..." on the OCaml side.
+ *   - a context is single-caller (the reference is non-reentrant:
+ *     global counters mcmc.ml:27-28 and the global Random state).
+ *   - there is NO CPU fallback: without a CUDA device mg_ctx_create fails.
+ */
+#ifndef MCMC_GPU_H
+#define MCMC_GPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MG_ABI_VERSION 1
+
+enum {
+  MG_OK = 0,
+  MG_EINVAL = 1, /* Invalid_argument */
+  MG_EFAIL = 2,  /* Failure */
+  MG_ECUDA = 3,  /* Failure "cuda: ..." */
+  MG_ENOMEM = 4
+};
+
+typedef struct mg_ctx mg_ctx;
+typedef struct mg_kdtree mg_kdtree;
+
+/* ------------------------------------------------------------------ */
+/* context                                                             */
+/* ------------------------------------------------------------------ */
+
+int mg_abi_version(void);
+/* Random.init seed (bin/rjmcmc_gaussian_cauchy.ml:24): one Philox4x32-10 key
+ * per context; every sampling call consumes one "epoch" of it. */
+int mg_ctx_create(int device, uint64_t seed, mg_ctx **out);
+void mg_ctx_destroy(mg_ctx *ctx);
+const char *mg_last_error(const mg_ctx *ctx);
+int mg_ctx_set_seed(mg_ctx *ctx, uint64_t seed);    /* resets epoch to 0 */
+int mg_ctx_set_epoch(mg_ctx *ctx, uint64_t epoch);  /* next call uses it  */
+uint64_t mg_ctx_get_epoch(const mg_ctx *ctx);
+int mg_ctx_set_stream(mg_ctx *ctx, void *cuda_stream); /* NULL = own stream */
+void *mg_ctx_get_stream(const mg_ctx *ctx);
+int mg_ctx_sync(mg_ctx *ctx);
+/* Mcmc.reset_counters / Mcmc.get_counters (mcmc.ml:30-35). */
+int mg_reset_counters(mg_ctx *ctx);
+int mg_get_counters(mg_ctx *ctx, int64_t *naccept, int64_t *nreject);
+/* number of kernels this context has launched (bench.py gpu_launches). */
+int64_t mg_ctx_launch_count(const mg_ctx *ctx);
+/* duration in ms of the dominant kernel of the last sampling / build call,
+ * from CUDA events recorded on the context's stream around that launch. */
+double mg_ctx_last_kernel_ms(const mg_ctx *ctx);
+
+/* diagnostics: device microbenchmarks for the roofline denominators that
+ * MEASURED_PEAKS.json lacks (FP64 FMA TFLOP/s; streaming-store GB/s). */
+int mg_measure_fp64_tflops(mg_ctx *ctx, int reps, double *out_tflops);
+int mg_measure_store_gbs(mg_ctx *ctx, int64_t nbytes, int reps, double *out_gbs);
+
+/* device / pinned memory helpers for callers without their own allocator */
+int mg_malloc_device(mg_ctx *ctx, int64_t nbytes, void **out);
+int mg_free_device(mg_ctx *ctx, void *p);
+int mg_malloc_pinned(mg_ctx *ctx, int64_t nbytes, void **out);
+int mg_free_pinned(mg_ctx *ctx, void *p);
+int mg_memcpy_h2d(mg_ctx *ctx, void *dst_dev, const void *src_host, int64_t nbytes);
+int mg_memcpy_d2h(mg_ctx *ctx, void *dst_host, const void *src_dev, int64_t nbytes);
+
+/* ------------------------------------------------------------------ */
+/* plugins: log-density functions and jump proposals                   */
+/* ------------------------------------------------------------------ */
+/* The reference passes OCaml closures (mcmc.mli:58-60).  Closures cannot
+ * cross to the GPU, so the GPU path takes *registered plugins*: a kind id
+ * plus a float64 parameter blob.  Built-in kinds cover the models the
+ * reference ships in bin/ and test/.  User kinds are added at run time with
+ * mg_plugin_register_source (NVRTC, inlined into the sampler kernel). */
+
+enum {
+  /* 0.0 */
+  MG_FN_ZERO = 0,
+  /* params: c -> c */
+  MG_FN_CONST = 1,
+  /* params: lo[D], hi[D], c -> c if lo<=x<=hi on every dim else -inf
+   * (bin/gaussian_cauchy_efficiency.ml:60-67, test/mcmc_test.ml:157-159) */
+  MG_FN_BOX_CLOSED = 2,
+  /* as above with strict inequalities (test/nested_test.ml:24-28) */
+  MG_FN_BOX_OPEN = 3,
+  /* params: mu[D], sigma[D] -> Stats.log_multi_gaussian (stats.ml:98-108) */
+  MG_FN_GAUSS_DIAG = 4,
+  /* params: mu[D], L[D(D+1)/2] (row-major lower triangle of the whitening
+   * matrix, L^T L = Sigma^-1), logc -> logc - 1/2 |L (x-mu)|^2
+   * (BASELINE.json config 2: 10-D correlated Gaussian) */
+  MG_FN_GAUSS_CORR = 5,
+  /* D = 2, x = (mu, sigma); params: data[nd] -> sum_i Stats.log_gaussian
+   * (bin/gaussian_cauchy_efficiency.ml:69-77) */
+  MG_FN_GAUSS_DATA = 6,
+  /* D = 2, x = (x0, gamma); params: data[nd] -> sum_i Stats.log_cauchy
+   * (bin/gaussian_cauchy_efficiency.ml:79-87) */
+  MG_FN_CAUCHY_DATA = 7,
+  /* params: c[D], r, w -> log N(|x-c| ; r, w)   (BASELINE.json config 4) */
+  MG_FN_SHELL = 8,
+  /* params: K, mu[K][D], sigma[D] -> log sum_k exp log_multi_gaussian
+   * (test/nested_test.ml:41-53) */
+  MG_FN_GAUSS_MIX = 9,
+  MG_FN_NKINDS = 10,
+  /* ids >= MG_FN_USER are returned by mg_plugin_register_source */
+  MG_FN_USER = 1000
+};
+
+typedef struct {
+  int32_t kind;
+  int32_t dim;
+  double scale;          /* result = scale * f(x); 1.0 for plain */
+  const double *params;  /* host pointer, copied by the call */
+  int64_t nparams;
+} mg_logfn;
+
+enum {
+  /* params: h[D]; x_i + random_between(-h_i, h_i); symmetric
+   * (bin/evidence_direct.ml:24-43) */
+  MG_PROP_BOX = 0,
+  /* params: lo[D], hi[D], dx[D]; Mcmc.uniform_wrapping per coordinate
+   * (mcmc.ml:187-196; reflects at the bounds); symmetric */
+  MG_PROP_WRAP = 1,
+  /* params: mu[D], sigma[D]; y_i = Stats.draw_gaussian mu_i sigma_i
+   * independent of x; log q = sum log_gaussian (test/mcmc_test.ml:119-127) */
+  MG_PROP_INDEP_GAUSS = 2,
+  /* 1-D; params: sigma; left with p=0.75 (test/mcmc_test.ml:66-73) */
+  MG_PROP_LEFT_BIASED = 3,
+  MG_PROP_NKINDS = 4
+};
+
+typedef struct {
+  int32_t kind;
+  int32_t dim;
+  const double *params;
+  int64_t nparams;
+} mg_proposal;
+
+/* Compile a user log-density as CUDA source with NVRTC and register it.
+ * `body` is the body of
+ *   __device__ double f(const double* x, int dim, const double* p, long np)
+ * The function is inlined into freshly compiled sampler kernels (no
+ * indirect call in the hot loop).  Returns the new kind id in *kind. */
+int mg_plugin_register_source(mg_ctx *ctx, const char *name, const char *body,
+                              int32_t *kind);
+
+/* Evaluate a log-density plugin on M points (host [M][D]); used by the
+ * parity tests and by Nested for the initial live points. */
+int mg_logfn_eval(mg_ctx *ctx, const mg_logfn *fn, const double *x, int64_t M,
+                  double *out);
+
+/* ------------------------------------------------------------------ */
+/* Mcmc: ensembles of independent Metropolis-Hastings chains           */
+/* ------------------------------------------------------------------ */
+
+/* Sample block layout (device and host): [n][D+2][C] float64 -- sample s,
+ * field f (0..D-1 coordinates, D log_likelihood, D+1 log_prior), chain c.
+ * A warp of 32 chains stores 256 contiguous bytes per field per step.
+ * MG_LAYOUT_CHAIN_MAJOR asks the host entry points for [C][n][D+2] instead
+ * (one 'a mcmc_sample array per chain, mcmc.mli:33-42), transposed on the
+ * device before the D2H copy. */
+enum { MG_LAYOUT_STEP_MAJOR = 0, MG_LAYOUT_CHAIN_MAJOR = 1 };
+
+typedef struct {
+  int64_t nchains;      /* C */
+  int32_t dim;          /* D */
+  int32_t layout;       /* MG_LAYOUT_* of out_samples (host entry only) */
+  int64_t nbin;         /* ?nbin, default 0   (mcmc.ml:58) */
+  int64_t nskip;        /* ?nskip, default 1  (mcmc.ml:58) */
+  int64_t n;            /* samples per chain; slot 0 = state after nbin */
+  uint64_t chain_offset;/* global id of chain 0 (shards across GPUs) */
+  int32_t x0_shared;    /* 1: x0 is one start point [D] used by all chains */
+  int32_t reserved;
+} mg_mcmc_cfg;
+
+/* Mcmc.mcmc_array (mcmc.ml:58-72) for C independent chains.
+ * x0: host [C][D] (or [D] if x0_shared).  out_samples: host, layout above,
+ * may be NULL (then only counters / final state are produced).
+ * out_accept / out_reject: per chain [C], may be NULL. */
+int mg_mcmc_array(mg_ctx *ctx, const mg_logfn *like, const mg_logfn *prior,
+                  const mg_proposal *prop, const mg_mcmc_cfg *cfg,
+                  const double *x0, double *out_samples, int64_t *out_accept,
+                  int64_t *out_reject);
+
+/* Device-resident form.  d_state: [D+2][C] in/out (coordinates, ll, lp; ll
+ * and lp are recomputed from the coordinates on entry, mcmc.ml:59-61).
+ * d_samples: [n][D+2][C] or NULL.  d_accept: int32 [C] accumulated, or NULL.
+ * Asynchronous on the context stream. */
+int mg_mcmc_array_dev(mg_ctx *ctx, const mg_logfn *like, const mg_logfn *prior,
+                      const mg_proposal *prop, const mg_mcmc_cfg *cfg,
+                      double *d_state, double *d_samples, int32_t *d_accept);
+
+/* Mcmc.mcmc_array whose sample block stays in HBM for the GPU consumers that
+ * follow it in every reference program (Interp.make, Evidence.*, Stats.*;
+ * e.g. bin/gaussian_cauchy_efficiency.ml:99-130), returning to the host what
+ * a caller inspects after a run: the final sample of every chain, the
+ * accept / reject counters and the per-field mean and std over all recorded
+ * samples (Stats.multi_mean / multi_std over the pooled chains).
+ * x0: host [C][D] or [D].  d_samples: device [n][D+2][C], caller owned.
+ * out_final: host [C][D+2] or NULL.  out_mean / out_std: host [D+2] or NULL. */
+int mg_mcmc_array_resident(mg_ctx *ctx, const mg_logfn *like,
+                           const mg_logfn *prior, const mg_proposal *prop,
+                           const mg_mcmc_cfg *cfg, const double *x0,
+                           double *d_samples, double *out_final,
+                           int64_t *out_accept, int64_t *out_reject,
+                           double *out_mean, double *out_std);
+
+/* Mcmc.remove_repeat_samples (mcmc.ml:74-81) on one chain: host [n][D+2]
+ * rows; writes kept rows to out, returns count in *nkept. */
+int mg_remove_repeat_samples(mg_ctx *ctx, const double *rows, int64_t n,
+                             int32_t dim, double *out, int64_t *nkept);
+
+/* ------------------------------------------------------------------ */
+/* Kd_tree + Interpolate_pdf                                           */
+/* ------------------------------------------------------------------ */
+
+/* Kd_tree.Make.tree_of_objects objs low high (kd_tree.ml:155-175), as flat
+ * node arrays in breadth-first order (node 0 = root; children of a split
+ * node are adjacent: left, left+1).  Bit-exact split dims / values / cell
+ * membership w.r.t. the reference rule.
+ * min_split: nodes with fewer objects are not split (2 = the reference's
+ * full tree; Evidence passes its ?n because collect_subvolumes never looks
+ * below the first cell with < n objects, evidence.ml:83-89).
+ * pts: host [N][D].  NaN coordinates -> MG_EINVAL. */
+int mg_kdtree_build(mg_ctx *ctx, const double *pts, int64_t N, int32_t D,
+                    const double *low, const double *high, int32_t min_split,
+                    mg_kdtree **out);
+/* d_pts: device [N][D] */
+int mg_kdtree_build_dev(mg_ctx *ctx, const double *d_pts, int64_t N, int32_t D,
+                        const double *low, const double *high,
+                        int32_t min_split, mg_kdtree **out);
+void mg_kdtree_destroy(mg_kdtree *t);
+int mg_kdtree_info(const mg_kdtree *t, int64_t *npoints, int32_t *dim,
+                   int64_t *nnodes, int32_t *nlevels);
+/* Export for bit-exact comparison; any pointer may be NULL.
+ * split_dim[nnodes] (-1 = leaf), split_val[nnodes], left[nnodes] (-1 = leaf),
+ * begin/end[nnodes]: the node's objects are perm[begin..end) in the
+ * reference's list order (stable partitions of the input order). */
+int mg_kdtree_export(const mg_kdtree *t, int32_t *split_dim, double *split_val,
+                     int32_t *left, int32_t *begin, int32_t *end,
+                     int32_t *perm);
+/* Serialise / rebuild the flat arrays, e.g. to broadcast a tree to the
+ * other GPUs of the box (NCCL broadcast of one contiguous device blob). */
+int mg_kdtree_blob_size(const mg_kdtree *t, int64_t *nbytes);
+int mg_kdtree_blob_dev(const mg_kdtree *t, void **d_blob); /* borrowed */
+int mg_kdtree_from_blob_dev(mg_ctx *ctx, const void *d_blob, int64_t nbytes,
+                            mg_kdtree **out);
+/* Kd_tree.bounds_volume (kd_tree.ml:177-182) */
+double mg_bounds_volume(const double *low, const double *high, int32_t D);
+
+/* Interpolate_pdf.find_cell (interpolate_pdf.ml:101-109): node id reached
+ * by descent for each query (host [M][D]).  nstop = 0: descend to a leaf;
+ * nstop > 0: stop at the first cell with <= nstop objects (the *_high_level
+ * forms, interpolate_pdf.ml:121-133,144-159). */
+int mg_interp_find_cell(mg_ctx *ctx, const mg_kdtree *t, const double *q,
+                        int64_t M, int32_t nstop, int32_t *out_node);
+/* Interpolate_pdf.jump_prob / jump_prob_high_level
+ * (interpolate_pdf.ml:135-159): nobjs / (V * N), a density, not a log. */
+int mg_interp_jump_prob(mg_ctx *ctx, const mg_kdtree *t, const double *q,
+                        int64_t M, int32_t nstop, double *out_prob);
+int mg_interp_jump_prob_dev(mg_ctx *ctx, const mg_kdtree *t, const double *d_q,
+                            int64_t M, int32_t nstop, double *d_out_prob,
+                            int32_t *d_out_node);
+/* Interpolate_pdf.draw / draw_high_level (interpolate_pdf.ml:114-133):
+ * M independent draws, host out [M][D]. */
+int mg_interp_draw(mg_ctx *ctx, const mg_kdtree *t, int64_t M, int32_t nstop,
+                   double *out);
+int mg_interp_draw_dev(mg_ctx *ctx, const mg_kdtree *t, int64_t M,
+                       int32_t nstop, double *d_out);
+
+/* ------------------------------------------------------------------ */
+/* Mcmc: two-model reversible jump                                     */
+/* ------------------------------------------------------------------ */
+
+/* how a chain proposes INTO a model (jintoa / jintob, mcmc.mli:132-140) */
+enum {
+  /* Interp.draw / log (Interp.jump_prob ...)  (test/mcmc_test.ml:175-178) */
+  MG_INTO_INTERP = 0,
+  /* independent Gaussian, params mu[D], sigma[D] (test/mcmc_test.ml:123-127) */
+  MG_INTO_INDEP_GAUSS = 1
+};
+
+typedef struct {
+  int32_t kind;
+  int32_t nstop;            /* MG_INTO_INTERP: 0 = draw, >0 = *_high_level */
+  const mg_kdtree *tree;    /* MG_INTO_INTERP */
+  const double *params;     /* MG_INTO_INDEP_GAUSS */
+  int64_t nparams;
+} mg_into;
+
+typedef struct {
+  mg_logfn like, prior;
+  mg_proposal prop;
+  mg_into into;             /* proposal into THIS model */
+  double p;                 /* model prior pa / pb */
+} mg_rj_model;
+
+typedef struct {
+  int64_t nchains;
+  int64_t nbin, nskip, n;
+  uint64_t chain_offset;
+  int32_t layout;
+  int32_t reserved;
+} mg_rjmcmc_cfg;
+
+/* Mcmc.rjmcmc_array (mcmc.ml:121-139) for C independent chains.
+ * a0 / b0: host start points [dA], [dB] shared by all chains.
+ * out_model: uint8 [n][C] (0 = A, 1 = B) or NULL.
+ * out_samples: [n][Dmax+2][C] or NULL (unused coordinates are 0).
+ * out_counts: {#A, #B} over all recorded samples (rjmcmc_model_counts,
+ * mcmc.ml:141-149). */
+int mg_rjmcmc_array(mg_ctx *ctx, const mg_rj_model *A, const mg_rj_model *B,
+                    const mg_rjmcmc_cfg *cfg, const double *a0,
+                    const double *b0, uint8_t *out_model, double *out_samples,
+                    int64_t out_counts[2]);
+
+/* ------------------------------------------------------------------ */
+/* Evidence + Stats                                                    */
+/* ------------------------------------------------------------------ */
+
+/* Evidence.evidence_harmonic_mean (evidence.ml:101-107).  ll: host [N]. */
+int mg_evidence_harmonic_mean(mg_ctx *ctx, const double *ll, int64_t N,
+                              double *out);
+int mg_evidence_harmonic_mean_dev(mg_ctx *ctx, const double *d_ll, int64_t N,
+                                  double *out);
+/* Evidence.evidence_lebesgue ?n ?eps (evidence.ml:202-221).
+ * pts host [N][D]; ll, lp host [N].  Defaults n = 64, eps = 0.1. */
+int mg_evidence_lebesgue(mg_ctx *ctx, const double *pts, const double *ll,
+                         const double *lp, int64_t N, int32_t D, int32_t n,
+                         double eps, double *out);
+int mg_evidence_lebesgue_dev(mg_ctx *ctx, const double *d_pts,
+                             const double *d_ll, const double *d_lp, int64_t N,
+                             int32_t D, int32_t n, double eps, double *out);
+/* Evidence.evidence_direct ?n (evidence.ml:148-165). */
+int mg_evidence_direct(mg_ctx *ctx, const double *pts, const double *ll,
+                       const double *lp, int64_t N, int32_t D, int32_t n,
+                       double *out);
+int mg_evidence_direct_dev(mg_ctx *ctx, const double *d_pts,
+                           const double *d_ll, const double *d_lp, int64_t N,
+                           int32_t D, int32_t n, double *out);
+
+/* Stats.mean / Stats.std ?mean (stats.ml:17-43); have_mean=0 computes it. */
+int mg_stats_mean(mg_ctx *ctx, const double *x, int64_t n, double *out);
+int mg_stats_std(mg_ctx *ctx, const double *x, int64_t n, int have_mean,
+                 double mean, double *out);
+/* Stats.multi_mean / multi_std (stats.ml:58-87); xs host [n][D]. */
+int mg_stats_multi_mean(mg_ctx *ctx, const double *xs, int64_t n, int32_t D,
+                        double *out);
+int mg_stats_multi_std(mg_ctx *ctx, const double *xs, int64_t n, int32_t D,
+                       const double *mean_or_null, double *out);
+/* The same over a device sample block [n][D+2][C] (all chains pooled):
+ * per-field mean and std, fields 0..D+1.  out_mean/out_std: host [D+2]. */
+int mg_stats_sample_block_dev(mg_ctx *ctx, const double *d_samples, int64_t n,
+                              int32_t D, int64_t C, double *out_mean,
+                              double *out_std);
+/* Stats.slow_autocorrelation nslides x (stats.ml:223-238) for lags
+ * 0..nslides-1 (the reference's loop bound overruns by one, SURVEY F6:
+ * parity unpinned).  Also the integrated autocorrelation length
+ * 1 + 2 sum_{i>=1} r_i up to the first non-positive r_i (an addition). */
+int mg_stats_autocorrelation(mg_ctx *ctx, const double *x, int64_t n,
+                             int32_t nslides, double *out_r,
+                             double *out_length);
+
+/* ------------------------------------------------------------------ */
+/* Nested sampling                                                     */
+/* ------------------------------------------------------------------ */
+
+typedef struct {
+  int32_t dim;
+  int32_t nlive;            /* ?nlive  default 1000 (nested.ml:122) */
+  int32_t nmcmc;            /* ?nmcmc  default 1000 */
+  int32_t batch;            /* K live points replaced per iteration; 1 =
+                               the reference's one-at-a-time schedule */
+  double epsrel;            /* ?epsrel default 0.01 */
+  double mode_hopping_frac; /* ?mode_hopping_frac default 0.1 */
+  int64_t max_points;       /* capacity of the output arrays */
+} mg_nested_cfg;
+
+/* Nested.nested_evidence (nested.ml:122-146).  draw_prior is uniform on the
+ * box [prior_lo, prior_hi] (every reference caller: nested_test.ml:34-35).
+ * Outputs: log_ev, log_dev, *npts points ascending in ll with their log
+ * weights.  pts host [max_points][D]; ll, lp, logw host [max_points].
+ * MG_EFAIL if a replacement ends below its threshold (nested.ml:70-72) or
+ * max_points is too small. */
+int mg_nested_evidence(mg_ctx *ctx, const mg_logfn *like, const mg_logfn *prior,
+                       const double *prior_lo, const double *prior_hi,
+                       const mg_nested_cfg *cfg, double *log_ev,
+                       double *log_dev, int64_t *npts, double *pts, double *ll,
+                       double *lp, double *logw);
+/* Nested.evidence_error_and_weights generalised to K-at-a-time shrinkage
+ * (nested.ml:81-120 when batch = 1).  ll: host [n] ascending. */
+int mg_nested_weights(mg_ctx *ctx, const double *ll, int64_t n, int32_t nlive,
+                      int32_t batch, double *log_ev, double *log_dev,
+                      double *logw);
+/* Nested.log_total_error_estimate (nested.ml:148-150) */
+double mg_nested_log_total_error(double log_ev, double log_dev, int32_t nlive);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MCMC_GPU_H */

@@ -1,0 +1,123 @@
+// capi.cu -- context management and memory helpers of the C ABI.
+#include "common.cuh"
+
+using namespace mg;
+
+extern "C" int mg_abi_version(void) { return MG_ABI_VERSION; }
+
+extern "C" int mg_ctx_create(int device, uint64_t seed, mg_ctx **out) {
+  if (!out) return MG_EINVAL;
+  *out = nullptr;
+  int ndev = 0;
+  // No CPU fallback: without a CUDA device the library refuses to work.
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) return MG_ECUDA;
+  if (cudaSetDevice(device) != cudaSuccess) return MG_ECUDA;
+  mg_ctx *ctx = new mg_ctx;
+  ctx->device = device; ctx->seed = seed; ctx->epoch = 0;
+  if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return MG_ECUDA; }
+  ctx->own_stream = true;
+  cudaEventCreate(&ctx->ev0); cudaEventCreate(&ctx->ev1);
+  cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
+  // keep freed stream-ordered allocations cached in the pool between calls
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+    uint64_t thr = ~0ull;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+  }
+  *out = ctx;
+  return MG_OK;
+}
+
+extern "C" void mg_ctx_destroy(mg_ctx *ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+  if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+extern "C" const char *mg_last_error(const mg_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+extern "C" int mg_ctx_set_seed(mg_ctx *ctx, uint64_t seed) { if (!ctx) return MG_EINVAL; ctx->seed = seed; ctx->epoch = 0; return MG_OK; }
+extern "C" int mg_ctx_set_epoch(mg_ctx *ctx, uint64_t epoch) { if (!ctx) return MG_EINVAL; ctx->epoch = epoch; return MG_OK; }
+extern "C" uint64_t mg_ctx_get_epoch(const mg_ctx *ctx) { return ctx ? ctx->epoch : 0; }
+
+extern "C" int mg_ctx_set_stream(mg_ctx *ctx, void *cuda_stream) {
+  if (!ctx) return MG_EINVAL;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  if (ctx->own_stream) { cudaStreamDestroy(ctx->stream); ctx->own_stream = false; }
+  if (cuda_stream) ctx->stream = (cudaStream_t)cuda_stream;
+  else {
+    MG_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    ctx->own_stream = true;
+  }
+  return MG_OK;
+}
+extern "C" void *mg_ctx_get_stream(const mg_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+extern "C" int mg_ctx_sync(mg_ctx *ctx) {
+  if (!ctx) return MG_EINVAL;
+  MG_CUDA(ctx, cudaSetDevice(ctx->device));
+  MG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return MG_OK;
+}
+extern "C" int mg_reset_counters(mg_ctx *ctx) { if (!ctx) return MG_EINVAL; ctx->naccept = ctx->nreject = 0; return MG_OK; }
+extern "C" int mg_get_counters(mg_ctx *ctx, int64_t *naccept, int64_t *nreject) {
+  if (!ctx) return MG_EINVAL;
+  if (naccept) *naccept = ctx->naccept;
+  if (nreject) *nreject = ctx->nreject;
+  return MG_OK;
+}
+extern "C" int64_t mg_ctx_launch_count(const mg_ctx *ctx) { return ctx ? ctx->launches : 0; }
+extern "C" double mg_ctx_last_kernel_ms(const mg_ctx *c) {
+  mg_ctx *ctx = const_cast<mg_ctx *>(c);
+  if (!ctx) return 0.0;
+  if (ctx->ev_pending) {
+    cudaSetDevice(ctx->device);
+    float ms = 0.f;
+    if (cudaEventSynchronize(ctx->ev1) == cudaSuccess && cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) == cudaSuccess)
+      ctx->last_kernel_ms = ms;
+    ctx->ev_pending = false;
+  }
+  return ctx->last_kernel_ms;
+}
+
+extern "C" int mg_malloc_device(mg_ctx *ctx, int64_t nbytes, void **out) {
+  if (!ctx || !out || nbytes < 0) return MG_EINVAL;
+  MG_CUDA(ctx, cudaSetDevice(ctx->device));
+  MG_CUDA(ctx, cudaMalloc(out, (size_t)(nbytes ? nbytes : 1)));
+  return MG_OK;
+}
+extern "C" int mg_free_device(mg_ctx *ctx, void *p) {
+  if (!ctx) return MG_EINVAL;
+  MG_CUDA(ctx, cudaSetDevice(ctx->device));
+  MG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  MG_CUDA(ctx, cudaFree(p));
+  return MG_OK;
+}
+extern "C" int mg_malloc_pinned(mg_ctx *ctx, int64_t nbytes, void **out) {
+  if (!ctx || !out || nbytes < 0) return MG_EINVAL;
+  MG_CUDA(ctx, cudaSetDevice(ctx->device));
+  MG_CUDA(ctx, cudaMallocHost(out, (size_t)(nbytes ? nbytes : 1)));
+  return MG_OK;
+}
+extern "C" int mg_free_pinned(mg_ctx *ctx, void *p) {
+  if (!ctx) return MG_EINVAL;
+  MG_CUDA(ctx, cudaFreeHost(p));
+  return MG_OK;
+}
+extern "C" int mg_memcpy_h2d(mg_ctx *ctx, void *dst, const void *src, int64_t nbytes) {
+  if (!ctx) return MG_EINVAL;
+  MG_CUDA(ctx, cudaSetDevice(ctx->device));
+  MG_CUDA(ctx, cudaMemcpyAsync(dst, src, (size_t)nbytes, cudaMemcpyHostToDevice, ctx->stream));
+  MG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return MG_OK;
+}
+extern "C" int mg_memcpy_d2h(mg_ctx *ctx, void *dst, const void *src, int64_t nbytes) {
+  if (!ctx) return MG_EINVAL;
+  MG_CUDA(ctx, cudaSetDevice(ctx->device));
+  MG_CUDA(ctx, cudaMemcpyAsync(dst, src, (size_t)nbytes, cudaMemcpyDeviceToHost, ctx->stream));
+  MG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return MG_OK;
+}

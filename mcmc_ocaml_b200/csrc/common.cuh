@@ -1,0 +1,88 @@
+// common.cuh -- context, error plumbing and small device helpers shared by the
+// translation units of libmcmcgpu.so.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/mcmc_gpu.h"
+#include "rng.cuh"
+
+struct mg_ctx {
+  int device = 0;
+  uint64_t seed = 0;
+  uint64_t epoch = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  bool ev_pending = false;
+  double last_kernel_ms = 0.0;
+  int64_t launches = 0;
+  int64_t naccept = 0, nreject = 0;  // Mcmc.get_counters (mcmc.ml:27-35)
+  int sm_count = 148;
+  std::string err;
+};
+
+namespace mg {
+
+inline int set_err(mg_ctx *ctx, int code, const char *fmt, ...) {
+  char buf[512];
+  va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+  if (ctx) ctx->err = buf;
+  return code;
+}
+
+#define MG_CUDA(ctx, call)                                                          \
+  do {                                                                              \
+    cudaError_t e_ = (call);                                                        \
+    if (e_ != cudaSuccess)                                                          \
+      return mg::set_err((ctx), e_ == cudaErrorMemoryAllocation ? MG_ENOMEM : MG_ECUDA, \
+                         "cuda: %s at %s:%d", cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+#define MG_CHECK_LAUNCH(ctx)                                                        \
+  do {                                                                              \
+    (ctx)->launches++;                                                              \
+    MG_CUDA(ctx, cudaGetLastError());                                               \
+  } while (0)
+
+#define MG_REQUIRE(ctx, cond, ...)                                                  \
+  do { if (!(cond)) return mg::set_err((ctx), MG_EINVAL, __VA_ARGS__); } while (0)
+
+// RAII device buffer freed on scope exit (stream-ordered).
+template <class T>
+struct DevBuf {
+  T *p = nullptr; size_t n = 0; cudaStream_t s = nullptr;
+  DevBuf() {}
+  DevBuf(const DevBuf &) = delete;
+  DevBuf &operator=(const DevBuf &) = delete;
+  cudaError_t alloc(size_t count, cudaStream_t stream) {
+    release(); n = count; s = stream;
+    if (count == 0) { p = nullptr; return cudaSuccess; }
+    return cudaMallocAsync((void **)&p, count * sizeof(T), stream);
+  }
+  void release() { if (p) { cudaFreeAsync(p, s); p = nullptr; } n = 0; }
+  ~DevBuf() { release(); }
+  T *get() const { return p; }
+};
+
+inline void time_begin(mg_ctx *ctx) { cudaEventRecord(ctx->ev0, ctx->stream); }
+inline void time_end(mg_ctx *ctx) { cudaEventRecord(ctx->ev1, ctx->stream); ctx->ev_pending = true; }
+
+inline CallKey next_key(mg_ctx *ctx) { CallKey k = derive_key(ctx->seed, ctx->epoch); ctx->epoch++; return k; }
+
+// upload a host parameter blob; empty blobs give a valid dummy pointer
+template <class T>
+inline cudaError_t upload(DevBuf<T> &buf, const T *host, size_t n, cudaStream_t s) {
+  cudaError_t e = buf.alloc(n ? n : 1, s);
+  if (e != cudaSuccess) return e;
+  if (n) e = cudaMemcpyAsync(buf.get(), host, n * sizeof(T), cudaMemcpyHostToDevice, s);
+  return e;
+}
+
+}  // namespace mg

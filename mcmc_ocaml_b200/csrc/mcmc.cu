@@ -1,0 +1,196 @@
+// mcmc.cu -- Mcmc.mcmc_array (mcmc.ml:37-72) as a batched ensemble of
+// independent Metropolis-Hastings chains: one thread per chain, chain state
+// in registers for the whole run, one fused kernel for propose / log-density /
+// accept-reject / record-sample.
+//
+// HBM layout.  state: [D+2][C] (coordinates, ll, lp), samples: [n][D+2][C].
+// Thread c of a warp owns chain c, so every store of a field is one fully
+// coalesced 256-byte warp transaction; the sample block is written once with
+// streaming (evict-first) stores and never read by this kernel.
+// Roofline: the only mandatory traffic is the recorded sample,
+// 8 (D+2) / nskip bytes per chain-step; at nskip = 1 and D = 10
+// that is 96 B/step against ~170 FP64 instructions + 6 Philox blocks per step.
+#include "mcmc_kernel.cuh"
+
+namespace mg {
+
+// instantiations live in mcmc_static.cu / mcmc_dyn.cu (one object per dimension)
+#define MG_STATIC_DIMS(X) X(2) X(4) X(8) X(10) X(16) X(20) X(32)
+#define MG_DYN_DIMS(X) X(2) X(4) X(8) X(16) X(32) X(64)
+#define MG_DECL_STATIC(DD)                                                                         \
+  int mh_static_gauss_##DD(mg_ctx *, const mg_logfn *, const mg_proposal *, const mg_mcmc_cfg *, \
+                           CallKey, double *, double *, int32_t *);
+#define MG_DECL_DYN(DD)                                                                          \
+  int mh_dyn_##DD(mg_ctx *, const DynFnParams &, const DynFnParams &, const DynPropParams &,     \
+                  const mg_mcmc_cfg *, CallKey, double *, double *, int32_t *);
+MG_STATIC_DIMS(MG_DECL_STATIC)
+MG_DYN_DIMS(MG_DECL_DYN)
+
+__global__ void init_state_kernel(const double *__restrict__ x0, int shared, int D, int64_t C,
+                                  double *__restrict__ state) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  for (int i = 0; i < D; ++i) state[(int64_t)i * C + c] = shared ? x0[i] : x0[c * D + i];
+  state[(int64_t)D * C + c] = 0.0;
+  state[(int64_t)(D + 1) * C + c] = 0.0;
+}
+
+// [n][F][C] -> [C][n][F] through a shared-memory tile (C is the contiguous
+// axis of the source, F*n the contiguous axis of the destination).
+__global__ void to_chain_major_kernel(const double *__restrict__ src, int64_t rows /* n*F */, int64_t C,
+                                      double *__restrict__ dst) {
+  __shared__ double tile[32][33];
+  const int64_t c0 = (int64_t)blockIdx.x * 32, r0 = (int64_t)blockIdx.y * 32;
+  for (int k = threadIdx.y; k < 32; k += blockDim.y) {
+    const int64_t r = r0 + k, c = c0 + threadIdx.x;
+    if (r < rows && c < C) tile[k][threadIdx.x] = src[r * C + c];
+  }
+  __syncthreads();
+  for (int k = threadIdx.y; k < 32; k += blockDim.y) {
+    const int64_t c = c0 + k, r = r0 + threadIdx.x;
+    if (r < rows && c < C) dst[c * rows + r] = tile[threadIdx.x][k];
+  }
+}
+
+int sample_block_stats(mg_ctx *ctx, const double *d_blk, int64_t n, int F, int64_t C, double *d_out);  // stats.cu
+
+static int validate_cfg(mg_ctx *ctx, const mg_mcmc_cfg *cfg) {
+  MG_REQUIRE(ctx, cfg != nullptr, "mcmc_array: null cfg");
+  MG_REQUIRE(ctx, cfg->nchains >= 1, "mcmc_array: nchains must be >= 1");
+  MG_REQUIRE(ctx, cfg->dim >= 1 && cfg->dim <= 64, "mcmc_array: dim must be in 1..64");
+  MG_REQUIRE(ctx, cfg->nbin >= 0 && cfg->nskip >= 1 && cfg->n >= 0, "mcmc_array: bad nbin/nskip/n");
+  MG_REQUIRE(ctx, cfg->nchains / MH_BLOCK < 2147483647LL, "mcmc_array: too many chains for one launch");
+  return MG_OK;
+}
+
+}  // namespace mg
+
+using namespace mg;
+
+extern "C" int mg_mcmc_array_dev(mg_ctx *ctx, const mg_logfn *like, const mg_logfn *prior,
+                                 const mg_proposal *prop, const mg_mcmc_cfg *cfg, double *d_state,
+                                 double *d_samples, int32_t *d_accept) {
+  if (!ctx) return MG_EINVAL;
+  int rc;
+  if ((rc = validate_cfg(ctx, cfg))) return rc;
+  if ((rc = validate_logfn(ctx, like, cfg->dim, "log_likelihood"))) return rc;
+  if ((rc = validate_logfn(ctx, prior, cfg->dim, "log_prior"))) return rc;
+  if ((rc = validate_proposal(ctx, prop, cfg->dim))) return rc;
+  MG_REQUIRE(ctx, d_state != nullptr, "mcmc_array: null state");
+  MG_CUDA(ctx, cudaSetDevice(ctx->device));
+  const CallKey key = next_key(ctx);
+  const int D = cfg->dim;
+
+  if (like->kind == MG_FN_GAUSS_CORR && like->scale == 1.0 && prior->kind == MG_FN_ZERO &&
+      prop->kind == MG_PROP_BOX) {
+    switch (D) {
+#define MG_CASE(DD) case DD: return mh_static_gauss_##DD(ctx, like, prop, cfg, key, d_state, d_samples, d_accept);
+      MG_STATIC_DIMS(MG_CASE)
+#undef MG_CASE
+      default: break;
+    }
+  }
+  DevLogFn dl, dp; DevProposal dj;
+  MG_CUDA(ctx, dl.upload_from(like, ctx->stream));
+  MG_CUDA(ctx, dp.upload_from(prior, ctx->stream));
+  MG_CUDA(ctx, dj.upload_from(prop, ctx->stream));
+#define MG_TRY(DD) if (D <= DD) rc = mh_dyn_##DD(ctx, dl.params, dp.params, dj.params, cfg, key, d_state, d_samples, d_accept); else
+  MG_DYN_DIMS(MG_TRY) rc = set_err(ctx, MG_EINVAL, "mcmc_array: dim too large");
+#undef MG_TRY
+  return rc;  // parameter blobs are freed stream-ordered after the kernel
+}
+
+extern "C" int mg_mcmc_array(mg_ctx *ctx, const mg_logfn *like, const mg_logfn *prior, const mg_proposal *prop,
+                             const mg_mcmc_cfg *cfg, const double *x0, double *out_samples, int64_t *out_accept,
+                             int64_t *out_reject) {
+  if (!ctx) return MG_EINVAL;
+  int rc;
+  if ((rc = validate_cfg(ctx, cfg))) return rc;
+  MG_REQUIRE(ctx, x0 != nullptr, "mcmc_array: null start point");
+  MG_CUDA(ctx, cudaSetDevice(ctx->device));
+  const int D = cfg->dim, F = D + 2;
+  const int64_t C = cfg->nchains, n = cfg->n;
+  cudaStream_t s = ctx->stream;
+  DevBuf<double> d_x0, d_state, d_samples, d_t;
+  DevBuf<int32_t> d_acc;
+  const size_t nx0 = cfg->x0_shared ? (size_t)D : (size_t)C * D;
+  MG_CUDA(ctx, upload(d_x0, x0, nx0, s));
+  MG_CUDA(ctx, d_state.alloc((size_t)F * C, s));
+  MG_CUDA(ctx, d_acc.alloc((size_t)C, s));
+  MG_CUDA(ctx, cudaMemsetAsync(d_acc.get(), 0, sizeof(int32_t) * C, s));
+  if (out_samples && n > 0) MG_CUDA(ctx, d_samples.alloc((size_t)n * F * C, s));
+  init_state_kernel<<<(unsigned)((C + 255) / 256), 256, 0, s>>>(d_x0.get(), cfg->x0_shared, D, C, d_state.get());
+  MG_CHECK_LAUNCH(ctx);
+  if ((rc = mg_mcmc_array_dev(ctx, like, prior, prop, cfg, d_state.get(), d_samples.get(), d_acc.get()))) return rc;
+  if (out_samples && n > 0) {
+    const double *src = d_samples.get();
+    if (cfg->layout == MG_LAYOUT_CHAIN_MAJOR) {
+      MG_CUDA(ctx, d_t.alloc((size_t)n * F * C, s));
+      dim3 grid((unsigned)((C + 31) / 32), (unsigned)((n * F + 31) / 32)), block(32, 8);
+      to_chain_major_kernel<<<grid, block, 0, s>>>(d_samples.get(), n * F, C, d_t.get());
+      MG_CHECK_LAUNCH(ctx);
+      src = d_t.get();
+    }
+    MG_CUDA(ctx, cudaMemcpyAsync(out_samples, src, sizeof(double) * (size_t)n * F * C, cudaMemcpyDeviceToHost, s));
+  }
+  std::vector<int32_t> acc((size_t)C);
+  MG_CUDA(ctx, cudaMemcpyAsync(acc.data(), d_acc.get(), sizeof(int32_t) * C, cudaMemcpyDeviceToHost, s));
+  MG_CUDA(ctx, cudaStreamSynchronize(s));
+  const int64_t steps = cfg->nbin + (n > 0 ? (n - 1) * cfg->nskip : 0);
+  for (int64_t c = 0; c < C; ++c) {
+    ctx->naccept += acc[c]; ctx->nreject += steps - acc[c];
+    if (out_accept) out_accept[c] = acc[c];
+    if (out_reject) out_reject[c] = steps - acc[c];
+  }
+  return MG_OK;
+}
+
+extern "C" int mg_mcmc_array_resident(mg_ctx *ctx, const mg_logfn *like, const mg_logfn *prior,
+                                      const mg_proposal *prop, const mg_mcmc_cfg *cfg, const double *x0,
+                                      double *d_samples, double *out_final, int64_t *out_accept,
+                                      int64_t *out_reject, double *out_mean, double *out_std) {
+  if (!ctx) return MG_EINVAL;
+  int rc;
+  if ((rc = validate_cfg(ctx, cfg))) return rc;
+  MG_REQUIRE(ctx, x0 != nullptr, "mcmc_array: null start point");
+  MG_REQUIRE(ctx, d_samples != nullptr || (!out_mean && !out_std), "mcmc_array: statistics need a sample block");
+  MG_CUDA(ctx, cudaSetDevice(ctx->device));
+  const int D = cfg->dim, F = D + 2;
+  const int64_t C = cfg->nchains, n = cfg->n;
+  cudaStream_t s = ctx->stream;
+  DevBuf<double> d_x0, d_state, d_final, d_stats;
+  DevBuf<int32_t> d_acc;
+  const size_t nx0 = cfg->x0_shared ? (size_t)D : (size_t)C * D;
+  MG_CUDA(ctx, upload(d_x0, x0, nx0, s));
+  MG_CUDA(ctx, d_state.alloc((size_t)F * C, s));
+  MG_CUDA(ctx, d_acc.alloc((size_t)C, s));
+  MG_CUDA(ctx, cudaMemsetAsync(d_acc.get(), 0, sizeof(int32_t) * C, s));
+  init_state_kernel<<<(unsigned)((C + 255) / 256), 256, 0, s>>>(d_x0.get(), cfg->x0_shared, D, C, d_state.get());
+  MG_CHECK_LAUNCH(ctx);
+  if ((rc = mg_mcmc_array_dev(ctx, like, prior, prop, cfg, d_state.get(), d_samples, d_acc.get()))) return rc;
+  std::vector<double> stats(2 * F);
+  if ((out_mean || out_std) && n > 0) {
+    MG_CUDA(ctx, d_stats.alloc(2 * F, s));
+    if ((rc = sample_block_stats(ctx, d_samples, n, F, C, d_stats.get()))) return rc;
+    MG_CUDA(ctx, cudaMemcpyAsync(stats.data(), d_stats.get(), sizeof(double) * 2 * F, cudaMemcpyDeviceToHost, s));
+  }
+  if (out_final) {
+    MG_CUDA(ctx, d_final.alloc((size_t)F * C, s));
+    dim3 grid((unsigned)((C + 31) / 32), (unsigned)((F + 31) / 32)), block(32, 8);
+    to_chain_major_kernel<<<grid, block, 0, s>>>(d_state.get(), F, C, d_final.get());
+    MG_CHECK_LAUNCH(ctx);
+    MG_CUDA(ctx, cudaMemcpyAsync(out_final, d_final.get(), sizeof(double) * F * C, cudaMemcpyDeviceToHost, s));
+  }
+  std::vector<int32_t> acc((size_t)C);
+  MG_CUDA(ctx, cudaMemcpyAsync(acc.data(), d_acc.get(), sizeof(int32_t) * C, cudaMemcpyDeviceToHost, s));
+  MG_CUDA(ctx, cudaStreamSynchronize(s));
+  const int64_t steps = cfg->nbin + (n > 0 ? (n - 1) * cfg->nskip : 0);
+  for (int64_t c = 0; c < C; ++c) {
+    ctx->naccept += acc[c]; ctx->nreject += steps - acc[c];
+    if (out_accept) out_accept[c] = acc[c];
+    if (out_reject) out_reject[c] = steps - acc[c];
+  }
+  if (out_mean) memcpy(out_mean, stats.data(), sizeof(double) * F);
+  if (out_std) memcpy(out_std, stats.data() + F, sizeof(double) * F);
+  return MG_OK;
+}

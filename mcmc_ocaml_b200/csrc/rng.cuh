@@ -1,0 +1,76 @@
+// rng.cuh -- counter-based Philox4x32-10 stream for the device (and the host
+// side of the library, which needs the call-key derivation).
+//
+// The reference draws from OCaml's global Random (mcmc.ml:47,
+// interpolate_pdf.ml:115, ...).  A global sequential generator cannot feed
+// 65,536 chains; the GPU path keys one Philox stream by (seed, epoch) and
+// addresses every draw by (purpose, global chain id, step, draw index), so a
+// chain's randomness does not depend on how chains are spread over threads,
+// blocks or GPUs.  The stream layout is specified in oracle/og_rng.hpp.
+#pragma once
+#include <cstdint>
+
+namespace mg {
+
+enum Purpose : uint32_t {
+  P_MH = 1, P_RJ = 2, P_RJ_INIT = 3, P_DRAW = 4, P_NEST_INIT = 5,
+  P_NEST_MCMC = 6, P_NEST_START = 7, P_POST = 8
+};
+
+#define MG_PHILOX_M0 0xD2511F53u
+#define MG_PHILOX_M1 0xCD9E8D57u
+#define MG_PHILOX_W0 0x9E3779B9u
+#define MG_PHILOX_W1 0xBB67AE85u
+
+__host__ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2,
+                                                       uint32_t c3, uint32_t k0, uint32_t k1,
+                                                       uint32_t (&out)[4]) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    // one IMAD.WIDE per product: hi and lo halves of 32x32 -> 64
+    const uint64_t p0 = (uint64_t)MG_PHILOX_M0 * c0;
+    const uint64_t p1 = (uint64_t)MG_PHILOX_M1 * c2;
+    const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+    const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+    c1 = (uint32_t)p1; c3 = (uint32_t)p0; c0 = n0; c2 = n2;
+    k0 += MG_PHILOX_W0; k1 += MG_PHILOX_W1;  // key is warp-uniform: folded by the compiler
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+struct CallKey { uint32_t k0, k1; };
+
+inline CallKey derive_key(uint64_t seed, uint64_t epoch) {
+  uint32_t w[4];
+  philox4x32_10((uint32_t)epoch, (uint32_t)(epoch >> 32), 0x6d636d63u, 0u, (uint32_t)seed,
+                (uint32_t)(seed >> 32), w);
+  return CallKey{w[0], w[1]};
+}
+
+// Sequential cursor over the draws of one (purpose, g, step).  In unrolled
+// code the cursor is a compile-time constant and the `(j & 1) == 0` tests fold.
+struct Rng {
+  uint32_t k0, k1, c1, c2, c3;
+  uint32_t w[4];
+  uint32_t j;
+  __device__ __forceinline__ Rng(CallKey ck, uint32_t purpose, uint64_t g, uint64_t step)
+      : k0(ck.k0), k1(ck.k1), c1((uint32_t)step), c2((uint32_t)g),
+        c3((uint32_t)((g >> 32) & 0xFFFFu) | ((purpose & 0xFFu) << 16) |
+           (uint32_t)(((step >> 32) & 0xFFu) << 24)),
+        j(0) {}
+  __device__ __forceinline__ uint64_t lane() {
+    if ((j & 1u) == 0u) philox4x32_10(j >> 1, c1, c2, c3, k0, k1, w);
+    const uint32_t a = (j & 1u) ? w[2] : w[0];
+    const uint32_t b = (j & 1u) ? w[3] : w[1];
+    ++j;
+    return ((uint64_t)a << 32) | b;
+  }
+  // Random.float 1.0: 52 random mantissa bits, [0, 1)
+  __device__ __forceinline__ double uniform() {
+    return __longlong_as_double((long long)((0x3FFull << 52) | (lane() >> 12))) - 1.0;
+  }
+  // Random.int n
+  __device__ __forceinline__ uint64_t below(uint64_t n) { return __umul64hi(lane(), n); }
+};
+
+}  // namespace mg

@@ -1,0 +1,183 @@
+"""Parity of the CUDA Metropolis-Hastings ensemble (mg_mcmc_array*) with the
+CPU oracle on the same seeded inputs, through the C ABI.
+
+Both sides address the same Philox stream and follow the reference's
+arithmetic operation by operation, so chains are compared value for value:
+bit-exact where the model uses only + - * / fma (GAUSS_CORR), and exact in
+the coordinates with ll to 1e-13 where a transcendental (CUDA libm vs glibc)
+enters the log-density.
+"""
+import numpy as np
+import pytest
+
+from mcmc_ocaml_b200 import InvalidArgument, mcmc, plugins as P
+
+pytestmark = pytest.mark.gpu
+
+
+def corr_model(D, rho=0.7, h=0.5):
+    mu = np.arange(D) / 10.0
+    cov = rho ** np.abs(np.subtract.outer(np.arange(D), np.arange(D)))
+    return mu, P.gauss_corr(mu, cov), P.zero(D), P.box_proposal(np.full(D, h))
+
+
+@pytest.mark.parametrize("D", [2, 4, 8, 10, 16, 20, 32])
+def test_static_path_bit_exact(ctx, og, D):
+    """compile-time-D kernels (BASELINE.json config 2 at test size)"""
+    mu, like, prior, prop = corr_model(D)
+    C, n = 200 + D, 40
+    ctx.set_seed(0x5EED0001)
+    got = mcmc.mcmc_array(n, like, prior, prop, mu, nchains=C, nbin=5, nskip=3, ctx=ctx)
+    want, acc, rej = og.mcmc_array(0x5EED0001, 0, n, like, prior, prop, mu, nchains=C, nbin=5, nskip=3, nthreads=8)
+    assert np.array_equal(got.block, want)
+    assert np.array_equal(got.accept, acc) and np.array_equal(got.reject, rej)
+
+
+@pytest.mark.parametrize("D", [1, 3, 5, 7, 12, 24, 33, 64])
+def test_dynamic_path_gauss_corr_bit_exact(ctx, og, D):
+    """dimensions without a static instantiation go through the dynamic plugins"""
+    mu, like, prior, prop = corr_model(D, h=0.3 if D > 20 else 0.5)
+    C, n = 96, 25
+    ctx.set_seed(7)
+    got = mcmc.mcmc_array(n, like, prior, prop, mu, nchains=C, nskip=2, ctx=ctx)
+    want, acc, rej = og.mcmc_array(7, 0, n, like, prior, prop, mu, nchains=C, nskip=2, nthreads=8)
+    assert np.array_equal(got.block, want)
+    assert np.array_equal(got.accept, acc)
+
+
+def test_dynamic_diag_box_wrap(ctx, og):
+    """Stats.log_multi_gaussian likelihood, box prior, uniform_wrapping proposal"""
+    D = 3
+    like = P.gauss_diag([0.3, 0.5, 0.7], [0.1, 0.2, 0.05])
+    prior = P.box(np.zeros(D), np.ones(D), value=0.0)
+    prop = P.wrap_proposal(np.zeros(D), np.ones(D), [0.2, 0.3, 0.1])
+    start = np.random.default_rng(0).random((300, D))
+    ctx.set_seed(99)
+    got = mcmc.mcmc_array(60, like, prior, prop, start, nbin=10, ctx=ctx)
+    want, acc, _ = og.mcmc_array(99, 0, 60, like, prior, prop, start, nbin=10, nthreads=8)
+    assert np.array_equal(got.block[:, :D, :], want[:, :D, :])          # coordinates exact
+    np.testing.assert_allclose(got.block[:, D, :], want[:, D, :], rtol=1e-13, atol=1e-13)
+    assert np.array_equal(got.block[:, D + 1, :], want[:, D + 1, :])
+    assert np.array_equal(got.accept, acc)
+
+
+def test_data_likelihoods(ctx, og):
+    """bin/gaussian_cauchy_efficiency.ml: 100-point dataset, (mu, sigma) with a
+    flat prior on [-1,1]x[0.5,1.5], uniform_wrapping width 0.1"""
+    from tests.golden.gc_data import DATA
+    prior = P.box([-1.0, 0.5], [1.0, 1.5], value=-0.693147)
+    prop = P.wrap_proposal([-1.0, 0.5], [1.0, 1.5], [0.1, 0.1])
+    for k, like in enumerate([P.gauss_data(DATA), P.cauchy_data(DATA)]):
+        ctx.set_seed(20111104 + k)
+        got = mcmc.mcmc_array(50, like, prior, prop, [0.0, 1.0], nchains=128, nbin=20, nskip=4, ctx=ctx)
+        want, acc, _ = og.mcmc_array(20111104 + k, 0, 50, like, prior, prop, [0.0, 1.0], nchains=128, nbin=20,
+                                     nskip=4, nthreads=8)
+        # transcendental log-likelihood: a last-ulp difference can flip one
+        # accept decision; require the overwhelming majority of chains identical
+        same = np.all(got.block[:, :2, :] == want[:, :2, :], axis=(0, 1))
+        assert same.mean() >= 0.98
+        np.testing.assert_allclose(got.block[:, 2, same], want[:, 2, same], rtol=1e-12)
+
+
+def test_asymmetric_proposals_hastings(ctx, og):
+    """log_jump_prob enters the acceptance (mcmc.ml:45-49)"""
+    mu, sigma = 0.4, 1.5
+    like, prior = P.gauss_diag([mu], [sigma]), P.zero(1)
+    for prop in (P.left_biased_proposal(sigma), P.indep_gauss_proposal([mu + 0.3], [2.0 * sigma])):
+        ctx.set_seed(5)
+        got = mcmc.mcmc_array(400, like, prior, prop, [mu], nchains=64, ctx=ctx)
+        want, acc, _ = og.mcmc_array(5, 0, 400, like, prior, prop, [mu], nchains=64, nthreads=8)
+        same = np.all(got.block[:, 0, :] == want[:, 0, :], axis=0)
+        assert same.mean() >= 0.95
+
+
+def test_sharding_is_rank_independent(ctx):
+    """chain_offset: chains [0,C) in one call == two shards run separately"""
+    mu, like, prior, prop = corr_model(10)
+    ctx.set_seed(42)
+    whole = mcmc.mcmc_array(20, like, prior, prop, mu, nchains=256, ctx=ctx)
+    ctx.set_seed(42)
+    a = mcmc.mcmc_array(20, like, prior, prop, mu, nchains=128, chain_offset=0, ctx=ctx)
+    ctx.epoch = 0
+    b = mcmc.mcmc_array(20, like, prior, prop, mu, nchains=128, chain_offset=128, ctx=ctx)
+    assert np.array_equal(whole.block[:, :, :128], a.block)
+    assert np.array_equal(whole.block[:, :, 128:], b.block)
+
+
+def test_chain_major_layout_and_counters(ctx):
+    mu, like, prior, prop = corr_model(4)
+    ctx.set_seed(3)
+    a = mcmc.mcmc_array(33, like, prior, prop, mu, nchains=70, nskip=2, ctx=ctx)
+    ctx.set_seed(3)
+    ctx.reset_counters()
+    b = mcmc.mcmc_array(33, like, prior, prop, mu, nchains=70, nskip=2, layout="chain", ctx=ctx)
+    assert np.array_equal(b.block, a.block.transpose(2, 0, 1))
+    na, nr = ctx.get_counters()                       # Mcmc.get_counters
+    assert na == a.accept.sum() and na + nr == 70 * 32 * 2
+    assert np.array_equal(a.accept + a.reject, np.full(70, 64))
+    # slot 0 is the state after burn-in (mcmc.ml:66): with nbin=0, the start
+    assert np.array_equal(a.block[0, :4, :], np.repeat(mu[:, None], 70, axis=1))
+
+
+def test_invalid_arguments(ctx):
+    mu, like, prior, prop = corr_model(4)
+    with pytest.raises(InvalidArgument):
+        mcmc.mcmc_array(10, like, P.zero(3), prop, mu, nchains=4, ctx=ctx)     # dim mismatch
+    with pytest.raises(InvalidArgument):
+        mcmc.mcmc_array(10, like, prior, prop, mu, nchains=4, nskip=0, ctx=ctx)
+    with pytest.raises(InvalidArgument):
+        mcmc.mcmc_array(10, P.LogFn(77, 4), prior, prop, mu, nchains=4, ctx=ctx)
+
+
+def test_gaussian_posterior_moments(ctx):
+    """test/mcmc_test.ml:40-59: mean and sigma of a 1-D Gaussian within
+    10 sigma / sqrt(N), here with N pooled over 4096 chains"""
+    mu, sigma = 0.37, 1.62
+    ctx.set_seed(2024)
+    r = mcmc.mcmc_array(200, P.gauss_diag([mu], [sigma]), P.zero(1), P.box_proposal([sigma]), [mu],
+                        nchains=4096, nbin=100, nskip=5, ctx=ctx)
+    x = r.block[:, 0, :].ravel()
+    tol = 10.0 * sigma / np.sqrt(x.size / 5)
+    assert abs(x.mean() - mu) < tol and abs(x.std() - sigma) < tol
+
+
+def test_prior_times_like(ctx):
+    """test/mcmc_test.ml:86-98: prior^0.25 * like^0.75 with nskip"""
+    mu, sigma = 0.61, 1.3
+    g = P.gauss_diag([mu], [sigma])
+    ctx.set_seed(11)
+    r = mcmc.mcmc_array(100, g.scaled(0.75), g.scaled(0.25), P.box_proposal([sigma]), [mu], nchains=2048, nskip=10,
+                        ctx=ctx)
+    x = r.block[10:, 0, :].ravel()
+    assert abs(x.mean() - mu) < 0.2 * abs(mu) and abs(x.std() - sigma) < 0.2 * sigma
+
+
+def test_resident_call_and_block_stats(ctx, og):
+    """mg_mcmc_array_resident: sample block stays on the device, host gets
+    final states, counters and Stats.multi_mean / multi_std of the pooled block"""
+    import ctypes as C
+
+    import torch
+
+    from mcmc_ocaml_b200 import _abi
+    D, Cn, n = 10, 512, 50
+    mu, like, prior, prop = corr_model(D)
+    F = D + 2
+    blk = torch.empty((n, F, Cn), dtype=torch.float64, device="cuda")
+    final = np.empty((Cn, F)); acc = np.empty(Cn, np.int64); rej = np.empty(Cn, np.int64)
+    mean = np.empty(F); std = np.empty(F)
+    cfg = _abi.mg_mcmc_cfg(Cn, D, 0, 3, 2, n, 0, 1, 0)
+    ls, ps, js = like.spec(), prior.spec(), prop.spec()
+    ctx.set_seed(77)
+    x0 = _abi.as_f64(mu)
+    ctx.check(ctx.lib.mg_mcmc_array_resident(ctx.h, C.byref(ls), C.byref(ps), C.byref(js), C.byref(cfg), _abi.ptr(x0),
+                                             C.c_void_p(blk.data_ptr()), _abi.ptr(final),
+                                             _abi.ptr(acc, _abi.c_int64_p), _abi.ptr(rej, _abi.c_int64_p),
+                                             _abi.ptr(mean), _abi.ptr(std)))
+    want, wacc, _ = og.mcmc_array(77, 0, n, like, prior, prop, mu, nchains=Cn, nbin=3, nskip=2, nthreads=8)
+    got = blk.cpu().numpy()
+    assert np.array_equal(got, want)
+    assert np.array_equal(final, want[-1].T) and np.array_equal(acc, wacc)
+    pooled = want.transpose(0, 2, 1).reshape(-1, F)
+    np.testing.assert_allclose(mean, og.multi_mean(pooled), rtol=1e-12, atol=1e-14)
+    np.testing.assert_allclose(std, og.multi_std(pooled), rtol=1e-12, atol=1e-14)

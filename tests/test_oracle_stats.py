@@ -1,0 +1,67 @@
+"""Pin the oracle's stats.ml restatement against every exact expectation the
+reference's own tests hold (test/stats_test.ml)."""
+import math
+
+import numpy as np
+import pytest
+
+
+def test_mean_golden(og):  # stats_test.ml:5-7
+    assert og.mean([0.0, 1.0, 2.0, 3.0]) == pytest.approx(6.0 / 4.0, rel=1e-8, abs=1e-8)
+
+
+def test_std_golden(og):  # stats_test.ml:13-15
+    assert og.std([1.0, 2.0, 3.0, 4.0, 5.0]) == pytest.approx(math.sqrt(10.0) / 2.0, rel=1e-8, abs=1e-8)
+
+
+def test_multi_mean_golden(og):  # stats_test.ml:40-46
+    mu = og.multi_mean([[0.0, 1.0], [2.0, 3.0], [4.0, -5.0]])
+    assert mu[0] == pytest.approx(2.0, abs=1e-8) and mu[1] == pytest.approx(-1.0 / 3.0, abs=1e-8)
+
+
+def test_multi_std_golden(og):  # stats_test.ml:48-55
+    xs = [[0.662891, 0.218155, 0.464706, 0.148477, 0.39616],
+          [0.43397, 0.161041, 0.625332, 0.508765, 0.261084],
+          [0.147267, 0.403388, 0.643601, 0.892214, 0.269893]]
+    want = [0.258351, 0.126692, 0.098436, 0.371928, 0.0755716]
+    np.testing.assert_allclose(og.multi_std(xs), want, rtol=1e-3, atol=1e-3)
+
+
+def test_log_lognormal_golden(og):  # stats_test.ml:94-99
+    assert og.log_lognormal(0.328077, 0.330877, 0.0553941) == pytest.approx(-44.3128, abs=1e-3)
+
+
+def test_gaussian_identities(og):  # stats_test.ml:23-29
+    mu, sigma = 0.37, 0.81
+    g0 = 1.0 / (math.sqrt(2.0 * math.pi) * sigma)
+    assert math.exp(og.log_gaussian(mu, sigma, mu)) == pytest.approx(g0, rel=1e-8)
+    assert math.exp(og.log_gaussian(mu, sigma, mu + sigma)) == pytest.approx(g0 * math.exp(-0.5), rel=1e-8)
+
+
+def test_log_sum_logs(og):  # stats_test.ml:109-120
+    rng = np.random.default_rng(1)
+    for x, y in rng.random((100, 2)):
+        assert og.log_sum_logs(math.log(x), math.log(y)) == pytest.approx(math.log(x + y), rel=1e-8, abs=1e-8)
+    assert og.log_sum_logs(-math.inf, -math.inf) == -math.inf
+
+
+def test_draw_gaussian_moments(og):  # stats_test.ml:31-38
+    xs = og.draw_gaussian(3, 0, 0.3, 0.7, 10000)
+    assert abs(xs.mean() - 0.3) < 0.1 and abs(xs.std(ddof=1) - 0.7) < 0.1
+    xs = og.draw_gaussian(3, 1, 0.0, 1.0, 400000)
+    from scipy import stats
+    assert stats.kstest(xs, "norm").pvalue > 1e-3
+
+
+def test_autocorrelation_unpinned(og):
+    """the reference's golden (stats_test.ml:101-107) is from an
+    unregistered test of a function whose loop overruns its buffer; it matches
+    no normalisation.  We pin our formula (lags 0..nslides-1, sigma^2 with
+    n-1, divide by n-i) against numpy and record that the golden is NOT met."""
+    data = np.array([-1.44898, -0.0762953, 2.25525, -0.284584, 1.16297, 0.00864677, 0.211493])
+    r, L = og.autocorrelation(data, 3)
+    mu, s2 = data.mean(), data.var(ddof=1)
+    want = [np.sum((data[: len(data) - i] - mu) * (data[i:] - mu)) / s2 / (len(data) - i) for i in range(3)]
+    np.testing.assert_allclose(r, want, rtol=1e-13)
+    golden = [1.0, -0.117926565125732, -0.043808623348460]
+    assert not np.allclose(r, golden, rtol=1e-5)  # parity unpinned, documented in DESIGN.md
