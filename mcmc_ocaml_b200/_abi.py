@@ -11,7 +11,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmcmcgpu.so")
+# MCMC_GPU_LIB selects another build of the same library (kernel-variant experiments)
+LIB_PATH = os.environ.get("MCMC_GPU_LIB") or os.path.join(_HERE, "libmcmcgpu.so")
 
 MG_OK, MG_EINVAL, MG_EFAIL, MG_ECUDA, MG_ENOMEM = 0, 1, 2, 3, 4
 

@@ -1,0 +1,558 @@
+// kdtree.cu -- Kd_tree.tree_of_objects (kd_tree.ml:155-175) built on the GPU,
+// bit-exact with the reference rule, plus the Interpolate_pdf kernels
+// (interpolate_pdf.ml:101-159).
+//
+// Build.  The reference recurses over OCaml lists and finds the pivot with a
+// randomized quickselect (kd_tree.ml:69-86).  Here every coordinate is sorted
+// ONCE (stable radix sort of order-preserving uint64 keys, one batch row per
+// dimension), giving D index lists; a (D+1)-th list keeps the input order.
+// The tree is then grown level by level on flat node arrays: inside a node's
+// range every list holds the same points, so
+//   tight bounds        = first / last element of each sorted list  (:96-110)
+//   n/2-th order stat.  = element at offset n/2 of the split dim's list (:162-167)
+//   <= pivot / > pivot  = a position threshold in that list (binary search)
+//   max L, min R        = the two elements around the threshold (:170-171)
+// and a level costs one flag pass plus one STABLE partition of the D+1 lists
+// (tile reduce -> scan -> scatter), which keeps each list sorted and the
+// input-order list in the reference's List.partition order (:168).
+// Algorithmic traffic per level: (D+1) lists x N x ~18 B (SURVEY.md 8d gives
+// (16 D + 16) N for a row-permuting build; index lists move 4-byte ids instead
+// of 8 D-byte rows).  All kernels are HBM / L2-gather bound.
+#include "kdtree.cuh"
+
+#include "common.cuh"
+#include "radix_sort.cuh"
+#include "scan.cuh"
+
+namespace mg {
+
+constexpr int KB = 256;  // generic block size
+
+__global__ void check_finite_kernel(const double *__restrict__ x, int64_t n, int *__restrict__ flag) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    if (x[i] != x[i]) *flag = 1;
+}
+
+// keys[d][i] = ordered(pts[i][d]), vals[d][i] = i; row D of vals = identity
+__global__ void make_keys_kernel(const double *__restrict__ pts, int64_t N, int D, uint64_t *__restrict__ keys,
+                                 int32_t *__restrict__ vals) {
+  const int d = blockIdx.y;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x) {
+    if (d < D) keys[(int64_t)d * N + i] = f64_to_ordered(pts[i * D + d]);
+    vals[(int64_t)d * N + i] = (int32_t)i;
+  }
+}
+
+struct BuildArrays {
+  const double *pts;
+  int64_t N;
+  int D, min_split;
+  int32_t *begin, *end, *dim, *left, *spos;
+  double *split;
+};
+
+__device__ __forceinline__ double key_at(const BuildArrays &a, const int32_t *lists, int d, int64_t pos) {
+  return a.pts[(int64_t)lists[(int64_t)d * a.N + pos] * a.D + d];
+}
+
+// kd_tree.ml:155-175 for the nodes [lb, le) of one level.
+__global__ void node_split_kernel(BuildArrays a, const int32_t *__restrict__ lists, int32_t lb, int32_t le,
+                                  int32_t *__restrict__ flags /* [2][nlvl]: is_split, nR */) {
+  const int32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  const int32_t nlvl = le - lb;
+  if (k >= nlvl) return;
+  const int32_t id = lb + k;
+  const int32_t b = a.begin[id], e = a.end[id], n = e - b;
+  int is_split = 0, nR = 0;
+  a.dim[id] = -1; a.left[id] = -1; a.split[id] = 0.0; a.spos[id] = e;
+  if (n > 1 && n >= a.min_split) {                   // :157-158 (+ truncation)
+    // bounds_of_objects (:96-110) and longest_dim (:120-130): first strictly largest spread
+    int sd = -1;
+    double dx_max = neg_inf();
+    bool all_eq = true;
+    for (int d = 0; d < a.D; ++d) {
+      const double lo = key_at(a, lists, d, b), hi = key_at(a, lists, d, e - 1);
+      if (lo != hi) all_eq = false;
+      const double dx = hi - lo;
+      if (dx > dx_max) { sd = d; dx_max = dx; }
+    }
+    if (!all_eq && sd >= 0) {                        // :159-160 identical coordinates -> leaf
+      const double v = key_at(a, lists, sd, b + n / 2);  // :162-167
+      // first position with key > v (List.partition (<= pvt), :168)
+      int32_t lo = b + n / 2, hi = e;
+      while (lo < hi) { const int32_t mid = lo + ((hi - lo) >> 1); if (key_at(a, lists, sd, mid) > v) hi = mid; else lo = mid + 1; }
+      int32_t pos = lo;
+      if (pos == e) {                                // adjust_for_empty_split :150-152: L = {k < max}
+        lo = b; hi = b + n / 2;
+        while (lo < hi) { const int32_t mid = lo + ((hi - lo) >> 1); if (key_at(a, lists, sd, mid) < v) lo = mid + 1; else hi = mid; }
+        pos = lo;
+      }
+      if (pos > b && pos < e) {
+        const double lt_bound = key_at(a, lists, sd, pos - 1), gt_bound = key_at(a, lists, sd, pos);  // :170-171
+        a.dim[id] = sd;
+        a.split[id] = 0.5 * (lt_bound + gt_bound);  // split_bounds :113
+        a.spos[id] = pos;
+        is_split = 1; nR = e - pos;
+      }
+    }
+  }
+  flags[k] = is_split;
+  flags[nlvl + k] = nR;
+}
+
+__global__ void make_children_kernel(BuildArrays a, int32_t lb, int32_t le, const int32_t *__restrict__ flags,
+                                     const int32_t *__restrict__ scans, int32_t next_base) {
+  const int32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= le - lb) return;
+  if (!flags[k]) return;
+  const int32_t id = lb + k;
+  const int32_t L = next_base + 2 * scans[k];
+  a.left[id] = L;
+  a.begin[L] = a.begin[id]; a.end[L] = a.spos[id];
+  a.begin[L + 1] = a.spos[id]; a.end[L + 1] = a.end[id];
+}
+
+// side[point] = 1 iff the point goes to the right child of its (splitting) node
+__global__ void mark_side_kernel(BuildArrays a, const int32_t *__restrict__ lists, const int32_t *__restrict__ seg,
+                                 int32_t lb, int32_t le, uint8_t *__restrict__ side) {
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < a.N; p += (int64_t)gridDim.x * blockDim.x) {
+    const int32_t id = seg[p];
+    if (id < lb || id >= le) continue;
+    const int32_t sd = a.dim[id];
+    if (sd < 0) continue;
+    side[lists[(int64_t)sd * a.N + p]] = (p >= a.spos[id]) ? 1 : 0;
+  }
+}
+
+__device__ __forceinline__ int part_flag(const BuildArrays &a, const int32_t *seg, const uint8_t *side,
+                                         const int32_t *list, int32_t lb, int32_t le, int64_t p, int32_t *node,
+                                         int32_t *idx) {
+  const int32_t id = seg[p];
+  *node = id; *idx = list[p];
+  if (id < lb || id >= le || a.dim[id] < 0) { *node = -1; return 0; }
+  return side[*idx];
+}
+
+__global__ void __launch_bounds__(SCAN_BLOCK)
+part_reduce_kernel(BuildArrays a, const int32_t *__restrict__ lists, const int32_t *__restrict__ seg,
+                   const uint8_t *__restrict__ side, int32_t lb, int32_t le, int64_t ntiles, int32_t *__restrict__ tsum) {
+  const int l = blockIdx.y;
+  const int32_t *list = lists + (int64_t)l * a.N;
+  const int64_t base = (int64_t)blockIdx.x * SCAN_TILE;
+  int acc = 0;
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; ++k) {
+    const int64_t p = base + k * SCAN_BLOCK + threadIdx.x;
+    if (p < a.N) { int32_t nd, ix; acc += part_flag(a, seg, side, list, lb, le, p, &nd, &ix); }
+  }
+  int total;
+  block_exclusive_scan<SCAN_BLOCK>(acc, &total);
+  if (threadIdx.x == 0) tsum[(int64_t)l * ntiles + blockIdx.x] = total;
+}
+
+// stable partition of every list inside every splitting node (List.partition, kd_tree.ml:168)
+__global__ void __launch_bounds__(SCAN_BLOCK)
+part_scatter_kernel(BuildArrays a, const int32_t *__restrict__ lists_in, int32_t *__restrict__ lists_out,
+                    const int32_t *__restrict__ seg_in, int32_t *__restrict__ seg_out,
+                    const uint8_t *__restrict__ side, int32_t lb, int32_t le, int64_t ntiles,
+                    const int32_t *__restrict__ tbase, const int32_t *__restrict__ ebegin /* [nlvl] */) {
+  const int l = blockIdx.y;
+  const int32_t *list = lists_in + (int64_t)l * a.N;
+  int32_t *out = lists_out + (int64_t)l * a.N;
+  const int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
+  int f[SCAN_ITEMS]; int32_t nd[SCAN_ITEMS], ix[SCAN_ITEMS];
+  int acc = 0;
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; ++k) {
+    const int64_t p = base + k;
+    f[k] = 0; nd[k] = -1; ix[k] = 0;
+    if (p < a.N) f[k] = part_flag(a, seg_in, side, list, lb, le, p, &nd[k], &ix[k]);
+    acc += f[k];
+  }
+  int total;
+  int E = block_exclusive_scan<SCAN_BLOCK>(acc, &total) + tbase[(int64_t)l * ntiles + blockIdx.x];
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; ++k) {
+    const int64_t p = base + k;
+    if (p < a.N) {
+      if (nd[k] < 0) {
+        out[p] = ix[k];
+        if (l == 0) seg_out[p] = seg_in[p];
+      } else {
+        const int32_t id = nd[k];
+        const int32_t b = a.begin[id], sp = a.spos[id];
+        const int32_t r = E - ebegin[id - lb];            // right-goers in [b, p)
+        const int64_t dst = f[k] ? (int64_t)sp + r : (int64_t)b + (p - b) - r;
+        out[dst] = ix[k];
+        if (l == 0) seg_out[p] = (p < sp) ? a.left[id] : a.left[id] + 1;
+      }
+    }
+    E += f[k];
+  }
+}
+
+__global__ void pack_nodes_kernel(BuildArrays a, int64_t nnodes, KdNode *__restrict__ nodes, int32_t *__restrict__ count,
+                                  int32_t *__restrict__ begin_out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nnodes; i += (int64_t)gridDim.x * blockDim.x) {
+    KdNode nd; nd.split = a.split[i]; nd.left = a.left[i]; nd.dim = a.dim[i];
+    nodes[i] = nd; count[i] = a.end[i] - a.begin[i]; begin_out[i] = a.begin[i];
+  }
+}
+
+__global__ void fill_i32_kernel(int32_t *p, int64_t n, int32_t v) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = v;
+}
+
+static inline unsigned grid1d(mg_ctx *ctx, int64_t n, int block = KB) {
+  int64_t g = (n + block - 1) / block;
+  const int64_t cap = (int64_t)ctx->sm_count * 16;
+  if (g > cap) g = cap;
+  return (unsigned)(g < 1 ? 1 : g);
+}
+static inline int64_t align256(int64_t x) { return (x + 255) & ~255LL; }
+
+static int build_tree(mg_ctx *ctx, const double *d_pts, int64_t N, int D, const double *low, const double *high,
+                      int min_split, mg_kdtree **out) {
+  cudaStream_t s = ctx->stream;
+  MG_REQUIRE(ctx, N >= 1, "tree_of_objects: no objects");
+  MG_REQUIRE(ctx, D >= 1 && D <= 64, "kd-tree: dim must be in 1..64");
+  MG_REQUIRE(ctx, N < (1LL << 30), "kd-tree: too many points for int32 indices");
+  if (min_split < 2) min_split = 2;
+  // NaN coordinates are rejected (Pervasives.compare orders them, IEEE does not)
+  DevBuf<int> d_flag;
+  MG_CUDA(ctx, d_flag.alloc(1, s));
+  MG_CUDA(ctx, cudaMemsetAsync(d_flag.get(), 0, sizeof(int), s));
+  check_finite_kernel<<<grid1d(ctx, N * D), KB, 0, s>>>(d_pts, N * D, d_flag.get());
+  MG_CHECK_LAUNCH(ctx);
+  int h_flag = 0;
+  MG_CUDA(ctx, cudaMemcpyAsync(&h_flag, d_flag.get(), sizeof(int), cudaMemcpyDeviceToHost, s));
+  MG_CUDA(ctx, cudaStreamSynchronize(s));
+  MG_REQUIRE(ctx, h_flag == 0, "kd-tree: NaN coordinate");
+
+  time_begin(ctx);
+  const int NL = D + 1;  // D sorted lists + the input-order list
+  DevBuf<int32_t> listsA, listsB, segA, segB, nd_begin, nd_end, nd_dim, nd_left, nd_spos, flags, scans, tsum, totals;
+  DevBuf<double> nd_split;
+  DevBuf<uint8_t> side;
+  MG_CUDA(ctx, listsA.alloc((size_t)NL * N, s));
+  MG_CUDA(ctx, listsB.alloc((size_t)NL * N, s));
+  {
+    DevBuf<uint64_t> keys;
+    MG_CUDA(ctx, keys.alloc((size_t)D * N, s));
+    make_keys_kernel<<<dim3(grid1d(ctx, N), NL), KB, 0, s>>>(d_pts, N, D, keys.get(), listsA.get());
+    MG_CHECK_LAUNCH(ctx);
+    int rc = radix_sort_pairs(ctx, keys.get(), listsA.get(), N, D);
+    if (rc) return rc;
+  }
+  const int64_t cap = 2 * N;
+  MG_CUDA(ctx, nd_begin.alloc(cap, s)); MG_CUDA(ctx, nd_end.alloc(cap, s)); MG_CUDA(ctx, nd_dim.alloc(cap, s));
+  MG_CUDA(ctx, nd_left.alloc(cap, s)); MG_CUDA(ctx, nd_spos.alloc(cap, s)); MG_CUDA(ctx, nd_split.alloc(cap, s));
+  MG_CUDA(ctx, segA.alloc(N, s)); MG_CUDA(ctx, segB.alloc(N, s)); MG_CUDA(ctx, side.alloc(N, s));
+  MG_CUDA(ctx, cudaMemsetAsync(segA.get(), 0, sizeof(int32_t) * N, s));
+  MG_CUDA(ctx, cudaMemsetAsync(side.get(), 0, N, s));
+  const int64_t ntiles = (N + SCAN_TILE - 1) / SCAN_TILE;
+  MG_CUDA(ctx, tsum.alloc((size_t)NL * ntiles, s));
+  MG_CUDA(ctx, totals.alloc(2, s));
+  BuildArrays a{d_pts, N, D, min_split, nd_begin.get(), nd_end.get(), nd_dim.get(), nd_left.get(), nd_spos.get(),
+                nd_split.get()};
+  {
+    const int32_t zero = 0, n32 = (int32_t)N;
+    MG_CUDA(ctx, cudaMemcpyAsync(nd_begin.get(), &zero, 4, cudaMemcpyHostToDevice, s));
+    MG_CUDA(ctx, cudaMemcpyAsync(nd_end.get(), &n32, 4, cudaMemcpyHostToDevice, s));
+    MG_CUDA(ctx, cudaStreamSynchronize(s));
+  }
+  int32_t *lin = listsA.get(), *lout = listsB.get(), *sin = segA.get(), *sout = segB.get();
+  int64_t lb = 0, le = 1, nnodes = 1;
+  int nlevels = 0;
+  int64_t flags_cap = 0;
+  DevBuf<int32_t> scan_tmp;
+  for (;;) {
+    ++nlevels;
+    if (nlevels > 100000) return set_err(ctx, MG_EFAIL, "kd-tree: too many levels");
+    const int64_t nlvl = le - lb;
+    if (2 * nlvl > flags_cap) {
+      flags_cap = 2 * nlvl * 2;
+      MG_CUDA(ctx, flags.alloc((size_t)flags_cap, s));
+      MG_CUDA(ctx, scans.alloc((size_t)flags_cap, s));
+      MG_CUDA(ctx, scan_tmp.alloc((size_t)scan_tmp_elems(flags_cap / 2, 2) + 2, s));
+    }
+    node_split_kernel<<<(unsigned)((nlvl + 127) / 128), 128, 0, s>>>(a, lin, (int32_t)lb, (int32_t)le, flags.get());
+    MG_CHECK_LAUNCH(ctx);
+    int rc = exclusive_scan_i32(ctx, flags.get(), scans.get(), nlvl, 2, scan_tmp.get(), totals.get());
+    if (rc) return rc;
+    int32_t h_tot[2];
+    MG_CUDA(ctx, cudaMemcpyAsync(h_tot, totals.get(), 8, cudaMemcpyDeviceToHost, s));
+    MG_CUDA(ctx, cudaStreamSynchronize(s));
+    const int64_t nsplit = h_tot[0];
+    if (nsplit == 0) break;
+    if (nnodes + 2 * nsplit > cap) return set_err(ctx, MG_EFAIL, "kd-tree: node capacity exceeded");
+    make_children_kernel<<<(unsigned)((nlvl + 127) / 128), 128, 0, s>>>(a, (int32_t)lb, (int32_t)le, flags.get(),
+                                                                       scans.get(), (int32_t)nnodes);
+    MG_CHECK_LAUNCH(ctx);
+    mark_side_kernel<<<grid1d(ctx, N), KB, 0, s>>>(a, lin, sin, (int32_t)lb, (int32_t)le, side.get());
+    MG_CHECK_LAUNCH(ctx);
+    dim3 pgrid((unsigned)ntiles, (unsigned)NL);
+    part_reduce_kernel<<<pgrid, SCAN_BLOCK, 0, s>>>(a, lin, sin, side.get(), (int32_t)lb, (int32_t)le, ntiles, tsum.get());
+    MG_CHECK_LAUNCH(ctx);
+    scan_tiles_kernel<<<(unsigned)NL, 1024, 0, s>>>(tsum.get(), ntiles, nullptr);
+    MG_CHECK_LAUNCH(ctx);
+    part_scatter_kernel<<<pgrid, SCAN_BLOCK, 0, s>>>(a, lin, lout, sin, sout, side.get(), (int32_t)lb, (int32_t)le,
+                                                     ntiles, tsum.get(), scans.get() + nlvl);
+    MG_CHECK_LAUNCH(ctx);
+    std::swap(lin, lout); std::swap(sin, sout);
+    lb = le; le = nnodes + 2 * nsplit; nnodes = le;
+  }
+  // ---- assemble the blob ----------------------------------------------------
+  KdHeader h{};
+  h.magic = KD_MAGIC; h.N = N; h.nnodes = nnodes; h.D = D; h.nlevels = nlevels; h.min_split = min_split;
+  int64_t off = align256(sizeof(KdHeader));
+  h.off_low = off; off = align256(off + 8 * D);
+  h.off_high = off; off = align256(off + 8 * D);
+  h.off_nodes = off; off = align256(off + 16 * nnodes);
+  h.off_count = off; off = align256(off + 4 * nnodes);
+  h.off_begin = off; off = align256(off + 4 * nnodes);
+  h.off_perm = off; off = align256(off + 4 * N);
+  h.off_pts = off; off = align256(off + 8 * N * D);
+  h.nbytes = off;
+  mg_kdtree *t = new mg_kdtree;
+  t->ctx = ctx; t->h = h;
+  cudaError_t e = cudaMalloc(&t->d_blob, (size_t)h.nbytes);
+  if (e != cudaSuccess) { delete t; return set_err(ctx, MG_ENOMEM, "cuda: %s (kd-tree blob of %lld bytes)", cudaGetErrorString(e), (long long)h.nbytes); }
+  char *blob = (char *)t->d_blob;
+  cudaMemcpyAsync(blob, &t->h, sizeof(KdHeader), cudaMemcpyHostToDevice, s);
+  cudaMemcpyAsync(blob + h.off_low, low, 8 * D, cudaMemcpyHostToDevice, s);
+  cudaMemcpyAsync(blob + h.off_high, high, 8 * D, cudaMemcpyHostToDevice, s);
+  pack_nodes_kernel<<<grid1d(ctx, nnodes), KB, 0, s>>>(a, nnodes, (KdNode *)(blob + h.off_nodes),
+                                                      (int32_t *)(blob + h.off_count), (int32_t *)(blob + h.off_begin));
+  ctx->launches++;
+  cudaMemcpyAsync(blob + h.off_perm, lin + (int64_t)D * N, 4 * N, cudaMemcpyDeviceToDevice, s);
+  cudaMemcpyAsync(blob + h.off_pts, d_pts, 8 * N * D, cudaMemcpyDeviceToDevice, s);
+  time_end(ctx);
+  e = cudaStreamSynchronize(s);
+  if (e != cudaSuccess) { cudaFree(t->d_blob); delete t; return set_err(ctx, MG_ECUDA, "cuda: %s (kd-tree build)", cudaGetErrorString(e)); }
+  *out = t;
+  return MG_OK;
+}
+
+// ---- Interpolate_pdf kernels ------------------------------------------------
+
+__global__ void jump_prob_kernel(KdView t, const double *__restrict__ q, int64_t M, int nstop,
+                                 double *__restrict__ out_prob, int32_t *__restrict__ out_node) {
+  extern __shared__ double smem[];
+  const KdScratch s = kd_scratch(smem, t.D);
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M) return;
+  for (int d = 0; d < t.D; ++d) s.Q(d) = q[i * t.D + d];
+  int32_t node;
+  const double p = kd_jump_prob(t, s, nstop, &node);
+  if (out_prob) out_prob[i] = p;
+  if (out_node) out_node[i] = node;
+}
+
+__global__ void draw_kernel(KdView t, CallKey key, uint64_t draw_offset, int64_t M, int nstop,
+                            double *__restrict__ out, int *__restrict__ fail) {
+  extern __shared__ double smem[];
+  const KdScratch s = kd_scratch(smem, t.D);
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M) return;
+  Rng r(key, P_DRAW, draw_offset + (uint64_t)i, 0);
+  if (!kd_draw(t, s, nstop, r)) { *fail = 1; for (int d = 0; d < t.D; ++d) out[i * t.D + d] = qnan(); return; }
+  for (int d = 0; d < t.D; ++d) out[i * t.D + d] = s.Q(d);
+}
+
+static int query_block(int D) { return D <= 16 ? 128 : (D <= 32 ? 64 : 32); }
+
+template <class K>
+static int prep_smem(mg_ctx *ctx, K kernel, size_t bytes) {
+  if (bytes > 48 * 1024) MG_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  return MG_OK;
+}
+
+}  // namespace mg
+
+using namespace mg;
+
+extern "C" int mg_kdtree_build_dev(mg_ctx *ctx, const double *d_pts, int64_t N, int32_t D, const double *low,
+                                   const double *high, int32_t min_split, mg_kdtree **out) {
+  if (!ctx) return MG_EINVAL;
+  MG_REQUIRE(ctx, d_pts && low && high && out, "kd-tree: null argument");
+  MG_CUDA(ctx, cudaSetDevice(ctx->device));
+  *out = nullptr;
+  return build_tree(ctx, d_pts, N, D, low, high, min_split, out);
+}
+
+extern "C" int mg_kdtree_build(mg_ctx *ctx, const double *pts, int64_t N, int32_t D, const double *low,
+                               const double *high, int32_t min_split, mg_kdtree **out) {
+  if (!ctx) return MG_EINVAL;
+  MG_REQUIRE(ctx, pts && low && high && out, "kd-tree: null argument");
+  MG_REQUIRE(ctx, N >= 1, "tree_of_objects: no objects");
+  MG_REQUIRE(ctx, D >= 1 && D <= 64, "kd-tree: dim must be in 1..64");
+  MG_CUDA(ctx, cudaSetDevice(ctx->device));
+  DevBuf<double> d_pts;
+  MG_CUDA(ctx, upload(d_pts, pts, (size_t)N * D, ctx->stream));
+  *out = nullptr;
+  return build_tree(ctx, d_pts.get(), N, D, low, high, min_split, out);
+}
+
+extern "C" void mg_kdtree_destroy(mg_kdtree *t) {
+  if (!t) return;
+  if (t->ctx) { cudaSetDevice(t->ctx->device); cudaStreamSynchronize(t->ctx->stream); }
+  if (t->owns_blob && t->d_blob) cudaFree(t->d_blob);
+  delete t;
+}
+
+extern "C" int mg_kdtree_info(const mg_kdtree *t, int64_t *npoints, int32_t *dim, int64_t *nnodes, int32_t *nlevels) {
+  if (!t) return MG_EINVAL;
+  if (npoints) *npoints = t->h.N;
+  if (dim) *dim = t->h.D;
+  if (nnodes) *nnodes = t->h.nnodes;
+  if (nlevels) *nlevels = t->h.nlevels;
+  return MG_OK;
+}
+
+extern "C" int mg_kdtree_export(const mg_kdtree *t, int32_t *split_dim, double *split_val, int32_t *left,
+                                int32_t *begin, int32_t *end, int32_t *perm) {
+  if (!t) return MG_EINVAL;
+  mg_ctx *ctx = t->ctx;
+  MG_CUDA(ctx, cudaSetDevice(ctx->device));
+  const int64_t nn = t->h.nnodes;
+  const char *blob = (const char *)t->d_blob;
+  std::vector<KdNode> nodes((size_t)nn);
+  std::vector<int32_t> count((size_t)nn), b((size_t)nn);
+  MG_CUDA(ctx, cudaMemcpyAsync(nodes.data(), blob + t->h.off_nodes, 16 * nn, cudaMemcpyDeviceToHost, ctx->stream));
+  MG_CUDA(ctx, cudaMemcpyAsync(count.data(), blob + t->h.off_count, 4 * nn, cudaMemcpyDeviceToHost, ctx->stream));
+  MG_CUDA(ctx, cudaMemcpyAsync(b.data(), blob + t->h.off_begin, 4 * nn, cudaMemcpyDeviceToHost, ctx->stream));
+  if (perm) MG_CUDA(ctx, cudaMemcpyAsync(perm, blob + t->h.off_perm, 4 * t->h.N, cudaMemcpyDeviceToHost, ctx->stream));
+  MG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  for (int64_t i = 0; i < nn; ++i) {
+    if (split_dim) split_dim[i] = nodes[i].dim;
+    if (split_val) split_val[i] = nodes[i].split;
+    if (left) left[i] = nodes[i].left;
+    if (begin) begin[i] = b[i];
+    if (end) end[i] = b[i] + count[i];
+  }
+  return MG_OK;
+}
+
+extern "C" int mg_kdtree_blob_size(const mg_kdtree *t, int64_t *nbytes) {
+  if (!t || !nbytes) return MG_EINVAL;
+  *nbytes = t->h.nbytes;
+  return MG_OK;
+}
+extern "C" int mg_kdtree_blob_dev(const mg_kdtree *t, void **d_blob) {
+  if (!t || !d_blob) return MG_EINVAL;
+  *d_blob = t->d_blob;
+  return MG_OK;
+}
+extern "C" int mg_kdtree_from_blob_dev(mg_ctx *ctx, const void *d_blob, int64_t nbytes, mg_kdtree **out) {
+  if (!ctx) return MG_EINVAL;
+  MG_REQUIRE(ctx, d_blob && out && nbytes >= (int64_t)sizeof(KdHeader), "kd-tree: bad blob");
+  MG_CUDA(ctx, cudaSetDevice(ctx->device));
+  KdHeader h;
+  MG_CUDA(ctx, cudaMemcpyAsync(&h, d_blob, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
+  MG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  MG_REQUIRE(ctx, h.magic == KD_MAGIC && h.nbytes == nbytes, "kd-tree: blob header mismatch");
+  mg_kdtree *t = new mg_kdtree;
+  t->ctx = ctx; t->h = h;
+  cudaError_t e = cudaMalloc(&t->d_blob, (size_t)nbytes);
+  if (e != cudaSuccess) { delete t; return set_err(ctx, MG_ENOMEM, "cuda: %s", cudaGetErrorString(e)); }
+  MG_CUDA(ctx, cudaMemcpyAsync(t->d_blob, d_blob, (size_t)nbytes, cudaMemcpyDeviceToDevice, ctx->stream));
+  MG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  *out = t;
+  return MG_OK;
+}
+
+extern "C" double mg_bounds_volume(const double *low, const double *high, int32_t D) {
+  double v = 1.0;  // kd_tree.ml:177-182
+  for (int i = 0; i < D; ++i) v = v * (high[i] - low[i]);
+  return v + 0.0;
+}
+
+extern "C" int mg_interp_jump_prob_dev(mg_ctx *ctx, const mg_kdtree *t, const double *d_q, int64_t M, int32_t nstop,
+                                       double *d_out_prob, int32_t *d_out_node) {
+  if (!ctx) return MG_EINVAL;
+  MG_REQUIRE(ctx, t && d_q && M >= 0, "jump_prob: bad arguments");
+  if (M == 0) return MG_OK;
+  MG_CUDA(ctx, cudaSetDevice(ctx->device));
+  const int block = query_block(t->h.D);
+  const size_t smem = kd_scratch_bytes(t->h.D, block);
+  int rc = prep_smem(ctx, jump_prob_kernel, smem);
+  if (rc) return rc;
+  time_begin(ctx);
+  jump_prob_kernel<<<(unsigned)((M + block - 1) / block), block, smem, ctx->stream>>>(t->view(), d_q, M, nstop,
+                                                                                      d_out_prob, d_out_node);
+  MG_CHECK_LAUNCH(ctx);
+  time_end(ctx);
+  return MG_OK;
+}
+
+static int interp_query_host(mg_ctx *ctx, const mg_kdtree *t, const double *q, int64_t M, int32_t nstop,
+                             double *out_prob, int32_t *out_node, const char *what) {
+  if (!ctx) return MG_EINVAL;
+  MG_REQUIRE(ctx, t && q && M >= 0, "%s: bad arguments", what);
+  if (M == 0) return MG_OK;
+  MG_CUDA(ctx, cudaSetDevice(ctx->device));
+  DevBuf<double> d_q, d_p;
+  DevBuf<int32_t> d_n;
+  MG_CUDA(ctx, upload(d_q, q, (size_t)M * t->h.D, ctx->stream));
+  MG_CUDA(ctx, d_p.alloc(M, ctx->stream));
+  MG_CUDA(ctx, d_n.alloc(M, ctx->stream));
+  int rc = mg_interp_jump_prob_dev(ctx, t, d_q.get(), M, nstop, d_p.get(), d_n.get());
+  if (rc) return rc;
+  std::vector<int32_t> nodes((size_t)M);
+  if (out_prob) MG_CUDA(ctx, cudaMemcpyAsync(out_prob, d_p.get(), 8 * M, cudaMemcpyDeviceToHost, ctx->stream));
+  MG_CUDA(ctx, cudaMemcpyAsync(nodes.data(), d_n.get(), 4 * M, cudaMemcpyDeviceToHost, ctx->stream));
+  MG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  bool bad = false;
+  for (int64_t i = 0; i < M; ++i) { if (out_node) out_node[i] = nodes[i]; if (nodes[i] < 0) bad = true; }
+  if (bad) return set_err(ctx, MG_EFAIL, "%s: encountered empty tree!", what);  // interpolate_pdf.ml:124,149
+  return MG_OK;
+}
+
+extern "C" int mg_interp_find_cell(mg_ctx *ctx, const mg_kdtree *t, const double *q, int64_t M, int32_t nstop,
+                                   int32_t *out_node) {
+  return interp_query_host(ctx, t, q, M, nstop, nullptr, out_node, "find_cell");
+}
+extern "C" int mg_interp_jump_prob(mg_ctx *ctx, const mg_kdtree *t, const double *q, int64_t M, int32_t nstop,
+                                   double *out_prob) {
+  return interp_query_host(ctx, t, q, M, nstop, out_prob, nullptr, "jump_prob_high_level");
+}
+
+extern "C" int mg_interp_draw_dev(mg_ctx *ctx, const mg_kdtree *t, int64_t M, int32_t nstop, double *d_out) {
+  if (!ctx) return MG_EINVAL;
+  MG_REQUIRE(ctx, t && d_out && M >= 0, "draw: bad arguments");
+  if (M == 0) return MG_OK;
+  MG_CUDA(ctx, cudaSetDevice(ctx->device));
+  const int block = query_block(t->h.D);
+  const size_t smem = kd_scratch_bytes(t->h.D, block);
+  int rc = prep_smem(ctx, draw_kernel, smem);
+  if (rc) return rc;
+  DevBuf<int> d_fail;
+  MG_CUDA(ctx, d_fail.alloc(1, ctx->stream));
+  MG_CUDA(ctx, cudaMemsetAsync(d_fail.get(), 0, sizeof(int), ctx->stream));
+  const CallKey key = next_key(ctx);
+  time_begin(ctx);
+  draw_kernel<<<(unsigned)((M + block - 1) / block), block, smem, ctx->stream>>>(t->view(), key, 0, M, nstop, d_out,
+                                                                                 d_fail.get());
+  MG_CHECK_LAUNCH(ctx);
+  time_end(ctx);
+  int h_fail = 0;
+  MG_CUDA(ctx, cudaMemcpyAsync(&h_fail, d_fail.get(), sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  MG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (h_fail) return set_err(ctx, MG_EFAIL, "draw_high_level: encountered empty tree!");
+  return MG_OK;
+}
+
+extern "C" int mg_interp_draw(mg_ctx *ctx, const mg_kdtree *t, int64_t M, int32_t nstop, double *out) {
+  if (!ctx) return MG_EINVAL;
+  MG_REQUIRE(ctx, t && out && M >= 0, "draw: bad arguments");
+  if (M == 0) return MG_OK;
+  MG_CUDA(ctx, cudaSetDevice(ctx->device));
+  DevBuf<double> d_out;
+  MG_CUDA(ctx, d_out.alloc((size_t)M * t->h.D, ctx->stream));
+  int rc = mg_interp_draw_dev(ctx, t, M, nstop, d_out.get());
+  if (rc) return rc;
+  MG_CUDA(ctx, cudaMemcpyAsync(out, d_out.get(), 8 * M * t->h.D, cudaMemcpyDeviceToHost, ctx->stream));
+  MG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return MG_OK;
+}

@@ -16,10 +16,8 @@ int MG_CAT(mh_static_gauss_, MG_SD)(mg_ctx *ctx, const mg_logfn *like, const mg_
                                     int32_t *d_accept) {
   constexpr int D = MG_SD;
   MhArgs<GaussCorr<D>, ZeroFn, BoxProp<D>, D> a;
-  memcpy(a.like.mu, like->params, sizeof(double) * D);
-  memcpy(a.like.L, like->params + D, sizeof(double) * (D * (D + 1) / 2));
-  a.like.logc = like->params[D + D * (D + 1) / 2];
-  memcpy(a.prop.h, prop->params, sizeof(double) * D);
+  GaussCorr<D>::pack(like->params, like->params + D, like->params[D + D * (D + 1) / 2], a.like);
+  BoxProp<D>::pack(prop->params, a.prop);
   fill_common(a, cfg, key, d_state, d_samples, d_accept);
   return launch_mh(ctx, a);
 }

@@ -53,7 +53,8 @@ __device__ __forceinline__ double log_sum_logs(double a, double b) {
   return a + log1p(r);
 }
 // stats.ml:113-124 (Leva)
-__device__ __forceinline__ double draw_gaussian(Rng &r, double mu, double sigma) {
+template <class R>
+__device__ __forceinline__ double draw_gaussian(R &r, double mu, double sigma) {
   for (;;) {
     const double u = r.uniform();
     const double v = 1.7156 * (r.uniform() - 0.5);
@@ -65,12 +66,14 @@ __device__ __forceinline__ double draw_gaussian(Rng &r, double mu, double sigma)
   }
 }
 // stats.ml:126-128
-__device__ __forceinline__ double draw_uniform(Rng &r, double a, double b) {
+template <class R>
+__device__ __forceinline__ double draw_uniform(R &r, double a, double b) {
   const double d = b - a;
   return a + d * r.uniform();
 }
 // mcmc.ml:187-196 (reflects at the bounds)
-__device__ __forceinline__ double uniform_wrapping(Rng &r, double xmin, double xmax, double dx, double x) {
+template <class R>
+__device__ __forceinline__ double uniform_wrapping(R &r, double xmin, double xmax, double dx, double x) {
   const double delta_x = (r.uniform() - 0.5) * dx;
   double new_x = x + delta_x;
   for (;;) {
@@ -84,51 +87,105 @@ __device__ __forceinline__ double uniform_wrapping(Rng &r, double xmin, double x
 // static plugins
 // ---------------------------------------------------------------------------
 
+// Static plugins read their parameters from SHARED memory with volatile
+// 16-byte loads.  On sm_100a a constant-bank operand is first loaded into a
+// uniform register (LDCU); with ~85 parameters live in the step loop ptxas
+// ran out of uniform registers and shuttled them through vector registers
+// (ncu, profiles/r01_mh_ncu_summary.md: 75 R2UR + 61 IMAD.U32 + 48 LDCU of
+// ~800 instructions per chain-step).  A broadcast LDS.128 per parameter pair
+// replaces all of that; `volatile` keeps the loads inside the loop instead of
+// being hoisted into 170 registers.
+__device__ __forceinline__ double2 lds2(const double *p) {
+  double2 v;
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];"
+               : "=d"(v.x), "=d"(v.y)
+               : "r"((unsigned)__cvta_generic_to_shared(p)));
+  return v;
+}
+__device__ __forceinline__ double lds1(const double *p) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"((unsigned)__cvta_generic_to_shared(p)));
+  return v;
+}
+
 struct ZeroFn {
   struct Params {};
+  static constexpr int kSmem = 0;
   template <int D>
-  static __device__ __forceinline__ double eval(const Params &, const double (&)[D], int) { return 0.0; }
+  static __device__ __forceinline__ double eval(const Params &, const double *, const double (&)[D], int) { return 0.0; }
 };
 
-// MG_FN_GAUSS_CORR: logc - 1/2 |L (x - mu)|^2, L lower triangular, packed by rows.
+// MG_FN_GAUSS_CORR: logc - 1/2 |L (x - mu)|^2, L lower triangular.
+// Parameter block (built on the host by GaussCorr<D>::pack): mu padded to an
+// even count, then the rows of L each padded to an even count, then logc.
 template <int D>
 struct GaussCorr {
-  struct Params { double mu[D]; double L[D * (D + 1) / 2]; double logc; };
+  static constexpr int kMu = (D + 1) & ~1;
+  // rows have padded lengths 2,2,4,4,6,6,...: offset(i) = kMu + sum_{r<i} pad(r+1)
+  static __host__ __device__ constexpr int pad_len(int i) { return (i + 2) & ~1; }
+  static __host__ __device__ constexpr int off(int i) { int o = kMu; for (int r = 0; r < i; ++r) o += pad_len(r); return o; }
+  static constexpr int kLogc = off(D);
+  static constexpr int kSmem = kLogc + 2;
+  struct Params { double s[kSmem]; };
+  static void pack(const double *mu, const double *Lpacked, double logc, Params &p) {
+    for (int k = 0; k < kSmem; ++k) p.s[k] = 0.0;
+    for (int j = 0; j < D; ++j) p.s[j] = mu[j];
+    for (int i = 0; i < D; ++i)
+      for (int j = 0; j <= i; ++j) p.s[off(i) + j] = Lpacked[i * (i + 1) / 2 + j];
+    p.s[kLogc] = logc;
+  }
   template <int DD>
-  static __device__ __forceinline__ double eval(const Params &p, const double (&x)[DD], int) {
+  static __device__ __forceinline__ double eval(const Params &, const double *s, const double (&x)[DD], int) {
     static_assert(DD == D, "GaussCorr: dimension mismatch");
     double z[D];
 #pragma unroll
-    for (int j = 0; j < D; ++j) z[j] = x[j] - p.mu[j];
+    for (int j = 0; j < D; j += 2) {
+      const double2 m = lds2(s + j);
+      z[j] = x[j] - m.x;
+      if (j + 1 < D) z[j + 1] = x[j + 1] - m.y;
+    }
     double q = 0.0;
 #pragma unroll
     for (int i = 0; i < D; ++i) {
-      double y = p.L[i * (i + 1) / 2] * z[0];
+      double y = 0.0;
 #pragma unroll
-      for (int j = 1; j <= i; ++j) y = fma(p.L[i * (i + 1) / 2 + j], z[j], y);
+      for (int j = 0; j <= i; j += 2) {
+        const double2 l = lds2(s + off(i) + j);
+        y = (j == 0) ? l.x * z[0] : fma(l.x, z[j], y);
+        if (j + 1 <= i) y = fma(l.y, z[j + 1], y);
+      }
       q = fma(y, y, q);
     }
-    return fma(-0.5, q, p.logc);
+    return fma(-0.5, q, lds1(s + kLogc));
   }
 };
 
 // MG_PROP_BOX: x_i + random_between (-h_i) h_i  (bin/evidence_direct.ml:24-43)
 template <int D>
 struct BoxProp {
-  struct Params { double h[D]; };
+  // (a_i, w_i) = (-h_i, h_i - (-h_i)) pairs, formed on the host: exactly the
+  // values the reference's random_between computes on every call.
+  static constexpr int kSmem = 2 * D;
+  struct Params { double s[kSmem]; };
   static constexpr bool kSymmetric = true;
-  template <int DD>
-  static __device__ __forceinline__ void propose(const Params &p, Rng &r, const double (&x)[DD],
+  static constexpr bool kStaticDim = true;
+  static constexpr int kDraws = D;  // uniforms consumed per proposal (fixed)
+  static void pack(const double *h, Params &p) {
+    for (int i = 0; i < D; ++i) { const double lo = -h[i], hi = h[i]; p.s[2 * i] = lo; p.s[2 * i + 1] = hi - lo; }
+  }
+  template <int DD, class R>
+  static __device__ __forceinline__ void propose(const Params &, const double *s, R &r, const double (&x)[DD],
                                                  double (&y)[DD], int) {
     static_assert(DD == D, "BoxProp: dimension mismatch");
 #pragma unroll
     for (int i = 0; i < D; ++i) {
-      const double a = -p.h[i], b = p.h[i];
-      y[i] = x[i] + (a + (b - a) * r.uniform());
+      const double2 aw = lds2(s + 2 * i);
+      y[i] = x[i] + (aw.x + aw.y * r.uniform());
     }
   }
   template <int DD>
-  static __device__ __forceinline__ double log_q(const Params &, const double (&)[DD], const double (&)[DD], int) {
+  static __device__ __forceinline__ double log_q(const Params &, const double *, const double (&)[DD],
+                                                 const double (&)[DD], int) {
     return 0.0;
   }
 };
@@ -156,6 +213,7 @@ __device__ __forceinline__ double dyn_log_multi_gaussian(const double *mu, const
 
 struct DynFn {
   typedef DynFnParams Params;
+  static constexpr int kSmem = 0;
   template <int DMAX>
   static __device__ __forceinline__ double raw(const Params &f, const double (&x)[DMAX], int d) {
     const double *p = f.p;
@@ -224,7 +282,7 @@ struct DynFn {
     return neg_inf();
   }
   template <int DMAX>
-  static __device__ __forceinline__ double eval(const Params &f, const double (&x)[DMAX], int d) {
+  static __device__ __forceinline__ double eval(const Params &f, const double *, const double (&x)[DMAX], int d) {
     const double v = raw<DMAX>(f, x, d);
     return f.scale == 1.0 ? v : f.scale * v;
   }
@@ -239,8 +297,11 @@ struct DynPropParams {
 struct DynProp {
   typedef DynPropParams Params;
   static constexpr bool kSymmetric = false;
-  template <int DMAX>
-  static __device__ __forceinline__ void propose(const Params &f, Rng &r, const double (&x)[DMAX],
+  static constexpr bool kStaticDim = false;
+  static constexpr int kDraws = -1;  // data dependent (rejection loops)
+  static constexpr int kSmem = 0;
+  template <int DMAX, class R>
+  static __device__ __forceinline__ void propose(const Params &f, const double *, R &r, const double (&x)[DMAX],
                                                  double (&y)[DMAX], int d) {
     const double *p = f.p;
     switch (f.kind) {
@@ -269,7 +330,7 @@ struct DynProp {
       if (i >= d) y[i] = 0.0;
   }
   template <int DMAX>
-  static __device__ __forceinline__ double log_q(const Params &f, const double (&x)[DMAX],
+  static __device__ __forceinline__ double log_q(const Params &f, const double *, const double (&x)[DMAX],
                                                  const double (&y)[DMAX], int d) {
     switch (f.kind) {
       case MG_PROP_INDEP_GAUSS: {  // test/mcmc_test.ml:123-126

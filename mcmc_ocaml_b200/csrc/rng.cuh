@@ -73,4 +73,20 @@ struct Rng {
   __device__ __forceinline__ uint64_t below(uint64_t n) { return __umul64hi(lane(), n); }
 };
 
+// N draws of one (purpose, g, step) generated up front: lets the sampler issue
+// the Philox rounds of step t+1 among the float64 work of step t.
+template <int N>
+struct RngBuf {
+  double u[N];
+  int j;
+  __device__ __forceinline__ RngBuf() : j(0) {}
+  __device__ __forceinline__ void fill(CallKey ck, uint32_t purpose, uint64_t g, uint64_t step) {
+    Rng r(ck, purpose, g, step);
+#pragma unroll
+    for (int k = 0; k < N; ++k) u[k] = r.uniform();
+    j = 0;
+  }
+  __device__ __forceinline__ double uniform() { return u[j++]; }
+};
+
 }  // namespace mg
