@@ -122,3 +122,71 @@ def remove_repeat_samples(rows: np.ndarray, dim: int) -> np.ndarray:
     keep = np.ones(rows.shape[0], dtype=bool)
     keep[1:] = np.any(rows[1:, :dim] != rows[:-1, :dim], axis=1)
     return rows[keep]
+
+
+# ---------------------------------------------------------------------------
+# two-model reversible jump (mcmc.mli:85-182)
+# ---------------------------------------------------------------------------
+
+class RjModel:
+    """One of the two models of ``make_rjmcmc_sampler`` (mcmc.ml:89-119): its
+    log-likelihood, log-prior, in-model proposal, model prior ``p`` and the
+    proposal used to jump INTO it (``jintoa`` / ``jintob`` with their
+    ``ljpintoa`` / ``ljpintob``): either an ``InterpPdf`` (``Interp.draw`` and
+    ``log (Interp.jump_prob ...)``, test/mcmc_test.ml:175-178; ``nstop`` > 0
+    selects the ``*_high_level`` forms) or an independent Gaussian
+    ``(mu, sigma)`` (test/mcmc_test.ml:123-127)."""
+
+    def __init__(self, log_likelihood: LogFn, log_prior: LogFn, jump_proposal: Proposal, p: float, *,
+                 interp=None, nstop: int = 0, into_gauss=None):
+        self.like, self.prior, self.prop, self.p = log_likelihood, log_prior, jump_proposal, float(p)
+        self.interp, self.nstop = interp, int(nstop)
+        self.into_gauss = None
+        if interp is None:
+            if into_gauss is None:
+                raise _abi.InvalidArgument("RjModel: need an InterpPdf or an independent Gaussian to jump into the model")
+            mu, sigma = into_gauss
+            self.into_gauss = _abi.as_f64(np.concatenate([np.atleast_1d(mu), np.atleast_1d(sigma)]))
+
+    def spec(self) -> _abi.mg_rj_model:
+        if self.interp is not None:
+            into = _abi.mg_into(_abi.INTO_INTERP, self.nstop, self.interp.tree.h, _abi.c_double_p(), 0)
+        else:
+            into = _abi.mg_into(_abi.INTO_INDEP_GAUSS, 0, None, _abi.ptr(self.into_gauss), self.into_gauss.size)
+        return _abi.mg_rj_model(self.like.spec(), self.prior.spec(), self.prop.spec(), into, self.p)
+
+
+@dataclass
+class RjSamples:
+    model: np.ndarray | None      # uint8 [n][C], 0 = A, 1 = B
+    block: np.ndarray | None      # [n][Dmax+2][C]
+    counts: tuple[int, int]       # rjmcmc_model_counts over every recorded sample
+
+
+def rjmcmc_array(n: int, A: RjModel, B: RjModel, a0, b0, *, nbin: int = 0, nskip: int = 1, nchains: int = 1,
+                 chain_offset: int = 0, record_model: bool = True, record_samples: bool = False,
+                 ctx: Context | None = None) -> RjSamples:
+    """``Mcmc.rjmcmc_array ?nbin ?nskip n (lla,llb) (lpa,lpb) (jpa,jpb) ... (pa,pb)
+    (a,b)`` (mcmc.ml:121-139) for ``nchains`` independent chains."""
+    ctx = ctx or default_context()
+    dm = max(A.like.dim, B.like.dim)
+    cfg = _abi.mg_rjmcmc_cfg(nchains, nbin, nskip, n, chain_offset, 0, 0)
+    model = np.empty((n, nchains), np.uint8) if record_model else None
+    block = np.empty((n, dm + 2, nchains)) if record_samples else None
+    counts = (C.c_int64 * 2)()
+    sa, sb = A.spec(), B.spec()
+    a0, b0 = _abi.as_f64(a0), _abi.as_f64(b0)
+    ctx.check(ctx.lib.mg_rjmcmc_array(ctx.h, C.byref(sa), C.byref(sb), C.byref(cfg), _abi.ptr(a0), _abi.ptr(b0),
+                                      _abi.ptr(model, _abi.c_uint8_p), _abi.ptr(block), counts))
+    return RjSamples(model, block, (int(counts[0]), int(counts[1])))
+
+
+def rjmcmc_model_counts(samples: RjSamples) -> tuple[int, int]:
+    """``Mcmc.rjmcmc_model_counts`` (mcmc.ml:141-149)."""
+    return samples.counts
+
+
+def rjmcmc_evidence_ratio(samples: RjSamples) -> float:
+    """``Mcmc.rjmcmc_evidence_ratio`` (mcmc.ml:151-153): #A / #B."""
+    na, nb = samples.counts
+    return float(na) / float(nb) if nb else float("inf")

@@ -1,0 +1,113 @@
+"""Reversible-jump ensembles (mg_rjmcmc_array) against the oracle and against
+the known answers of the reference's tests (test/mcmc_test.ml:114-182)."""
+import numpy as np
+import pytest
+from scipy import stats
+
+from mcmc_ocaml_b200 import Failure, interpolate_pdf, mcmc, plugins as P
+
+pytestmark = pytest.mark.gpu
+
+
+def tophat_setup(ctx, og, nsamp=10000):
+    """test/mcmc_test.ml:150-182: unit square vs the central 0.5 x 0.5 square"""
+    prior = P.box([0, 0], [1, 1], 0.0)
+    like1 = P.box([0, 0], [1, 1], 0.0)
+    like2 = P.box([0.25, 0.25], [0.75, 0.75], 0.0)
+    prop = P.wrap_proposal([0, 0], [1, 1], [0.5, 0.5])
+    ctx.set_seed(1001)
+    s1 = mcmc.mcmc_array(nsamp, like1, prior, prop, [0.5, 0.5], nskip=100, ctx=ctx)
+    s2 = mcmc.mcmc_array(nsamp, like2, prior, prop, [0.5, 0.5], nskip=100, ctx=ctx)
+    p1, p2 = s1.values(), s2.values()
+    return prior, like1, like2, prop, p1, p2
+
+
+def test_tophat_interp_matches_oracle_and_known_ratio(ctx, og):
+    prior, like1, like2, prop, p1, p2 = tophat_setup(ctx, og)
+    i1 = interpolate_pdf.InterpPdf(p1, [0, 0], [1, 1], ctx=ctx)
+    i2 = interpolate_pdf.InterpPdf(p2, [0, 0], [1, 1], ctx=ctx)
+    A = mcmc.RjModel(like1, prior, prop, 0.5, interp=i1)
+    B = mcmc.RjModel(like2, prior, prop, 0.5, interp=i2)
+    # (1) chain-for-chain against the oracle on the same Philox stream
+    ctx.set_seed(77)
+    g = mcmc.rjmcmc_array(300, A, B, [0.5, 0.5], [0.5, 0.5], nskip=3, nbin=10, nchains=256, record_samples=True, ctx=ctx)
+    t1, t2 = og.Tree(p1, [0, 0], [1, 1]), og.Tree(p2, [0, 0], [1, 1])
+    oa = og.rj_model(like1, prior, prop, 0.5, tree=t1)
+    ob = og.rj_model(like2, prior, prop, 0.5, tree=t2)
+    o = og.rjmcmc_array(77, 0, 300, oa, ob, [0.5, 0.5], [0.5, 0.5], nskip=3, nbin=10, nchains=256, nthreads=8,
+                        record_samples=True)
+    same = np.all(g.model == o["model"], axis=0)
+    assert same.mean() >= 0.97          # log(jump_prob): CUDA libm vs glibc may flip a rare decision
+    assert np.array_equal(g.block[:, :2, same], o["samples"][:, :2, same])
+    assert abs(g.counts[0] - o["counts"][0]) <= 0.03 * 300 * 256
+    # (2) the reference's known answer: evidence ratio 4.0 +- 0.1 (mcmc_test.ml:181-182),
+    # here with 4096 chains x 250 samples at nskip = 10 (1.02e6 samples, as the test's 1e6)
+    ctx.set_seed(78)
+    r = mcmc.rjmcmc_array(250, A, B, [0.5, 0.5], [0.5, 0.5], nskip=10, nbin=50, nchains=4096, record_model=False, ctx=ctx)
+    assert mcmc.rjmcmc_evidence_ratio(r) == pytest.approx(4.0, abs=0.1)
+    # high-level jumps (draw_high_level / jump_prob_high_level) give the same answer
+    A64 = mcmc.RjModel(like1, prior, prop, 0.5, interp=i1, nstop=64)
+    B64 = mcmc.RjModel(like2, prior, prop, 0.5, interp=i2, nstop=64)
+    r = mcmc.rjmcmc_array(250, A64, B64, [0.5, 0.5], [0.5, 0.5], nskip=10, nbin=50, nchains=4096, record_model=False, ctx=ctx)
+    assert mcmc.rjmcmc_evidence_ratio(r) == pytest.approx(4.0, abs=0.15)
+
+
+def test_rjmcmc_gaussians_priors_recovered(ctx, og):
+    """test/mcmc_test.ml:114-148: two normalised 1-D Gaussians, priors (0.1, 0.9)"""
+    mu1, s1, mu2, s2 = 0.31, 0.62, 0.77, 0.45
+    g1, g2 = P.gauss_diag([mu1], [s1]), P.gauss_diag([mu2], [s2])
+    A = mcmc.RjModel(g1.scaled(0.5), g1.scaled(0.5), P.indep_gauss_proposal([mu1], [s1]), 0.1, into_gauss=([mu1], [s1]))
+    B = mcmc.RjModel(g2.scaled(0.3), g2.scaled(0.7), P.indep_gauss_proposal([mu2], [s2]), 0.9, into_gauss=([mu2], [s2]))
+    ctx.set_seed(5)
+    r = mcmc.rjmcmc_array(250, A, B, [mu1], [mu2], nskip=10, nchains=4096, ctx=ctx)
+    n1, n2 = r.counts
+    pp1, pp2 = n1 / (n1 + n2), n2 / (n1 + n2)
+    assert pp1 == pytest.approx(0.1, rel=0.1) and pp2 == pytest.approx(0.9, rel=0.1)
+    assert mcmc.rjmcmc_evidence_ratio(r) == pytest.approx(0.1 / 0.9, abs=0.1)
+    # binomial test of the model fraction over (nearly independent) chains at the last sample
+    last = r.model[-1]
+    assert stats.binomtest(int((last == 0).sum()), last.size, 0.1).pvalue > 1e-4
+    # same stream in the oracle: model sequences agree chain for chain
+    oa = og.rj_model(g1.scaled(0.5), g1.scaled(0.5), P.indep_gauss_proposal([mu1], [s1]), 0.1, into_gauss=([mu1], [s1]))
+    ob = og.rj_model(g2.scaled(0.3), g2.scaled(0.7), P.indep_gauss_proposal([mu2], [s2]), 0.9, into_gauss=([mu2], [s2]))
+    ctx.set_seed(6)
+    g = mcmc.rjmcmc_array(100, A, B, [mu1], [mu2], nskip=2, nchains=128, ctx=ctx)
+    o = og.rjmcmc_array(6, 0, 100, oa, ob, [mu1], [mu2], nskip=2, nchains=128, nthreads=8)
+    assert np.all(g.model == o["model"], axis=0).mean() >= 0.95
+
+
+def test_gaussian_vs_cauchy_config1(ctx, og):
+    """BASELINE.json config 1 at test size: Gaussian-vs-Cauchy on the fixed
+    100-point dataset, interpolated jumps (bin/gaussian_cauchy_efficiency.ml)."""
+    from tests.golden.gc_data import DATA
+    prior = P.box([-1.0, 0.5], [1.0, 1.5], value=-0.693147)
+    prop = P.wrap_proposal([-1.0, 0.5], [1.0, 1.5], [0.1, 0.1])
+    lg, lc = P.gauss_data(DATA), P.cauchy_data(DATA)
+    ctx.set_seed(20111104)
+    gs = mcmc.mcmc_array(200, lg, prior, prop, [0.0, 1.0], nchains=64, nbin=500, nskip=20, ctx=ctx).values()
+    cs = mcmc.mcmc_array(200, lc, prior, prop, [0.0, 1.0], nchains=64, nbin=500, nskip=20, ctx=ctx).values()
+    lo, hi = [-1.0, 0.5], [1.0, 1.5]
+    gi = interpolate_pdf.InterpPdf(gs, lo, hi, ctx=ctx)
+    ci = interpolate_pdf.InterpPdf(cs, lo, hi, ctx=ctx)
+    A = mcmc.RjModel(lg, prior, prop, 0.5, interp=gi)
+    B = mcmc.RjModel(lc, prior, prop, 0.5, interp=ci)
+    ctx.set_seed(9)
+    g = mcmc.rjmcmc_array(400, A, B, [0.0, 1.0], [0.0, 1.0], nskip=5, nbin=100, nchains=2048, record_model=False, ctx=ctx)
+    oa = og.rj_model(lg, prior, prop, 0.5, tree=og.Tree(gs, lo, hi))
+    ob = og.rj_model(lc, prior, prop, 0.5, tree=og.Tree(cs, lo, hi))
+    o = og.rjmcmc_array(10, 0, 400, oa, ob, [0.0, 1.0], [0.0, 1.0], nskip=5, nbin=100, nchains=512, nthreads=8,
+                        record_model=False)
+    fg = g.counts[0] / sum(g.counts)
+    fo = o["counts"][0] / sum(o["counts"])
+    # the data were drawn from a Gaussian: the Gaussian model must dominate, and
+    # GPU and oracle (independent streams) must agree within Monte Carlo error
+    assert fg > 0.8
+    assert abs(fg - fo) < 0.03
+
+
+def test_prior_assertion(ctx):
+    g = P.gauss_diag([0.0], [1.0])
+    A = mcmc.RjModel(g, P.zero(1), P.box_proposal([1.0]), 0.7, into_gauss=([0.0], [1.0]))
+    B = mcmc.RjModel(g, P.zero(1), P.box_proposal([1.0]), 0.6, into_gauss=([0.0], [1.0]))
+    with pytest.raises(Failure):          # assert (pa +. pb -. 1.0 < sqrt epsilon_float), mcmc.ml:90
+        mcmc.rjmcmc_array(10, A, B, [0.0], [0.0], ctx=ctx)
