@@ -1,0 +1,420 @@
+// evidence.cu -- Evidence.evidence_harmonic_mean / evidence_lebesgue /
+// evidence_direct (evidence.ml:101-107, 202-221, 148-165) on the GPU.
+//
+// Pipeline (device resident; every stage HBM-bound):
+//   harmonic  one pass over ll (8 B/sample), compensated block reduction.
+//   lebesgue  stable radix sort of -ll (evidence.ml:180) -> first gap in 1/L
+//             above eps (parallel min, :167-179) -> mean 1/L of the prefix
+//             (:182-189) -> drop equal-ll runs keeping the last, reversed
+//             (:191-200; flag + scan + gather) -> kd-tree of the survivors,
+//             not split below n objects (collect_subvolumes never looks
+//             further, :83-89) -> one warp per cell: tight bounds, volume in
+//             the reference's product order, median log-prior (:109-120) ->
+//             compensated sum over cells / mean 1/L.
+//   direct    D stable radix sorts (last coordinate first) = List.sort by
+//             coordinates (:143-146) -> drop equal rows keeping the last,
+//             reversed (:126-141) -> tree -> per cell volume * mean
+//             posterior, summed by lane 0 in the reference's list order
+//             (:122-124,150-160).
+// Per-cell terms are bit-exact up to exp(); the sum over cells is compensated,
+// i.e. closer to the exact sum than the reference's left-to-right fold.
+#include "common.cuh"
+#include "kdtree.cuh"
+#include "radix_sort.cuh"
+#include "reduce.cuh"
+#include "scan.cuh"
+
+namespace mg {
+
+int build_tree(mg_ctx *ctx, const double *d_pts, int64_t N, int D, const double *low, const double *high,
+               int min_split, mg_kdtree **out);  // kdtree.cu
+
+constexpr int EB = 256;
+
+static inline unsigned egrid(mg_ctx *ctx, int64_t n, int block = EB) {
+  int64_t g = (n + block - 1) / block;
+  const int64_t cap = (int64_t)ctx->sm_count * 8;
+  if (g > cap) g = cap;
+  return (unsigned)(g < 1 ? 1 : g);
+}
+
+// partial[b] = sum over this block's elements of f(i)
+template <class F>
+__global__ void __launch_bounds__(EB) reduce_kernel(int64_t n, F f, double *__restrict__ partial) {
+  Comp acc;
+  for (int64_t i = (int64_t)blockIdx.x * EB + threadIdx.x; i < n; i += (int64_t)gridDim.x * EB) acc.add(f(i));
+  const double t = block_reduce_comp<EB>(acc);
+  if (threadIdx.x == 0) partial[blockIdx.x] = t;
+}
+
+template <class F>
+static int reduce_sum(mg_ctx *ctx, int64_t n, F f, double *out) {
+  const unsigned g = egrid(ctx, n);
+  DevBuf<double> partial;
+  MG_CUDA(ctx, partial.alloc(g, ctx->stream));
+  reduce_kernel<<<g, EB, 0, ctx->stream>>>(n, f, partial.get());
+  MG_CHECK_LAUNCH(ctx);
+  std::vector<double> h(g);
+  MG_CUDA(ctx, cudaMemcpyAsync(h.data(), partial.get(), sizeof(double) * g, cudaMemcpyDeviceToHost, ctx->stream));
+  MG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  Comp acc;
+  for (unsigned b = 0; b < g; ++b) acc.add(h[b]);  // fixed order
+  *out = acc.value();
+  return MG_OK;
+}
+
+__global__ void neg_ll_keys_kernel(const double *__restrict__ ll, int64_t n, uint64_t *__restrict__ keys,
+                                   int32_t *__restrict__ vals) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    keys[i] = f64_to_ordered(-ll[i]);  // compare_inverse_like, evidence.ml:99
+    vals[i] = (int32_t)i;
+  }
+}
+
+__global__ void coord_keys_kernel(const double *__restrict__ pts, const int32_t *__restrict__ order, int64_t n, int D,
+                                  int d, uint64_t *__restrict__ keys) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    keys[i] = f64_to_ordered(pts[(int64_t)order[i] * D + d]);
+}
+
+__global__ void iota_kernel(int32_t *__restrict__ v, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) v[i] = (int32_t)i;
+}
+
+// first i with exp(-ll[o[i+1]]) - exp(-ll[o[i]]) > eps (evidence.ml:170-177); also flags delta < 0 / NaN
+__global__ void first_gap_kernel(const double *__restrict__ ll, const int32_t *__restrict__ order, int64_t n,
+                                 double eps, unsigned long long *__restrict__ first, int *__restrict__ bad) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i + 1 < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const double ilx = exp(-ll[order[i]]), ily = exp(-ll[order[i + 1]]);
+    const double delta = ily - ilx;
+    if (!(delta >= 0.0)) *bad = 1;   // assert(delta >= 0.0), :175
+    if (delta > eps) atomicMin(first, (unsigned long long)i);
+  }
+}
+
+// remove_dups_rev (evidence.ml:191-200): keep i iff it is the last of its equal-ll run
+__global__ void keep_ll_kernel(const double *__restrict__ ll, const int32_t *__restrict__ order, int64_t m,
+                               int32_t *__restrict__ keep) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (int64_t)gridDim.x * blockDim.x)
+    keep[i] = (i == m - 1 || !(ll[order[i]] == ll[order[i + 1]])) ? 1 : 0;
+}
+
+// rev_remove_dups compare_samples (evidence.ml:126-141): keep the last of each run of equal rows
+__global__ void keep_rows_kernel(const double *__restrict__ pts, const int32_t *__restrict__ order, int64_t m, int D,
+                                 int32_t *__restrict__ keep) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (int64_t)gridDim.x * blockDim.x) {
+    int k = 1;
+    if (i < m - 1) {
+      const double *a = pts + (int64_t)order[i] * D, *b = pts + (int64_t)order[i + 1] * D;
+      bool eq = true;
+      for (int d = 0; d < D && eq; ++d) eq = (a[d] == b[d]);   // compare = 0 on non-NaN floats (-0.0 = 0.0)
+      k = eq ? 0 : 1;
+    }
+    keep[i] = k;
+  }
+}
+
+// survivors in REVERSED order: dst = K-1-rank
+__global__ void gather_kernel(const double *__restrict__ pts, const double *__restrict__ ll,
+                              const double *__restrict__ lp, const int32_t *__restrict__ order,
+                              const int32_t *__restrict__ keep, const int32_t *__restrict__ rank, int64_t m, int64_t K,
+                              int D, double *__restrict__ spts, double *__restrict__ sll, double *__restrict__ slp) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (int64_t)gridDim.x * blockDim.x) {
+    if (!keep[i]) continue;
+    const int64_t dst = K - 1 - rank[i], src = order[i];
+    for (int d = 0; d < D; ++d) spts[dst * D + d] = pts[src * D + d];
+    sll[dst] = ll[src]; slp[dst] = lp[src];
+  }
+}
+
+// One warp per node of a tree that was not split below nmax objects.
+// collect_subvolumes (evidence.ml:83-89) emits exactly the leaves with < nmax
+// objects; a leaf of >= nmax identical points contributes nothing.
+// MODE 0: exp(median log_prior) * tight volume   (evidence_lebesgue :209-220)
+// MODE 1: tight volume * mean exp(ll + lp)       (evidence_direct_tree :150-160)
+template <int MODE>
+__global__ void __launch_bounds__(EB)
+cell_terms_kernel(const KdNode *__restrict__ nodes, const int32_t *__restrict__ count, const int32_t *__restrict__ begin,
+                  const int32_t *__restrict__ perm, const double *__restrict__ pts, const double *__restrict__ ll,
+                  const double *__restrict__ lp, int64_t nnodes, int D, int nmax, double *__restrict__ partial,
+                  unsigned long long *__restrict__ ncells) {
+  extern __shared__ double sh[];  // [warps][nmax] scratch values
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = EB / 32;
+  double *vals = sh + (size_t)w * nmax;
+  Comp acc;
+  unsigned cells = 0;
+  for (int64_t id = (int64_t)blockIdx.x * nw + w; id < nnodes; id += (int64_t)gridDim.x * nw) {
+    const int cnt = count[id];
+    if (nodes[id].left >= 0 || cnt >= nmax) continue;   // not (length_at_least nmax objs) -> [c]
+    const int b = begin[id];
+    // bounds_of_objects (kd_tree.ml:96-110) + bounds_volume (:177-182, product in dimension order)
+    double v = 1.0;
+    for (int d = 0; d < D; ++d) {
+      double lo = __longlong_as_double(0x7FF0000000000000ll), hi = -lo;
+      for (int k = lane; k < cnt; k += 32) {
+        const double c = pts[(int64_t)perm[b + k] * D + d];
+        lo = fmin(lo, c); hi = fmax(hi, c);
+      }
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) {
+        lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, off));
+        hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, off));
+      }
+      v = v * (hi - lo);
+    }
+    v = v + 0.0;
+    for (int k = lane; k < cnt; k += 32) {
+      const int32_t p = perm[b + k];
+      vals[k] = (MODE == 0) ? lp[p] : exp(ll[p] + lp[p]);   // posterior, evidence.ml:95-97
+    }
+    __syncwarp();
+    double term = 0.0;
+    if (MODE == 0) {
+      // median_sample (:109-120): rank every value (ties by position = stable sort)
+      double lo_mid = 0.0, hi_mid = 0.0;
+      const int r_hi = cnt / 2, r_lo = cnt / 2 - 1;
+      for (int k = lane; k < cnt; k += 32) {
+        const double x = vals[k];
+        int r = 0;
+        for (int j = 0; j < cnt; ++j) { const double y = vals[j]; r += (y < x || (y == x && j < k)) ? 1 : 0; }
+        if (r == r_hi) hi_mid = x;
+        if (r == r_lo) lo_mid = x;
+      }
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) {   // exactly one lane holds each (others hold 0.0): OR the bits
+        hi_mid = __longlong_as_double(__double_as_longlong(hi_mid) | __shfl_xor_sync(0xffffffffu, __double_as_longlong(hi_mid), off));
+        lo_mid = __longlong_as_double(__double_as_longlong(lo_mid) | __shfl_xor_sync(0xffffffffu, __double_as_longlong(lo_mid), off));
+      }
+      const double med = (cnt % 2 == 0) ? 0.5 * (lo_mid + hi_mid) : hi_mid;
+      const double prior = exp(med);
+      term = prior * v;
+    } else {
+      // mean_sample posterior (:122-124): left-to-right fold in list order, by lane 0
+      double sum = 0.0;
+      if (lane == 0) for (int k = 0; k < cnt; ++k) sum = sum + vals[k];
+      sum = __shfl_sync(0xffffffffu, sum, 0);
+      const double post = sum / (double)cnt;
+      term = v * post;
+    }
+    __syncwarp();
+    if (lane == 0) { acc.add(term); ++cells; }
+  }
+  const double t = block_reduce_comp<EB>(acc);
+  if (threadIdx.x == 0) partial[blockIdx.x] = t;
+  if (lane == 0 && cells) atomicAdd(ncells, (unsigned long long)cells);
+}
+
+struct Survivors {
+  DevBuf<double> pts, ll, lp;
+  int64_t K = 0;
+};
+
+// flag -> scan -> gather (reversed) of the first m entries of `order`
+static int compact_reversed(mg_ctx *ctx, const double *d_pts, const double *d_ll, const double *d_lp,
+                            const int32_t *d_order, const int32_t *d_keep, int64_t m, int D, Survivors &sv) {
+  cudaStream_t s = ctx->stream;
+  DevBuf<int32_t> rank, tmp, total;
+  MG_CUDA(ctx, rank.alloc(m, s));
+  MG_CUDA(ctx, tmp.alloc((size_t)scan_tmp_elems(m, 1) + 1, s));
+  MG_CUDA(ctx, total.alloc(1, s));
+  int rc = exclusive_scan_i32(ctx, d_keep, rank.get(), m, 1, tmp.get(), total.get());
+  if (rc) return rc;
+  int32_t K = 0;
+  MG_CUDA(ctx, cudaMemcpyAsync(&K, total.get(), 4, cudaMemcpyDeviceToHost, s));
+  MG_CUDA(ctx, cudaStreamSynchronize(s));
+  sv.K = K;
+  MG_CUDA(ctx, sv.pts.alloc((size_t)K * D, s));
+  MG_CUDA(ctx, sv.ll.alloc(K, s));
+  MG_CUDA(ctx, sv.lp.alloc(K, s));
+  gather_kernel<<<egrid(ctx, m), EB, 0, s>>>(d_pts, d_ll, d_lp, d_order, d_keep, rank.get(), m, K, D, sv.pts.get(),
+                                            sv.ll.get(), sv.lp.get());
+  MG_CHECK_LAUNCH(ctx);
+  return MG_OK;
+}
+
+// tree of the survivors (not split below nmax) and the sum of the per-cell terms
+template <int MODE>
+static int integrate_cells(mg_ctx *ctx, const Survivors &sv, int D, int nmax, double *out, int64_t *ncells_out) {
+  cudaStream_t s = ctx->stream;
+  std::vector<double> zeros(D, 0.0);
+  mg_kdtree *t = nullptr;
+  // The root box (bounds_of_objects, evidence.ml:164,206) does not influence
+  // any split nor the tight per-cell volumes, so it is not computed.
+  int rc = build_tree(ctx, sv.pts.get(), sv.K, D, zeros.data(), zeros.data(), nmax < 2 ? 2 : nmax, &t);
+  if (rc) return rc;
+  const char *blob = (const char *)t->d_blob;
+  const int64_t nn = t->h.nnodes;
+  const unsigned g = egrid(ctx, nn, EB / 32);
+  DevBuf<double> partial;
+  DevBuf<unsigned long long> ncells;
+  cudaError_t e = partial.alloc(g, s);
+  if (e == cudaSuccess) e = ncells.alloc(1, s);
+  if (e == cudaSuccess) e = cudaMemsetAsync(ncells.get(), 0, 8, s);
+  if (e != cudaSuccess) { mg_kdtree_destroy(t); return set_err(ctx, MG_ECUDA, "cuda: %s", cudaGetErrorString(e)); }
+  const size_t smem = (size_t)(EB / 32) * (nmax > 0 ? nmax : 1) * sizeof(double);
+  if (smem > 48 * 1024) cudaFuncSetAttribute(cell_terms_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cell_terms_kernel<MODE><<<g, EB, smem, s>>>((const KdNode *)(blob + t->h.off_nodes), (const int32_t *)(blob + t->h.off_count),
+                                              (const int32_t *)(blob + t->h.off_begin), (const int32_t *)(blob + t->h.off_perm),
+                                              sv.pts.get(), sv.ll.get(), sv.lp.get(), nn, D, nmax, partial.get(), ncells.get());
+  ctx->launches++;
+  std::vector<double> h(g);
+  unsigned long long nc = 0;
+  e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaMemcpyAsync(h.data(), partial.get(), sizeof(double) * g, cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(&nc, ncells.get(), 8, cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  mg_kdtree_destroy(t);
+  if (e != cudaSuccess) return set_err(ctx, MG_ECUDA, "cuda: %s (evidence cells)", cudaGetErrorString(e));
+  Comp acc;
+  for (unsigned b = 0; b < g; ++b) acc.add(h[b]);
+  *out = acc.value();
+  if (ncells_out) *ncells_out = (int64_t)nc;
+  return MG_OK;
+}
+
+}  // namespace mg
+
+using namespace mg;
+
+extern "C" int mg_evidence_harmonic_mean_dev(mg_ctx *ctx, const double *d_ll, int64_t N, double *out) {
+  if (!ctx) return MG_EINVAL;
+  MG_REQUIRE(ctx, d_ll && out && N >= 1, "evidence_harmonic_mean: bad arguments");
+  MG_CUDA(ctx, cudaSetDevice(ctx->device));
+  double linv = 0.0;
+  time_begin(ctx);
+  int rc = reduce_sum(ctx, N, [d_ll] __device__(int64_t i) { return 1.0 / exp(d_ll[i]); }, &linv);  // evidence.ml:105
+  time_end(ctx);
+  if (rc) return rc;
+  *out = (double)N / linv;
+  return MG_OK;
+}
+
+extern "C" int mg_evidence_harmonic_mean(mg_ctx *ctx, const double *ll, int64_t N, double *out) {
+  if (!ctx) return MG_EINVAL;
+  MG_REQUIRE(ctx, ll && out && N >= 1, "evidence_harmonic_mean: bad arguments");
+  MG_CUDA(ctx, cudaSetDevice(ctx->device));
+  DevBuf<double> d_ll;
+  MG_CUDA(ctx, upload(d_ll, ll, (size_t)N, ctx->stream));
+  return mg_evidence_harmonic_mean_dev(ctx, d_ll.get(), N, out);
+}
+
+extern "C" int mg_evidence_lebesgue_dev(mg_ctx *ctx, const double *d_pts, const double *d_ll, const double *d_lp,
+                                        int64_t N, int32_t D, int32_t n, double eps, double *out) {
+  if (!ctx) return MG_EINVAL;
+  MG_REQUIRE(ctx, d_pts && d_ll && d_lp && out, "evidence_lebesgue: null argument");
+  MG_REQUIRE(ctx, N >= 1, "bounds_of_objects: no objects");
+  MG_REQUIRE(ctx, D >= 1 && D <= 64 && n >= 1 && N < (1LL << 30), "evidence_lebesgue: bad sizes");
+  MG_CUDA(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t s = ctx->stream;
+  // collect_samples_up_to_eps (:167-180)
+  DevBuf<uint64_t> keys;
+  DevBuf<int32_t> order, keep;
+  MG_CUDA(ctx, keys.alloc(N, s));
+  MG_CUDA(ctx, order.alloc(N, s));
+  neg_ll_keys_kernel<<<egrid(ctx, N), EB, 0, s>>>(d_ll, N, keys.get(), order.get());
+  MG_CHECK_LAUNCH(ctx);
+  int rc = radix_sort_pairs(ctx, keys.get(), order.get(), N, 1);
+  if (rc) return rc;
+  keys.release();
+  DevBuf<unsigned long long> first;
+  DevBuf<int> bad;
+  MG_CUDA(ctx, first.alloc(1, s));
+  MG_CUDA(ctx, bad.alloc(1, s));
+  const unsigned long long none = ~0ull;
+  MG_CUDA(ctx, cudaMemcpyAsync(first.get(), &none, 8, cudaMemcpyHostToDevice, s));
+  MG_CUDA(ctx, cudaMemsetAsync(bad.get(), 0, sizeof(int), s));
+  first_gap_kernel<<<egrid(ctx, N), EB, 0, s>>>(d_ll, order.get(), N, eps, first.get(), bad.get());
+  MG_CHECK_LAUNCH(ctx);
+  unsigned long long h_first = 0;
+  int h_bad = 0;
+  MG_CUDA(ctx, cudaMemcpyAsync(&h_first, first.get(), 8, cudaMemcpyDeviceToHost, s));
+  MG_CUDA(ctx, cudaMemcpyAsync(&h_bad, bad.get(), sizeof(int), cudaMemcpyDeviceToHost, s));
+  MG_CUDA(ctx, cudaStreamSynchronize(s));
+  const int64_t m = (h_first == none) ? N : (int64_t)h_first + 1;
+  // the assertion only covers pairs up to the cut in the reference (it stops there)
+  if (h_bad) {
+    // re-check restricted to the kept prefix: delta >= 0 must hold for i < m
+    // (NaN log-likelihoods sort last under the ordered-key transform)
+    double chk = 0.0;
+    const int32_t *o = order.get();
+    rc = reduce_sum(ctx, m > 1 ? m - 1 : 0, [d_ll, o] __device__(int64_t i) {
+      const double d = exp(-d_ll[o[i + 1]]) - exp(-d_ll[o[i]]);
+      return (d >= 0.0) ? 0.0 : 1.0; }, &chk);
+    if (rc) return rc;
+    if (chk != 0.0) return set_err(ctx, MG_EFAIL, "Assert_failure evidence.ml:175");
+  }
+  // mean_inv_like (:182-189)
+  double tot_il = 0.0;
+  {
+    const int32_t *o = order.get();
+    rc = reduce_sum(ctx, m, [d_ll, o] __device__(int64_t i) { return exp(-d_ll[o[i]]); }, &tot_il);
+    if (rc) return rc;
+  }
+  const double mean_il = tot_il / (double)m;
+  // remove_dups_rev (:191-200)
+  MG_CUDA(ctx, keep.alloc(m, s));
+  keep_ll_kernel<<<egrid(ctx, m), EB, 0, s>>>(d_ll, order.get(), m, keep.get());
+  MG_CHECK_LAUNCH(ctx);
+  Survivors sv;
+  if ((rc = compact_reversed(ctx, d_pts, d_ll, d_lp, order.get(), keep.get(), m, D, sv))) return rc;
+  order.release(); keep.release();
+  double pm = 0.0;
+  if ((rc = integrate_cells<0>(ctx, sv, D, n, &pm, nullptr))) return rc;
+  *out = pm / mean_il;  // :221
+  return MG_OK;
+}
+
+extern "C" int mg_evidence_direct_dev(mg_ctx *ctx, const double *d_pts, const double *d_ll, const double *d_lp,
+                                      int64_t N, int32_t D, int32_t n, double *out) {
+  if (!ctx) return MG_EINVAL;
+  MG_REQUIRE(ctx, d_pts && d_ll && d_lp && out, "evidence_direct: null argument");
+  MG_REQUIRE(ctx, N >= 1, "bounds_of_objects: no objects");
+  MG_REQUIRE(ctx, D >= 1 && D <= 64 && n >= 1 && N < (1LL << 30), "evidence_direct: bad sizes");
+  MG_CUDA(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t s = ctx->stream;
+  // array_to_list_remove_dups (:143-146): List.sort compare_samples = LSD radix over the coordinates
+  DevBuf<uint64_t> keys;
+  DevBuf<int32_t> order, keep;
+  MG_CUDA(ctx, keys.alloc(N, s));
+  MG_CUDA(ctx, order.alloc(N, s));
+  iota_kernel<<<egrid(ctx, N), EB, 0, s>>>(order.get(), N);
+  MG_CHECK_LAUNCH(ctx);
+  int rc;
+  for (int d = D - 1; d >= 0; --d) {
+    coord_keys_kernel<<<egrid(ctx, N), EB, 0, s>>>(d_pts, order.get(), N, D, d, keys.get());
+    MG_CHECK_LAUNCH(ctx);
+    if ((rc = radix_sort_pairs(ctx, keys.get(), order.get(), N, 1))) return rc;
+  }
+  keys.release();
+  MG_CUDA(ctx, keep.alloc(N, s));
+  keep_rows_kernel<<<egrid(ctx, N), EB, 0, s>>>(d_pts, order.get(), N, D, keep.get());
+  MG_CHECK_LAUNCH(ctx);
+  Survivors sv;
+  if ((rc = compact_reversed(ctx, d_pts, d_ll, d_lp, order.get(), keep.get(), N, D, sv))) return rc;
+  order.release(); keep.release();
+  return integrate_cells<1>(ctx, sv, D, n, out, nullptr);
+}
+
+static int evidence_host(mg_ctx *ctx, int which, const double *pts, const double *ll, const double *lp, int64_t N,
+                         int32_t D, int32_t n, double eps, double *out) {
+  if (!ctx) return MG_EINVAL;
+  MG_REQUIRE(ctx, pts && ll && lp && out, "evidence: null argument");
+  MG_REQUIRE(ctx, N >= 1, "bounds_of_objects: no objects");
+  MG_REQUIRE(ctx, D >= 1 && D <= 64, "evidence: dim must be in 1..64");
+  MG_CUDA(ctx, cudaSetDevice(ctx->device));
+  DevBuf<double> d_pts, d_ll, d_lp;
+  MG_CUDA(ctx, upload(d_pts, pts, (size_t)N * D, ctx->stream));
+  MG_CUDA(ctx, upload(d_ll, ll, (size_t)N, ctx->stream));
+  MG_CUDA(ctx, upload(d_lp, lp, (size_t)N, ctx->stream));
+  return which == 0 ? mg_evidence_lebesgue_dev(ctx, d_pts.get(), d_ll.get(), d_lp.get(), N, D, n, eps, out)
+                    : mg_evidence_direct_dev(ctx, d_pts.get(), d_ll.get(), d_lp.get(), N, D, n, out);
+}
+
+extern "C" int mg_evidence_lebesgue(mg_ctx *ctx, const double *pts, const double *ll, const double *lp, int64_t N,
+                                    int32_t D, int32_t n, double eps, double *out) {
+  return evidence_host(ctx, 0, pts, ll, lp, N, D, n, eps, out);
+}
+extern "C" int mg_evidence_direct(mg_ctx *ctx, const double *pts, const double *ll, const double *lp, int64_t N,
+                                  int32_t D, int32_t n, double *out) {
+  return evidence_host(ctx, 1, pts, ll, lp, N, D, n, 0.0, out);
+}

@@ -211,7 +211,7 @@ static inline unsigned grid1d(mg_ctx *ctx, int64_t n, int block = KB) {
 }
 static inline int64_t align256(int64_t x) { return (x + 255) & ~255LL; }
 
-static int build_tree(mg_ctx *ctx, const double *d_pts, int64_t N, int D, const double *low, const double *high,
+int build_tree(mg_ctx *ctx, const double *d_pts, int64_t N, int D, const double *low, const double *high,
                       int min_split, mg_kdtree **out) {
   cudaStream_t s = ctx->stream;
   MG_REQUIRE(ctx, N >= 1, "tree_of_objects: no objects");

@@ -36,7 +36,7 @@ __host__ __device__ __forceinline__ uint64_t f64_to_ordered(double x) {
   return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
 }
 
-__global__ void __launch_bounds__(RS_BLOCK)
+static __global__ void __launch_bounds__(RS_BLOCK)
 rs_hist_kernel(const uint64_t *__restrict__ keys, int64_t n, int64_t ntiles, int shift,
                int32_t *__restrict__ hist /* [nb][256][ntiles] */) {
   __shared__ int sh[RS_RADIX];
@@ -54,7 +54,7 @@ rs_hist_kernel(const uint64_t *__restrict__ keys, int64_t n, int64_t ntiles, int
   hist[(b * RS_RADIX + threadIdx.x) * ntiles + t] = sh[threadIdx.x];
 }
 
-__global__ void __launch_bounds__(RS_BLOCK)
+static __global__ void __launch_bounds__(RS_BLOCK)
 rs_scatter_kernel(const uint64_t *__restrict__ keys_in, const int32_t *__restrict__ vals_in, int64_t n,
                   int64_t ntiles, int shift, const int32_t *__restrict__ offs /* scanned hist */,
                   uint64_t *__restrict__ keys_out, int32_t *__restrict__ vals_out) {

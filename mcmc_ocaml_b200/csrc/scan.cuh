@@ -45,7 +45,7 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int *total) {
 }
 
 // tile sums: sums[b][t] = sum in[b][t*TILE .. (t+1)*TILE)
-__global__ void __launch_bounds__(SCAN_BLOCK)
+static __global__ void __launch_bounds__(SCAN_BLOCK)
 scan_reduce_kernel(const int32_t *__restrict__ in, int64_t n, int64_t ntiles, int32_t *__restrict__ sums) {
   const int64_t b = blockIdx.y, t = blockIdx.x;
   const int32_t *src = in + b * n;
@@ -63,7 +63,7 @@ scan_reduce_kernel(const int32_t *__restrict__ in, int64_t n, int64_t ntiles, in
 
 // in-place exclusive scan of sums[b][0..ntiles) by one block per batch row;
 // also writes the row total to totals[b] if non-null
-__global__ void __launch_bounds__(1024)
+static __global__ void __launch_bounds__(1024)
 scan_tiles_kernel(int32_t *__restrict__ sums, int64_t ntiles, int32_t *__restrict__ totals) {
   const int64_t b = blockIdx.x;
   int32_t *row = sums + b * ntiles;
@@ -85,7 +85,7 @@ scan_tiles_kernel(int32_t *__restrict__ sums, int64_t ntiles, int32_t *__restric
 }
 
 // out[b][i] = tile_base[b][t] + exclusive prefix within the tile
-__global__ void __launch_bounds__(SCAN_BLOCK)
+static __global__ void __launch_bounds__(SCAN_BLOCK)
 scan_down_kernel(const int32_t *__restrict__ in, int64_t n, int64_t ntiles, const int32_t *__restrict__ sums,
                  int32_t *__restrict__ out) {
   const int64_t b = blockIdx.y, t = blockIdx.x;
