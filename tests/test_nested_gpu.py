@@ -1,0 +1,93 @@
+"""Nested sampling with batched constrained replacement against the oracle
+(same Philox stream: point-for-point) and the reference's known answers
+(test/nested_test.ml)."""
+import math
+
+import numpy as np
+import pytest
+
+from mcmc_ocaml_b200 import Failure, InvalidArgument, nested, plugins as P
+
+pytestmark = pytest.mark.gpu
+
+PRIOR = P.box([0, 0], [1, 1], 0.0, closed=False)
+
+
+@pytest.mark.parametrize("batch", [1, 16])
+def test_point_for_point_vs_oracle(ctx, og, batch):
+    like = P.gauss_diag([0.5, 0.5], [0.1, 0.1])
+    ctx.set_seed(21)
+    g = nested.nested_evidence(like, PRIOR, [0, 0], [1, 1], nlive=128, nmcmc=30, batch=batch, ctx=ctx)
+    o = og.nested_evidence(21, 0, like, PRIOR, [0, 0], [1, 1], nlive=128, nmcmc=30, batch=batch)
+    assert len(g.log_likelihood) == len(o["ll"])
+    # the likelihood uses log(sigma) (CUDA libm vs glibc): coordinates exact, ll to 1e-13
+    assert np.array_equal(g.points, o["pts"])
+    np.testing.assert_allclose(g.log_likelihood, o["ll"], rtol=1e-13, atol=1e-13)
+    assert g.log_evidence == pytest.approx(o["log_ev"], abs=1e-11)
+    assert g.log_delta_evidence == pytest.approx(o["log_dev"], abs=1e-9)
+    np.testing.assert_allclose(g.log_weights, o["logw"], rtol=0, atol=1e-10)
+
+
+def test_weights_deterministic_parity(ctx, og):
+    """N5: evidence_error_and_weights given identical inputs, K = 1 and batched"""
+    rng = np.random.default_rng(3)
+    for nlive, batch, nret in [(100, 1, 5000), (1000, 1, 40000), (512, 64, 64 * 300), (1000, 7, 7 * 1234)]:
+        ll = np.sort(rng.normal(-20, 8, nret + nlive))
+        lev, ldev, lw = nested.evidence_error_and_weights(ll, nlive, batch, ctx=ctx)
+        olev, oldev, olw = og.nested_weights(ll, nlive, batch)
+        assert lev == pytest.approx(olev, abs=1e-12 * max(1.0, abs(olev)))
+        assert ldev == pytest.approx(oldev, abs=1e-9)
+        np.testing.assert_allclose(lw, olw, rtol=0, atol=1e-11)
+        assert np.exp(lw).sum() == pytest.approx(1.0, abs=1e-8)          # nested_test.ml:66-85
+    assert nested.log_total_error_estimate(-1.3, -4.0, 1000) == pytest.approx(og.nested_log_total_error(-1.3, -4.0, 1000), rel=1e-15)
+
+
+def test_single_gaussian_reference_defaults(ctx):
+    """nested_test.ml:23-39 with the reference defaults nlive=1000, nmcmc=1000,
+    epsrel=0.01, mode_hopping_frac=0.1; batch = 1 and batch = 64"""
+    like = P.gauss_diag([0.5, 0.5], [0.1, 0.1])
+    for batch, seed in [(64, 31), (1, 32)]:
+        ctx.set_seed(seed)
+        r = nested.nested_evidence(like, PRIOR, [0, 0], [1, 1], batch=batch, nmcmc=1000 if batch > 1 else 100, ctx=ctx)
+        ev = math.exp(r.log_evidence)
+        err = math.exp(nested.log_total_error_estimate(r.log_evidence, r.log_delta_evidence, 1000))
+        assert abs(ev - 1.0) <= 2.0 * err and err < 0.1
+        assert np.exp(r.log_weights).sum() == pytest.approx(1.0, abs=1e-8)
+        mean = np.sum(np.exp(r.log_weights) * r.points[:, 0])
+        assert mean == pytest.approx(0.5, abs=0.1)
+        post = nested.posterior_samples(100, r, rng=np.random.default_rng(1))      # nested_test.ml:87-105
+        assert len(r.log_likelihood) > 100 and post[:, 0].mean() == pytest.approx(0.5, abs=0.05)
+
+
+def test_four_gaussians(ctx):  # nested_test.ml:41-64
+    like = P.gauss_mix([[0.25, 0.25], [0.25, 0.75], [0.75, 0.25], [0.75, 0.75]], [0.05, 0.05])
+    ctx.set_seed(33)
+    r = nested.nested_evidence(like, PRIOR, [0, 0], [1, 1], batch=50, ctx=ctx)
+    ev = math.exp(r.log_evidence)
+    err = math.exp(nested.log_total_error_estimate(r.log_evidence, r.log_delta_evidence, 1000))
+    assert abs(ev - 4.0) <= 2.0 * err and err < 0.5
+
+
+def test_gaussian_shell_config4_small(ctx):
+    """BASELINE.json config 4 at test size: 16-D Gaussian shell (r=2, w=0.1)
+    on [-6,6]^16, analytic Z by radial quadrature"""
+    from scipy import integrate, special
+    D, r0, w = 16, 2.0, 0.1
+    like = P.shell(np.zeros(D), r0, w)
+    prior = P.box(np.full(D, -6.0), np.full(D, 6.0), -D * math.log(12.0))
+    area = 2 * math.pi ** (D / 2) / special.gamma(D / 2)
+    Z, _ = integrate.quad(lambda r: area * r ** (D - 1) * math.exp(-(r - r0) ** 2 / (2 * w * w)) / math.sqrt(2 * math.pi * w * w), 0, 6)
+    logZ = math.log(Z) - D * math.log(12.0)
+    ctx.set_seed(34)
+    res = nested.nested_evidence(like, prior, np.full(D, -6.0), np.full(D, 6.0), nlive=2000, nmcmc=300, batch=256, ctx=ctx)
+    err = nested.log_total_error_estimate(res.log_evidence, res.log_delta_evidence, 2000) - res.log_evidence
+    # log-evidence within 5 relative-error units (nmcmc=300 DE steps leave some correlation)
+    assert abs(res.log_evidence - logZ) < max(0.5, 5 * math.exp(err))
+
+
+def test_errors(ctx):
+    like = P.gauss_diag([0.5, 0.5], [0.1, 0.1])
+    with pytest.raises(InvalidArgument):
+        nested.nested_evidence(like, PRIOR, [0, 0], [1, 1], nlive=10, batch=10, ctx=ctx)
+    with pytest.raises(Failure):                     # output arrays too small
+        nested.nested_evidence(like, PRIOR, [0, 0], [1, 1], nlive=100, nmcmc=10, max_points=150, ctx=ctx)
