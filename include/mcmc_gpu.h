@@ -78,6 +78,7 @@ int mg_malloc_pinned(mg_ctx *ctx, int64_t nbytes, void **out);
 int mg_free_pinned(mg_ctx *ctx, void *p);
 int mg_memcpy_h2d(mg_ctx *ctx, void *dst_dev, const void *src_host, int64_t nbytes);
 int mg_memcpy_d2h(mg_ctx *ctx, void *dst_host, const void *src_dev, int64_t nbytes);
+int mg_memcpy_d2d(mg_ctx *ctx, void *dst_dev, const void *src_dev, int64_t nbytes);
 
 /* ------------------------------------------------------------------ */
 /* plugins: log-density functions and jump proposals                   */

@@ -121,3 +121,10 @@ extern "C" int mg_memcpy_d2h(mg_ctx *ctx, void *dst, const void *src, int64_t nb
   MG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return MG_OK;
 }
+extern "C" int mg_memcpy_d2d(mg_ctx *ctx, void *dst, const void *src, int64_t nbytes) {
+  if (!ctx) return MG_EINVAL;
+  MG_CUDA(ctx, cudaSetDevice(ctx->device));
+  MG_CUDA(ctx, cudaMemcpyAsync(dst, src, (size_t)nbytes, cudaMemcpyDeviceToDevice, ctx->stream));
+  MG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return MG_OK;
+}

@@ -1,0 +1,97 @@
+"""Multi-GPU plumbing: one process per GPU, ``torch.distributed`` for the
+collectives (NCCL over NVLink on the GPU box, gloo in the CPU tests).
+
+The hot path shards without any data-path collective:
+  * MH / RJ chains are independent: rank r runs global chain ids
+    [r*C, (r+1)*C); Philox is keyed by the global id, so results do not depend
+    on the number of ranks;
+  * point-location / density / draw queries are independent: the kd-tree is
+    built on one rank and broadcast as ONE contiguous device blob;
+  * per-rank statistics (counts, sums, partial evidence terms) are tens of
+    bytes: all-gathered and combined in rank order, so the result is
+    deterministic.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def shard_range(n: int, rank: int, world: int) -> tuple[int, int]:
+    """Contiguous [begin, end) of n items owned by `rank` (sizes differ by at most 1)."""
+    base, rem = divmod(n, world)
+    b = rank * base + min(rank, rem)
+    return b, b + base + (1 if rank < rem else 0)
+
+
+def combine_moments(counts, means, m2s):
+    """Pooled mean and std (n-1) from per-rank (count, mean, sum of squared
+    deviations) -- Chan et al. pairwise update applied in rank order."""
+    n = 0.0
+    mean = np.zeros_like(np.asarray(means[0], dtype=np.float64))
+    m2 = np.zeros_like(mean)
+    for c, mu, s in zip(counts, means, m2s):
+        c = float(c)
+        if c == 0:
+            continue
+        mu, s = np.asarray(mu, np.float64), np.asarray(s, np.float64)
+        delta = mu - mean
+        tot = n + c
+        mean = mean + delta * (c / tot)
+        m2 = m2 + s + delta * delta * (n * c / tot)
+        n = tot
+    return n, mean, np.sqrt(m2 / (n - 1.0))
+
+
+def all_gather_array(x: np.ndarray, device=None) -> np.ndarray:
+    """All-gather a small float64 array from every rank; returns [world, ...]."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return np.asarray(x, np.float64)[None]
+    t = torch.as_tensor(np.ascontiguousarray(x, dtype=np.float64))
+    if device is not None:
+        t = t.to(device)
+    out = [torch.empty_like(t) for _ in range(dist.get_world_size())]
+    dist.all_gather(out, t)
+    return np.stack([o.cpu().numpy() for o in out])
+
+
+def gather_ensemble_stats(n_samples: int, mean: np.ndarray, std: np.ndarray, accept: int, reject: int, device=None):
+    """Combine per-rank sample-block statistics of a sharded ensemble run."""
+    mean, std = np.asarray(mean, np.float64), np.asarray(std, np.float64)
+    m2 = std * std * (n_samples - 1.0)
+    payload = np.concatenate([[float(n_samples), float(accept), float(reject)], mean, m2])
+    g = all_gather_array(payload, device)
+    F = mean.size
+    n, mu, sd = combine_moments(g[:, 0], g[:, 3:3 + F], g[:, 3 + F:3 + 2 * F])
+    return dict(n=n, mean=mu, std=sd, accept=int(g[:, 1].sum()), reject=int(g[:, 2].sum()))
+
+
+def broadcast_tree(tree, src: int = 0, ctx=None):
+    """Replicate a KdTree built on rank `src` to every rank: one broadcast of
+    the serialised device blob.  Returns the local KdTree."""
+    import torch
+    import torch.distributed as dist
+
+    from .kd_tree import KdTree
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return tree
+    rank = dist.get_rank()
+    ctx = ctx or (tree.ctx if tree is not None else None)
+    dev = torch.device("cuda", ctx.device)
+    nbytes = torch.zeros(1, dtype=torch.int64, device=dev)
+    if rank == src:
+        p, n = tree.blob()
+        nbytes[0] = n
+    dist.broadcast(nbytes, src)
+    n = int(nbytes.item())
+    buf = torch.empty(n, dtype=torch.uint8, device=dev)
+    if rank == src:
+        import ctypes as C
+        ctx.sync()
+        ctx.check(ctx.lib.mg_memcpy_d2d(ctx.h, C.c_void_p(buf.data_ptr()), C.c_void_p(p), C.c_int64(n)))
+    dist.broadcast(buf, src)
+    if rank == src:
+        return tree
+    torch.cuda.synchronize(dev)
+    return KdTree.from_blob(buf.data_ptr(), n, ctx=ctx)

@@ -1,0 +1,55 @@
+(** GPU path of the sampling-and-evidence modules, same shapes as [Mcmc],
+    [Interpolate_pdf] and [Evidence], with closures replaced by registered
+    plugins and ['a] fixed to [float array] (what every program in bin/ uses,
+    e.g. bin/evidence_tool.ml:35-40).  NOT COMPILED in this repository's image
+    (no OCaml toolchain, SURVEY.md F1). *)
+
+open Bigarray
+
+type ctx
+(** One GPU, one Philox key, one CUDA stream.  Single caller, like the
+    reference's global counters and [Random] state. *)
+
+type logfn = { kind : int; dim : int; scale : float; params : (float, float64_elt, c_layout) Array1.t }
+(** A registered log-likelihood / log-prior plugin (MG_FN_* kinds). *)
+
+type proposal = { pkind : int; pdim : int; pparams : (float, float64_elt, c_layout) Array1.t }
+(** A jump proposal with its log jump probability (MG_PROP_* kinds). *)
+
+val create : ?device:int -> ?seed:int64 -> unit -> ctx
+val set_seed : ctx -> int64 -> unit  (** [Random.init] *)
+
+val reset_counters : ctx -> unit     (** [Mcmc.reset_counters] *)
+val get_counters : ctx -> int * int  (** [Mcmc.get_counters] *)
+
+(** Built-in plugins (the models shipped in bin/ and test/). *)
+val gaussian : float array -> float array -> logfn           (* Stats.log_multi_gaussian mu sigma *)
+val gaussian_data : float array -> logfn                      (* sum_i Stats.log_gaussian mu sigma data_i *)
+val cauchy_data : float array -> logfn                        (* sum_i Stats.log_cauchy x0 gamma data_i *)
+val box_prior : ?value:float -> float array -> float array -> logfn
+val flat : int -> logfn
+val box_proposal : float array -> proposal                    (* x_i + random_between (-h_i) h_i *)
+val uniform_wrapping : float array -> float array -> float array -> proposal  (* Mcmc.uniform_wrapping *)
+
+val mcmc_array :
+  ctx -> ?nbin:int -> ?nskip:int -> ?nchains:int -> int -> logfn -> logfn -> proposal -> float array ->
+  float array Mcmc.mcmc_sample array array
+(** [mcmc_array ctx ?nbin ?nskip ?nchains n log_likelihood log_prior
+    jump_proposal start]: [Mcmc.mcmc_array] for [nchains] independent chains
+    (default 1); element [c] of the result is chain [c]'s sample array. *)
+
+module Interp : sig
+  type interp_pdf
+  val make : ctx -> float array array -> float array -> float array -> interp_pdf
+  val draw : ctx -> interp_pdf -> float array
+  val draw_high_level : ctx -> int -> interp_pdf -> float array
+  val jump_prob : ctx -> interp_pdf -> 'a -> float array -> float
+  val jump_prob_high_level : ctx -> int -> interp_pdf -> 'a -> float array -> float
+  val jump_prob_batch : ctx -> ?n:int -> interp_pdf -> float array array -> float array
+end
+
+module Evidence : sig
+  val evidence_harmonic_mean : ctx -> float array Mcmc.mcmc_sample array -> float
+  val evidence_lebesgue : ctx -> ?n:int -> ?eps:float -> float array Mcmc.mcmc_sample array -> float
+  val evidence_direct : ctx -> ?n:int -> float array Mcmc.mcmc_sample array -> float
+end

@@ -1,0 +1,203 @@
+/* mcmc_gpu_stubs.c -- thin OCaml C stubs over include/mcmc_gpu.h.
+ *
+ * NOT COMPILED IN THIS REPOSITORY'S IMAGE: there is no OCaml toolchain here
+ * (no caml/*.h, ocamlfind, ocamlopt).  The file is the binding a
+ * maintainer of farr/mcmc-ocaml adds next to mcmc.ml; it is kept small enough
+ * to review by eye.  Build (on a machine with OCaml >= 4.08 and CUDA):
+ *
+ *   ocamlfind ocamlopt -package bigarray -c mcmc_gpu_stubs.c -ccopt -I../include
+ *   ocamlfind ocamlopt -package bigarray mcmc_gpu.mli mcmc_gpu.ml mcmc_gpu_stubs.o \
+ *       -cclib -L../mcmc_ocaml_b200 -cclib -lmcmcgpu -a -o mcmc_gpu.cmxa
+ *
+ * Conventions: float64 Bigarray.Array{1,2,3} in c_layout carry all bulk data
+ * (the host entry points copy to / from the device themselves; use
+ * `Mcmc_gpu.pinned_*` allocators for pinned buffers); contexts and trees are
+ * custom blocks with finalisers; every status other than MG_OK raises the
+ * exception the reference raises in the same situation:
+ *   MG_EINVAL -> Invalid_argument, MG_EFAIL / MG_ECUDA / MG_ENOMEM -> Failure.
+ * The runtime lock is released around every call that launches kernels.
+ */
+#include <string.h>
+
+#include <caml/alloc.h>
+#include <caml/bigarray.h>
+#include <caml/custom.h>
+#include <caml/fail.h>
+#include <caml/memory.h>
+#include <caml/mlvalues.h>
+#include <caml/threads.h>
+
+#include "mcmc_gpu.h"
+
+/* ---- handles ---------------------------------------------------------- */
+#define Ctx_val(v) (*((mg_ctx **)Data_custom_val(v)))
+#define Tree_val(v) (*((mg_kdtree **)Data_custom_val(v)))
+
+static void ctx_finalize(value v) { if (Ctx_val(v)) { mg_ctx_destroy(Ctx_val(v)); Ctx_val(v) = NULL; } }
+static void tree_finalize(value v) { if (Tree_val(v)) { mg_kdtree_destroy(Tree_val(v)); Tree_val(v) = NULL; } }
+
+static struct custom_operations ctx_ops = {"mcmc_gpu.ctx", ctx_finalize, custom_compare_default, custom_hash_default,
+                                           custom_serialize_default, custom_deserialize_default,
+                                           custom_compare_ext_default, custom_fixed_length_default};
+static struct custom_operations tree_ops = {"mcmc_gpu.kdtree", tree_finalize, custom_compare_default,
+                                            custom_hash_default, custom_serialize_default, custom_deserialize_default,
+                                            custom_compare_ext_default, custom_fixed_length_default};
+
+static void check(mg_ctx *ctx, int rc) {
+  if (rc == MG_OK) return;
+  const char *msg = ctx ? mg_last_error(ctx) : "mcmc_gpu: no context";
+  if (rc == MG_EINVAL) caml_invalid_argument(msg);
+  caml_failwith(msg);
+}
+
+/* ---- plugins: OCaml records -> mg_logfn / mg_proposal -------------------
+ * type logfn = { kind : int; dim : int; scale : float; params : (float, float64_elt, c_layout) Array1.t }
+ * type proposal = { pkind : int; pdim : int; pparams : (float, float64_elt, c_layout) Array1.t } */
+static mg_logfn logfn_of_value(value v) {
+  mg_logfn f;
+  f.kind = Int_val(Field(v, 0)); f.dim = Int_val(Field(v, 1)); f.scale = Double_val(Field(v, 2));
+  f.params = (const double *)Caml_ba_data_val(Field(v, 3));
+  f.nparams = Caml_ba_array_val(Field(v, 3))->dim[0];
+  return f;
+}
+static mg_proposal proposal_of_value(value v) {
+  mg_proposal p;
+  p.kind = Int_val(Field(v, 0)); p.dim = Int_val(Field(v, 1));
+  p.params = (const double *)Caml_ba_data_val(Field(v, 2));
+  p.nparams = Caml_ba_array_val(Field(v, 2))->dim[0];
+  return p;
+}
+
+/* ---- context ---------------------------------------------------------- */
+CAMLprim value mcmcgpu_ctx_create(value device, value seed) {
+  CAMLparam2(device, seed);
+  CAMLlocal1(v);
+  mg_ctx *ctx = NULL;
+  int rc = mg_ctx_create(Int_val(device), (uint64_t)Int64_val(seed), &ctx);
+  if (rc != MG_OK) caml_failwith("cuda: cannot create a GPU context (no CPU fallback)");
+  v = caml_alloc_custom(&ctx_ops, sizeof(mg_ctx *), 0, 1);
+  Ctx_val(v) = ctx;
+  CAMLreturn(v);
+}
+/* Random.init seed */
+CAMLprim value mcmcgpu_set_seed(value ctx, value seed) {
+  check(Ctx_val(ctx), mg_ctx_set_seed(Ctx_val(ctx), (uint64_t)Int64_val(seed)));
+  return Val_unit;
+}
+/* Mcmc.reset_counters / Mcmc.get_counters (mcmc.ml:30-35) */
+CAMLprim value mcmcgpu_reset_counters(value ctx) { check(Ctx_val(ctx), mg_reset_counters(Ctx_val(ctx))); return Val_unit; }
+CAMLprim value mcmcgpu_get_counters(value ctx) {
+  CAMLparam1(ctx);
+  CAMLlocal1(r);
+  int64_t a = 0, b = 0;
+  check(Ctx_val(ctx), mg_get_counters(Ctx_val(ctx), &a, &b));
+  r = caml_alloc_tuple(2);
+  Store_field(r, 0, Val_long(a)); Store_field(r, 1, Val_long(b));
+  CAMLreturn(r);
+}
+
+/* ---- Mcmc.mcmc_array (mcmc.ml:58-72) -----------------------------------
+ * external mcmc_array : ctx -> logfn -> logfn -> proposal -> nbin:int -> nskip:int -> n:int -> nchains:int ->
+ *   chain_offset:int -> (float, float64_elt, c_layout) Array2.t (* x0 [C][D] *) ->
+ *   (float, float64_elt, c_layout) Array3.t (* out [C][n][D+2] *) -> unit
+ * More than 5 arguments: bytecode / native pair. */
+CAMLprim value mcmcgpu_mcmc_array_native(value ctx, value like, value prior, value prop, value nbin, value nskip,
+                                         value n, value nchains, value chain_offset, value x0, value out) {
+  CAMLparam5(ctx, like, prior, prop, x0);
+  CAMLxparam1(out);
+  mg_logfn l = logfn_of_value(like), p = logfn_of_value(prior);
+  mg_proposal j = proposal_of_value(prop);
+  mg_mcmc_cfg cfg;
+  memset(&cfg, 0, sizeof cfg);
+  cfg.nchains = Long_val(nchains); cfg.dim = l.dim; cfg.layout = MG_LAYOUT_CHAIN_MAJOR;
+  cfg.nbin = Long_val(nbin); cfg.nskip = Long_val(nskip); cfg.n = Long_val(n);
+  cfg.chain_offset = (uint64_t)Long_val(chain_offset);
+  cfg.x0_shared = (Caml_ba_array_val(x0)->dim[0] == 1 && cfg.nchains > 1);
+  const double *px0 = (const double *)Caml_ba_data_val(x0);
+  double *pout = (double *)Caml_ba_data_val(out);
+  mg_ctx *c = Ctx_val(ctx);
+  caml_release_runtime_system();   /* Bigarray data does not move */
+  int rc = mg_mcmc_array(c, &l, &p, &j, &cfg, px0, pout, NULL, NULL);
+  caml_acquire_runtime_system();
+  check(c, rc);
+  CAMLreturn(Val_unit);
+}
+CAMLprim value mcmcgpu_mcmc_array_bytecode(value *a, int argn) {
+  (void)argn;
+  return mcmcgpu_mcmc_array_native(a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], a[8], a[9], a[10]);
+}
+
+/* ---- Kd_tree / Interpolate_pdf ----------------------------------------- */
+/* Interpolate_pdf.make pts low high (interpolate_pdf.ml:111-112) */
+CAMLprim value mcmcgpu_interp_make(value ctx, value pts, value low, value high) {
+  CAMLparam4(ctx, pts, low, high);
+  CAMLlocal1(v);
+  mg_kdtree *t = NULL;
+  struct caml_ba_array *b = Caml_ba_array_val(pts);
+  mg_ctx *c = Ctx_val(ctx);
+  const double *pp = (const double *)Caml_ba_data_val(pts), *pl = (const double *)Caml_ba_data_val(low),
+               *ph = (const double *)Caml_ba_data_val(high);
+  int64_t N = b->dim[0]; int32_t D = (int32_t)b->dim[1];
+  caml_release_runtime_system();
+  int rc = mg_kdtree_build(c, pp, N, D, pl, ph, 2, &t);
+  caml_acquire_runtime_system();
+  check(c, rc);
+  v = caml_alloc_custom(&tree_ops, sizeof(mg_kdtree *), 0, 1);
+  Tree_val(v) = t;
+  CAMLreturn(v);
+}
+/* Interpolate_pdf.jump_prob / jump_prob_high_level n (interpolate_pdf.ml:135-159) on a batch */
+CAMLprim value mcmcgpu_interp_jump_prob(value ctx, value tree, value nstop, value q, value out) {
+  CAMLparam5(ctx, tree, nstop, q, out);
+  mg_ctx *c = Ctx_val(ctx);
+  int rc = mg_interp_jump_prob(c, Tree_val(tree), (const double *)Caml_ba_data_val(q),
+                               Caml_ba_array_val(q)->dim[0], Int_val(nstop), (double *)Caml_ba_data_val(out));
+  check(c, rc);
+  CAMLreturn(Val_unit);
+}
+/* Interpolate_pdf.draw / draw_high_level n (interpolate_pdf.ml:114-133), m draws */
+CAMLprim value mcmcgpu_interp_draw(value ctx, value tree, value nstop, value out) {
+  CAMLparam4(ctx, tree, nstop, out);
+  mg_ctx *c = Ctx_val(ctx);
+  int rc = mg_interp_draw(c, Tree_val(tree), Caml_ba_array_val(out)->dim[0], Int_val(nstop),
+                          (double *)Caml_ba_data_val(out));
+  check(c, rc);
+  CAMLreturn(Val_unit);
+}
+
+/* ---- Evidence (evidence.ml:101-107,148-165,202-221) ---------------------- */
+CAMLprim value mcmcgpu_evidence_harmonic_mean(value ctx, value ll) {
+  CAMLparam2(ctx, ll);
+  double out = 0.0;
+  mg_ctx *c = Ctx_val(ctx);
+  check(c, mg_evidence_harmonic_mean(c, (const double *)Caml_ba_data_val(ll), Caml_ba_array_val(ll)->dim[0], &out));
+  CAMLreturn(caml_copy_double(out));
+}
+CAMLprim value mcmcgpu_evidence_lebesgue_native(value ctx, value n, value eps, value pts, value ll, value lp) {
+  CAMLparam5(ctx, n, eps, pts, ll);
+  CAMLxparam1(lp);
+  double out = 0.0;
+  mg_ctx *c = Ctx_val(ctx);
+  struct caml_ba_array *b = Caml_ba_array_val(pts);
+  const double *pp = (const double *)Caml_ba_data_val(pts), *pll = (const double *)Caml_ba_data_val(ll),
+               *plp = (const double *)Caml_ba_data_val(lp);
+  int64_t N = b->dim[0]; int32_t D = (int32_t)b->dim[1]; int32_t nn = Int_val(n); double e = Double_val(eps);
+  caml_release_runtime_system();
+  int rc = mg_evidence_lebesgue(c, pp, pll, plp, N, D, nn, e, &out);
+  caml_acquire_runtime_system();
+  check(c, rc);
+  CAMLreturn(caml_copy_double(out));
+}
+CAMLprim value mcmcgpu_evidence_lebesgue_bytecode(value *a, int argn) {
+  (void)argn;
+  return mcmcgpu_evidence_lebesgue_native(a[0], a[1], a[2], a[3], a[4], a[5]);
+}
+CAMLprim value mcmcgpu_evidence_direct(value ctx, value n, value pts, value ll, value lp) {
+  CAMLparam5(ctx, n, pts, ll, lp);
+  double out = 0.0;
+  mg_ctx *c = Ctx_val(ctx);
+  struct caml_ba_array *b = Caml_ba_array_val(pts);
+  check(c, mg_evidence_direct(c, (const double *)Caml_ba_data_val(pts), (const double *)Caml_ba_data_val(ll),
+                              (const double *)Caml_ba_data_val(lp), b->dim[0], (int32_t)b->dim[1], Int_val(n), &out));
+  CAMLreturn(caml_copy_double(out));
+}

@@ -1,0 +1,61 @@
+"""Host-side logic of the multi-GPU path on CPU: world_size-2 gloo group."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch.multiprocessing as mp
+
+from mcmc_ocaml_b200 import distributed as D
+
+
+def test_shard_range_partitions():
+    for n in (0, 1, 7, 64, 65537):
+        for world in (1, 2, 3, 8):
+            spans = [D.shard_range(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [e - b for b, e in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_combine_moments_matches_pooled():
+    rng = np.random.default_rng(0)
+    parts = [rng.normal(3, 2, (n, 4)) for n in (1000, 1, 2500, 333)]
+    n, mu, sd = D.combine_moments([len(p) for p in parts], [p.mean(0) for p in parts],
+                                  [((p - p.mean(0)) ** 2).sum(0) for p in parts])
+    allx = np.concatenate(parts)
+    assert n == len(allx)
+    np.testing.assert_allclose(mu, allx.mean(0), rtol=1e-13)
+    np.testing.assert_allclose(sd, allx.std(0, ddof=1), rtol=1e-13)
+
+
+def _worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(100 + rank)
+    b, e = D.shard_range(1001, rank, world)
+    x = np.random.default_rng(5).normal(1.0, 3.0, (1001, 3))[b:e]       # this rank's shard of a common data set
+    res = D.gather_ensemble_stats(len(x), x.mean(0), x.std(0, ddof=1), accept=10 * (rank + 1), reject=5)
+    g = D.all_gather_array(np.array([float(rank), rng.random()]))
+    q.put((rank, res["n"], res["mean"], res["std"], res["accept"], res["reject"], g[:, 0].tolist()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_gloo_world2_gather_and_combine():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in procs]
+    out = [q.get(timeout=120) for _ in procs]
+    [p.join(timeout=60) for p in procs]
+    assert all(p.exitcode == 0 for p in procs)
+    x = np.random.default_rng(5).normal(1.0, 3.0, (1001, 3))
+    for rank, n, mu, sd, acc, rej, ranks in out:
+        assert n == 1001 and acc == 30 and rej == 10 and ranks == [0.0, 1.0]
+        np.testing.assert_allclose(mu, x.mean(0), rtol=1e-12)
+        np.testing.assert_allclose(sd, x.std(0, ddof=1), rtol=1e-12)
