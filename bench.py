@@ -48,6 +48,16 @@ def model():
     return mu, P.gauss_corr(mu, cov), P.zero(D), P.box_proposal(np.full(D, 0.5))
 
 
+def workload_config(Cn=NCHAINS, T=NSTEPS):
+    n, F = T + 1, D + 2
+    return {"workload": f"cfg2: {Cn} independent MH chains per GPU, {D}-D correlated Gaussian "
+                        f"(Sigma_ij=0.7^|i-j|), box proposal h=0.5, {T} steps each, nskip=1, "
+                        f"every sample recorded ([n][D+2][C] f64, {n * F * Cn * 8 / 1e9:.1f} GB/pass)",
+            "chains_per_gpu": Cn, "dim": D, "steps_per_chain": T, "nskip": 1,
+            "l2": "outputs (62.9 GB/pass) far exceed the 126 MB L2; no flush needed",
+            "rng": "Philox4x32-10, 52-bit uniforms, 6 blocks/step"}
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -107,8 +117,10 @@ def cpu_reference(nthreads, target_seconds=12.0):
     og.mcmc_array(SEED, 0, n0, like, prior, prop, mu, nchains=c0, nthreads=nthreads, record=False)
     dt = time.perf_counter() - t
     rate = c0 * (n0 - 1) / dt
-    chains = max(nthreads * 8, 64)
-    steps = int(min(NSTEPS, max(200, rate * target_seconds / chains)))
+    # the sample keeps the real chain length (1e4 steps) and bounds the number of chains
+    steps = NSTEPS
+    chains = int(max(nthreads, min(NCHAINS, rate * target_seconds / steps)))
+    chains = max(nthreads, (chains // nthreads) * nthreads)
     t = time.perf_counter()
     og.mcmc_array(SEED, 1, steps + 1, like, prior, prop, mu, nchains=chains, nthreads=nthreads, record=True)
     dt = time.perf_counter() - t
@@ -133,8 +145,8 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": "chain-steps/sec", "value": v, "unit": "chain-steps/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / max(1, args.steps),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "cfg2: 65,536 MH chains, 10-D correlated Gaussian, 1e4 steps, nskip=1 "
-                               "(bounded sample per step, see cpu_baseline.sample)"},
+        "config": dict(workload_config(args.chains, args.chain_steps),
+                       note="CPU arm: each step is a bounded sample of this workload, see cpu_baseline.sample"),
         "cpu_baseline": {"value": v, "unit": "chain-steps/s", "cores": nthreads, "kind": "port", "sample": sample,
                          "note": "C++ restatement of farr/mcmc-ocaml (oracle/), not OCaml: no OCaml toolchain here"},
         "e2e": {"value": v, "unit": "chain-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -144,12 +156,13 @@ def run_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--chains", type=int, default=NCHAINS)
     ap.add_argument("--chain-steps", type=int, default=NSTEPS)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-evidence", action="store_true", help="skip the config-3 evidence leg")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -197,10 +210,10 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    sampler = ClockSampler(local_rank)
     for _ in range(args.warmup):
         step_dev()
     barrier()
-    sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
     l0 = ctx.launch_count
@@ -288,12 +301,7 @@ def main():
             "metric": "chain-steps/sec", "value": value, "unit": "chain-steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"cfg2: {Cn} independent MH chains per GPU, {D}-D correlated Gaussian "
-                                   f"(Sigma_ij=0.7^|i-j|), box proposal h=0.5, {T} steps each, nskip=1, "
-                                   f"every sample recorded to HBM ([n][D+2][C] f64, {n * F * Cn * 8 / 1e9:.1f} GB/pass)",
-                       "chains_per_gpu": Cn, "dim": D, "steps_per_chain": T, "nskip": 1,
-                       "l2": "outputs (62.9 GB/pass) far exceed the 126 MB L2; no flush needed",
-                       "rng": "Philox4x32-10, 52-bit uniforms, 6 blocks/step"},
+            "config": workload_config(Cn, T),
             "e2e": {"value": e2e_value, "unit": "chain-steps/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps,
                     "call": "mg_mcmc_array_resident: pinned x0 -> device, MH kernel, sample block stays in HBM, "
@@ -310,6 +318,23 @@ def main():
             "accept_rate_per_rank": [float(r.item()) for r in rates],
             "posterior_mean_err_max": float(np.max(np.abs(mean_h[:D] - mu))),
         }
+        if world == 1 and not args.no_evidence:
+            # second metric of BASELINE.json: evidence samples/s (config 3 on this GPU)
+            try:
+                del samples
+                torch.cuda.empty_cache()
+                sys.path.insert(0, os.path.join(ROOT, "tools"))
+                import bench_evidence
+                ev = bench_evidence.run(bench_evidence._Args(reps=2, device=local_rank), ctx=ctx)
+                out["evidence"] = {
+                    "workload": "cfg3: Weinberg (Lebesgue) kd-tree evidence + harmonic mean, 1e7 synthetic 20-D "
+                                "posterior samples, device resident, one GPU",
+                    "lebesgue_samples_per_s": ev["lebesgue_samples_per_s"], "lebesgue_s": ev["lebesgue_s"],
+                    "harmonic_s": ev["harmonic_s"], "direct_s": ev["direct_s"],
+                    "kdtree_full_build_s": ev.get("tree_full_s"), "kdtree_nodes": ev.get("tree_full_nodes"),
+                    "interp_jump_prob_per_s": ev.get("jump_prob_queries_per_s"), "interp_draw_per_s": ev.get("draw_per_s")}
+            except Exception as e:  # the headline line must still be printed
+                out["evidence"] = {"error": repr(e)}
         if world == 1 and not args.no_cpu:
             nthreads = os.cpu_count() or 1
             v, sample = cpu_reference(nthreads, 12.0)

@@ -65,9 +65,15 @@ struct Rng {
     ++j;
     return ((uint64_t)a << 32) | b;
   }
-  // Random.float 1.0: 52 random mantissa bits, [0, 1)
+  // Random.float 1.0: 52 random mantissa bits, [0, 1).  The mantissa is the
+  // low 20 bits of the first word followed by the second word: one LOP3 to
+  // build the high half, the low half is the Philox word itself.
   __device__ __forceinline__ double uniform() {
-    return __longlong_as_double((long long)((0x3FFull << 52) | (lane() >> 12))) - 1.0;
+    if ((j & 1u) == 0u) philox4x32_10(j >> 1, c1, c2, c3, k0, k1, w);
+    const uint32_t a = (j & 1u) ? w[2] : w[0];
+    const uint32_t b = (j & 1u) ? w[3] : w[1];
+    ++j;
+    return __hiloint2double((int)((a & 0xFFFFFu) | 0x3FF00000u), (int)b) - 1.0;
   }
   // Random.int n
   __device__ __forceinline__ uint64_t below(uint64_t n) { return __umul64hi(lane(), n); }

@@ -14,7 +14,8 @@
 //                         g_hi16 | purpose << 16 | step_hi8 << 24), key = call key)
 //   draw j of (purpose, g, step) = the 64-bit lane  (w[2(j&1)] << 32 | w[2(j&1)+1])
 //                  of block j >> 1
-//   Random.float 1.0  ->  u52 = bits(0x3FF<<52 | lane >> 12) - 1.0   in [0,1)
+//   Random.float 1.0  ->  u52 = bits(0x3FF<<52 | lane & (2^52-1)) - 1.0   in [0,1)
+//                         (mantissa = low 20 bits of the first word : second word)
 //   Random.int n      ->  mulhi64(lane, n)
 //
 // Philox4x32-10: Salmon et al., "Parallel random numbers: as easy as 1, 2, 3"
@@ -82,7 +83,7 @@ struct Rng {
   }
   // Random.float 1.0
   inline double uniform() {
-    uint64_t bits = (0x3FFull << 52) | (lane() >> 12);
+    uint64_t bits = (0x3FFull << 52) | (lane() & 0xFFFFFFFFFFFFFull);
     double d; std::memcpy(&d, &bits, 8);
     return d - 1.0;
   }

@@ -15,8 +15,8 @@ def test_uniform_range_and_moments(og):
     u, lanes = og.rng_stream(7, 0, 1, 3, 9, 200000)
     assert u.min() >= 0.0 and u.max() < 1.0
     assert abs(u.mean() - 0.5) < 5e-3 and abs(u.var() - 1 / 12) < 2e-3
-    # u52 = top 52 bits of the lane
-    assert np.array_equal(u, (lanes >> np.uint64(12)).astype(np.float64) * 2.0 ** -52)
+    # u52 = low 52 bits of the lane
+    assert np.array_equal(u, (lanes & np.uint64((1 << 52) - 1)).astype(np.float64) * 2.0 ** -52)
 
 
 def test_streams_are_distinct(og):

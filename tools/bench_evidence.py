@@ -16,22 +16,21 @@ import time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--n", type=int, default=10_000_000)
-    ap.add_argument("--d", type=int, default=20)
-    ap.add_argument("--reps", type=int, default=3)
-    ap.add_argument("--dups", type=float, default=0.0, help="fraction of rows repeating their predecessor")
-    ap.add_argument("--queries", type=int, default=10_000_000)
-    ap.add_argument("--skip-full-tree", action="store_true")
-    a = ap.parse_args()
+class _Args:
+    def __init__(self, **kw):
+        self.n, self.d, self.reps, self.dups, self.queries, self.skip_full_tree, self.device = 10_000_000, 20, 3, 0.0, 10_000_000, False, 0
+        self.__dict__.update(kw)
+
+
+def run(a, ctx=None):
+    import ctypes as C
+
     import numpy as np
     import torch
 
-    from mcmc_ocaml_b200 import Context, evidence, interpolate_pdf, kd_tree
-    import ctypes as C
-    dev = torch.device("cuda", 0)
-    ctx = Context(0, 12345)
+    from mcmc_ocaml_b200 import Context, evidence, kd_tree
+    dev = torch.device("cuda", a.device)
+    ctx = ctx or Context(a.device, 12345)
     g = torch.Generator(device=dev); g.manual_seed(12345)
     N, D = a.n, a.d
     x = torch.empty((N, D), dtype=torch.float64, device=dev).normal_(0.5, 0.05, generator=g)
@@ -92,7 +91,20 @@ def main():
         t, _ = timed(dr)
         out["draw_s"] = t; out["draw_per_s"] = M / t
         out["draw_mean0"] = float(outd[:, 0].mean())
-    print(json.dumps(out))
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--n", type=int, default=10_000_000)
+    ap.add_argument("--d", type=int, default=20)
+    ap.add_argument("--reps", type=int, default=3)
+    ap.add_argument("--dups", type=float, default=0.0, help="fraction of rows repeating their predecessor")
+    ap.add_argument("--queries", type=int, default=10_000_000)
+    ap.add_argument("--skip-full-tree", action="store_true")
+    ap.add_argument("--device", type=int, default=0)
+    a = ap.parse_args()
+    print(json.dumps(run(a)))
 
 
 if __name__ == "__main__":
