@@ -1,0 +1,51 @@
+#!/usr/bin/env python
+"""BASELINE.json config 4 on one GPU: nested sampling, nlive live points,
+D-dimensional Gaussian shell (r = 2, w = 0.1) on [-6,6]^D, batched constrained
+replacement; analytic Z by radial quadrature."""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--nlive", type=int, default=100_000)
+    ap.add_argument("--dim", type=int, default=16)
+    ap.add_argument("--nmcmc", type=int, default=1000)
+    ap.add_argument("--batch", type=int, default=8192)
+    ap.add_argument("--epsrel", type=float, default=0.01)
+    a = ap.parse_args()
+    import numpy as np
+    from scipy import integrate, special
+
+    from mcmc_ocaml_b200 import Context, nested, plugins as P
+    D, r0, w = a.dim, 2.0, 0.1
+    ctx = Context(0, 4)
+    like = P.shell(np.zeros(D), r0, w)
+    prior = P.box(np.full(D, -6.0), np.full(D, 6.0), -D * math.log(12.0))
+    area = 2 * math.pi ** (D / 2) / special.gamma(D / 2)
+    Z, _ = integrate.quad(lambda r: area * r ** (D - 1) * math.exp(-(r - r0) ** 2 / (2 * w * w)) / math.sqrt(2 * math.pi * w * w), 0, 6)
+    logZ = math.log(Z) - D * math.log(12.0)
+    l0 = ctx.launch_count
+    t = time.perf_counter()
+    res = nested.nested_evidence(like, prior, np.full(D, -6.0), np.full(D, 6.0), nlive=a.nlive, nmcmc=a.nmcmc,
+                                 batch=a.batch, epsrel=a.epsrel, max_points=a.nlive * 80, ctx=ctx)
+    dt = time.perf_counter() - t
+    nret = len(res.log_likelihood) - a.nlive
+    out = {"nlive": a.nlive, "dim": D, "nmcmc": a.nmcmc, "batch": a.batch, "seconds": dt, "retired": nret,
+           "likelihood_evals": nret * (a.nmcmc + 1), "evals_per_s": nret * (a.nmcmc + 1) / dt,
+           "log_ev": res.log_evidence, "log_ev_analytic": logZ,
+           "log_total_error": nested.log_total_error_estimate(res.log_evidence, res.log_delta_evidence, a.nlive),
+           "launches": ctx.launch_count - l0, "weights_sum": float(np.exp(res.log_weights).sum())}
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()
