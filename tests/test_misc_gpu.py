@@ -1,0 +1,82 @@
+"""Small C-ABI entry points: plugin evaluation, remove_repeat_samples, device helpers."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from mcmc_ocaml_b200 import Failure, _abi, mcmc, plugins as P
+
+pytestmark = pytest.mark.gpu
+
+
+def eval_gpu(ctx, fn, x):
+    x = _abi.as_f64(x).reshape(-1, fn.dim)
+    out = np.empty(x.shape[0])
+    s = fn.spec()
+    ctx.check(ctx.lib.mg_logfn_eval(ctx.h, C.byref(s), _abi.ptr(x), C.c_int64(x.shape[0]), _abi.ptr(out)))
+    return out
+
+
+def test_every_builtin_logfn_matches_oracle(ctx, og):
+    from tests.golden.gc_data import DATA
+    rng = np.random.default_rng(0)
+    D = 5
+    mu = rng.random(D); sig = 0.5 + rng.random(D)
+    A = rng.normal(size=(D, D)); cov = A @ A.T + D * np.eye(D)
+    fns = [P.zero(D), P.const(D, -1.25), P.box(np.zeros(D), np.ones(D), -0.3), P.box(np.zeros(D), np.ones(D), 0.0, closed=False),
+           P.gauss_diag(mu, sig), P.gauss_corr(mu, cov), P.shell(mu, 2.0, 0.1),
+           P.gauss_mix(rng.random((3, D)), sig), P.gauss_diag(mu, sig).scaled(0.75)]
+    x = rng.normal(0.5, 1.0, (2000, D))
+    x[:10] = np.clip(x[:10], 0, 1)
+    for fn in fns:
+        got, want = eval_gpu(ctx, fn, x), og.logfn_eval(fn, x)
+        exact = fn.kind in (_abi.FN_ZERO, _abi.FN_CONST, _abi.FN_BOX_CLOSED, _abi.FN_BOX_OPEN, _abi.FN_GAUSS_CORR)
+        if exact:
+            assert np.array_equal(got, want), fn.kind
+        else:
+            np.testing.assert_allclose(got, want, rtol=1e-13, atol=1e-13, err_msg=str(fn.kind))
+    x2 = np.stack([rng.uniform(-1, 1, 500), rng.uniform(0.5, 1.5, 500)], axis=1)
+    for fn in (P.gauss_data(DATA), P.cauchy_data(DATA)):
+        np.testing.assert_allclose(eval_gpu(ctx, fn, x2), og.logfn_eval(fn, x2), rtol=1e-13)
+
+
+def test_remove_repeat_samples(ctx, og):
+    """Mcmc.remove_repeat_samples (mcmc.ml:74-81) on the GPU, on a real MH chain (test/mcmc_test.ml:100-112)"""
+    g = P.gauss_diag([0.4], [1.3])
+    ctx.set_seed(8)
+    rows = mcmc.mcmc_array(1000, g.scaled(0.75), g.scaled(0.25), P.box_proposal([1.3]), [0.4], ctx=ctx).chain(0)
+    rows = np.ascontiguousarray(rows)
+    out = np.empty_like(rows)
+    k = C.c_int64()
+    ctx.check(ctx.lib.mg_remove_repeat_samples(ctx.h, _abi.ptr(rows), C.c_int64(rows.shape[0]), C.c_int32(1), _abi.ptr(out), C.byref(k)))
+    got = out[: k.value]
+    assert np.array_equal(got, og.remove_repeat_samples(rows, 1))
+    assert np.array_equal(got, mcmc.remove_repeat_samples(rows, 1))
+    assert np.all(got[1:, 0] != got[:-1, 0]) and 1 < len(got) < len(rows)
+
+
+def test_memory_helpers_and_stream(ctx):
+    p = C.c_void_p()
+    ctx.check(ctx.lib.mg_malloc_device(ctx.h, C.c_int64(1 << 20), C.byref(p)))
+    h = C.c_void_p()
+    ctx.check(ctx.lib.mg_malloc_pinned(ctx.h, C.c_int64(1 << 20), C.byref(h)))
+    src = np.arange(1 << 17, dtype=np.float64)
+    C.memmove(h, src.ctypes.data, src.nbytes)
+    ctx.check(ctx.lib.mg_memcpy_h2d(ctx.h, p, h, C.c_int64(src.nbytes)))
+    back = np.empty_like(src)
+    ctx.check(ctx.lib.mg_memcpy_d2h(ctx.h, back.ctypes.data_as(C.c_void_p), p, C.c_int64(src.nbytes)))
+    assert np.array_equal(back, src)
+    ctx.check(ctx.lib.mg_free_pinned(ctx.h, h))
+    ctx.check(ctx.lib.mg_free_device(ctx.h, p))
+    assert ctx.launch_count >= 0 and ctx.last_kernel_ms >= 0.0
+    tf, gbs = C.c_double(), C.c_double()
+    ctx.check(ctx.lib.mg_measure_fp64_tflops(ctx.h, 1, C.byref(tf)))
+    ctx.check(ctx.lib.mg_measure_store_gbs(ctx.h, C.c_int64(1 << 28), 1, C.byref(gbs)))
+    assert tf.value > 1.0 and gbs.value > 100.0
+
+
+def test_runtime_plugins_say_they_are_unavailable(ctx):
+    kind = C.c_int32()
+    rc = ctx.lib.mg_plugin_register_source(ctx.h, b"mylike", b"return -0.5*x[0]*x[0];", C.byref(kind))
+    with pytest.raises(Failure):
+        ctx.check(rc)
