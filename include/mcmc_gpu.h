@@ -22,7 +22,9 @@
 #ifndef MCMC_GPU_H
 #define MCMC_GPU_H
 
+#ifndef __CUDACC_RTC__
 #include <stdint.h>
+#endif
 
 #ifdef __cplusplus
 extern "C" {

@@ -31,7 +31,7 @@ struct mg_ctx {
 namespace mg {
 
 inline int set_err(mg_ctx *ctx, int code, const char *fmt, ...) {
-  char buf[512];
+  char buf[2048];
   va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
   if (ctx) ctx->err = buf;
   return code;

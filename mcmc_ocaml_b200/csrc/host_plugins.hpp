@@ -5,6 +5,8 @@
 
 namespace mg {
 
+bool user_kind_registered(int kind);  // jit.cu
+
 inline int64_t logfn_expected_nparams(const mg_logfn *f) {
   const int64_t D = f->dim;
   switch (f->kind) {
@@ -18,7 +20,7 @@ inline int64_t logfn_expected_nparams(const mg_logfn *f) {
     case MG_FN_GAUSS_MIX:
       if (f->nparams < 1 || !f->params) return -2;
       return 1 + (int64_t)f->params[0] * D + D;
-    default: return -2;
+    default: return user_kind_registered(f->kind) ? -1 : -2;
   }
 }
 

@@ -52,6 +52,8 @@ __global__ void to_chain_major_kernel(const double *__restrict__ src, int64_t ro
   }
 }
 
+int jit_launch_mh(mg_ctx *ctx, const DynFnParams &like, const DynFnParams &prior, const DynPropParams &prop,
+                  const mg_mcmc_cfg *cfg, CallKey key, double *d_state, double *d_samples, int32_t *d_accept);  // jit.cu
 int sample_block_stats(mg_ctx *ctx, const double *d_blk, int64_t n, int F, int64_t C, double *d_out);  // stats.cu
 
 static int validate_cfg(mg_ctx *ctx, const mg_mcmc_cfg *cfg) {
@@ -94,6 +96,8 @@ extern "C" int mg_mcmc_array_dev(mg_ctx *ctx, const mg_logfn *like, const mg_log
   MG_CUDA(ctx, dl.upload_from(like, ctx->stream));
   MG_CUDA(ctx, dp.upload_from(prior, ctx->stream));
   MG_CUDA(ctx, dj.upload_from(prop, ctx->stream));
+  if (like->kind >= MG_FN_USER || prior->kind >= MG_FN_USER)  // user plugins: kernel compiled at run time
+    return jit_launch_mh(ctx, dl.params, dp.params, dj.params, cfg, key, d_state, d_samples, d_accept);
 #define MG_TRY(DD) if (D <= DD) rc = mh_dyn_##DD(ctx, dl.params, dp.params, dj.params, cfg, key, d_state, d_samples, d_accept); else
   MG_DYN_DIMS(MG_TRY) rc = set_err(ctx, MG_EINVAL, "mcmc_array: dim too large");
 #undef MG_TRY

@@ -7,6 +7,8 @@
 
 namespace mg {
 
+int jit_logfn_eval(mg_ctx *ctx, const DynFnParams &f, const double *d_x, int64_t M, double *d_out);  // jit.cu
+
 template <int DMAX>
 __global__ void logfn_eval_kernel(DynFnParams f, const double *__restrict__ x, int64_t M, double *__restrict__ out) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -56,7 +58,9 @@ extern "C" int mg_logfn_eval(mg_ctx *ctx, const mg_logfn *fn, const double *x, i
   MG_CUDA(ctx, d_out.alloc(M, s));
   const unsigned grid = (unsigned)((M + 127) / 128);
   const int D = fn->dim;
-  if (D <= 2) logfn_eval_kernel<2><<<grid, 128, 0, s>>>(df.params, d_x.get(), M, d_out.get());
+  if (fn->kind >= MG_FN_USER) {
+    if ((rc = jit_logfn_eval(ctx, df.params, d_x.get(), M, d_out.get()))) return rc;
+  } else if (D <= 2) logfn_eval_kernel<2><<<grid, 128, 0, s>>>(df.params, d_x.get(), M, d_out.get());
   else if (D <= 4) logfn_eval_kernel<4><<<grid, 128, 0, s>>>(df.params, d_x.get(), M, d_out.get());
   else if (D <= 8) logfn_eval_kernel<8><<<grid, 128, 0, s>>>(df.params, d_x.get(), M, d_out.get());
   else if (D <= 16) logfn_eval_kernel<16><<<grid, 128, 0, s>>>(df.params, d_x.get(), M, d_out.get());
@@ -99,13 +103,3 @@ extern "C" int mg_remove_repeat_samples(mg_ctx *ctx, const double *rows, int64_t
   return MG_OK;
 }
 
-// User plugins compiled at run time are the next step of the plugin registry
-// (DESIGN.md "what comes next"); this build ships the built-in kinds only and
-// says so instead of silently ignoring the source.
-extern "C" int mg_plugin_register_source(mg_ctx *ctx, const char *name, const char *body, int32_t *kind) {
-  if (!ctx) return MG_EINVAL;
-  (void)body;
-  if (kind) *kind = -1;
-  return set_err(ctx, MG_EFAIL, "plugin_register_source(%s): run-time (NVRTC) plugins are not available in this build; "
-                 "use the built-in kinds MG_FN_* / MG_PROP_*", name ? name : "?");
-}

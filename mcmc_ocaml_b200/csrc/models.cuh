@@ -13,7 +13,9 @@
 // operation by operation (file is compiled with -fmad=false; the only fused
 // multiply-adds are the explicit fma() calls of the GAUSS_CORR model).
 #pragma once
+#ifndef __CUDACC_RTC__
 #include <cstdint>
+#endif
 
 #include "../../include/mcmc_gpu.h"
 #include "rng.cuh"
@@ -26,6 +28,10 @@ __device__ __forceinline__ double qnan() { return __longlong_as_double(0x7FF8000
 // Dynamic plugins unroll their per-dimension loops only for small DMAX (state
 // in registers); larger DMAX keep rolled loops over local-memory arrays.
 #define MG_DYN_UNROLL(DMAX) ((DMAX) <= 8 ? (DMAX) : 1)
+
+#ifndef MG_USER_EVAL
+#define MG_USER_EVAL(kind, x, d, p, np) (mg::neg_inf())
+#endif
 
 #define MG_PI 3.14159265358979311600  /* 4.0 *. atan 1.0, stats.ml:56 */
 
@@ -279,7 +285,9 @@ struct DynFn {
         return log(tot);
       }
     }
-    return neg_inf();
+    // kinds >= MG_FN_USER: functions registered with mg_plugin_register_source; they
+    // exist only in kernels compiled at run time (jit.cu), where MG_USER_EVAL is defined
+    return MG_USER_EVAL(f.kind, x, d, p, f.np);
   }
   template <int DMAX>
   static __device__ __forceinline__ double eval(const Params &f, const double *, const double (&x)[DMAX], int d) {

@@ -282,6 +282,8 @@ extern "C" int mg_nested_evidence(mg_ctx *ctx, const mg_logfn *like, const mg_lo
   int rc;
   if ((rc = validate_logfn(ctx, like, D, "log_likelihood"))) return rc;
   if ((rc = validate_logfn(ctx, prior, D, "log_prior"))) return rc;
+  MG_REQUIRE(ctx, like->kind < MG_FN_USER && prior->kind < MG_FN_USER,
+             "nested_evidence: run-time plugins are supported by mcmc_array and logfn_eval only");
   MG_CUDA(ctx, cudaSetDevice(ctx->device));
   cudaStream_t s = ctx->stream;
   DevLogFn dl, dp;

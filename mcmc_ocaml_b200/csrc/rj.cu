@@ -180,6 +180,8 @@ extern "C" int mg_rjmcmc_array(mg_ctx *ctx, const mg_rj_model *A, const mg_rj_mo
     MG_REQUIRE(ctx, D >= 1 && D <= 64, "rjmcmc_array: dim must be in 1..64");
     if ((rc = validate_logfn(ctx, &M[k]->like, D, "log_likelihood"))) return rc;
     if ((rc = validate_logfn(ctx, &M[k]->prior, D, "log_prior"))) return rc;
+    MG_REQUIRE(ctx, M[k]->like.kind < MG_FN_USER && M[k]->prior.kind < MG_FN_USER,
+               "rjmcmc_array: run-time plugins are supported by mcmc_array and logfn_eval only");
     if ((rc = validate_proposal(ctx, &M[k]->prop, D))) return rc;
     if (M[k]->into.kind == MG_INTO_INTERP) {
       MG_REQUIRE(ctx, M[k]->into.tree != nullptr, "rjmcmc_array: interpolated jump without a tree");

@@ -8,7 +8,9 @@
 // chain's randomness does not depend on how chains are spread over threads,
 // blocks or GPUs.  The stream layout is specified in oracle/og_rng.hpp.
 #pragma once
+#ifndef __CUDACC_RTC__
 #include <cstdint>
+#endif
 
 namespace mg {
 

@@ -115,3 +115,17 @@ def indep_gauss_proposal(mu, sigma):
 
 def left_biased_proposal(sigma):
     return Proposal(_abi.PROP_LEFT_BIASED, 1, [sigma])
+
+
+def register_source(name: str, body: str, dim: int, params=(), *, ctx=None) -> LogFn:
+    """Register a user log-density given as CUDA source (``mg_plugin_register_source``):
+    ``body`` is the body of ``__device__ double f(const double* x, int dim, const double* p, long long np)``.
+    NVRTC compiles the sampler kernel with the function inlined.  Supported by
+    ``mcmc.mcmc_array`` and ``mg_logfn_eval``."""
+    import ctypes as C
+
+    from .context import default_context
+    ctx = ctx or default_context()
+    kind = C.c_int32()
+    ctx.check(ctx.lib.mg_plugin_register_source(ctx.h, name.encode(), body.encode(), C.byref(kind)))
+    return LogFn(kind.value, dim, params)
