@@ -5,7 +5,8 @@
 //   -> exclusive scan of the [digit][tile] table (scan.cuh)
 //   -> stable scatter: each warp ranks its contiguous 512-key chunk with
 //      match.any, warps are ordered inside the tile by a per-digit prefix.
-// A pass in which every key has the same digit is skipped by the host.
+// A pass in which every key has the same digit is skipped (one up-front pass
+// builds all eight global digit histograms).
 // HBM-bound: 8 B read (histogram) + 12 B read + 12 B written (scatter) per
 // pair per executed pass.
 //
@@ -54,19 +55,35 @@ rs_hist_kernel(const uint64_t *__restrict__ keys, int64_t n, int64_t ntiles, int
   hist[(b * RS_RADIX + threadIdx.x) * ntiles + t] = sh[threadIdx.x];
 }
 
+// Stable scatter of one 4096-key tile.  Ranks: each warp walks its contiguous
+// 512-key chunk in 16 rounds of 32 consecutive keys and ranks equal digits
+// with match.any (stable by construction); warps are ordered by a per-digit
+// prefix.  The tile is then written to shared memory IN DIGIT ORDER and copied
+// out from there, so that every digit's run leaves as contiguous, coalesced
+// global stores (a direct scatter writes 8-byte keys to 256 different streams:
+// one 32-byte sector per key).
+constexpr size_t RS_SCATTER_SMEM = (size_t)RS_TILE * (sizeof(uint64_t) + sizeof(int32_t)) +
+                                   (size_t)(RS_WARPS * RS_RADIX + 2 * RS_RADIX) * sizeof(int);
+
 static __global__ void __launch_bounds__(RS_BLOCK)
 rs_scatter_kernel(const uint64_t *__restrict__ keys_in, const int32_t *__restrict__ vals_in, int64_t n,
                   int64_t ntiles, int shift, const int32_t *__restrict__ offs /* scanned hist */,
                   uint64_t *__restrict__ keys_out, int32_t *__restrict__ vals_out) {
-  __shared__ int cnt[RS_WARPS][RS_RADIX];   // per-warp digit counts, then per-warp bases
+  extern __shared__ __align__(16) unsigned char rs_smem[];
+  uint64_t *skeys = reinterpret_cast<uint64_t *>(rs_smem);
+  int32_t *svals = reinterpret_cast<int32_t *>(skeys + RS_TILE);
+  int (*cnt)[RS_RADIX] = reinterpret_cast<int (*)[RS_RADIX]>(svals + RS_TILE);  // [RS_WARPS][RS_RADIX]
+  int *dbase = &cnt[RS_WARPS][0];   // digit start inside the tile
+  int *gdelta = dbase + RS_RADIX;   // global offset of the digit minus dbase
   const int64_t b = blockIdx.y, t = blockIdx.x;
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int k = threadIdx.x; k < RS_WARPS * RS_RADIX; k += RS_BLOCK) (&cnt[0][0])[k] = 0;
   __syncthreads();
   const uint64_t *ksrc = keys_in + b * n;
   const int32_t *vsrc = vals_in + b * n;
-  // warp w owns keys [base + w*512, base + (w+1)*512), 16 rounds of 32 consecutive keys
-  const int64_t wbase = t * RS_TILE + (int64_t)w * (32 * RS_ROUNDS);
+  const int64_t tile0 = t * RS_TILE;
+  const int64_t wbase = tile0 + (int64_t)w * (32 * RS_ROUNDS);
+  const int nvalid = (int)((n - tile0 < RS_TILE) ? (n - tile0) : RS_TILE);
   uint64_t key[RS_ROUNDS];
   int rank[RS_ROUNDS];
 #pragma unroll
@@ -85,25 +102,56 @@ rs_scatter_kernel(const uint64_t *__restrict__ keys_in, const int32_t *__restric
     rank[r] = old + before;
   }
   __syncthreads();
-  // per digit: exclusive prefix over the warps of this tile + global base
   {
+    // thread d: prefix over warps, then block-wide exclusive scan over digits
     const int d = threadIdx.x;
-    int run = offs[(b * RS_RADIX + d) * ntiles + t];
+    int run = 0;
 #pragma unroll
     for (int ww = 0; ww < RS_WARPS; ++ww) { const int c = cnt[ww][d]; cnt[ww][d] = run; run += c; }
+    int total;
+    const int start = block_exclusive_scan<RS_BLOCK>(run, &total);
+    dbase[d] = start;
+    gdelta[d] = offs[(b * RS_RADIX + d) * ntiles + t] - start;
   }
   __syncthreads();
-  uint64_t *kdst = keys_out + b * n;
-  int32_t *vdst = vals_out + b * n;
 #pragma unroll
   for (int r = 0; r < RS_ROUNDS; ++r) {
     const int64_t i = wbase + r * 32 + lane;
     if (i < n) {
       const int d = (int)((key[r] >> shift) & 0xFF);
-      const int64_t pos = (int64_t)cnt[w][d] + rank[r];
-      kdst[pos] = key[r];
-      vdst[pos] = vsrc[i];
+      const int pos = dbase[d] + cnt[w][d] + rank[r];
+      skeys[pos] = key[r];
+      svals[pos] = vsrc[i];
     }
+  }
+  __syncthreads();
+  uint64_t *kdst = keys_out + b * n;
+  int32_t *vdst = vals_out + b * n;
+  for (int i = threadIdx.x; i < nvalid; i += RS_BLOCK) {
+    const uint64_t k = skeys[i];
+    const int64_t pos = (int64_t)gdelta[(int)((k >> shift) & 0xFF)] + i;
+    kdst[pos] = k;
+    vdst[pos] = svals[i];
+  }
+}
+
+// all eight global digit histograms in one pass over the keys: [nb][8][256]
+static __global__ void __launch_bounds__(RS_BLOCK)
+rs_prehist_kernel(const uint64_t *__restrict__ keys, int64_t n, unsigned int *__restrict__ ghist) {
+  __shared__ unsigned int sh[8][RS_RADIX];
+  const int64_t b = blockIdx.y;
+  for (int k = threadIdx.x; k < 8 * RS_RADIX; k += RS_BLOCK) (&sh[0][0])[k] = 0u;
+  __syncthreads();
+  const uint64_t *src = keys + b * n;
+  for (int64_t i = (int64_t)blockIdx.x * RS_BLOCK + threadIdx.x; i < n; i += (int64_t)gridDim.x * RS_BLOCK) {
+    const uint64_t k = src[i];
+#pragma unroll
+    for (int p = 0; p < 8; ++p) atomicAdd(&sh[p][(k >> (8 * p)) & 0xFF], 1u);
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < 8 * RS_RADIX; k += RS_BLOCK) {
+    const unsigned int v = (&sh[0][0])[k];
+    if (v) atomicAdd(ghist + b * 8 * RS_RADIX + k, v);
   }
 }
 
@@ -115,7 +163,7 @@ struct RadixSortTemp {
 
 // Sorts in place (result ends in d_keys / d_vals).  key_bits: number of
 // significant low bits (64 for doubles).  Returns MG_OK or an error.
-inline int radix_sort_pairs(mg_ctx *ctx, uint64_t *d_keys, int32_t *d_vals, int64_t n, int64_t nb, int key_bits = 64) {
+static inline int radix_sort_pairs(mg_ctx *ctx, uint64_t *d_keys, int32_t *d_vals, int64_t n, int64_t nb, int key_bits = 64) {
   if (n <= 1 || nb <= 0) return MG_OK;
   cudaStream_t s = ctx->stream;
   const int64_t ntiles = (n + RS_TILE - 1) / RS_TILE;
@@ -129,12 +177,37 @@ inline int radix_sort_pairs(mg_ctx *ctx, uint64_t *d_keys, int32_t *d_vals, int6
   uint64_t *kin = d_keys, *kout = tmp.keys_alt.get();
   int32_t *vin = d_vals, *vout = tmp.vals_alt.get();
   dim3 grid((unsigned)ntiles, (unsigned)nb);
+  // a pass whose digit is the same for every key of every row moves nothing: find those up front
+  bool skip[8] = {false, false, false, false, false, false, false, false};
+  if (n >= 4 * RS_TILE) {
+    DevBuf<unsigned int> ghist;
+    MG_CUDA(ctx, ghist.alloc((size_t)nb * 8 * RS_RADIX, s));
+    MG_CUDA(ctx, cudaMemsetAsync(ghist.get(), 0, sizeof(unsigned int) * nb * 8 * RS_RADIX, s));
+    int64_t gx = (n + RS_BLOCK * 8 - 1) / (RS_BLOCK * 8);
+    if (gx > (int64_t)ctx->sm_count * 8) gx = (int64_t)ctx->sm_count * 8;
+    rs_prehist_kernel<<<dim3((unsigned)gx, (unsigned)nb), RS_BLOCK, 0, s>>>(d_keys, n, ghist.get());
+    MG_CHECK_LAUNCH(ctx);
+    std::vector<unsigned int> h((size_t)nb * 8 * RS_RADIX);
+    MG_CUDA(ctx, cudaMemcpyAsync(h.data(), ghist.get(), sizeof(unsigned int) * h.size(), cudaMemcpyDeviceToHost, s));
+    MG_CUDA(ctx, cudaStreamSynchronize(s));
+    for (int p = 0; p < 8; ++p) {
+      bool all_const = true;
+      for (int64_t b = 0; b < nb && all_const; ++b) {
+        bool row_const = false;
+        for (int d = 0; d < RS_RADIX; ++d) if (h[((size_t)b * 8 + p) * RS_RADIX + d] == (unsigned int)n) { row_const = true; break; }
+        all_const = row_const;
+      }
+      skip[p] = all_const;
+    }
+  }
+  MG_CUDA(ctx, cudaFuncSetAttribute(rs_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RS_SCATTER_SMEM));
   for (int shift = 0; shift < key_bits; shift += 8) {
+    if (skip[shift / 8]) continue;
     rs_hist_kernel<<<grid, RS_BLOCK, 0, s>>>(kin, n, ntiles, shift, tmp.hist.get());
     MG_CHECK_LAUNCH(ctx);
     int rc = exclusive_scan_i32(ctx, tmp.hist.get(), tmp.hist.get(), hist_n, nb, tmp.scan_tmp.get(), nullptr);
     if (rc) return rc;
-    rs_scatter_kernel<<<grid, RS_BLOCK, 0, s>>>(kin, vin, n, ntiles, shift, tmp.hist.get(), kout, vout);
+    rs_scatter_kernel<<<grid, RS_BLOCK, RS_SCATTER_SMEM, s>>>(kin, vin, n, ntiles, shift, tmp.hist.get(), kout, vout);
     MG_CHECK_LAUNCH(ctx);
     std::swap(kin, kout); std::swap(vin, vout);
   }

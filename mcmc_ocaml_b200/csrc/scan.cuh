@@ -106,7 +106,7 @@ scan_down_kernel(const int32_t *__restrict__ in, int64_t n, int64_t ntiles, cons
 // Exclusive scan of nb rows of n int32 each.  d_tmp must hold nb * ceil(n/TILE) int32.
 inline int64_t scan_tmp_elems(int64_t n, int64_t nb) { return nb * ((n + SCAN_TILE - 1) / SCAN_TILE); }
 
-inline int exclusive_scan_i32(mg_ctx *ctx, const int32_t *d_in, int32_t *d_out, int64_t n, int64_t nb,
+static inline int exclusive_scan_i32(mg_ctx *ctx, const int32_t *d_in, int32_t *d_out, int64_t n, int64_t nb,
                               int32_t *d_tmp, int32_t *d_totals) {
   if (n <= 0 || nb <= 0) return MG_OK;
   const int64_t ntiles = (n + SCAN_TILE - 1) / SCAN_TILE;

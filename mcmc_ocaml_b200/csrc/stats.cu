@@ -15,16 +15,21 @@ namespace mg {
 
 constexpr int RED_BLOCK = 256;
 
-// ---- sample block [n][F][C]: per-field sum of (x - shift_f)^pow ------------
-template <int POW>
+// ---- sample block [n][F][C] ---------------------------------------------------
+// One pass for both moments: sums of (x - s_f) and (x - s_f)^2 about a pivot
+// s_f (the field's first sample), so that
+//   mean = s + S1/N,   var = (S2 - S1^2/N) / (N - 1)
+// read the 62.9 GB sample block once instead of twice.  With the pivot inside
+// the distribution the subtraction loses less than a digit, and both sums are
+// compensated; agreement with Stats.multi_mean / multi_std stays within 1e-12
+// (tests/test_mcmc_gpu.py::test_resident_call_and_block_stats).
 __global__ void __launch_bounds__(RED_BLOCK)
-block_field_reduce_kernel(const double *__restrict__ blk, int64_t n, int F, int64_t C,
-                          const double *__restrict__ shift, double *__restrict__ partial /* [F][gridDim.x] */) {
+block_field_moments_kernel(const double *__restrict__ blk, int64_t n, int F, int64_t C,
+                           double *__restrict__ partial /* [2][F][gridDim.x] */) {
   const int f = blockIdx.y;
-  const double sh = shift ? shift[f] : 0.0;
-  Comp acc;
-  // rows of field f: sample s -> blk[(s*F + f)*C ...], C contiguous doubles
-  const int64_t nvec = C / 2;  // C even -> 16-byte loads
+  const double sh = blk[(int64_t)f * C];   // pivot: sample 0, chain 0
+  Comp a1, a2;
+  const int64_t nvec = C / 2;
   const bool vec_ok = (C % 2 == 0);
   for (int64_t s = blockIdx.x; s < n; s += gridDim.x) {
     const double *row = blk + (s * F + f) * C;
@@ -33,29 +38,34 @@ block_field_reduce_kernel(const double *__restrict__ blk, int64_t n, int F, int6
       for (int64_t c = threadIdx.x; c < nvec; c += RED_BLOCK) {
         const double2 v = __ldcs(row2 + c);
         const double a = v.x - sh, b = v.y - sh;
-        acc.add(POW == 1 ? a : a * a);
-        acc.add(POW == 1 ? b : b * b);
+        a1.add(a); a1.add(b); a2.add(a * a); a2.add(b * b);
       }
     } else {
       for (int64_t c = threadIdx.x; c < C; c += RED_BLOCK) {
         const double a = __ldcs(row + c) - sh;
-        acc.add(POW == 1 ? a : a * a);
+        a1.add(a); a2.add(a * a);
       }
     }
   }
-  const double tot = block_reduce_comp<RED_BLOCK>(acc);
-  if (threadIdx.x == 0) partial[(int64_t)f * gridDim.x + blockIdx.x] = tot;
+  const double t1 = block_reduce_comp<RED_BLOCK>(a1);
+  const double t2 = block_reduce_comp<RED_BLOCK>(a2);
+  if (threadIdx.x == 0) {
+    partial[(int64_t)f * gridDim.x + blockIdx.x] = t1;
+    partial[((int64_t)F + f) * gridDim.x + blockIdx.x] = t2;
+  }
 }
 
-// out[f] = finish(sum_b partial[f][b]) -- fixed order, one thread per field
-__global__ void finish_fields_kernel(const double *__restrict__ partial, int nb, int F, double denom, int do_sqrt,
-                                     double *__restrict__ out) {
+__global__ void finish_moments_kernel(const double *__restrict__ partial, int nb, int F, double cnt,
+                                      const double *__restrict__ blk, int64_t C, double *__restrict__ out) {
   const int f = blockIdx.x * blockDim.x + threadIdx.x;
   if (f >= F) return;
-  Comp acc;
-  for (int b = 0; b < nb; ++b) acc.add(partial[(int64_t)f * nb + b]);
-  const double v = acc.value() / denom;
-  out[f] = do_sqrt ? sqrt(v) : v;
+  Comp s1, s2;
+  for (int b = 0; b < nb; ++b) { s1.add(partial[(int64_t)f * nb + b]); s2.add(partial[((int64_t)F + f) * nb + b]); }
+  const double sh = blk[(int64_t)f * C];
+  const double S1 = s1.value(), S2 = s2.value();
+  out[f] = sh + S1 / cnt;
+  const double var = (S2 - S1 * (S1 / cnt)) / (cnt - 1.0);
+  out[F + f] = sqrt(var > 0.0 ? var : 0.0);
 }
 
 // ---- row-major table [n][D]: column sums ----------------------------------
@@ -123,16 +133,11 @@ int sample_block_stats(mg_ctx *ctx, const double *d_blk, int64_t n, int F, int64
   cudaStream_t s = ctx->stream;
   const int gx = grid_for(ctx, n);
   DevBuf<double> partial;
-  MG_CUDA(ctx, partial.alloc((size_t)F * gx, s));
+  MG_CUDA(ctx, partial.alloc((size_t)2 * F * gx, s));
   const double cnt = (double)n * (double)C;
-  dim3 grid(gx, F);
-  block_field_reduce_kernel<1><<<grid, RED_BLOCK, 0, s>>>(d_blk, n, F, C, nullptr, partial.get());
+  block_field_moments_kernel<<<dim3(gx, F), RED_BLOCK, 0, s>>>(d_blk, n, F, C, partial.get());
   MG_CHECK_LAUNCH(ctx);
-  finish_fields_kernel<<<(F + 63) / 64, 64, 0, s>>>(partial.get(), gx, F, cnt, 0, d_out);
-  MG_CHECK_LAUNCH(ctx);
-  block_field_reduce_kernel<2><<<grid, RED_BLOCK, 0, s>>>(d_blk, n, F, C, d_out, partial.get());
-  MG_CHECK_LAUNCH(ctx);
-  finish_fields_kernel<<<(F + 63) / 64, 64, 0, s>>>(partial.get(), gx, F, cnt - 1.0, 1, d_out + F);
+  finish_moments_kernel<<<(F + 63) / 64, 64, 0, s>>>(partial.get(), gx, F, cnt, d_blk, C, d_out);
   MG_CHECK_LAUNCH(ctx);
   return MG_OK;
 }
