@@ -104,10 +104,10 @@ mh_ws_kernel(const __grid_constant__ MhArgs<GaussCorr<D>, ZeroFn, BoxProp<D>, D>
           Rng r(a.key, P_MH, g, (uint64_t)t);
           double2 *slot = dst + q * WS_SLOTS * 32;
 #pragma unroll
-          for (int p = 0; p < 5; ++p) {       // BoxProp: a_i + w_i * u_i (bin/evidence_direct.ml:24-25)
+          for (int p = 0; p < 5; ++p) {       // BoxProp offset fma(w_i, 1 + u_i, c_i) (bin/evidence_direct.ml:24-25)
             double o0 = 0.0, o1 = 0.0;
-            if (2 * p < D) { const double2 aw = lds2(sj + 4 * p); o0 = aw.x + aw.y * r.uniform(); }
-            if (2 * p + 1 < D) { const double2 aw = lds2(sj + 4 * p + 2); o1 = aw.x + aw.y * r.uniform(); }
+            if (2 * p < D) { const double2 cw = lds2(sj + 4 * p); o0 = fma(cw.y, r.uniform12(), cw.x); }
+            if (2 * p + 1 < D) { const double2 cw = lds2(sj + 4 * p + 2); o1 = fma(cw.y, r.uniform12(), cw.x); }
             sts2(reinterpret_cast<double *>(slot + p * 32), o0, o1);
           }
           const double logu = log(r.uniform());   // log (Random.float 1.0), mcmc.ml:47

@@ -169,15 +169,16 @@ struct GaussCorr {
 // MG_PROP_BOX: x_i + random_between (-h_i) h_i  (bin/evidence_direct.ml:24-43)
 template <int D>
 struct BoxProp {
-  // (a_i, w_i) = (-h_i, h_i - (-h_i)) pairs, formed on the host: exactly the
-  // values the reference's random_between computes on every call.
+  // x_i + random_between (-h_i) h_i = x_i + (a + (b - a) u), evaluated with
+  // m = 1 + u in [1, 2) as ONE fused multiply-add: x_i + fma(w_i, m, c_i),
+  // (c_i, w_i) = (a - (b - a), b - a) pairs formed on the host (oracle: og_models.hpp).
   static constexpr int kSmem = 2 * D;
   struct Params { double s[kSmem]; };
   static constexpr bool kSymmetric = true;
   static constexpr bool kStaticDim = true;
   static constexpr int kDraws = D;  // uniforms consumed per proposal (fixed)
   static void pack(const double *h, Params &p) {
-    for (int i = 0; i < D; ++i) { const double lo = -h[i], hi = h[i]; p.s[2 * i] = lo; p.s[2 * i + 1] = hi - lo; }
+    for (int i = 0; i < D; ++i) { const double lo = -h[i], hi = h[i], w = hi - lo; p.s[2 * i] = lo - w; p.s[2 * i + 1] = w; }
   }
   template <int DD, class R>
   static __device__ __forceinline__ void propose(const Params &, const double *s, R &r, const double (&x)[DD],
@@ -185,8 +186,8 @@ struct BoxProp {
     static_assert(DD == D, "BoxProp: dimension mismatch");
 #pragma unroll
     for (int i = 0; i < D; ++i) {
-      const double2 aw = lds2(s + 2 * i);
-      y[i] = x[i] + (aw.x + aw.y * r.uniform());
+      const double2 cw = lds2(s + 2 * i);
+      y[i] = x[i] + fma(cw.y, r.uniform12(), cw.x);
     }
   }
   template <int DD>
@@ -316,7 +317,7 @@ struct DynProp {
       case MG_PROP_BOX:
 #pragma unroll (DMAX <= 8 ? DMAX : 1)
         for (int i = 0; i < DMAX; ++i)
-          if (i < d) { const double a = -__ldg(p + i), b = __ldg(p + i); y[i] = x[i] + (a + (b - a) * r.uniform()); }
+          if (i < d) { const double a = -__ldg(p + i), b = __ldg(p + i), w = b - a; y[i] = x[i] + fma(w, r.uniform12(), a - w); }
         break;
       case MG_PROP_WRAP:
 #pragma unroll (DMAX <= 8 ? DMAX : 1)

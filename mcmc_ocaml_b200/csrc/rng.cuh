@@ -70,13 +70,14 @@ struct Rng {
   // Random.float 1.0: 52 random mantissa bits, [0, 1).  The mantissa is the
   // low 20 bits of the first word followed by the second word: one LOP3 to
   // build the high half, the low half is the Philox word itself.
-  __device__ __forceinline__ double uniform() {
+  __device__ __forceinline__ double uniform12() {  // 1 + Random.float 1.0, in [1, 2)
     if ((j & 1u) == 0u) philox4x32_10(j >> 1, c1, c2, c3, k0, k1, w);
     const uint32_t a = (j & 1u) ? w[2] : w[0];
     const uint32_t b = (j & 1u) ? w[3] : w[1];
     ++j;
-    return __hiloint2double((int)((a & 0xFFFFFu) | 0x3FF00000u), (int)b) - 1.0;
+    return __hiloint2double((int)((a & 0xFFFFFu) | 0x3FF00000u), (int)b);
   }
+  __device__ __forceinline__ double uniform() { return uniform12() - 1.0; }
   // Random.int n
   __device__ __forceinline__ uint64_t below(uint64_t n) { return __umul64hi(lane(), n); }
 };
@@ -95,6 +96,7 @@ struct RngBuf {
     j = 0;
   }
   __device__ __forceinline__ double uniform() { return u[j++]; }
+  __device__ __forceinline__ double uniform12() { return u[j++] + 1.0; }
 };
 
 }  // namespace mg

@@ -87,6 +87,12 @@ struct Rng {
     double d; std::memcpy(&d, &bits, 8);
     return d - 1.0;
   }
+  // 1 + Random.float 1.0, in [1, 2): the raw mantissa pattern, no subtraction
+  inline double uniform12() {
+    uint64_t bits = (0x3FFull << 52) | (lane() & 0xFFFFFFFFFFFFFull);
+    double d; std::memcpy(&d, &bits, 8);
+    return d;
+  }
   // Random.int n
   inline uint64_t below(uint64_t n) {
     return (uint64_t)(((unsigned __int128)lane() * n) >> 64);
