@@ -124,60 +124,100 @@ __global__ void mark_side_kernel(BuildArrays a, const int32_t *__restrict__ list
   }
 }
 
-__device__ __forceinline__ int part_flag(const BuildArrays &a, const int32_t *seg, const uint8_t *side,
-                                         const int32_t *list, int32_t lb, int32_t le, int64_t p, int32_t *node,
-                                         int32_t *idx) {
-  const int32_t id = seg[p];
-  *node = id; *idx = list[p];
-  if (id < lb || id >= le || a.dim[id] < 0) { *node = -1; return 0; }
-  return side[*idx];
-}
+// Stable partition of every list inside every splitting node (List.partition,
+// kd_tree.ml:168) in ONE pass per level: a chained scan with decoupled
+// look-back over the tiles of each list gives every element the number of
+// right-going elements before it; combined with the per-node offsets (a scan
+// over the level's nodes) that is its destination.  Tiles take their index from
+// a per-list ticket counter, so a tile only ever waits for tiles that are
+// already running.
+constexpr unsigned long long LB_AGG = 1ull << 62, LB_PREFIX = 2ull << 62, LB_MASK = 3ull << 62;
 
+template <bool VEC>
 __global__ void __launch_bounds__(SCAN_BLOCK)
-part_reduce_kernel(BuildArrays a, const int32_t *__restrict__ lists, const int32_t *__restrict__ seg,
-                   const uint8_t *__restrict__ side, int32_t lb, int32_t le, int64_t ntiles, int32_t *__restrict__ tsum) {
+part_fused_kernel(BuildArrays a, const int32_t *__restrict__ lists_in, int32_t *__restrict__ lists_out,
+                  const int32_t *__restrict__ seg_in, int32_t *__restrict__ seg_out,
+                  const uint8_t *__restrict__ side, int32_t lb, int32_t le, int64_t ntiles,
+                  unsigned long long *__restrict__ status /* [NL][ntiles] */, unsigned int *__restrict__ ticket /* [NL] */,
+                  const int32_t *__restrict__ ebegin /* [nlvl] */) {
   const int l = blockIdx.y;
-  const int32_t *list = lists + (int64_t)l * a.N;
-  const int64_t base = (int64_t)blockIdx.x * SCAN_TILE;
-  int acc = 0;
-#pragma unroll
-  for (int k = 0; k < SCAN_ITEMS; ++k) {
-    const int64_t p = base + k * SCAN_BLOCK + threadIdx.x;
-    if (p < a.N) { int32_t nd, ix; acc += part_flag(a, seg, side, list, lb, le, p, &nd, &ix); }
-  }
-  int total;
-  block_exclusive_scan<SCAN_BLOCK>(acc, &total);
-  if (threadIdx.x == 0) tsum[(int64_t)l * ntiles + blockIdx.x] = total;
-}
-
-// stable partition of every list inside every splitting node (List.partition, kd_tree.ml:168)
-__global__ void __launch_bounds__(SCAN_BLOCK)
-part_scatter_kernel(BuildArrays a, const int32_t *__restrict__ lists_in, int32_t *__restrict__ lists_out,
-                    const int32_t *__restrict__ seg_in, int32_t *__restrict__ seg_out,
-                    const uint8_t *__restrict__ side, int32_t lb, int32_t le, int64_t ntiles,
-                    const int32_t *__restrict__ tbase, const int32_t *__restrict__ ebegin /* [nlvl] */) {
-  const int l = blockIdx.y;
+  __shared__ unsigned int s_tile;
+  __shared__ int s_base;
+  if (threadIdx.x == 0) s_tile = atomicAdd(ticket + l, 1u);
+  __syncthreads();
+  const int64_t t = s_tile;
   const int32_t *list = lists_in + (int64_t)l * a.N;
   int32_t *out = lists_out + (int64_t)l * a.N;
-  const int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
+  unsigned long long *st = status + (int64_t)l * ntiles;
+  const int64_t base = t * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
   int f[SCAN_ITEMS]; int32_t nd[SCAN_ITEMS], ix[SCAN_ITEMS];
+  if (VEC && base + SCAN_ITEMS <= a.N) {
+    const int4 *lp = reinterpret_cast<const int4 *>(list + base), *sp = reinterpret_cast<const int4 *>(seg_in + base);
+#pragma unroll
+    for (int v = 0; v < SCAN_ITEMS / 4; ++v) {
+      const int4 li = __ldg(lp + v), si = __ldg(sp + v);
+      ix[4 * v] = li.x; ix[4 * v + 1] = li.y; ix[4 * v + 2] = li.z; ix[4 * v + 3] = li.w;
+      nd[4 * v] = si.x; nd[4 * v + 1] = si.y; nd[4 * v + 2] = si.z; nd[4 * v + 3] = si.w;
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) {
+      const int64_t p = base + k;
+      ix[k] = 0; nd[k] = -1;
+      if (p < a.N) { ix[k] = list[p]; nd[k] = seg_in[p]; }
+    }
+  }
   int acc = 0;
 #pragma unroll
   for (int k = 0; k < SCAN_ITEMS; ++k) {
-    const int64_t p = base + k;
-    f[k] = 0; nd[k] = -1; ix[k] = 0;
-    if (p < a.N) f[k] = part_flag(a, seg_in, side, list, lb, le, p, &nd[k], &ix[k]);
+    const int32_t id = nd[k];
+    const bool active = (base + k < a.N) && id >= lb && id < le && a.dim[id] >= 0;
+    f[k] = active ? (int)side[ix[k]] : 0;
+    if (!active && base + k < a.N) nd[k] = -1 - id;   // remember the node id of a pass-through element as -1-id
+    if (base + k >= a.N) nd[k] = -1;
     acc += f[k];
   }
   int total;
-  int E = block_exclusive_scan<SCAN_BLOCK>(acc, &total) + tbase[(int64_t)l * ntiles + blockIdx.x];
+  const int ex = block_exclusive_scan<SCAN_BLOCK>(acc, &total);
+  if (threadIdx.x < 32) {                  // warp 0: publish the aggregate, then look back 32 tiles at a time
+    const int lane = threadIdx.x;
+    if (lane == 0 && t > 0) atomicExch(st + t, LB_AGG | (unsigned long long)total);
+    unsigned long long prefix = 0;
+    int64_t end = t - 1;                   // nearest predecessor not yet accounted for
+    bool done = (t == 0);
+    while (!done) {
+      const int64_t k = end - lane;
+      unsigned long long v = LB_PREFIX;    // tiles before the list start: prefix 0
+      if (k >= 0) {
+        unsigned spins = 0;
+        do {
+          v = *reinterpret_cast<volatile unsigned long long *>(st + k);
+          if (!(v & LB_MASK) && ++spins > (1u << 28)) __trap();
+        } while (!(v & LB_MASK));
+      }
+      const unsigned has_prefix = __ballot_sync(0xffffffffu, (v & LB_MASK) == LB_PREFIX);
+      const int first = __ffs(has_prefix) - 1;            // nearest tile that already knows its inclusive prefix
+      unsigned long long part = (first < 0 || lane <= first) ? (v & ~LB_MASK) : 0ull;
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) part += __shfl_xor_sync(0xffffffffu, part, off);
+      prefix += part;
+      if (first >= 0) done = true; else end -= 32;        // (first is always >= 0 once k runs below 0)
+    }
+    if (lane == 0) {
+      __threadfence();
+      atomicExch(st + t, LB_PREFIX | (prefix + (unsigned long long)total));
+      s_base = (int)prefix;
+    }
+  }
+  __syncthreads();
+  int E = ex + s_base;
 #pragma unroll
   for (int k = 0; k < SCAN_ITEMS; ++k) {
     const int64_t p = base + k;
     if (p < a.N) {
-      if (nd[k] < 0) {
+      if (nd[k] < 0) {                       // element of a node that does not split at this level
         out[p] = ix[k];
-        if (l == 0) seg_out[p] = seg_in[p];
+        if (l == 0) seg_out[p] = -1 - nd[k];
       } else {
         const int32_t id = nd[k];
         const int32_t b = a.begin[id], sp = a.spos[id];
@@ -251,7 +291,10 @@ int build_tree(mg_ctx *ctx, const double *d_pts, int64_t N, int D, const double 
   MG_CUDA(ctx, cudaMemsetAsync(segA.get(), 0, sizeof(int32_t) * N, s));
   MG_CUDA(ctx, cudaMemsetAsync(side.get(), 0, N, s));
   const int64_t ntiles = (N + SCAN_TILE - 1) / SCAN_TILE;
-  MG_CUDA(ctx, tsum.alloc((size_t)NL * ntiles, s));
+  DevBuf<unsigned long long> lb_status;
+  DevBuf<unsigned int> lb_ticket;
+  MG_CUDA(ctx, lb_status.alloc((size_t)NL * ntiles, s));
+  MG_CUDA(ctx, lb_ticket.alloc((size_t)NL, s));
   MG_CUDA(ctx, totals.alloc(2, s));
   BuildArrays a{d_pts, N, D, min_split, nd_begin.get(), nd_end.get(), nd_dim.get(), nd_left.get(), nd_spos.get(),
                 nd_split.get()};
@@ -292,12 +335,14 @@ int build_tree(mg_ctx *ctx, const double *d_pts, int64_t N, int D, const double 
     mark_side_kernel<<<grid1d(ctx, N), KB, 0, s>>>(a, lin, sin, (int32_t)lb, (int32_t)le, side.get());
     MG_CHECK_LAUNCH(ctx);
     dim3 pgrid((unsigned)ntiles, (unsigned)NL);
-    part_reduce_kernel<<<pgrid, SCAN_BLOCK, 0, s>>>(a, lin, sin, side.get(), (int32_t)lb, (int32_t)le, ntiles, tsum.get());
-    MG_CHECK_LAUNCH(ctx);
-    scan_tiles_kernel<<<(unsigned)NL, 1024, 0, s>>>(tsum.get(), ntiles, nullptr);
-    MG_CHECK_LAUNCH(ctx);
-    part_scatter_kernel<<<pgrid, SCAN_BLOCK, 0, s>>>(a, lin, lout, sin, sout, side.get(), (int32_t)lb, (int32_t)le,
-                                                     ntiles, tsum.get(), scans.get() + nlvl);
+    MG_CUDA(ctx, cudaMemsetAsync(lb_status.get(), 0, sizeof(unsigned long long) * NL * ntiles, s));
+    MG_CUDA(ctx, cudaMemsetAsync(lb_ticket.get(), 0, sizeof(unsigned int) * NL, s));
+    if (N % 4 == 0)
+      part_fused_kernel<true><<<pgrid, SCAN_BLOCK, 0, s>>>(a, lin, lout, sin, sout, side.get(), (int32_t)lb, (int32_t)le,
+                                                           ntiles, lb_status.get(), lb_ticket.get(), scans.get() + nlvl);
+    else
+      part_fused_kernel<false><<<pgrid, SCAN_BLOCK, 0, s>>>(a, lin, lout, sin, sout, side.get(), (int32_t)lb, (int32_t)le,
+                                                            ntiles, lb_status.get(), lb_ticket.get(), scans.get() + nlvl);
     MG_CHECK_LAUNCH(ctx);
     std::swap(lin, lout); std::swap(sin, sout);
     lb = le; le = nnodes + 2 * nsplit; nnodes = le;
