@@ -143,7 +143,15 @@ enum {
   MG_PROP_INDEP_GAUSS = 2,
   /* 1-D; params: sigma; left with p=0.75 (test/mcmc_test.ml:66-73) */
   MG_PROP_LEFT_BIASED = 3,
-  MG_PROP_NKINDS = 4
+  /* 1-D; params: sign, width; y = x + sign * width * u; log q = -log width
+   * on the reachable side, -inf elsewhere (test/mcmc_test.ml:186-199) */
+  MG_PROP_ONE_SIDED = 4,
+  /* Mcmc.combine_jump_proposals (mcmc.ml:165-185): params: K, then for each
+   * component: weight, kind, nparams, params[nparams].  A component is
+   * chosen with probability weight / sum; log q is the log-sum-exp over ALL
+   * components (Mcmc.log_sum_logs, mcmc.ml:155-163). */
+  MG_PROP_MIXTURE = 5,
+  MG_PROP_NKINDS = 6
 };
 
 typedef struct {

@@ -47,6 +47,23 @@ inline int validate_proposal(mg_ctx *ctx, const mg_proposal *f, int dim) {
     case MG_PROP_WRAP: need = 3 * (int64_t)dim; break;
     case MG_PROP_INDEP_GAUSS: need = 2 * (int64_t)dim; break;
     case MG_PROP_LEFT_BIASED: need = 1; if (dim != 1) return set_err(ctx, MG_EINVAL, "left-biased proposal is 1-D"); break;
+    case MG_PROP_ONE_SIDED: need = 2; if (dim != 1) return set_err(ctx, MG_EINVAL, "one-sided proposal is 1-D"); break;
+    case MG_PROP_MIXTURE: {  // K, then (weight, kind, nparams, params...) per component
+      if (f->nparams < 1 || !f->params) return set_err(ctx, MG_EINVAL, "combine_jump_proposals: no components");
+      const int K = (int)f->params[0];
+      int64_t k = 1;
+      if (K < 1 || K > 64) return set_err(ctx, MG_EINVAL, "combine_jump_proposals: need 1..64 components");
+      for (int c = 0; c < K; ++c) {
+        if (k + 3 > f->nparams) return set_err(ctx, MG_EINVAL, "combine_jump_proposals: truncated parameter block");
+        mg_proposal comp{(int32_t)f->params[k + 1], dim, f->params + k + 3, (int64_t)f->params[k + 2]};
+        if (comp.kind == MG_PROP_MIXTURE || comp.nparams < 0 || k + 3 + comp.nparams > f->nparams || !(f->params[k] > 0.0))
+          return set_err(ctx, MG_EINVAL, "combine_jump_proposals: bad component %d", c);
+        const int rc = validate_proposal(ctx, &comp, dim);
+        if (rc) return rc;
+        k += 3 + comp.nparams;
+      }
+      need = k; break;
+    }
     default: return set_err(ctx, MG_EINVAL, "jump_proposal: unknown kind %d", f->kind);
   }
   if (f->nparams != need || !f->params)

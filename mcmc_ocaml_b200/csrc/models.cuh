@@ -303,17 +303,25 @@ struct DynPropParams {
   int64_t np;
 };
 
+// mcmc.ml:155-163 (the Mcmc copy of log_sum_logs: log (1 + exp), not log1p)
+__device__ __forceinline__ double mcmc_log_sum_logs(double la, double lb) {
+  if (la == neg_inf() && lb == neg_inf()) return neg_inf();
+  if (la > lb) { const double lr = lb - la; return la + log(1.0 + exp(lr)); }
+  const double lr = la - lb;
+  return lb + log(1.0 + exp(lr));
+}
+
 struct DynProp {
   typedef DynPropParams Params;
   static constexpr bool kSymmetric = false;
   static constexpr bool kStaticDim = false;
   static constexpr int kDraws = -1;  // data dependent (rejection loops)
   static constexpr int kSmem = 0;
+  // one basic (non-mixture) proposal kind with parameters at p
   template <int DMAX, class R>
-  static __device__ __forceinline__ void propose(const Params &f, const double *, R &r, const double (&x)[DMAX],
-                                                 double (&y)[DMAX], int d) {
-    const double *p = f.p;
-    switch (f.kind) {
+  static __device__ __forceinline__ void propose_basic(int kind, const double *p, R &r, const double (&x)[DMAX],
+                                                       double (&y)[DMAX], int d) {
+    switch (kind) {
       case MG_PROP_BOX:
 #pragma unroll (DMAX <= 8 ? DMAX : 1)
         for (int i = 0; i < DMAX; ++i)
@@ -333,6 +341,49 @@ struct DynProp {
         if (r.uniform() < 0.75) y[0] = x[0] - __ldg(p) * r.uniform();
         else y[0] = x[0] + __ldg(p) * r.uniform();
         break;
+      case MG_PROP_ONE_SIDED:    // test/mcmc_test.ml:186-189
+        y[0] = x[0] + __ldg(p) * (__ldg(p + 1) * r.uniform());
+        break;
+    }
+  }
+  template <int DMAX>
+  static __device__ __forceinline__ double log_q_basic(int kind, const double *p, const double (&x)[DMAX],
+                                                       const double (&y)[DMAX], int d) {
+    switch (kind) {
+      case MG_PROP_INDEP_GAUSS: {  // test/mcmc_test.ml:123-126
+        double s = 0.0;
+#pragma unroll (DMAX <= 8 ? DMAX : 1)
+        for (int i = 0; i < DMAX; ++i)
+          if (i < d) s = s + log_gaussian(__ldg(p + i), __ldg(p + d + i), y[i]);
+        return s;
+      }
+      case MG_PROP_LEFT_BIASED: return x[0] > y[0] ? log(0.75) : log(0.25);
+      case MG_PROP_ONE_SIDED: {    // test/mcmc_test.ml:190-199
+        const double dd = __ldg(p) * (y[0] - x[0]);
+        return (dd >= 0.0 && dd <= __ldg(p + 1)) ? 0.0 - log(__ldg(p + 1)) : neg_inf();
+      }
+      default: return 0.0;
+    }
+  }
+  template <int DMAX, class R>
+  static __device__ __forceinline__ void propose(const Params &f, const double *, R &r, const double (&x)[DMAX],
+                                                 double (&y)[DMAX], int d) {
+    const double *p = f.p;
+    if (f.kind == MG_PROP_MIXTURE) {  // combine_jump_proposals, mcmc.ml:165-176
+      const int K = (int)__ldg(p);
+      double ptot = 0.0;
+      { const double *q = p + 1; for (int c = 0; c < K; ++c) { ptot = ptot + __ldg(q); q += 3 + (int)__ldg(q + 2); } }
+      double prob = r.uniform();
+      const double *q = p + 1;
+      for (int c = 0; c < K; ++c) {
+        const double w = __ldg(q) / ptot;
+        if (prob < w || c == K - 1) break;   // (the reference raises Failure if nothing is selected)
+        prob = prob - w;
+        q += 3 + (int)__ldg(q + 2);
+      }
+      propose_basic<DMAX, R>((int)__ldg(q + 1), q + 3, r, x, y, d);
+    } else {
+      propose_basic<DMAX, R>(f.kind, p, r, x, y, d);
     }
 #pragma unroll (DMAX <= 8 ? DMAX : 1)
     for (int i = 0; i < DMAX; ++i)
@@ -341,17 +392,19 @@ struct DynProp {
   template <int DMAX>
   static __device__ __forceinline__ double log_q(const Params &f, const double *, const double (&x)[DMAX],
                                                  const double (&y)[DMAX], int d) {
-    switch (f.kind) {
-      case MG_PROP_INDEP_GAUSS: {  // test/mcmc_test.ml:123-126
-        double s = 0.0;
-#pragma unroll (DMAX <= 8 ? DMAX : 1)
-        for (int i = 0; i < DMAX; ++i)
-          if (i < d) s = s + log_gaussian(__ldg(f.p + i), __ldg(f.p + d + i), y[i]);
-        return s;
-      }
-      case MG_PROP_LEFT_BIASED: return x[0] > y[0] ? log(0.75) : log(0.25);
-      default: return 0.0;
+    if (f.kind != MG_PROP_MIXTURE) return log_q_basic<DMAX>(f.kind, f.p, x, y, d);
+    const double *p = f.p;            // mcmc.ml:177-184
+    const int K = (int)__ldg(p);
+    double ptot = 0.0;
+    { const double *q = p + 1; for (int c = 0; c < K; ++c) { ptot = ptot + __ldg(q); q += 3 + (int)__ldg(q + 2); } }
+    double log_jump = neg_inf();
+    const double *q = p + 1;
+    for (int c = 0; c < K; ++c) {
+      const double log_local = log(__ldg(q) / ptot) + log_q_basic<DMAX>((int)__ldg(q + 1), q + 3, x, y, d);
+      log_jump = mcmc_log_sum_logs(log_jump, log_local);
+      q += 3 + (int)__ldg(q + 2);
     }
+    return log_jump;
   }
 };
 

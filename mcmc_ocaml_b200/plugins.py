@@ -117,6 +117,24 @@ def left_biased_proposal(sigma):
     return Proposal(_abi.PROP_LEFT_BIASED, 1, [sigma])
 
 
+def one_sided_proposal(sign, width=1.0):
+    """y = x + sign * width * U(0,1) (test/mcmc_test.ml:186-199)."""
+    return Proposal(_abi.PROP_ONE_SIDED, 1, [float(sign), float(width)])
+
+
+def combine_jump_proposals(props):
+    """``Mcmc.combine_jump_proposals [(p, proposal); ...]`` (mcmc.ml:165-185): a
+    mixture proposal whose log jump probability is the log-sum-exp over all components."""
+    props = list(props)
+    dim = props[0][1].dim
+    blob = [float(len(props))]
+    for w, pr in props:
+        if pr.dim != dim or pr.kind == _abi.PROP_MIXTURE:
+            raise _abi.InvalidArgument("combine_jump_proposals: components must be basic proposals of one dimension")
+        blob += [float(w), float(pr.kind), float(pr.params.size)] + list(pr.params)
+    return Proposal(_abi.PROP_MIXTURE, dim, blob)
+
+
 def register_source(name: str, body: str, dim: int, params=(), *, ctx=None) -> LogFn:
     """Register a user log-density given as CUDA source (``mg_plugin_register_source``):
     ``body`` is the body of ``__device__ double f(const double* x, int dim, const double* p, long long np)``.

@@ -215,15 +215,34 @@ struct LogFn {
 struct Proposal {
   int kind = MG_PROP_BOX, D = 0;
   std::vector<double> p;
+  std::vector<double> w;          // MG_PROP_MIXTURE: normalised weights
+  std::vector<Proposal> comps;    // MG_PROP_MIXTURE: components
   Proposal() {}
-  explicit Proposal(const mg_proposal *f) : kind(f->kind), D(f->dim) {
-    if (f->nparams > 0) p.assign(f->params, f->params + f->nparams);
+  Proposal(int kind_, int D_, const double *pp, int64_t np) : kind(kind_), D(D_) { init(pp, np); }
+  explicit Proposal(const mg_proposal *f) : kind(f->kind), D(f->dim) { init(f->params, f->nparams); }
+  void init(const double *pp, int64_t np) {
+    if (np > 0) p.assign(pp, pp + np);
     int64_t need = 0;
     switch (kind) {
       case MG_PROP_BOX: need = D; break;
       case MG_PROP_WRAP: need = 3 * D; break;
       case MG_PROP_INDEP_GAUSS: need = 2 * D; break;
       case MG_PROP_LEFT_BIASED: need = 1; if (D != 1) throw std::invalid_argument("left-biased is 1-D"); break;
+      case MG_PROP_ONE_SIDED: need = 2; if (D != 1) throw std::invalid_argument("one-sided is 1-D"); break;
+      case MG_PROP_MIXTURE: {  // combine_jump_proposals mcmc.ml:165-167
+        if (p.empty()) throw std::invalid_argument("mixture: no params");
+        int K = (int)p[0]; size_t k = 1; double ptot = 0.0;
+        for (int c = 0; c < K; ++c) {
+          if (k + 3 > p.size()) throw std::invalid_argument("mixture: truncated params");
+          double wt = p[k]; int ck = (int)p[k + 1]; int64_t cn = (int64_t)p[k + 2];
+          if (ck == MG_PROP_MIXTURE || k + 3 + cn > p.size()) throw std::invalid_argument("mixture: bad component");
+          ptot = ptot + wt; w.push_back(wt);
+          comps.emplace_back(ck, D, p.data() + k + 3, cn);
+          k += 3 + cn;
+        }
+        for (auto &x : w) x = x / ptot;
+        need = (int64_t)k; break;
+      }
       default: throw std::invalid_argument("unknown proposal kind");
     }
     if ((int64_t)p.size() != need) throw std::invalid_argument("bad proposal nparams");
@@ -262,6 +281,17 @@ struct Proposal {
         if (r.uniform() < 0.75) y[0] = x[0] - p[0] * r.uniform();
         else y[0] = x[0] + p[0] * r.uniform();
         break;
+      case MG_PROP_ONE_SIDED:  // test/mcmc_test.ml:186-189
+        y[0] = x[0] + p[0] * (p[1] * r.uniform());
+        break;
+      case MG_PROP_MIXTURE: {  // mcmc.ml:168-176
+        double prob = r.uniform();
+        size_t c = 0;
+        for (; c < comps.size(); ++c) { if (prob < w[c]) break; prob = prob - w[c]; }
+        if (c == comps.size()) c = comps.size() - 1;  // the reference raises Failure here (prob ~ 1e-16)
+        comps[c].propose(r, x, y);
+        break;
+      }
     }
   }
   // log q(x -> y)
@@ -274,6 +304,18 @@ struct Proposal {
       }
       case MG_PROP_LEFT_BIASED:  // test/mcmc_test.ml:73
         return x[0] > y[0] ? std::log(0.75) : std::log(0.25);
+      case MG_PROP_ONE_SIDED: {  // test/mcmc_test.ml:190-199
+        double d = p[0] * (y[0] - x[0]);
+        return (d >= 0.0 && d <= p[1]) ? 0.0 - std::log(p[1]) : NEG_INF;
+      }
+      case MG_PROP_MIXTURE: {  // mcmc.ml:177-184
+        double log_jump = NEG_INF;
+        for (size_t c = 0; c < comps.size(); ++c) {
+          double log_local = std::log(w[c]) + comps[c].log_q(x, y);
+          log_jump = mcmc_log_sum_logs(log_jump, log_local);
+        }
+        return log_jump;
+      }
       default: return 0.0;
     }
   }

@@ -181,3 +181,30 @@ def test_resident_call_and_block_stats(ctx, og):
     pooled = want.transpose(0, 2, 1).reshape(-1, F)
     np.testing.assert_allclose(mean, og.multi_mean(pooled), rtol=1e-12, atol=1e-14)
     np.testing.assert_allclose(std, og.multi_std(pooled), rtol=1e-12, atol=1e-14)
+
+
+def test_combine_jump_proposals(ctx, og):
+    """Mcmc.combine_jump_proposals (mcmc.ml:165-185; test/mcmc_test.ml:184-208): a
+    1:2 mixture of a left and a right one-sided uniform jump; the mixture's log
+    jump probability (log-sum-exp over all components) enters the Hastings ratio"""
+    prop = P.combine_jump_proposals([(1.0, P.one_sided_proposal(-1.0)), (2.0, P.one_sided_proposal(+1.0))])
+    like, prior = P.gauss_diag([0.0], [1.0]), P.zero(1)
+    ctx.set_seed(17)
+    got = mcmc.mcmc_array(300, like, prior, prop, [0.0], nchains=128, nskip=2, ctx=ctx)
+    want, acc, _ = og.mcmc_array(17, 0, 300, like, prior, prop, [0.0], nchains=128, nskip=2, nthreads=8)
+    same = np.all(got.block[:, 0, :] == want[:, 0, :], axis=0)
+    assert same.mean() >= 0.95                      # log / exp: CUDA libm vs glibc may flip a rare decision
+    ctx.set_seed(18)
+    r = mcmc.mcmc_array(250, like, prior, prop, [0.0], nchains=4096, nbin=50, nskip=5, ctx=ctx)
+    x = r.block[:, 0, :].ravel()                    # 1.02e6 samples, as the reference test
+    assert abs(x.mean()) < 0.05 and x.std(ddof=1) == pytest.approx(1.0, rel=1e-2)
+    # a mixture of multi-dimensional components
+    D = 3
+    mix = P.combine_jump_proposals([(0.7, P.box_proposal(np.full(D, 0.1))), (0.3, P.wrap_proposal(np.zeros(D), np.ones(D), np.full(D, 0.5)))])
+    like3 = P.gauss_diag(np.full(D, 0.5), np.full(D, 0.1)); prior3 = P.box(np.zeros(D), np.ones(D), 0.0)
+    ctx.set_seed(19)
+    got = mcmc.mcmc_array(100, like3, prior3, mix, np.full(D, 0.5), nchains=200, ctx=ctx)
+    want, _, _ = og.mcmc_array(19, 0, 100, like3, prior3, mix, np.full(D, 0.5), nchains=200, nthreads=8)
+    assert np.array_equal(got.block[:, :D, :], want[:, :D, :])    # symmetric components: log q = log(sum p) = 0 terms cancel exactly
+    with pytest.raises(InvalidArgument):
+        mcmc.mcmc_array(10, like, prior, P.Proposal(5, 1, [2.0, 1.0, 0.0, 2.0]), [0.0], ctx=ctx)   # truncated block

@@ -1,0 +1,64 @@
+"""Pin the oracle's mcmc.ml restatement against test/mcmc_test.ml (statistical
+expectations, scaled down in sample count to keep the CPU suite short)."""
+import numpy as np
+import pytest
+
+from mcmc_ocaml_b200 import plugins as P
+
+
+def test_gaussian_post_uniform_proposal(og):  # mcmc_test.ml:40-59
+    mu, sigma, n = 0.37, 1.62, 100000
+    out, _, _ = og.mcmc_array(1, 0, n, P.gauss_diag([mu], [sigma]), P.zero(1), P.box_proposal([sigma]), [mu])
+    x = out[:, 0, 0]
+    tol = 10.0 * sigma / np.sqrt(n)
+    assert abs(x.mean() - mu) < tol and abs(x.std() - sigma) < tol
+
+
+def test_gaussian_post_left_biased_proposal(og):  # mcmc_test.ml:61-84: Hastings ratio
+    mu, sigma, n = 0.61, 1.3, 100000
+    out, _, _ = og.mcmc_array(2, 0, n, P.gauss_diag([mu], [sigma]), P.zero(1), P.left_biased_proposal(sigma), [mu])
+    x = out[:, 0, 0]
+    tol = 20.0 * sigma / np.sqrt(n)
+    assert abs(x.mean() - mu) < tol and abs(x.std() - sigma) < tol
+
+
+def test_prior_like_and_remove_repeat(og):  # mcmc_test.ml:86-112
+    mu, sigma = 0.5, 1.5
+    g = P.gauss_diag([mu], [sigma])
+    out, _, _ = og.mcmc_array(3, 0, 20000, g.scaled(0.75), g.scaled(0.25), P.box_proposal([sigma]), [mu], nskip=10)
+    x = out[:, 0, 0]
+    assert abs(x.mean() - mu) < 0.2 * mu and abs(x.std() - sigma) < 0.2 * sigma
+    rows = np.ascontiguousarray(out[:1000, :, 0])
+    nr = og.remove_repeat_samples(rows, 1)
+    assert np.all(nr[1:, 0] != nr[:-1, 0])
+
+
+def test_rjmcmc_gaussians(og):  # mcmc_test.ml:114-148
+    mu1, s1, mu2, s2 = 0.31, 0.62, 0.77, 0.45
+    g1, g2 = P.gauss_diag([mu1], [s1]), P.gauss_diag([mu2], [s2])
+    A = og.rj_model(g1.scaled(0.5), g1.scaled(0.5), P.indep_gauss_proposal([mu1], [s1]), 0.1, into_gauss=([mu1], [s1]))
+    B = og.rj_model(g2.scaled(0.3), g2.scaled(0.7), P.indep_gauss_proposal([mu2], [s2]), 0.9, into_gauss=([mu2], [s2]))
+    r = og.rjmcmc_array(4, 0, 2000, A, B, [mu1], [mu2], nskip=10, nchains=64, nthreads=8)
+    n1, n2 = r["counts"]
+    assert n1 / (n1 + n2) == pytest.approx(0.1, rel=0.1) and n2 / (n1 + n2) == pytest.approx(0.9, rel=0.1)
+    assert n1 / n2 == pytest.approx(0.1 / 0.9, abs=0.1)
+
+
+def test_rjmcmc_top_hats_interp(og):  # mcmc_test.ml:150-182: ratio 4.0 +- 0.1
+    prior = P.box([0, 0], [1, 1], 0.0)
+    like1, like2 = P.box([0, 0], [1, 1], 0.0), P.box([0.25, 0.25], [0.75, 0.75], 0.0)
+    prop = P.wrap_proposal([0, 0], [1, 1], [0.5, 0.5])
+    s1, _, _ = og.mcmc_array(5, 0, 10000, like1, prior, prop, [0.5, 0.5], nskip=20)
+    s2, _, _ = og.mcmc_array(5, 1, 10000, like2, prior, prop, [0.5, 0.5], nskip=20)
+    t1 = og.Tree(np.ascontiguousarray(s1[:, :2, 0]), [0, 0], [1, 1])
+    t2 = og.Tree(np.ascontiguousarray(s2[:, :2, 0]), [0, 0], [1, 1])
+    A, B = og.rj_model(like1, prior, prop, 0.5, tree=t1), og.rj_model(like2, prior, prop, 0.5, tree=t2)
+    r = og.rjmcmc_array(6, 0, 4000, A, B, [0.5, 0.5], [0.5, 0.5], nskip=10, nchains=64, nthreads=8, record_model=False)
+    assert r["counts"][0] / r["counts"][1] == pytest.approx(4.0, abs=0.15)
+
+
+def test_combine_jump_proposal(og):  # mcmc_test.ml:184-208
+    prop = P.combine_jump_proposals([(1.0, P.one_sided_proposal(-1.0)), (2.0, P.one_sided_proposal(+1.0))])
+    out, _, _ = og.mcmc_array(7, 0, 4000, P.gauss_diag([0.0], [1.0]), P.zero(1), prop, [0.0], nskip=5, nchains=64, nthreads=8)
+    x = out[:, 0, :].ravel()
+    assert abs(x.mean()) < 0.05 and x.std(ddof=1) == pytest.approx(1.0, rel=2e-2)
