@@ -72,6 +72,9 @@ double mg_ctx_last_kernel_ms(const mg_ctx *ctx);
  * MEASURED_PEAKS.json lacks (FP64 FMA TFLOP/s; streaming-store GB/s). */
 int mg_measure_fp64_tflops(mg_ctx *ctx, int reps, double *out_tflops);
 int mg_measure_store_gbs(mg_ctx *ctx, int64_t nbytes, int reps, double *out_gbs);
+/* diagnostic: stable radix sort of n float64 keys on the device (the sort
+ * under Kd_tree and Evidence); counts order / stability violations. */
+int mg_debug_sort_check(mg_ctx *ctx, const double *d_x, int64_t n, int64_t *violations);
 
 /* device / pinned memory helpers for callers without their own allocator */
 int mg_malloc_device(mg_ctx *ctx, int64_t nbytes, void **out);

@@ -385,3 +385,40 @@ extern "C" int mg_evidence_direct(mg_ctx *ctx, const double *pts, const double *
                                   int32_t D, int32_t n, double *out) {
   return evidence_host(ctx, 1, pts, ll, lp, N, D, n, 0.0, out);
 }
+
+// Diagnostic (tests only): stable-sort float64 keys on the device and count
+// order violations / non-permutation entries of the result.
+namespace mg {
+__global__ void sort_check_kernel(const double *__restrict__ x, const int32_t *__restrict__ order, int64_t n,
+                                  unsigned long long *__restrict__ bad) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i + 1 < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const double a = x[order[i]], b = x[order[i + 1]];
+    if (a > b || (a == b && order[i] > order[i + 1])) atomicAdd(bad, 1ull);   // sorted and stable
+  }
+}
+}  // namespace mg
+extern "C" int mg_debug_sort_check(mg_ctx *ctx, const double *d_x, int64_t n, int64_t *violations) {
+  if (!ctx) return MG_EINVAL;
+  MG_CUDA(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t s = ctx->stream;
+  DevBuf<uint64_t> keys; DevBuf<int32_t> order; DevBuf<unsigned long long> bad;
+  MG_CUDA(ctx, keys.alloc(n, s)); MG_CUDA(ctx, order.alloc(n, s)); MG_CUDA(ctx, bad.alloc(1, s));
+  MG_CUDA(ctx, cudaMemsetAsync(bad.get(), 0, 8, s));
+  // keys of +x: reuse the -ll key kernel on the negated ordering is not needed; build keys directly
+  DevBuf<double> neg;
+  MG_CUDA(ctx, neg.alloc(n, s));
+  const double *xx = d_x; double *ng = neg.get();
+  double dummy;
+  int rc = reduce_sum(ctx, n, [xx, ng] __device__(int64_t i) { ng[i] = -xx[i]; return 0.0; }, &dummy);
+  if (rc) return rc;
+  neg_ll_keys_kernel<<<egrid(ctx, n), EB, 0, s>>>(neg.get(), n, keys.get(), order.get());   // keys of -(-x) = x
+  MG_CHECK_LAUNCH(ctx);
+  if ((rc = radix_sort_pairs(ctx, keys.get(), order.get(), n, 1))) return rc;
+  sort_check_kernel<<<egrid(ctx, n), EB, 0, s>>>(d_x, order.get(), n, bad.get());
+  MG_CHECK_LAUNCH(ctx);
+  unsigned long long h = 0;
+  MG_CUDA(ctx, cudaMemcpyAsync(&h, bad.get(), 8, cudaMemcpyDeviceToHost, s));
+  MG_CUDA(ctx, cudaStreamSynchronize(s));
+  *violations = (int64_t)h;
+  return MG_OK;
+}

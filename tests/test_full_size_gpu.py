@@ -1,0 +1,108 @@
+"""Parity at BASELINE.json's full sizes through size-independent properties
+(the oracle cannot run these sizes in seconds): configs 2 and 3 on one GPU."""
+import ctypes as C
+import math
+
+import numpy as np
+import pytest
+
+from mcmc_ocaml_b200 import _abi, evidence, kd_tree, plugins as P
+
+pytestmark = pytest.mark.gpu
+
+
+def test_config3_tree_and_evidence_properties(ctx):
+    import torch
+    N, D = 10_000_000, 20
+    g = torch.Generator(device="cuda"); g.manual_seed(12345)
+    x = torch.empty((N, D), dtype=torch.float64, device="cuda").normal_(0.5, 0.05, generator=g)
+    ll = (-0.91893853320467274178 - math.log(0.05) - 0.5 * ((x - 0.5) / 0.05) ** 2).sum(1)
+    lp = torch.zeros(N, dtype=torch.float64, device="cuda")
+    torch.cuda.synchronize()
+    # ---- full kd-tree: structural invariants of kd_tree.ml:155-175 at 1e7 points
+    t = kd_tree.KdTree.from_device(x.data_ptr(), N, D, np.zeros(D), np.ones(D), ctx=ctx)
+    ex = t.export()
+    cnt = ex["end"] - ex["begin"]
+    split = ex["left"] >= 0
+    L = ex["left"][split]
+    assert t.nnodes == 2 * N - 1                                   # distinct points: N leaves of one object
+    assert np.all(cnt[~split] == 1)
+    assert np.array_equal(np.sort(ex["perm"]), np.arange(N, dtype=np.int32))
+    # children tile the parent's range; the left child is the heavy one: floor(n/2)+1 (n > 2), SURVEY F7
+    assert np.array_equal(ex["begin"][L], ex["begin"][split]) and np.array_equal(ex["end"][L], ex["begin"][L + 1])
+    assert np.array_equal(ex["end"][L + 1], ex["end"][split])
+    n = cnt[split]
+    assert np.array_equal(cnt[L], np.where(n > 2, n // 2 + 1, 1))
+    # breadth-first numbering: children indices increase with the parent index
+    assert np.all(np.diff(L) == 2)
+    # the split plane separates the children along the split dimension (checked on a sample of nodes)
+    xs = None
+    rng = np.random.default_rng(0)
+    sample = rng.choice(np.nonzero(split)[0], 2000, replace=False)
+    perm_t = torch.as_tensor(ex["perm"].astype(np.int64), device="cuda")
+    for nd in sample[:200]:
+        d, s, l = ex["split_dim"][nd], ex["split_val"][nd], ex["left"][nd]
+        li = perm_t[ex["begin"][l]:ex["end"][l]]; ri = perm_t[ex["begin"][l + 1]:ex["end"][l + 1]]
+        ml, mr = float(x[li, d].max()), float(x[ri, d].min())
+        assert ml < mr and s == 0.5 * (ml + mr)
+    # point location: every stored point descends to a leaf that contains it (sample), densities integrate to ~1
+    from mcmc_ocaml_b200 import interpolate_pdf
+    ip = interpolate_pdf.InterpPdf(None, None, None, tree=t)
+    idx = rng.choice(N, 100000, replace=False)
+    pts = x[torch.as_tensor(idx, device="cuda")].cpu().numpy()
+    leaf = ip.find_cell(pts)
+    assert np.all(ex["left"][leaf] < 0)
+    assert np.mean(ex["perm"][ex["begin"][leaf]] == idx) > 0.9999   # (a split plane rounding onto a point moves it left)
+    t.close()
+    # ---- evidence: invariance under a permutation of the samples (sums differ only in rounding)
+    z1 = evidence.evidence_lebesgue_dev(x.data_ptr(), ll.data_ptr(), lp.data_ptr(), N, D, ctx=ctx)
+    pi = torch.randperm(N, device="cuda", generator=g)
+    x2, ll2, lp2 = x[pi].contiguous(), ll[pi].contiguous(), lp[pi].contiguous()
+    torch.cuda.synchronize()      # the context has its own (non-blocking) stream: torch's work must be complete
+    z2 = evidence.evidence_lebesgue_dev(x2.data_ptr(), ll2.data_ptr(), lp2.data_ptr(), N, D, ctx=ctx)
+    assert z1 == pytest.approx(z2, rel=1e-12)
+    # linearity in the prior density: lp + c scales the Lebesgue estimate by e^c exactly up to rounding
+    lp3 = lp + 0.25
+    torch.cuda.synchronize()
+    z3 = evidence.evidence_lebesgue_dev(x.data_ptr(), ll.data_ptr(), lp3.data_ptr(), N, D, ctx=ctx)
+    assert z3 == pytest.approx(z1 * math.exp(0.25), rel=1e-12)
+    # harmonic mean against an independent float64 evaluation with pairwise summation
+    h = evidence.evidence_harmonic_mean_dev(ll.data_ptr(), N, ctx=ctx)
+    want = N / float(torch.exp(-ll).sum())
+    assert h == pytest.approx(want, rel=1e-11)
+
+
+def test_config2_full_size_posterior(ctx):
+    """65,536 chains x 10,000 steps of the 10-D correlated Gaussian: moments of
+    the pooled 6.6e8 samples against the analytic target (KS on a thinned subset)"""
+    import torch
+    from scipy import stats as sst
+    D, Cn, T = 10, 65536, 10000
+    mu = np.arange(D) / 10.0
+    cov = 0.7 ** np.abs(np.subtract.outer(np.arange(D), np.arange(D)))
+    like, prior, prop = P.gauss_corr(mu, cov), P.zero(D), P.box_proposal(np.full(D, 0.5))
+    F, n = D + 2, T + 1
+    blk = torch.empty((n, F, Cn), dtype=torch.float64, device="cuda")
+    torch.cuda.synchronize()
+    final = np.empty((Cn, F)); acc = np.empty(Cn, np.int64); rej = np.empty(Cn, np.int64)
+    mean = np.empty(F); std = np.empty(F)
+    cfg = _abi.mg_mcmc_cfg(Cn, D, 0, 0, 1, n, 0, 1, 0)
+    ls, ps, js = like.spec(), prior.spec(), prop.spec()
+    ctx.set_seed(0x5EED0001)
+    x0 = _abi.as_f64(mu)
+    ctx.check(ctx.lib.mg_mcmc_array_resident(ctx.h, C.byref(ls), C.byref(ps), C.byref(js), C.byref(cfg), _abi.ptr(x0),
+                                             C.c_void_p(blk.data_ptr()), _abi.ptr(final), _abi.ptr(acc, _abi.c_int64_p),
+                                             _abi.ptr(rej, _abi.c_int64_p), _abi.ptr(mean), _abi.ptr(std)))
+    assert np.all(acc + rej == T) and 0.44 < acc.sum() / (Cn * T) < 0.49
+    # the chains start AT the mode and forget it within ~100 steps: pooled moments within a few 1e-3
+    np.testing.assert_allclose(mean[:D], mu, atol=4e-3)
+    np.testing.assert_allclose(std[:D], 1.0, atol=6e-3)
+    # recorded ll is the log-density of the recorded point (checked on the last sample of every chain)
+    from scipy.stats import multivariate_normal
+    np.testing.assert_allclose(final[:, D], multivariate_normal(mu, cov).logpdf(final[:, :D]), rtol=1e-12, atol=1e-11)
+    # last samples of the 65,536 independent chains: each coordinate ~ N(mu_i, 1) (KS)
+    for i in (0, 4, 9):
+        assert sst.kstest(final[:, i] - mu[i], "norm").pvalue > 1e-4
+    # slot 0 is the start, the block statistics agree with torch's own reduction over the resident block
+    assert torch.equal(blk[0, :D, 0].cpu(), torch.as_tensor(mu))
+    np.testing.assert_allclose(mean[3], float(blk[:, 3, :].mean()), rtol=1e-12)

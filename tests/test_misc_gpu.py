@@ -116,3 +116,20 @@ def test_runtime_plugin_matches_builtin(ctx, og):
     from mcmc_ocaml_b200 import nested
     with pytest.raises(InvalidArgument):                                        # not wired into Nested yet
         nested.nested_evidence(banana, P.zero(2), [-1, -1], [1, 1], nlive=10, nmcmc=2, ctx=ctx)
+
+
+def test_radix_sort_sorted_and_stable(ctx):
+    """the hand-written radix sort under Kd_tree / Evidence: sorted and stable at ragged sizes,
+    with ties, signed zeros, negative values and constant-digit passes"""
+    import torch
+    g = torch.Generator(device="cuda"); g.manual_seed(3)
+    cases = [torch.rand(n, dtype=torch.float64, device="cuda", generator=g) for n in (2, 4095, 4096, 4097, 12293, 1 << 20, (1 << 20) + 1)]
+    cases.append(torch.randn(300001, dtype=torch.float64, device="cuda", generator=g) * 1e6)
+    cases.append(torch.randint(0, 7, (200000,), device="cuda", generator=g).double() - 3.0)      # heavy ties
+    cases.append(torch.tensor([0.0, -0.0, 0.0, -0.0, 1.0, -1.0] * 5000, dtype=torch.float64, device="cuda"))
+    cases.append(torch.full((70000,), 0.5, dtype=torch.float64, device="cuda"))                   # every pass skipped
+    torch.cuda.synchronize()
+    for v in cases:
+        k = C.c_int64(-1)
+        ctx.check(ctx.lib.mg_debug_sort_check(ctx.h, C.c_void_p(v.data_ptr()), C.c_int64(v.numel()), C.byref(k)))
+        assert k.value == 0, v.numel()
