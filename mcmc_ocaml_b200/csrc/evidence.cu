@@ -81,6 +81,22 @@ __global__ void keep_rows_kernel(const double *__restrict__ pts, const int32_t *
   }
 }
 
+// after a stable sort on coordinate 0 only: is the order already lexicographic?  It is unless two
+// neighbours share coordinate 0 and are out of order in a later coordinate.
+__global__ void lex_order_check_kernel(const double *__restrict__ pts, const int32_t *__restrict__ order, int64_t n,
+                                       int D, int *__restrict__ bad) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i + 1 < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const double *a = pts + (int64_t)order[i] * D, *b = pts + (int64_t)order[i + 1] * D;
+    if (a[0] == b[0]) {
+      for (int d = 1; d < D; ++d) {
+        if (a[d] < b[d]) break;
+        if (a[d] > b[d]) { *bad = 1; break; }
+      }
+      // equal rows keep their input order (the sort is stable), as List.sort does
+    }
+  }
+}
+
 // survivors in REVERSED order: dst = K-1-rank
 __global__ void gather_kernel(const double *__restrict__ pts, const double *__restrict__ ll,
                               const double *__restrict__ lp, const int32_t *__restrict__ order,
@@ -347,11 +363,30 @@ extern "C" int mg_evidence_direct_dev(mg_ctx *ctx, const double *d_pts, const do
   iota_kernel<<<egrid(ctx, N), EB, 0, s>>>(order.get(), N);
   MG_CHECK_LAUNCH(ctx);
   int rc;
-  for (int d = D - 1; d >= 0; --d) {
-    coord_keys_kernel<<<egrid(ctx, N), EB, 0, s>>>(d_pts, order.get(), N, D, d, keys.get());
+  // Fast path: sort on coordinate 0 alone.  Ties in coordinate 0 are almost always whole repeated rows
+  // (Metropolis-Hastings rejections), for which the stable order already is the lexicographic one.
+  bool need_full = (D > 1);
+  if (D > 1) {
+    coord_keys_kernel<<<egrid(ctx, N), EB, 0, s>>>(d_pts, order.get(), N, D, 0, keys.get());
     MG_CHECK_LAUNCH(ctx);
     if ((rc = radix_sort_pairs(ctx, keys.get(), order.get(), N, 1))) return rc;
+    DevBuf<int> d_bad;
+    MG_CUDA(ctx, d_bad.alloc(1, s));
+    MG_CUDA(ctx, cudaMemsetAsync(d_bad.get(), 0, sizeof(int), s));
+    lex_order_check_kernel<<<egrid(ctx, N), EB, 0, s>>>(d_pts, order.get(), N, D, d_bad.get());
+    MG_CHECK_LAUNCH(ctx);
+    int h_bad = 0;
+    MG_CUDA(ctx, cudaMemcpyAsync(&h_bad, d_bad.get(), sizeof(int), cudaMemcpyDeviceToHost, s));
+    MG_CUDA(ctx, cudaStreamSynchronize(s));
+    need_full = (h_bad != 0);
+    if (need_full) { iota_kernel<<<egrid(ctx, N), EB, 0, s>>>(order.get(), N); MG_CHECK_LAUNCH(ctx); }
   }
+  if (need_full || D == 1)
+    for (int d = D - 1; d >= 0; --d) {   // full LSD pass over the coordinates, last first
+      coord_keys_kernel<<<egrid(ctx, N), EB, 0, s>>>(d_pts, order.get(), N, D, d, keys.get());
+      MG_CHECK_LAUNCH(ctx);
+      if ((rc = radix_sort_pairs(ctx, keys.get(), order.get(), N, 1))) return rc;
+    }
   keys.release();
   MG_CUDA(ctx, keep.alloc(N, s));
   keep_rows_kernel<<<egrid(ctx, N), EB, 0, s>>>(d_pts, order.get(), N, D, keep.get());

@@ -201,3 +201,111 @@ CAMLprim value mcmcgpu_evidence_direct(value ctx, value n, value pts, value ll, 
                               (const double *)Caml_ba_data_val(lp), b->dim[0], (int32_t)b->dim[1], Int_val(n), &out));
   CAMLreturn(caml_copy_double(out));
 }
+
+/* ---- Stats (stats.ml:17-87) ---------------------------------------------- */
+CAMLprim value mcmcgpu_stats_multi_mean(value ctx, value xs, value out) {
+  CAMLparam3(ctx, xs, out);
+  mg_ctx *c = Ctx_val(ctx);
+  struct caml_ba_array *b = Caml_ba_array_val(xs);
+  check(c, mg_stats_multi_mean(c, (const double *)Caml_ba_data_val(xs), b->dim[0], (int32_t)b->dim[1],
+                               (double *)Caml_ba_data_val(out)));
+  CAMLreturn(Val_unit);
+}
+/* mean_opt: float array option as a Bigarray of length 0 (None) or D (Some mu) */
+CAMLprim value mcmcgpu_stats_multi_std(value ctx, value xs, value mean_opt, value out) {
+  CAMLparam4(ctx, xs, mean_opt, out);
+  mg_ctx *c = Ctx_val(ctx);
+  struct caml_ba_array *b = Caml_ba_array_val(xs);
+  const double *mu = Caml_ba_array_val(mean_opt)->dim[0] > 0 ? (const double *)Caml_ba_data_val(mean_opt) : NULL;
+  check(c, mg_stats_multi_std(c, (const double *)Caml_ba_data_val(xs), b->dim[0], (int32_t)b->dim[1], mu,
+                              (double *)Caml_ba_data_val(out)));
+  CAMLreturn(Val_unit);
+}
+
+/* ---- Mcmc.rjmcmc_array (mcmc.ml:121-139) -----------------------------------
+ * type rj_model = { like : logfn; prior : logfn; prop : proposal; into : tree option;
+ *                   into_gauss : (float, float64_elt, c_layout) Array1.t; nstop : int; p : float }
+ * Returns (#A, #B) = Mcmc.rjmcmc_model_counts; out_model : (int, int8_unsigned_elt, c_layout) Array2.t [n][C]. */
+static mg_rj_model rj_of_value(value v) {
+  mg_rj_model m;
+  memset(&m, 0, sizeof m);
+  m.like = logfn_of_value(Field(v, 0));
+  m.prior = logfn_of_value(Field(v, 1));
+  m.prop = proposal_of_value(Field(v, 2));
+  if (Is_block(Field(v, 3))) {              /* Some tree: Interp.draw / log (Interp.jump_prob) */
+    m.into.kind = MG_INTO_INTERP;
+    m.into.tree = Tree_val(Field(Field(v, 3), 0));
+    m.into.nstop = Int_val(Field(v, 5));
+  } else {                                  /* None: independent Gaussian (mu, sigma) */
+    m.into.kind = MG_INTO_INDEP_GAUSS;
+    m.into.params = (const double *)Caml_ba_data_val(Field(v, 4));
+    m.into.nparams = Caml_ba_array_val(Field(v, 4))->dim[0];
+  }
+  m.p = Double_val(Field(v, 6));
+  return m;
+}
+CAMLprim value mcmcgpu_rjmcmc_array_native(value ctx, value ma, value mb, value nbin, value nskip, value n,
+                                           value nchains, value a0, value b0, value out_model) {
+  CAMLparam5(ctx, ma, mb, a0, b0);
+  CAMLxparam1(out_model);
+  CAMLlocal1(r);
+  mg_rj_model A = rj_of_value(ma), B = rj_of_value(mb);
+  mg_rjmcmc_cfg cfg;
+  memset(&cfg, 0, sizeof cfg);
+  cfg.nchains = Long_val(nchains); cfg.nbin = Long_val(nbin); cfg.nskip = Long_val(nskip); cfg.n = Long_val(n);
+  int64_t counts[2] = {0, 0};
+  mg_ctx *c = Ctx_val(ctx);
+  const double *pa = (const double *)Caml_ba_data_val(a0), *pb = (const double *)Caml_ba_data_val(b0);
+  uint8_t *pm = (uint8_t *)Caml_ba_data_val(out_model);
+  caml_release_runtime_system();
+  int rc = mg_rjmcmc_array(c, &A, &B, &cfg, pa, pb, pm, NULL, counts);
+  caml_acquire_runtime_system();
+  check(c, rc);                             /* incl. Assert_failure mcmc.ml:90 -> Failure */
+  r = caml_alloc_tuple(2);
+  Store_field(r, 0, Val_long(counts[0])); Store_field(r, 1, Val_long(counts[1]));
+  CAMLreturn(r);
+}
+CAMLprim value mcmcgpu_rjmcmc_array_bytecode(value *a, int argn) {
+  (void)argn;
+  return mcmcgpu_rjmcmc_array_native(a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], a[8], a[9]);
+}
+
+/* ---- Nested.nested_evidence (nested.ml:122-146) ----------------------------
+ * external nested_evidence : ctx -> logfn -> logfn -> lo -> hi -> epsrel:float -> nmcmc:int -> nlive:int ->
+ *   mode_hopping_frac:float -> batch:int -> pts [cap][D] -> ll [cap] -> lp [cap] -> logw [cap] ->
+ *   float * float * int   (log_ev, log_dev, number of points) */
+CAMLprim value mcmcgpu_nested_evidence_native(value ctx, value like, value prior, value lo, value hi, value epsrel,
+                                              value nmcmc, value nlive, value mode_hop, value batch, value pts,
+                                              value ll, value lp, value logw) {
+  CAMLparam5(ctx, like, prior, lo, hi);
+  CAMLxparam4(pts, ll, lp, logw);
+  CAMLlocal1(r);
+  mg_logfn l = logfn_of_value(like), p = logfn_of_value(prior);
+  mg_nested_cfg cfg;
+  memset(&cfg, 0, sizeof cfg);
+  cfg.dim = l.dim; cfg.nlive = Int_val(nlive); cfg.nmcmc = Int_val(nmcmc); cfg.batch = Int_val(batch);
+  cfg.epsrel = Double_val(epsrel); cfg.mode_hopping_frac = Double_val(mode_hop);
+  cfg.max_points = Caml_ba_array_val(ll)->dim[0];
+  double log_ev = 0.0, log_dev = 0.0; int64_t npts = 0;
+  mg_ctx *c = Ctx_val(ctx);
+  const double *plo = (const double *)Caml_ba_data_val(lo), *phi = (const double *)Caml_ba_data_val(hi);
+  double *ppts = (double *)Caml_ba_data_val(pts), *pll = (double *)Caml_ba_data_val(ll),
+         *plp = (double *)Caml_ba_data_val(lp), *plw = (double *)Caml_ba_data_val(logw);
+  caml_release_runtime_system();
+  int rc = mg_nested_evidence(c, &l, &p, plo, phi, &cfg, &log_ev, &log_dev, &npts, ppts, pll, plp, plw);
+  caml_acquire_runtime_system();
+  check(c, rc);                             /* nested.ml:70-72 -> Failure */
+  r = caml_alloc_tuple(3);
+  Store_field(r, 0, caml_copy_double(log_ev)); Store_field(r, 1, caml_copy_double(log_dev));
+  Store_field(r, 2, Val_long(npts));
+  CAMLreturn(r);
+}
+CAMLprim value mcmcgpu_nested_evidence_bytecode(value *a, int argn) {
+  (void)argn;
+  return mcmcgpu_nested_evidence_native(a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], a[8], a[9], a[10], a[11],
+                                        a[12], a[13]);
+}
+/* Nested.log_total_error_estimate (nested.ml:148-150) */
+CAMLprim value mcmcgpu_log_total_error_estimate(value log_ev, value log_dev, value nlive) {
+  return caml_copy_double(mg_nested_log_total_error(Double_val(log_ev), Double_val(log_dev), Int_val(nlive)));
+}

@@ -50,6 +50,19 @@ def test_direct_matches_oracle(ctx, og, D, n, nb):
     assert got == pytest.approx(want["value"], rel=1e-11)
 
 
+def test_direct_lexicographic_fallback(ctx, og):
+    """ties in coordinate 0 that are NOT whole repeated rows force the full lexicographic sort"""
+    rng = np.random.default_rng(12)
+    pts = np.round(rng.random((6000, 3)), 1)            # a coarse grid: many partial ties, many exact duplicates
+    pts[:, 2] = rng.random(6000)
+    pts[100:200] = pts[0:100]                           # and whole repeated rows
+    ll = rng.normal(-2.0, 1.0, 6000); lp = rng.normal(-1.0, 0.3, 6000)
+    ll[100:200] = ll[0:100]; lp[100:200] = lp[0:100]
+    want = og.evidence_direct(pts, ll, lp, n=16)
+    got = evidence.evidence_direct(pts, ll, lp, n=16, ctx=ctx)
+    assert got == pytest.approx(want["value_ld"], rel=RTOL)
+
+
 def test_lebesgue_pooled_chains_and_known_answer(ctx, og):
     """evidence_test.ml:74-81 (Lebesgue ~ 1 for a normalised Gaussian in the
     unit box), on 64 pooled chains"""
