@@ -34,6 +34,7 @@ extern "C" void mg_ctx_destroy(mg_ctx *ctx) {
   cudaStreamSynchronize(ctx->stream);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  if (ctx->aux) cudaStreamDestroy(ctx->aux);
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }

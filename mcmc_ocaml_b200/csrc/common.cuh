@@ -19,6 +19,7 @@ struct mg_ctx {
   uint64_t epoch = 0;
   cudaStream_t stream = nullptr;
   bool own_stream = false;
+  cudaStream_t aux = nullptr;      // second stream: Stats passes overlapped with sampling segments
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool ev_pending = false;
   double last_kernel_ms = 0.0;

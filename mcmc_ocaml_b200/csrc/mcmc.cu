@@ -12,6 +12,8 @@
 // that is 96 B/step against ~170 FP64 instructions + 6 Philox blocks per step.
 #include "mcmc_kernel.cuh"
 
+#include <cstdlib>
+
 namespace mg {
 
 // instantiations live in mcmc_static.cu / mcmc_dyn.cu (one object per dimension)
@@ -19,10 +21,10 @@ namespace mg {
 #define MG_DYN_DIMS(X) X(2) X(4) X(8) X(16) X(32) X(64)
 #define MG_DECL_STATIC(DD)                                                                         \
   int mh_static_gauss_##DD(mg_ctx *, const mg_logfn *, const mg_proposal *, const mg_mcmc_cfg *, \
-                           CallKey, double *, double *, int32_t *);
+                           CallKey, uint64_t, int, double *, double *, int32_t *);
 #define MG_DECL_DYN(DD)                                                                          \
   int mh_dyn_##DD(mg_ctx *, const DynFnParams &, const DynFnParams &, const DynPropParams &,     \
-                  const mg_mcmc_cfg *, CallKey, double *, double *, int32_t *);
+                  const mg_mcmc_cfg *, CallKey, uint64_t, int, double *, double *, int32_t *);
 MG_STATIC_DIMS(MG_DECL_STATIC)
 MG_DYN_DIMS(MG_DECL_DYN)
 
@@ -53,8 +55,13 @@ __global__ void to_chain_major_kernel(const double *__restrict__ src, int64_t ro
 }
 
 int jit_launch_mh(mg_ctx *ctx, const DynFnParams &like, const DynFnParams &prior, const DynPropParams &prop,
-                  const mg_mcmc_cfg *cfg, CallKey key, double *d_state, double *d_samples, int32_t *d_accept);  // jit.cu
+                  const mg_mcmc_cfg *cfg, CallKey key, uint64_t t0, int record_first, double *d_state, double *d_samples, int32_t *d_accept);  // jit.cu
 int sample_block_stats(mg_ctx *ctx, const double *d_blk, int64_t n, int F, int64_t C, double *d_out);  // stats.cu
+int moments_grid(mg_ctx *ctx, int64_t n);
+int sample_block_moments_async(mg_ctx *ctx, cudaStream_t st, const double *blk_base, const double *seg, int64_t n,
+                               int F, int64_t C, int gx, double *partial);
+int sample_block_moments_finish(mg_ctx *ctx, cudaStream_t st, const double *partial, int nseg, int gx, int F, double cnt,
+                                const double *blk_base, int64_t C, double *d_out);
 
 static int validate_cfg(mg_ctx *ctx, const mg_mcmc_cfg *cfg) {
   MG_REQUIRE(ctx, cfg != nullptr, "mcmc_array: null cfg");
@@ -69,10 +76,10 @@ static int validate_cfg(mg_ctx *ctx, const mg_mcmc_cfg *cfg) {
 
 using namespace mg;
 
-extern "C" int mg_mcmc_array_dev(mg_ctx *ctx, const mg_logfn *like, const mg_logfn *prior,
-                                 const mg_proposal *prop, const mg_mcmc_cfg *cfg, double *d_state,
-                                 double *d_samples, int32_t *d_accept) {
-  if (!ctx) return MG_EINVAL;
+// One launch of the ensemble kernel: steps t0 .. of the run keyed by `key`.
+static int mcmc_launch_segment(mg_ctx *ctx, const mg_logfn *like, const mg_logfn *prior, const mg_proposal *prop,
+                               const mg_mcmc_cfg *cfg, CallKey key, uint64_t t0, int record_first, double *d_state,
+                               double *d_samples, int32_t *d_accept) {
   int rc;
   if ((rc = validate_cfg(ctx, cfg))) return rc;
   if ((rc = validate_logfn(ctx, like, cfg->dim, "log_likelihood"))) return rc;
@@ -80,13 +87,12 @@ extern "C" int mg_mcmc_array_dev(mg_ctx *ctx, const mg_logfn *like, const mg_log
   if ((rc = validate_proposal(ctx, prop, cfg->dim))) return rc;
   MG_REQUIRE(ctx, d_state != nullptr, "mcmc_array: null state");
   MG_CUDA(ctx, cudaSetDevice(ctx->device));
-  const CallKey key = next_key(ctx);
   const int D = cfg->dim;
 
   if (like->kind == MG_FN_GAUSS_CORR && like->scale == 1.0 && prior->kind == MG_FN_ZERO &&
       prop->kind == MG_PROP_BOX) {
     switch (D) {
-#define MG_CASE(DD) case DD: return mh_static_gauss_##DD(ctx, like, prop, cfg, key, d_state, d_samples, d_accept);
+#define MG_CASE(DD) case DD: return mh_static_gauss_##DD(ctx, like, prop, cfg, key, t0, record_first, d_state, d_samples, d_accept);
       MG_STATIC_DIMS(MG_CASE)
 #undef MG_CASE
       default: break;
@@ -97,11 +103,20 @@ extern "C" int mg_mcmc_array_dev(mg_ctx *ctx, const mg_logfn *like, const mg_log
   MG_CUDA(ctx, dp.upload_from(prior, ctx->stream));
   MG_CUDA(ctx, dj.upload_from(prop, ctx->stream));
   if (like->kind >= MG_FN_USER || prior->kind >= MG_FN_USER)  // user plugins: kernel compiled at run time
-    return jit_launch_mh(ctx, dl.params, dp.params, dj.params, cfg, key, d_state, d_samples, d_accept);
-#define MG_TRY(DD) if (D <= DD) rc = mh_dyn_##DD(ctx, dl.params, dp.params, dj.params, cfg, key, d_state, d_samples, d_accept); else
+    return jit_launch_mh(ctx, dl.params, dp.params, dj.params, cfg, key, t0, record_first, d_state, d_samples, d_accept);
+#define MG_TRY(DD) if (D <= DD) rc = mh_dyn_##DD(ctx, dl.params, dp.params, dj.params, cfg, key, t0, record_first, d_state, d_samples, d_accept); else
   MG_DYN_DIMS(MG_TRY) rc = set_err(ctx, MG_EINVAL, "mcmc_array: dim too large");
 #undef MG_TRY
   return rc;  // parameter blobs are freed stream-ordered after the kernel
+}
+
+extern "C" int mg_mcmc_array_dev(mg_ctx *ctx, const mg_logfn *like, const mg_logfn *prior,
+                                 const mg_proposal *prop, const mg_mcmc_cfg *cfg, double *d_state,
+                                 double *d_samples, int32_t *d_accept) {
+  if (!ctx) return MG_EINVAL;
+  int rc;
+  if ((rc = validate_cfg(ctx, cfg))) return rc;
+  return mcmc_launch_segment(ctx, like, prior, prop, cfg, next_key(ctx), 0, 1, d_state, d_samples, d_accept);
 }
 
 extern "C" int mg_mcmc_array(mg_ctx *ctx, const mg_logfn *like, const mg_logfn *prior, const mg_proposal *prop,
@@ -171,12 +186,60 @@ extern "C" int mg_mcmc_array_resident(mg_ctx *ctx, const mg_logfn *like, const m
   MG_CUDA(ctx, cudaMemsetAsync(d_acc.get(), 0, sizeof(int32_t) * C, s));
   init_state_kernel<<<(unsigned)((C + 255) / 256), 256, 0, s>>>(d_x0.get(), cfg->x0_shared, D, C, d_state.get());
   MG_CHECK_LAUNCH(ctx);
-  if ((rc = mg_mcmc_array_dev(ctx, like, prior, prop, cfg, d_state.get(), d_samples, d_acc.get()))) return rc;
+  // The run can be cut into segments with the Stats pass over segment k (an HBM-bound read) on a second
+  // stream while the sampler computes segment k+1.  Measured on B200 (profiles/r01_mh_ncu_summary.md): no
+  // gain -- the sampler's 4 warps x 122 registers fill every scheduler's 16K-register slice, so the Stats
+  // CTAs find no room until the segment ends.  One segment unless MCMC_GPU_STATS_SEGMENTS says otherwise.
+  const bool want_stats = (out_mean || out_std) && n > 0;
   std::vector<double> stats(2 * F);
-  if ((out_mean || out_std) && n > 0) {
-    MG_CUDA(ctx, d_stats.alloc(2 * F, s));
-    if ((rc = sample_block_stats(ctx, d_samples, n, F, C, d_stats.get()))) return rc;
-    MG_CUDA(ctx, cudaMemcpyAsync(stats.data(), d_stats.get(), sizeof(double) * 2 * F, cudaMemcpyDeviceToHost, s));
+  {
+    const int64_t nrec = n > 0 ? n - 1 : 0;          // samples after slot 0
+    int nseg = 1;
+    if (const char *e = getenv("MCMC_GPU_STATS_SEGMENTS")) nseg = atoi(e);
+    if (nseg < 1 || !want_stats || nrec < 8 * (int64_t)nseg) nseg = 1;
+    const CallKey key = next_key(ctx);
+    DevBuf<double> d_partial;
+    std::vector<cudaEvent_t> evs;
+    int gx = 1;
+    if (want_stats) {
+      gx = moments_grid(ctx, (n + nseg - 1) / nseg);
+      MG_CUDA(ctx, d_partial.alloc((size_t)nseg * 2 * F * gx, s));
+      MG_CUDA(ctx, d_stats.alloc(2 * F, s));
+      if (!ctx->aux) MG_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->aux, cudaStreamNonBlocking));
+    }
+    int64_t done = 0;                                 // recorded samples after slot 0 handled so far
+    for (int k = 0; k < nseg; ++k) {
+      const int64_t m = nrec / nseg + (k < nrec % nseg ? 1 : 0);
+      mg_mcmc_cfg seg = *cfg;
+      seg.nbin = (k == 0) ? cfg->nbin : 0;
+      seg.n = (n > 0) ? m + 1 : 0;
+      const uint64_t t0 = (k == 0) ? 0 : (uint64_t)(cfg->nbin + done * cfg->nskip);
+      double *dst = d_samples ? d_samples + (size_t)((k == 0) ? 0 : 1 + done) * F * C : nullptr;
+      if ((rc = mcmc_launch_segment(ctx, like, prior, prop, &seg, key, t0, k == 0 ? 1 : 0, d_state.get(), dst, d_acc.get())))
+        return rc;
+      if (want_stats) {
+        cudaEvent_t e;
+        MG_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        evs.push_back(e);
+        MG_CUDA(ctx, cudaEventRecord(e, s));
+        MG_CUDA(ctx, cudaStreamWaitEvent(ctx->aux, e, 0));
+        const int64_t cnt = (k == 0) ? m + 1 : m;     // segment 0 also holds slot 0
+        if ((rc = sample_block_moments_async(ctx, ctx->aux, d_samples, dst, cnt, F, C, gx,
+                                             d_partial.get() + (size_t)k * 2 * F * gx))) return rc;
+      }
+      done += m;
+    }
+    if (want_stats) {
+      cudaEvent_t e;
+      MG_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      evs.push_back(e);
+      MG_CUDA(ctx, cudaEventRecord(e, ctx->aux));
+      MG_CUDA(ctx, cudaStreamWaitEvent(s, e, 0));
+      if ((rc = sample_block_moments_finish(ctx, s, d_partial.get(), nseg, gx, F, (double)n * (double)C, d_samples, C,
+                                            d_stats.get()))) return rc;
+      MG_CUDA(ctx, cudaMemcpyAsync(stats.data(), d_stats.get(), sizeof(double) * 2 * F, cudaMemcpyDeviceToHost, s));
+    }
+    for (cudaEvent_t e : evs) cudaEventDestroy(e);    // released once the recorded work has completed
   }
   if (out_final) {
     MG_CUDA(ctx, d_final.alloc((size_t)F * C, s));

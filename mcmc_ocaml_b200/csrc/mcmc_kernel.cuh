@@ -20,10 +20,11 @@ static int launch_mh(mg_ctx *ctx, const MhArgs<Like, Prior, Prop, D> &a) {
 }
 
 template <class A>
-static void fill_common(A &a, const mg_mcmc_cfg *cfg, CallKey key, double *d_state, double *d_samples,
+static void fill_common(A &a, const mg_mcmc_cfg *cfg, CallKey key, uint64_t t0, int record_first, double *d_state, double *d_samples,
                         int32_t *d_accept) {
   a.d = cfg->dim; a.pad = 0; a.C = cfg->nchains; a.chain_offset = cfg->chain_offset;
   a.nbin = cfg->nbin; a.nskip = cfg->nskip; a.n = cfg->n; a.key = key;
+  a.t0 = t0; a.record_first = record_first; a.pad2 = 0;
   a.state = d_state; a.samples = d_samples; a.accept = d_accept;
 }
 

@@ -27,6 +27,9 @@ struct MhArgs {
   int64_t C;
   uint64_t chain_offset;
   int64_t nbin, nskip, n;
+  uint64_t t0;          // index of the first step of this launch (a run may be split into segments)
+  int32_t record_first; // 1: slot 0 = the state after burn-in (mcmc.ml:66); 0: a continuation segment
+  int32_t pad2;
   CallKey key;
   double *state;    // [D+2][C] in/out
   double *samples;  // [n][D+2][C] or null
@@ -90,14 +93,14 @@ __device__ __forceinline__ void mh_ensemble_body(const MhArgs<Like, Prior, Prop,
   double ll = Like::template eval<D>(a.like, sl, x, dd);
   double lp = Prior::template eval<D>(a.prior, sp, x, dd);
   int nacc = 0;
-  uint64_t t = 0;
+  uint64_t t = a.t0;
   // Fixed-draw proposals: the uniforms of step t+1 are generated while step t
   // computes (software pipelining across the loop edge, which the compiler
   // cannot do by itself).  Data-dependent proposals draw on demand.
   constexpr bool kPipe = (Prop::kDraws >= 0) && MG_MH_PIPELINE;
   constexpr int kNU = kPipe ? Prop::kDraws + 1 : 1;
   RngBuf<kNU> cur;
-  if (kPipe) cur.fill(a.key, P_MH, g, 0);
+  if (kPipe) cur.fill(a.key, P_MH, g, a.t0);
   auto step = [&]() -> int {
     int r_acc;
     if constexpr (kPipe) {
@@ -125,7 +128,7 @@ __device__ __forceinline__ void mh_ensemble_body(const MhArgs<Like, Prior, Prop,
       out += sample_stride;
     }
   };
-  if (a.n > 0) record();  // :66 slot 0 = state after burn-in
+  if (a.n > 0 && a.record_first) record();  // :66 slot 0 = state after burn-in
   for (int64_t s = 1; s < a.n; ++s) {  // :67-71
     for (int64_t k = 0; k < a.nskip; ++k) nacc += step();
     record();

@@ -18,13 +18,13 @@
 
 namespace mg {
 int MG_CAT(mh_static_gauss_, MG_SD)(mg_ctx *ctx, const mg_logfn *like, const mg_proposal *prop,
-                                    const mg_mcmc_cfg *cfg, CallKey key, double *d_state, double *d_samples,
+                                    const mg_mcmc_cfg *cfg, CallKey key, uint64_t t0, int record_first, double *d_state, double *d_samples,
                                     int32_t *d_accept) {
   constexpr int D = MG_SD;
   MhArgs<GaussCorr<D>, ZeroFn, BoxProp<D>, D> a;
   GaussCorr<D>::pack(like->params, like->params + D, like->params[D + D * (D + 1) / 2], a.like);
   BoxProp<D>::pack(prop->params, a.prop);
-  fill_common(a, cfg, key, d_state, d_samples, d_accept);
+  fill_common(a, cfg, key, t0, record_first, d_state, d_samples, d_accept);
 #if MG_SD <= 10
   // warp-specialised kernel (mcmc_ws.cuh); MCMC_GPU_MH_WS=0 selects the single-role kernel
   static const bool use_ws = [] { const char *e = getenv("MCMC_GPU_MH_WS"); return e ? atoi(e) != 0 : MG_MH_WS_DEFAULT; }();

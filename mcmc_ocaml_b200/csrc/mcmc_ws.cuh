@@ -93,7 +93,7 @@ mh_ws_kernel(const __grid_constant__ MhArgs<GaussCorr<D>, ZeroFn, BoxProp<D>, D>
 
   if (producer) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
-    int64_t t = 0;
+    int64_t t = 0;                                 // steps done in this launch; the RNG step index is t0 + t
     for (int64_t k = 0; t < total; ++k) {
       const int s = (int)(k % WS_NSTAGE);
       mbar_wait(empty + s, (unsigned)(((k / WS_NSTAGE) & 1) ^ 1));
@@ -101,7 +101,7 @@ mh_ws_kernel(const __grid_constant__ MhArgs<GaussCorr<D>, ZeroFn, BoxProp<D>, D>
 #pragma unroll
       for (int q = 0; q < WS_SPS; ++q) {
         if (t < total) {
-          Rng r(a.key, P_MH, g, (uint64_t)t);
+          Rng r(a.key, P_MH, g, a.t0 + (uint64_t)t);
           double2 *slot = dst + q * WS_SLOTS * 32;
 #pragma unroll
           for (int p = 0; p < 5; ++p) {       // BoxProp offset fma(w_i, 1 + u_i, c_i) (bin/evidence_direct.ml:24-25)
@@ -173,7 +173,7 @@ mh_ws_kernel(const __grid_constant__ MhArgs<GaussCorr<D>, ZeroFn, BoxProp<D>, D>
         out += sample_stride;
       }
     };
-    if (a.n > 0) record();                         // :66
+    if (a.n > 0 && a.record_first) record();       // :66
     for (int64_t smp = 1; smp < a.n; ++smp) {      // :67-71
       for (int64_t kk = 0; kk < a.nskip; ++kk) step();
       record();

@@ -21,7 +21,7 @@ namespace mg {
 
 constexpr int RS_BLOCK = 256;
 constexpr int RS_WARPS = RS_BLOCK / 32;
-constexpr int RS_ROUNDS = 16;                       // 32 keys per warp per round
+constexpr int RS_ROUNDS = 8;                       // 32 keys per warp per round
 constexpr int RS_TILE = RS_BLOCK * RS_ROUNDS;       // 4096 keys per CTA
 constexpr int RS_RADIX = 256;
 

@@ -23,11 +23,12 @@ constexpr int RED_BLOCK = 256;
 // the distribution the subtraction loses less than a digit, and both sums are
 // compensated; agreement with Stats.multi_mean / multi_std stays within 1e-12
 // (tests/test_mcmc_gpu.py::test_resident_call_and_block_stats).
-__global__ void __launch_bounds__(RED_BLOCK)
-block_field_moments_kernel(const double *__restrict__ blk, int64_t n, int F, int64_t C,
-                           double *__restrict__ partial /* [2][F][gridDim.x] */) {
+constexpr int MOM_BLOCK = 128;   // small CTAs with <= 32 registers: they fit beside the resident sampler CTAs
+__global__ void __maxnreg__(32)
+block_field_moments_kernel(const double *__restrict__ pivot_src, const double *__restrict__ blk, int64_t n, int F,
+                           int64_t C, double *__restrict__ partial /* [2][F][gridDim.x] */) {
   const int f = blockIdx.y;
-  const double sh = blk[(int64_t)f * C];   // pivot: sample 0, chain 0
+  const double sh = pivot_src[(int64_t)f * C];   // pivot: sample 0, chain 0 of the whole block
   Comp a1, a2;
   const int64_t nvec = C / 2;
   const bool vec_ok = (C % 2 == 0);
@@ -35,32 +36,47 @@ block_field_moments_kernel(const double *__restrict__ blk, int64_t n, int F, int
     const double *row = blk + (s * F + f) * C;
     if (vec_ok) {
       const double2 *row2 = reinterpret_cast<const double2 *>(row);
-      for (int64_t c = threadIdx.x; c < nvec; c += RED_BLOCK) {
+      int64_t c = threadIdx.x;
+      for (; c + 3 * MOM_BLOCK < nvec; c += 4 * MOM_BLOCK) {   // four independent 16-byte loads in flight
+        const double2 v0 = __ldcs(row2 + c), v1 = __ldcs(row2 + c + MOM_BLOCK), v2 = __ldcs(row2 + c + 2 * MOM_BLOCK),
+                      v3 = __ldcs(row2 + c + 3 * MOM_BLOCK);
+        const double d0 = v0.x - sh, d1 = v0.y - sh, d2 = v1.x - sh, d3 = v1.y - sh;
+        const double d4 = v2.x - sh, d5 = v2.y - sh, d6 = v3.x - sh, d7 = v3.y - sh;
+        a1.add(d0); a1.add(d1); a1.add(d2); a1.add(d3); a1.add(d4); a1.add(d5); a1.add(d6); a1.add(d7);
+        a2.add(d0 * d0); a2.add(d1 * d1); a2.add(d2 * d2); a2.add(d3 * d3);
+        a2.add(d4 * d4); a2.add(d5 * d5); a2.add(d6 * d6); a2.add(d7 * d7);
+      }
+      for (; c < nvec; c += MOM_BLOCK) {
         const double2 v = __ldcs(row2 + c);
         const double a = v.x - sh, b = v.y - sh;
         a1.add(a); a1.add(b); a2.add(a * a); a2.add(b * b);
       }
     } else {
-      for (int64_t c = threadIdx.x; c < C; c += RED_BLOCK) {
+      for (int64_t c = threadIdx.x; c < C; c += MOM_BLOCK) {
         const double a = __ldcs(row + c) - sh;
         a1.add(a); a2.add(a * a);
       }
     }
   }
-  const double t1 = block_reduce_comp<RED_BLOCK>(a1);
-  const double t2 = block_reduce_comp<RED_BLOCK>(a2);
+  const double t1 = block_reduce_comp<MOM_BLOCK>(a1);
+  const double t2 = block_reduce_comp<MOM_BLOCK>(a2);
   if (threadIdx.x == 0) {
     partial[(int64_t)f * gridDim.x + blockIdx.x] = t1;
     partial[((int64_t)F + f) * gridDim.x + blockIdx.x] = t2;
   }
 }
 
-__global__ void finish_moments_kernel(const double *__restrict__ partial, int nb, int F, double cnt,
+// partial: [nseg][2][F][nb]
+__global__ void finish_moments_kernel(const double *__restrict__ partial, int nseg, int nb, int F, double cnt,
                                       const double *__restrict__ blk, int64_t C, double *__restrict__ out) {
   const int f = blockIdx.x * blockDim.x + threadIdx.x;
   if (f >= F) return;
   Comp s1, s2;
-  for (int b = 0; b < nb; ++b) { s1.add(partial[(int64_t)f * nb + b]); s2.add(partial[((int64_t)F + f) * nb + b]); }
+  for (int g = 0; g < nseg; ++g)
+    for (int b = 0; b < nb; ++b) {
+      s1.add(partial[(((int64_t)g * 2 + 0) * F + f) * nb + b]);
+      s2.add(partial[(((int64_t)g * 2 + 1) * F + f) * nb + b]);
+    }
   const double sh = blk[(int64_t)f * C];
   const double S1 = s1.value(), S2 = s2.value();
   out[f] = sh + S1 / cnt;
@@ -128,18 +144,31 @@ static int grid_for(mg_ctx *ctx, int64_t work_items) {
   return (int)(g < 1 ? 1 : g);
 }
 
+int moments_grid(mg_ctx *ctx, int64_t n) { return grid_for(ctx, n); }
+
+// partial moments of the samples [seg, seg + n) about the block's pivot, on stream `st`
+int sample_block_moments_async(mg_ctx *ctx, cudaStream_t st, const double *blk_base, const double *seg, int64_t n,
+                               int F, int64_t C, int gx, double *partial) {
+  block_field_moments_kernel<<<dim3(gx, F), MOM_BLOCK, 0, st>>>(blk_base, seg, n, F, C, partial);
+  MG_CHECK_LAUNCH(ctx);
+  return MG_OK;
+}
+int sample_block_moments_finish(mg_ctx *ctx, cudaStream_t st, const double *partial, int nseg, int gx, int F, double cnt,
+                                const double *blk_base, int64_t C, double *d_out) {
+  finish_moments_kernel<<<(F + 63) / 64, 64, 0, st>>>(partial, nseg, gx, F, cnt, blk_base, C, d_out);
+  MG_CHECK_LAUNCH(ctx);
+  return MG_OK;
+}
+
 // per-field mean and std of a device sample block; results in d_out[0..F) (mean), d_out[F..2F) (std)
 int sample_block_stats(mg_ctx *ctx, const double *d_blk, int64_t n, int F, int64_t C, double *d_out) {
   cudaStream_t s = ctx->stream;
   const int gx = grid_for(ctx, n);
   DevBuf<double> partial;
   MG_CUDA(ctx, partial.alloc((size_t)2 * F * gx, s));
-  const double cnt = (double)n * (double)C;
-  block_field_moments_kernel<<<dim3(gx, F), RED_BLOCK, 0, s>>>(d_blk, n, F, C, partial.get());
-  MG_CHECK_LAUNCH(ctx);
-  finish_moments_kernel<<<(F + 63) / 64, 64, 0, s>>>(partial.get(), gx, F, cnt, d_blk, C, d_out);
-  MG_CHECK_LAUNCH(ctx);
-  return MG_OK;
+  int rc = sample_block_moments_async(ctx, s, d_blk, d_blk, n, F, C, gx, partial.get());
+  if (rc) return rc;
+  return sample_block_moments_finish(ctx, s, partial.get(), 1, gx, F, (double)n * (double)C, d_blk, C, d_out);
 }
 
 // column mean (pow 1) or std about `d_shift` (pow 2) of a device table [n][D]
