@@ -14,7 +14,7 @@ __global__ void logfn_eval_kernel(DynFnParams f, const double *__restrict__ x, i
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= M) return;
   double v[DMAX];
-#pragma unroll (DMAX <= 8 ? DMAX : 1)
+#pragma unroll (DMAX <= 16 ? DMAX : 1)
   for (int d = 0; d < DMAX; ++d) v[d] = (d < f.dim) ? x[i * f.dim + d] : 0.0;
   out[i] = DynFn::eval<DMAX>(f, nullptr, v, f.dim);
 }

@@ -212,7 +212,7 @@ template <int DMAX>
 __device__ __forceinline__ double dyn_log_multi_gaussian(const double *mu, const double *sigma,
                                                          const double (&x)[DMAX], int d) {
   double result = 0.0;  // stats.ml:103-108
-#pragma unroll (DMAX <= 8 ? DMAX : 1)
+#pragma unroll (DMAX <= 16 ? DMAX : 1)
   for (int i = 0; i < DMAX; ++i)
     if (i < d) result = result + log_gaussian(__ldg(mu + i), __ldg(sigma + i), x[i]);
   return result + 0.0;
@@ -229,14 +229,14 @@ struct DynFn {
       case MG_FN_CONST: return __ldg(p);
       case MG_FN_BOX_CLOSED: {  // bin/gaussian_cauchy_efficiency.ml:60-67
         bool out = false;
-#pragma unroll (DMAX <= 8 ? DMAX : 1)
+#pragma unroll (DMAX <= 16 ? DMAX : 1)
         for (int i = 0; i < DMAX; ++i)
           if (i < d) out = out || (x[i] < __ldg(p + i)) || (x[i] > __ldg(p + d + i));
         return out ? neg_inf() : __ldg(p + 2 * d);
       }
       case MG_FN_BOX_OPEN: {  // test/nested_test.ml:24-28
         bool in = true;
-#pragma unroll (DMAX <= 8 ? DMAX : 1)
+#pragma unroll (DMAX <= 16 ? DMAX : 1)
         for (int i = 0; i < DMAX; ++i)
           if (i < d) in = in && (x[i] > __ldg(p + i)) && (x[i] < __ldg(p + d + i));
         return in ? __ldg(p + 2 * d) : neg_inf();
@@ -245,14 +245,14 @@ struct DynFn {
       case MG_FN_GAUSS_CORR: {
         const double *mu = p, *L = p + d;
         double z[DMAX];
-#pragma unroll (DMAX <= 8 ? DMAX : 1)
+#pragma unroll (DMAX <= 16 ? DMAX : 1)
         for (int j = 0; j < DMAX; ++j) z[j] = (j < d) ? x[j] - __ldg(mu + j) : 0.0;
         double q = 0.0;
-#pragma unroll (DMAX <= 8 ? DMAX : 1)
+#pragma unroll (DMAX <= 16 ? DMAX : 1)
         for (int i = 0; i < DMAX; ++i) {
           if (i < d) {
             double y = __ldg(L + i * (i + 1) / 2) * z[0];
-#pragma unroll (DMAX <= 8 ? DMAX : 1)
+#pragma unroll (DMAX <= 16 ? DMAX : 1)
             for (int j = 1; j < DMAX; ++j)
               if (j <= i) y = fma(__ldg(L + i * (i + 1) / 2 + j), z[j], y);
             q = fma(y, y, q);
@@ -274,7 +274,7 @@ struct DynFn {
       }
       case MG_FN_SHELL: {
         double s = 0.0;
-#pragma unroll (DMAX <= 8 ? DMAX : 1)
+#pragma unroll (DMAX <= 16 ? DMAX : 1)
         for (int i = 0; i < DMAX; ++i)
           if (i < d) { const double dx = x[i] - __ldg(p + i); s = s + dx * dx; }
         return log_gaussian(__ldg(p + d), __ldg(p + d + 1), sqrt(s));
@@ -323,17 +323,17 @@ struct DynProp {
                                                        double (&y)[DMAX], int d) {
     switch (kind) {
       case MG_PROP_BOX:
-#pragma unroll (DMAX <= 8 ? DMAX : 1)
+#pragma unroll (DMAX <= 16 ? DMAX : 1)
         for (int i = 0; i < DMAX; ++i)
           if (i < d) { const double a = -__ldg(p + i), b = __ldg(p + i), w = b - a; y[i] = x[i] + fma(w, r.uniform12(), a - w); }
         break;
       case MG_PROP_WRAP:
-#pragma unroll (DMAX <= 8 ? DMAX : 1)
+#pragma unroll (DMAX <= 16 ? DMAX : 1)
         for (int i = 0; i < DMAX; ++i)
           if (i < d) y[i] = uniform_wrapping(r, __ldg(p + i), __ldg(p + d + i), __ldg(p + 2 * d + i), x[i]);
         break;
       case MG_PROP_INDEP_GAUSS:
-#pragma unroll (DMAX <= 8 ? DMAX : 1)
+#pragma unroll (DMAX <= 16 ? DMAX : 1)
         for (int i = 0; i < DMAX; ++i)
           if (i < d) y[i] = draw_gaussian(r, __ldg(p + i), __ldg(p + d + i));
         break;
@@ -352,7 +352,7 @@ struct DynProp {
     switch (kind) {
       case MG_PROP_INDEP_GAUSS: {  // test/mcmc_test.ml:123-126
         double s = 0.0;
-#pragma unroll (DMAX <= 8 ? DMAX : 1)
+#pragma unroll (DMAX <= 16 ? DMAX : 1)
         for (int i = 0; i < DMAX; ++i)
           if (i < d) s = s + log_gaussian(__ldg(p + i), __ldg(p + d + i), y[i]);
         return s;
@@ -385,7 +385,7 @@ struct DynProp {
     } else {
       propose_basic<DMAX, R>(f.kind, p, r, x, y, d);
     }
-#pragma unroll (DMAX <= 8 ? DMAX : 1)
+#pragma unroll (DMAX <= 16 ? DMAX : 1)
     for (int i = 0; i < DMAX; ++i)
       if (i >= d) y[i] = 0.0;
   }

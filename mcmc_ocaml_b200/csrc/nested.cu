@@ -44,9 +44,9 @@ __global__ void nest_init_kernel(NestArgs a, double *__restrict__ x_out, double 
   if (i >= a.nlive) return;
   Rng r(a.key, P_NEST_INIT, (uint64_t)i, 0);
   double x[DMAX];
-#pragma unroll (DMAX <= 8 ? DMAX : 1)
+#pragma unroll (DMAX <= 16 ? DMAX : 1)
   for (int d = 0; d < DMAX; ++d) x[d] = (d < a.D) ? draw_uniform(r, __ldg(a.plo + d), __ldg(a.phi + d)) : 0.0;
-#pragma unroll (DMAX <= 8 ? DMAX : 1)
+#pragma unroll (DMAX <= 16 ? DMAX : 1)
   for (int d = 0; d < DMAX; ++d)
     if (d < a.D) x_out[(int64_t)i * a.D + d] = x[d];
   ll_out[i] = DynFn::eval<DMAX>(a.like, nullptr, x, a.D);
@@ -63,7 +63,7 @@ __global__ void nest_replace_kernel(NestArgs a) {
   // livepts.(Random.int nlive) (:63); with K > 1 the start must satisfy the common threshold
   const int start = (a.K - 1) + (int)rs.below((uint64_t)(a.nlive - a.K + 1));
   double x[DMAX], y[DMAX];
-#pragma unroll (DMAX <= 8 ? DMAX : 1)
+#pragma unroll (DMAX <= 16 ? DMAX : 1)
   for (int d = 0; d < DMAX; ++d) x[d] = (d < a.D) ? a.live_x[(int64_t)start * a.D + d] : 0.0;
   const double thr = a.threshold;
   auto mcmc_logl = [&](const double (&pt)[DMAX]) {           // :54-59
@@ -83,7 +83,7 @@ __global__ void nest_replace_kernel(NestArgs a) {
     if (a.mode_hop != 0.0 && r.uniform() < a.mode_hop) dscale = 1.0;
     else dscale = draw_gaussian(r, 0.0, a.de_sigma);
     const double *px = a.live_x + (int64_t)i0 * a.D, *py = a.live_x + (int64_t)j0 * a.D;
-#pragma unroll (DMAX <= 8 ? DMAX : 1)
+#pragma unroll (DMAX <= 16 ? DMAX : 1)
     for (int d = 0; d < DMAX; ++d) y[d] = (d < a.D) ? x[d] + dscale * (__ldg(py + d) - __ldg(px + d)) : 0.0;
     // make_mcmc_sampler (mcmc.ml:37-56) with the closures of :54-61
     const double start_log_post = cl + cp;
@@ -91,7 +91,7 @@ __global__ void nest_replace_kernel(NestArgs a) {
     const double proposed_log_posterior = proposed_like + 0.0;
     const double log_accept_prob = proposed_log_posterior - start_log_post + 0.0 - 0.0;
     if (log(r.uniform()) < log_accept_prob) {
-#pragma unroll (DMAX <= 8 ? DMAX : 1)
+#pragma unroll (DMAX <= 16 ? DMAX : 1)
       for (int d = 0; d < DMAX; ++d) x[d] = y[d];
       cl = proposed_like;
     }
@@ -99,7 +99,7 @@ __global__ void nest_replace_kernel(NestArgs a) {
   const double nl = DynFn::eval<DMAX>(a.like, nullptr, x, a.D);   // :68-69
   const double np = DynFn::eval<DMAX>(a.prior, nullptr, x, a.D);
   if (!(nl >= thr)) *a.fail = 1;                                   // :70-72
-#pragma unroll (DMAX <= 8 ? DMAX : 1)
+#pragma unroll (DMAX <= 16 ? DMAX : 1)
   for (int d = 0; d < DMAX; ++d)
     if (d < a.D) a.fresh_x[(int64_t)j * a.D + d] = x[d];
   a.fresh_ll[j] = nl; a.fresh_lp[j] = np;

@@ -41,10 +41,10 @@ template <int DMAX>
 __device__ __forceinline__ bool rj_draw_into(const RjModelDev &m, const KdScratch &s, Rng &r, double (&y)[DMAX]) {
   if (m.into_kind == MG_INTO_INTERP) {
     if (!kd_draw(m.tree, s, m.nstop, r)) return false;
-#pragma unroll (DMAX <= 8 ? DMAX : 1)
+#pragma unroll (DMAX <= 16 ? DMAX : 1)
     for (int i = 0; i < DMAX; ++i) y[i] = (i < m.D) ? s.Q(i) : 0.0;
   } else {
-#pragma unroll (DMAX <= 8 ? DMAX : 1)
+#pragma unroll (DMAX <= 16 ? DMAX : 1)
     for (int i = 0; i < DMAX; ++i)
       y[i] = (i < m.D) ? draw_gaussian(r, __ldg(m.into_p + i), __ldg(m.into_p + m.D + i)) : 0.0;
   }
@@ -55,13 +55,13 @@ __device__ __forceinline__ bool rj_draw_into(const RjModelDev &m, const KdScratc
 template <int DMAX>
 __device__ __forceinline__ double rj_log_into(const RjModelDev &m, const KdScratch &s, const double (&to)[DMAX]) {
   if (m.into_kind == MG_INTO_INTERP) {
-#pragma unroll (DMAX <= 8 ? DMAX : 1)
+#pragma unroll (DMAX <= 16 ? DMAX : 1)
     for (int i = 0; i < DMAX; ++i)
       if (i < m.D) s.Q(i) = to[i];
     return log(kd_jump_prob(m.tree, s, m.nstop, nullptr));  // test/mcmc_test.ml:177-178
   }
   double acc = 0.0;
-#pragma unroll (DMAX <= 8 ? DMAX : 1)
+#pragma unroll (DMAX <= 16 ? DMAX : 1)
   for (int i = 0; i < DMAX; ++i)
     if (i < m.D) acc = acc + log_gaussian(__ldg(m.into_p + i), __ldg(m.into_p + m.D + i), to[i]);
   return acc;
@@ -82,10 +82,10 @@ __global__ void rj_ensemble_kernel(const __grid_constant__ RjArgs a) {
     Rng r0(a.key, P_RJ_INIT, g, 0);
     int model = (r0.uniform() < 0.5) ? 0 : 1;
     double x[DMAX], y[DMAX];
-#pragma unroll (DMAX <= 8 ? DMAX : 1)
+#pragma unroll (DMAX <= 16 ? DMAX : 1)
     for (int i = 0; i < DMAX; ++i) x[i] = 0.0;
     const double *start = a.start + (size_t)model * 64;
-#pragma unroll (DMAX <= 8 ? DMAX : 1)
+#pragma unroll (DMAX <= 16 ? DMAX : 1)
     for (int i = 0; i < DMAX; ++i)
       if (i < a.m[model].D) x[i] = start[i];
     double ll = DynFn::eval<DMAX>(a.m[model].like, nullptr, x, a.m[model].D);
@@ -121,7 +121,7 @@ __global__ void rj_ensemble_kernel(const __grid_constant__ RjArgs a) {
           proposed_log_posterior - start_log_post + log_backward_jump - log_forward_jump;
       if (log(r.uniform()) < log_accept_prob) {
         model = pmodel;
-#pragma unroll (DMAX <= 8 ? DMAX : 1)
+#pragma unroll (DMAX <= 16 ? DMAX : 1)
         for (int i = 0; i < DMAX; ++i) x[i] = y[i];
         ll = proposed_like; lp = proposed_prior; ++nacc;
       }
@@ -131,7 +131,7 @@ __global__ void rj_ensemble_kernel(const __grid_constant__ RjArgs a) {
       if (a.out_model) a.out_model[smp * C + c] = (uint8_t)model;
       if (a.out_samples) {
         double *o = a.out_samples + smp * (int64_t)F * C + c;
-#pragma unroll (DMAX <= 8 ? DMAX : 1)
+#pragma unroll (DMAX <= 16 ? DMAX : 1)
         for (int i = 0; i < DMAX; ++i)
           if (i < a.Dm) __stcs(o + (int64_t)i * C, x[i]);
         __stcs(o + (int64_t)a.Dm * C, ll);
