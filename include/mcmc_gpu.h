@@ -351,6 +351,11 @@ int mg_evidence_harmonic_mean(mg_ctx *ctx, const double *ll, int64_t N,
                               double *out);
 int mg_evidence_harmonic_mean_dev(mg_ctx *ctx, const double *d_ll, int64_t N,
                                   double *out);
+/* bin/harmonic_evidence.ml:41-52: nbstrap bootstrap replicates of the
+ * harmonic-mean evidence (n indices resampled with Random.int n each).
+ * out_evs: host [nbstrap], unsorted (replicate b uses Philox stream b). */
+int mg_evidence_harmonic_bootstrap(mg_ctx *ctx, const double *ll, int64_t N,
+                                   int32_t nbstrap, double *out_evs);
 /* Evidence.evidence_lebesgue ?n ?eps (evidence.ml:202-221).
  * pts host [N][D]; ll, lp host [N].  Defaults n = 64, eps = 0.1. */
 int mg_evidence_lebesgue(mg_ctx *ctx, const double *pts, const double *ll,
@@ -422,6 +427,26 @@ int mg_nested_weights(mg_ctx *ctx, const double *ll, int64_t n, int32_t nlive,
                       double *logw);
 /* Nested.log_total_error_estimate (nested.ml:148-150) */
 double mg_nested_log_total_error(double log_ev, double log_dev, int32_t nlive);
+
+/* ------------------------------------------------------------------ */
+/* Read_write: the text format of the reference's tools (host only)    */
+/* ------------------------------------------------------------------ */
+/* Read_write.write / read (read_write.ml:19-58): one sample per line,
+ * "%g " per coordinate then "%g %g\n" (log_likelihood, log_prior).
+ * rows: [n][D+2].  precision 0 = the reference's "%g" (6 digits, lossy),
+ * 17 = "%.17g" (same grammar, exact round trip).  path "-" = stdout / stdin.
+ * Readers return malloc'ed arrays: release with mg_free_host.
+ * MG_EFAIL <-> Sys_error / Scanf failure / End_of_file. */
+int mg_write_samples(const char *path, const double *rows, int64_t n,
+                     int32_t D, int32_t precision);
+int mg_read_samples(const char *path, double **rows, int64_t *n, int32_t *D);
+/* Read_write.write_nested / read_nested (read_write.ml:60-101) */
+int mg_write_nested(const char *path, double log_ev, double log_dev,
+                    const double *rows, const double *logw, int64_t n,
+                    int32_t D, int32_t precision);
+int mg_read_nested(const char *path, double *log_ev, double *log_dev,
+                   double **rows, double **logw, int64_t *n, int32_t *D);
+void mg_free_host(void *p);
 
 #ifdef __cplusplus
 }

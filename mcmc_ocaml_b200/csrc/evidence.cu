@@ -421,6 +421,53 @@ extern "C" int mg_evidence_direct(mg_ctx *ctx, const double *pts, const double *
   return evidence_host(ctx, 1, pts, ll, lp, N, D, n, 0.0, out);
 }
 
+// bin/harmonic_evidence.ml:41-52: one CTA per bootstrap replicate.  Draw j of replicate b is lane j & 1 of
+// Philox block j >> 1 of stream (P_BOOT, b, 0) -- the sequence a sequential Random.int loop would consume.
+namespace mg {
+__global__ void inv_like_kernel(const double *__restrict__ ll, int64_t n, double *__restrict__ il) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    il[i] = 1.0 / exp(ll[i]);     // evidence.ml:105
+}
+__global__ void __launch_bounds__(EB)
+harmonic_bootstrap_kernel(const double *__restrict__ il, int64_t n, CallKey key, double *__restrict__ evs) {
+  const uint64_t b = blockIdx.x;
+  const uint32_t c3 = (uint32_t)((b >> 32) & 0xFFFFu) | ((uint32_t)P_BOOT << 16);
+  Comp acc;
+  const int64_t nblocks = (n + 1) / 2;
+  for (int64_t q = threadIdx.x; q < nblocks; q += EB) {
+    uint32_t w[4];
+    philox4x32_10((uint32_t)q, 0u, (uint32_t)b, c3, key.k0, key.k1, w);
+    const uint64_t l0 = ((uint64_t)w[0] << 32) | w[1], l1 = ((uint64_t)w[2] << 32) | w[3];
+    acc.add(il[__umul64hi(l0, (uint64_t)n)]);
+    if (2 * q + 1 < n) acc.add(il[__umul64hi(l1, (uint64_t)n)]);
+  }
+  const double t = block_reduce_comp<EB>(acc);
+  if (threadIdx.x == 0) evs[b] = (double)n / t;
+}
+}  // namespace mg
+
+extern "C" int mg_evidence_harmonic_bootstrap(mg_ctx *ctx, const double *ll, int64_t N, int32_t nbstrap, double *out_evs) {
+  if (!ctx) return MG_EINVAL;
+  MG_REQUIRE(ctx, ll && out_evs && N >= 1 && nbstrap >= 1, "harmonic bootstrap: bad arguments");
+  MG_REQUIRE(ctx, (N + 1) / 2 < (1LL << 32), "harmonic bootstrap: too many samples");
+  MG_CUDA(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t s = ctx->stream;
+  DevBuf<double> d_ll, d_il, d_evs;
+  MG_CUDA(ctx, upload(d_ll, ll, (size_t)N, s));
+  MG_CUDA(ctx, d_il.alloc(N, s));
+  MG_CUDA(ctx, d_evs.alloc(nbstrap, s));
+  inv_like_kernel<<<egrid(ctx, N), EB, 0, s>>>(d_ll.get(), N, d_il.get());
+  MG_CHECK_LAUNCH(ctx);
+  const CallKey key = next_key(ctx);
+  time_begin(ctx);
+  harmonic_bootstrap_kernel<<<(unsigned)nbstrap, EB, 0, s>>>(d_il.get(), N, key, d_evs.get());
+  MG_CHECK_LAUNCH(ctx);
+  time_end(ctx);
+  MG_CUDA(ctx, cudaMemcpyAsync(out_evs, d_evs.get(), sizeof(double) * nbstrap, cudaMemcpyDeviceToHost, s));
+  MG_CUDA(ctx, cudaStreamSynchronize(s));
+  return MG_OK;
+}
+
 // Diagnostic (tests only): stable-sort float64 keys on the device and count
 // order violations / non-permutation entries of the result.
 namespace mg {

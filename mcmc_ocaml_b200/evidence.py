@@ -38,6 +38,16 @@ def evidence_harmonic_mean(samples=None, ll=None, *, ctx: Context | None = None)
     return out.value
 
 
+def harmonic_bootstrap(ll, nbstrap: int = 10000, *, ctx: Context | None = None) -> np.ndarray:
+    """Bootstrap replicates of the harmonic-mean evidence (bin/harmonic_evidence.ml:41-52),
+    sorted ascending like the reference's ``Array.fast_sort``."""
+    ctx = ctx or default_context()
+    ll = _abi.as_f64(ll)
+    out = np.empty(nbstrap)
+    ctx.check(ctx.lib.mg_evidence_harmonic_bootstrap(ctx.h, _abi.ptr(ll), C.c_int64(ll.size), C.c_int32(nbstrap), _abi.ptr(out)))
+    return np.sort(out)
+
+
 def evidence_lebesgue(samples, ll=None, lp=None, *, n: int = 64, eps: float = 0.1, ctx: Context | None = None) -> float:
     """``Evidence.evidence_lebesgue ?n ?eps`` (evidence.ml:202-221), Weinberg's
     Lebesgue integral of 1/L over kd-tree cells."""

@@ -48,7 +48,7 @@ struct Philox {
 
 enum Purpose : uint32_t {
   P_MH = 1, P_RJ = 2, P_RJ_INIT = 3, P_DRAW = 4, P_NEST_INIT = 5,
-  P_NEST_MCMC = 6, P_NEST_START = 7, P_POST = 8
+  P_NEST_MCMC = 6, P_NEST_START = 7, P_POST = 8, P_BOOT = 9
 };
 
 struct CallKey { uint32_t k[2]; };

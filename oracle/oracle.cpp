@@ -609,6 +609,18 @@ int og_evidence_direct(const double *pts, const double *ll, const double *lp, in
   return evidence_direct(s, n, full_tree, out, ncells);
   OG_CATCH
 }
+// bin/harmonic_evidence.ml:41-52: bootstrap replicates of the harmonic-mean evidence
+// (resample n indices with Random.int n, recompute).  evs is returned UNSORTED.
+int og_harmonic_bootstrap(uint64_t seed, uint64_t epoch, const double *ll, int64_t n, int32_t nbstrap, double *evs) {
+  CallKey ck = derive_key(seed, epoch);
+  for (int32_t b = 0; b < nbstrap; ++b) {
+    Rng r(ck, P_BOOT, (uint64_t)b, 0);
+    double linv = 0.0;
+    for (int64_t i = 0; i < n; ++i) linv = linv + 1.0 / std::exp(ll[r.below((uint64_t)n)]);
+    evs[b] = (double)n / linv;
+  }
+  return MG_OK;
+}
 // mcmc.ml:74-81 remove_repeat_samples on rows [n][F] comparing the first D
 int64_t og_remove_repeat_samples(const double *rows, int64_t n, int32_t D, double *out) {
   int F = D + 2; int64_t k = 0;

@@ -198,6 +198,13 @@ def evidence_harmonic_mean(ll):
     return out[0], out[1]
 
 
+def harmonic_bootstrap(seed, epoch, ll, nbstrap):
+    ll = as_f64(ll)
+    out = np.empty(nbstrap)
+    _check(lib().og_harmonic_bootstrap(U64(seed), U64(epoch), ptr(ll), C.c_int64(ll.size), C.c_int32(nbstrap), ptr(out)))
+    return out
+
+
 def evidence_lebesgue(pts, ll, lp, n=64, eps=0.1, full_tree=False):
     pts, ll, lp = as_f64(pts), as_f64(ll), as_f64(lp)
     if pts.ndim == 1:

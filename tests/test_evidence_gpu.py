@@ -111,3 +111,33 @@ def test_stats_goldens_and_oracle(ctx, og):
     ro, Lo = og.autocorrelation(x, 50)
     np.testing.assert_allclose(r, ro, rtol=1e-10, atol=1e-13)
     assert L == pytest.approx(Lo, rel=1e-10)
+
+
+def test_harmonic_bootstrap_and_cli_tools(ctx, og, tmp_path):
+    """bin/harmonic_evidence.ml (bootstrap) and bin/evidence_tool.ml equivalents, through the
+    Read_write text format"""
+    import subprocess
+    import sys as _sys
+    import os as _os
+    from mcmc_ocaml_b200 import read_write
+    rng = np.random.default_rng(5)
+    ll = rng.normal(-1.0, 0.7, 4001)
+    ctx.set_seed(9)
+    evs = evidence.harmonic_bootstrap(ll, 300, ctx=ctx)
+    want = np.sort(og.harmonic_bootstrap(9, 0, ll, 300))
+    np.testing.assert_allclose(evs, want, rtol=1e-11)       # same resampled indices, compensated vs sequential sum
+    pts, l2, lp = mh_samples(ctx, 41, 2, 3000)
+    rows = np.concatenate([pts, l2[:, None], lp[:, None]], axis=1)
+    f = str(tmp_path / "chain.dat")
+    read_write.write(f, rows, lossless=True)
+    root = _os.path.dirname(_os.path.dirname(_os.path.abspath(__file__)))
+    out = subprocess.run([_sys.executable, _os.path.join(root, "tools", "evidence_tool.py"), "-nbox", "32", "-lebeps", "0.2", "-i", f],
+                         capture_output=True, text=True, check=True).stdout.split()
+    h, l, d = (float(x) for x in out)
+    assert h == pytest.approx(og.evidence_harmonic_mean(l2)[0], rel=1e-5)          # printed with %g
+    assert l == pytest.approx(og.evidence_lebesgue(pts, l2, lp, n=32, eps=0.2)["value"], rel=1e-5)
+    assert d == pytest.approx(og.evidence_direct(pts, l2, lp, n=32)["value"], rel=1e-5)
+    out = subprocess.run([_sys.executable, _os.path.join(root, "tools", "harmonic_evidence.py"), "-nbstrap", "200", "-seed", "3", "-i", f],
+                         capture_output=True, text=True, check=True).stdout.splitlines()
+    best, lo, hi = (float(x) for x in out[1].split())
+    assert lo <= best * 1.5 and hi >= best * 0.5 and lo < hi
