@@ -25,6 +25,7 @@ static void fill_common(A &a, const mg_mcmc_cfg *cfg, CallKey key, uint64_t t0, 
   a.d = cfg->dim; a.pad = 0; a.C = cfg->nchains; a.chain_offset = cfg->chain_offset;
   a.nbin = cfg->nbin; a.nskip = cfg->nskip; a.n = cfg->n; a.key = key;
   a.t0 = t0; a.record_first = record_first; a.pad2 = 0;
+  a.rk = make_round_keys(key);
   a.state = d_state; a.samples = d_samples; a.accept = d_accept;
 }
 

@@ -31,6 +31,7 @@ struct MhArgs {
   int32_t record_first; // 1: slot 0 = the state after burn-in (mcmc.ml:66); 0: a continuation segment
   int32_t pad2;
   CallKey key;
+  RoundKeys rk;     // key + r * W for the ten Philox rounds
   double *state;    // [D+2][C] in/out
   double *samples;  // [n][D+2][C] or null
   int32_t *accept;  // [C] accumulated, or null
@@ -109,7 +110,7 @@ __device__ __forceinline__ void mh_ensemble_body(const MhArgs<Like, Prior, Prop,
       r_acc = mh_step<Like, Prior, Prop, D>(a, sl, sp, sj, cur, x, ll, lp);
       cur = nxt;
     } else {
-      Rng r(a.key, P_MH, g, t);
+      Rng r(a.key, P_MH, g, t, &a.rk);
       r_acc = mh_step<Like, Prior, Prop, D>(a, sl, sp, sj, r, x, ll, lp);
     }
     ++t;

@@ -101,7 +101,7 @@ mh_ws_kernel(const __grid_constant__ MhArgs<GaussCorr<D>, ZeroFn, BoxProp<D>, D>
 #pragma unroll
       for (int q = 0; q < WS_SPS; ++q) {
         if (t < total) {
-          Rng r(a.key, P_MH, g, a.t0 + (uint64_t)t);
+          Rng r(a.key, P_MH, g, a.t0 + (uint64_t)t, &a.rk);
           double2 *slot = dst + q * WS_SLOTS * 32;
 #pragma unroll
           for (int p = 0; p < 5; ++p) {       // BoxProp offset fma(w_i, 1 + u_i, c_i) (bin/evidence_direct.ml:24-25)
