@@ -425,6 +425,12 @@ int mg_nested_evidence(mg_ctx *ctx, const mg_logfn *like, const mg_logfn *prior,
 int mg_nested_weights(mg_ctx *ctx, const double *ll, int64_t n, int32_t nlive,
                       int32_t batch, double *log_ev, double *log_dev,
                       double *logw);
+/* Nested.posterior_samples n nested_output (nested.ml:152-178): indices of n
+ * draws from the weighted points (inverse CDF over the running sums of
+ * exp log_weight, weight_binary_search_index :152-165).  logw: host [npts];
+ * out_idx: host [n].  Consumes one epoch of the context's Philox key. */
+int mg_nested_posterior_indices(mg_ctx *ctx, const double *logw, int64_t npts,
+                                int64_t n, int64_t *out_idx);
 /* Nested.log_total_error_estimate (nested.ml:148-150) */
 double mg_nested_log_total_error(double log_ev, double log_dev, int32_t nlive);
 

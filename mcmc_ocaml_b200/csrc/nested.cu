@@ -247,6 +247,30 @@ static int weights_dev(mg_ctx *ctx, const double *d_ll, int64_t n, int nlive, in
 
 using namespace mg;
 
+// nested.ml:152-178 on the host: n is small (the reference asks for ~100 draws) and the running sums are a
+// sequential float64 scan in the reference's order.
+extern "C" int mg_nested_posterior_indices(mg_ctx *ctx, const double *logw, int64_t npts, int64_t n, int64_t *out_idx) {
+  if (!ctx) return MG_EINVAL;
+  MG_REQUIRE(ctx, logw && out_idx && npts >= 1 && n >= 0, "posterior_samples: bad arguments");
+  const CallKey key = next_key(ctx);
+  std::vector<double> sw((size_t)npts);
+  sw[0] = std::exp(logw[0]);
+  for (int64_t i = 1; i < npts; ++i) sw[i] = std::exp(logw[i]) + sw[i - 1];      // :171-173
+  for (int64_t k = 0; k < n; ++k) {
+    uint32_t w[4];
+    const uint64_t g = (uint64_t)k;
+    philox4x32_10(0u, 0u, (uint32_t)g, (uint32_t)((g >> 32) & 0xFFFFu) | ((uint32_t)P_POST << 16), key.k0, key.k1, w);
+    uint64_t bits = (0x3FFull << 52) | ((((uint64_t)w[0] << 32) | w[1]) & 0xFFFFFFFFFFFFFull);
+    double m; memcpy(&m, &bits, 8);
+    const double x = m - 1.0;                                                     // Random.float 1.0
+    int64_t idx;
+    if (x <= sw[0]) idx = 0;                                                      // weight_binary_search_index :152-165
+    else { int64_t lo = 0, hi = npts - 1; while (hi - lo > 1) { const int64_t mid = (lo + hi) / 2; if (x <= sw[mid]) hi = mid; else lo = mid; } idx = hi; }
+    out_idx[k] = idx;
+  }
+  return MG_OK;
+}
+
 extern "C" double mg_nested_log_total_error(double log_ev, double log_dev, int32_t nlive) {
   const double log_rel_error2 = -std::log((double)nlive);          // nested.ml:148-150
   return 0.5 * h_log_sum_logs(2.0 * log_dev, log_rel_error2 + 2.0 * log_ev);

@@ -23,8 +23,8 @@ constexpr int RED_BLOCK = 256;
 // the distribution the subtraction loses less than a digit, and both sums are
 // compensated; agreement with Stats.multi_mean / multi_std stays within 1e-12
 // (tests/test_mcmc_gpu.py::test_resident_call_and_block_stats).
-constexpr int MOM_BLOCK = 128;   // small CTAs with <= 32 registers: they fit beside the resident sampler CTAs
-__global__ void __maxnreg__(32)
+constexpr int MOM_BLOCK = RED_BLOCK;
+__global__ void __launch_bounds__(MOM_BLOCK)
 block_field_moments_kernel(const double *__restrict__ pivot_src, const double *__restrict__ blk, int64_t n, int F,
                            int64_t C, double *__restrict__ partial /* [2][F][gridDim.x] */) {
   const int f = blockIdx.y;
@@ -36,17 +36,7 @@ block_field_moments_kernel(const double *__restrict__ pivot_src, const double *_
     const double *row = blk + (s * F + f) * C;
     if (vec_ok) {
       const double2 *row2 = reinterpret_cast<const double2 *>(row);
-      int64_t c = threadIdx.x;
-      for (; c + 3 * MOM_BLOCK < nvec; c += 4 * MOM_BLOCK) {   // four independent 16-byte loads in flight
-        const double2 v0 = __ldcs(row2 + c), v1 = __ldcs(row2 + c + MOM_BLOCK), v2 = __ldcs(row2 + c + 2 * MOM_BLOCK),
-                      v3 = __ldcs(row2 + c + 3 * MOM_BLOCK);
-        const double d0 = v0.x - sh, d1 = v0.y - sh, d2 = v1.x - sh, d3 = v1.y - sh;
-        const double d4 = v2.x - sh, d5 = v2.y - sh, d6 = v3.x - sh, d7 = v3.y - sh;
-        a1.add(d0); a1.add(d1); a1.add(d2); a1.add(d3); a1.add(d4); a1.add(d5); a1.add(d6); a1.add(d7);
-        a2.add(d0 * d0); a2.add(d1 * d1); a2.add(d2 * d2); a2.add(d3 * d3);
-        a2.add(d4 * d4); a2.add(d5 * d5); a2.add(d6 * d6); a2.add(d7 * d7);
-      }
-      for (; c < nvec; c += MOM_BLOCK) {
+      for (int64_t c = threadIdx.x; c < nvec; c += MOM_BLOCK) {
         const double2 v = __ldcs(row2 + c);
         const double a = v.x - sh, b = v.y - sh;
         a1.add(a); a1.add(b); a2.add(a * a); a2.add(b * b);

@@ -15,6 +15,7 @@ class KdTree:
 
     def __init__(self, pts, low, high, *, min_split: int = 2, ctx: Context | None = None, _handle=None):
         self.ctx = ctx or default_context()
+        self._box = None
         if _handle is not None:
             self.h = _handle
         else:
@@ -29,6 +30,7 @@ class KdTree:
                                                         C.c_int32(pts.shape[1]), _abi.ptr(low), _abi.ptr(high),
                                                         C.c_int32(min_split), C.byref(h)))
             self.h = h
+            self._box = (low.copy(), high.copy())
         info = self.info()
         self.N, self.D, self.nnodes, self.nlevels = info["npoints"], info["dim"], info["nnodes"], info["nlevels"]
 
@@ -40,7 +42,9 @@ class KdTree:
         h = C.c_void_p()
         ctx.check(ctx.lib.mg_kdtree_build_dev(ctx.h, C.c_void_p(pts_ptr), C.c_int64(N), C.c_int32(D), _abi.ptr(low),
                                               _abi.ptr(high), C.c_int32(min_split), C.byref(h)))
-        return cls(None, None, None, ctx=ctx, _handle=h)
+        t = cls(None, None, None, ctx=ctx, _handle=h)
+        t._box = (low.copy(), high.copy())
+        return t
 
     @classmethod
     def from_blob(cls, blob_ptr: int, nbytes: int, *, ctx: Context | None = None):
@@ -82,6 +86,12 @@ class KdTree:
                                                      _abi.ptr(left, _abi.c_int32_p), _abi.ptr(b, _abi.c_int32_p),
                                                      _abi.ptr(e, _abi.c_int32_p), _abi.ptr(perm, _abi.c_int32_p)))
         return dict(split_dim=sd, split_val=sv, left=left, begin=b, end=e, perm=perm)
+
+    def volume(self) -> float:
+        """``Kd_tree.volume tree`` (kd_tree.ml:184-186): the volume of the root cell's (caller supplied) box."""
+        if self._box is None:
+            raise _abi.InvalidArgument("volume: the root box of a tree rebuilt from a blob is held on the device only")
+        return bounds_volume(*self._box)
 
     def depth(self) -> int:
         """``depth`` of test/kd_tree_test.ml:66-71 (number of levels)."""

@@ -64,12 +64,13 @@ def log_total_error_estimate(log_ev: float, log_dev: float, nlive: int) -> float
     return float(_abi.load_library().mg_nested_log_total_error(log_ev, log_dev, nlive))
 
 
-def posterior_samples(n: int, out: NestedOutput, *, rng: np.random.Generator | None = None) -> np.ndarray:
-    """``Nested.posterior_samples n nested_output`` (nested.ml:152-178): inverse
-    CDF resampling of the weighted points (host side; n draws, O(n log N))."""
-    rng = rng or np.random.default_rng()
-    sw = np.cumsum(np.exp(out.log_weights))
-    x = rng.random(n)
-    # weight_binary_search_index: first i with x <= running_sums.(i)
-    idx = np.minimum(np.searchsorted(sw, x, side="left"), len(sw) - 1)
+def posterior_samples(n: int, out: NestedOutput, *, ctx: Context | None = None) -> np.ndarray:
+    """``Nested.posterior_samples n nested_output`` (nested.ml:152-178): n points drawn from the
+    weighted samples by inverse CDF (``weight_binary_search_index``); repeats are expected when n
+    approaches the number of points, as the reference warns."""
+    ctx = ctx or default_context()
+    lw = _abi.as_f64(out.log_weights)
+    idx = np.empty(n, dtype=np.int64)
+    ctx.check(ctx.lib.mg_nested_posterior_indices(ctx.h, _abi.ptr(lw), C.c_int64(lw.size), C.c_int64(n),
+                                                  _abi.ptr(idx, _abi.c_int64_p)))
     return out.points[idx]

@@ -97,6 +97,13 @@ def test_reference_structural_tests(ctx):
         stack += [(ex["left"][node], l, lh), (ex["left"][node] + 1, rl, h)]
 
 
+def test_volume(ctx, og):
+    pts = np.random.default_rng(2).random((100, 3))
+    t = kd_tree.KdTree(pts, [0.0, -1.0, 0.5], [1.0, 2.0, 0.75], ctx=ctx)
+    assert t.volume() == og.bounds_volume([0.0, -1.0, 0.5], [1.0, 2.0, 0.75]) == 1.0 * 3.0 * 0.25
+    assert kd_tree.bounds_volume([0, 0], [0.1, 0.3]) == og.bounds_volume([0, 0], [0.1, 0.3])
+
+
 def test_invalid_input(ctx):
     with pytest.raises(InvalidArgument):
         kd_tree.KdTree(np.array([[0.1, np.nan]]), [0, 0], [1, 1], ctx=ctx)

@@ -55,7 +55,7 @@ def test_single_gaussian_reference_defaults(ctx):
         assert np.exp(r.log_weights).sum() == pytest.approx(1.0, abs=1e-8)
         mean = np.sum(np.exp(r.log_weights) * r.points[:, 0])
         assert mean == pytest.approx(0.5, abs=0.1)
-        post = nested.posterior_samples(100, r, rng=np.random.default_rng(1))      # nested_test.ml:87-105
+        post = nested.posterior_samples(100, r, ctx=ctx)                           # nested_test.ml:87-105
         assert len(r.log_likelihood) > 100 and post[:, 0].mean() == pytest.approx(0.5, abs=0.05)
 
 
@@ -91,3 +91,18 @@ def test_errors(ctx):
         nested.nested_evidence(like, PRIOR, [0, 0], [1, 1], nlive=10, batch=10, ctx=ctx)
     with pytest.raises(Failure):                     # output arrays too small
         nested.nested_evidence(like, PRIOR, [0, 0], [1, 1], nlive=100, nmcmc=10, max_points=150, ctx=ctx)
+
+
+def test_posterior_samples_match_oracle(ctx, og):
+    """nested.ml:152-178 (weight_binary_search_index) on the same Philox stream"""
+    rng = np.random.default_rng(2)
+    lw = np.log(rng.dirichlet(np.ones(5000)))
+    fake = nested.NestedOutput(0.0, 0.0, np.arange(5000, dtype=float)[:, None], np.zeros(5000), np.zeros(5000), lw, 100, 1)
+    ctx.set_seed(44)
+    got = nested.posterior_samples(2000, fake, ctx=ctx)[:, 0].astype(np.int64)
+    want = og.nested_posterior_indices(44, 0, lw, 2000)
+    assert np.array_equal(got, want)
+    # drawn in proportion to the weights
+    counts = np.bincount(got, minlength=5000)
+    top = np.argsort(lw)[-50:]
+    assert counts[top].sum() / 2000 == pytest.approx(np.exp(lw[top]).sum(), abs=0.03)
