@@ -55,7 +55,7 @@ __device__ __forceinline__ int mh_step(const MhArgs<Like, Prior, Prop, D> &a, co
     log_accept_prob = log_accept_prob + log_backward_jump - log_forward_jump;
   }
   // log (Random.float 1.0) < log_accept_prob, strict (mcmc.ml:47).  NaN rejects.
-  const bool acc = log(r.uniform()) < log_accept_prob;
+  const bool acc = log_u_less_than(r.uniform(), log_accept_prob);
 #pragma unroll
   for (int i = 0; i < D; ++i) x[i] = acc ? y[i] : x[i];
   ll = acc ? proposed_like : ll;

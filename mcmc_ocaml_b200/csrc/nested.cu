@@ -90,7 +90,7 @@ __global__ void nest_replace_kernel(NestArgs a) {
     const double proposed_like = mcmc_logl(y);
     const double proposed_log_posterior = proposed_like + 0.0;
     const double log_accept_prob = proposed_log_posterior - start_log_post + 0.0 - 0.0;
-    if (log(r.uniform()) < log_accept_prob) {
+    if (log_u_less_than(r.uniform(), log_accept_prob)) {
 #pragma unroll (DMAX <= 16 ? DMAX : 1)
       for (int d = 0; d < DMAX; ++d) x[d] = y[d];
       cl = proposed_like;

@@ -119,7 +119,7 @@ __global__ void rj_ensemble_kernel(const __grid_constant__ RjArgs a) {
       }
       const double log_accept_prob =
           proposed_log_posterior - start_log_post + log_backward_jump - log_forward_jump;
-      if (log(r.uniform()) < log_accept_prob) {
+      if (log_u_less_than(r.uniform(), log_accept_prob)) {
         model = pmodel;
 #pragma unroll (DMAX <= 16 ? DMAX : 1)
         for (int i = 0; i < DMAX; ++i) x[i] = y[i];

@@ -107,6 +107,30 @@ struct Rng {
   __device__ __forceinline__ uint64_t below(uint64_t n) { return __umul64hi(lane(), n); }
 };
 
+// Acceptance test  log u < delta  (mcmc.ml:47, strict), decided exactly as the
+// float64 comparison would decide it, but without the float64 logarithm in all
+// but ~1e-5 of the calls: a single-precision estimate of log u (F2F + MUFU.LG2)
+// settles the comparison whenever it is further from delta than a rigorous
+// error bound; the rest take the float64 path.
+//   |(float)u - u| <= 2^-24 u for u > 1e-30 -> log error <= 6e-8;  __logf: <= 2^-21.41
+//   absolute on [0.5, 2], 3 ulp elsewhere -> <= 3.6e-7 (1 + |log u|);  (float)delta and the float subtraction add
+//   <= 1.2e-7 (|log u| + |delta|).  Total < 1e-6 (1 + |lf| + |df|); the tolerance used is ten times that.
+// u = 0, u < 1e-30, NaN or infinite-minus-infinite cases fail both comparisons and take the exact path.
+#ifndef MG_ACCEPT_PREFILTER
+#define MG_ACCEPT_PREFILTER 1
+#endif
+__device__ __forceinline__ bool log_u_less_than(double u, double delta) {
+#if MG_ACCEPT_PREFILTER
+  const float uf = __double2float_rn(u);
+  const float lf = __logf(uf);
+  const float df = __double2float_rn(delta);
+  const float d = lf - df;
+  const float tol = 1e-5f * (1.0f + fabsf(lf) + fabsf(df));
+  if (uf > 1e-30f && fabsf(d) > tol) return d < 0.0f;
+#endif
+  return log(u) < delta;
+}
+
 // N draws of one (purpose, g, step) generated up front: lets the sampler issue
 // the Philox rounds of step t+1 among the float64 work of step t.
 template <int N>
