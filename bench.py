@@ -310,7 +310,7 @@ def main():
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": f"{peak_kind} hbm_gbs (burst copy)",
-                         "kernel": "mh_ensemble_kernel<GaussCorr<10>,ZeroFn,BoxProp<10>,10>",
+                         "kernel": "mh_balanced_kernel<GaussCorr<10>,ZeroFn,BoxProp<10>,10>",
                          "kernel_ms": k_ms, "kernel_ms_last_launch_lib_events": k_ms_lib, "bytes_per_chain_step": BYTES_PER_STEP,
                          "store_only_peak_gbs": store.value, "fp64_fma_tflops_measured": fp64.value,
                          "fp64_flops_per_chain_step": D * D + 8 * D + 3,

@@ -1,0 +1,196 @@
+// mcmc_balanced.cuh -- the Metropolis-Hastings ensemble kernel with the chain
+// groups handed out dynamically, so that every warp scheduler of the GPU
+// carries the same load.
+//
+// Why: the step is issue-bound, and one scheduler saturates at three resident
+// warps (measured, tools/occupancy_sweep.sh: 56,832 chains = 3 warps on each
+// of the 592 schedulers run at 4.27e10 chain-steps/s, 75,776 = 4 warps at
+// 4.31e10).  An ensemble whose warps do not divide evenly over the schedulers
+// -- config 2: 65,536 chains = 2,048 warps = 3.46 per scheduler -- then runs at
+// the pace of the schedulers that hold four (17.5 ms/pass where 15.2 ms would
+// do).  Chains cannot be split, but their runs can be cut in time: a task is
+// (group of 32 chains, segment of ~128 steps).  A persistent grid of one-warp
+// CTAs fills every warp slot of the machine; each warp takes a ticket, waits
+// for that ticket's entry in a ring of ready groups, runs the segment with the
+// state in registers, writes the state back and pushes the group for its next
+// segment.  Tickets are served first-in first-out, so idleness rotates over
+// all warps and every scheduler sees the same mean number of busy warps.
+// The chains themselves do not change: the random stream of a step depends on
+// (chain, step) only, so results are bit-identical to the static kernel.
+//
+// Progress: ticket k waits for the k-th push; pushes come from segments of
+// lower tickets, which are held by running warps and never wait once started,
+// so the scheme cannot deadlock even if part of the grid is not resident.
+// Every wait is bounded (clock64 budget); running out of it traps (the launch fails with a CUDA error).
+#pragma once
+#include "mcmc_kernel_dev.cuh"
+
+namespace mg {
+
+#ifndef MG_MHB_MAXNREG
+#define MG_MHB_MAXNREG(D) MG_MH_MAXNREG(D)
+#endif
+
+struct MhQueue {
+  unsigned long long *ring;  // [cap]: (ticket + 1) << 32 | group; 0 = empty
+  unsigned int *ctr;         // [0] next pop ticket, [1] next push ticket
+  int32_t *seg_next;         // [ngroups] next segment of each group
+  long long *prof;           // debug: [grid][4] cycles waiting / loading / stepping / releasing, or null
+  uint32_t cap;              // power of two >= 2 * ngroups
+  uint32_t ngroups;
+  uint32_t total;            // ngroups * nseg tickets
+  int32_t nseg;              // nseg_burn + nseg_rec
+  int32_t nseg_burn;         // segments of seg_steps burn-in steps (the last one records slot 0)
+  int64_t seg_steps;         // steps per burn-in segment
+  int64_t seg_slots;         // recorded samples per sampling segment (nskip steps each)
+};
+
+constexpr long long kQueueWaitCycles = 1ll << 33;  // ~4 s at 2 GHz
+
+static __global__ void mh_queue_init_kernel(MhQueue q) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < q.cap) q.ring[i] = (i < q.ngroups) ? (((unsigned long long)(i + 1u) << 32) | i) : 0ull;
+  if (i < q.ngroups) q.seg_next[i] = 0;
+  if (i == 0) { q.ctr[0] = 0u; q.ctr[1] = q.ngroups; }
+}
+
+template <class Like, class Prior, class Prop, int D>
+__global__ void __maxnreg__(MG_MHB_MAXNREG(D))
+mh_balanced_kernel(const __grid_constant__ MhArgs<Like, Prior, Prop, D> a, const __grid_constant__ MhQueue q) {
+  static_assert(MH_BLOCK == 32, "one warp per CTA");
+  const int dd = Prop::kStaticDim ? D : a.d;
+  const int F = dd + 2;
+  const int64_t C = a.C;
+  __shared__ __align__(16) double smem_params[Like::kSmem + Prior::kSmem + Prop::kSmem + 2];
+  double *sl = smem_params, *sp = sl + Like::kSmem, *sj = sp + Prior::kSmem;
+  if (Like::kSmem + Prior::kSmem + Prop::kSmem > 0) {
+    const double *gl = reinterpret_cast<const double *>(&a.like);
+    const double *gp = reinterpret_cast<const double *>(&a.prior);
+    const double *gj = reinterpret_cast<const double *>(&a.prop);
+    for (int k = threadIdx.x; k < Like::kSmem; k += MH_BLOCK) sl[k] = gl[k];
+    for (int k = threadIdx.x; k < Prior::kSmem; k += MH_BLOCK) sp[k] = gp[k];
+    for (int k = threadIdx.x; k < Prop::kSmem; k += MH_BLOCK) sj[k] = gj[k];
+    __syncwarp();
+  }
+  const unsigned lane = threadIdx.x;
+  const int64_t sample_stride = (int64_t)F * C;
+  for (;;) {
+    // ---- take a ticket and wait for its group
+    const long long tp0 = clock64();
+    unsigned long long e = 0ull;
+    if (lane == 0) {
+      const unsigned ticket = atomicAdd(&q.ctr[0], 1u);
+      if (ticket >= q.total) {
+        e = ~0ull;
+      } else {
+        volatile unsigned long long *slot = q.ring + (ticket & (q.cap - 1u));
+        const unsigned long long want = (unsigned long long)ticket + 1ull;
+        const long long t_begin = clock64();
+        unsigned ns = 64;
+        for (;;) {
+          e = *slot;
+          if ((e >> 32) == want) break;
+          __nanosleep(ns);
+          if (ns < 2048) ns *= 2;
+          if (clock64() - t_begin > kQueueWaitCycles) __trap();
+        }
+        if (e != ~0ull) *slot = 0ull;
+        __threadfence();
+      }
+    }
+    e = __shfl_sync(0xffffffffu, e, 0);
+    if (e == ~0ull) break;
+    const uint32_t grp = (uint32_t)e;
+    const long long tp1 = clock64();
+    int64_t c = (int64_t)grp * MH_BLOCK + lane;
+    const bool live = c < C;
+    if (!live) c = C - 1;
+    const uint64_t g = a.chain_offset + (uint64_t)c;
+    const int32_t k = __ldcg(q.seg_next + grp);
+
+    // ---- state into registers
+    double x[D];
+#pragma unroll
+    for (int i = 0; i < D; ++i) x[i] = (i < dd) ? __ldcg(a.state + (int64_t)i * C + c) : 0.0;
+    double ll, lp;
+    if (k == 0) {  // mcmc.ml:59-61: the start point is evaluated, not trusted
+      ll = Like::template eval<D>(a.like, sl, x, dd);
+      lp = Prior::template eval<D>(a.prior, sp, x, dd);
+    } else {
+      ll = __ldcg(a.state + (int64_t)dd * C + c);
+      lp = __ldcg(a.state + (int64_t)(dd + 1) * C + c);
+    }
+    // slot j of the output holds the state after nbin + j * nskip steps (mcmc.ml:63-71); a continuation launch
+    // (record_first == 0) owns slots 1.. only and its block starts at slot 1
+    double *out = (a.samples && live) ? a.samples + c - (a.record_first ? 0 : sample_stride) : nullptr;
+    auto record = [&]() {
+      if (out) {
+#pragma unroll
+        for (int i = 0; i < D; ++i)
+          if (i < dd) __stcs(out + (int64_t)i * C, x[i]);
+        __stcs(out + (int64_t)dd * C, ll);
+        __stcs(out + (int64_t)(dd + 1) * C, lp);
+        out += sample_stride;
+      }
+    };
+    const long long tp2 = clock64();
+    int nacc = 0;
+    uint64_t t;
+    if (k < q.nseg_burn) {  // :63-65 burn-in, nothing recorded until its last step
+      const int64_t s0 = (int64_t)k * q.seg_steps;
+      const int64_t s1 = (s0 + q.seg_steps < a.nbin) ? s0 + q.seg_steps : a.nbin;
+      t = a.t0 + (uint64_t)s0;
+      for (int64_t s = s0; s < s1; ++s, ++t) {
+        Rng r(a.key, P_MH, g, t, &a.rk);
+        nacc += mh_step<Like, Prior, Prop, D>(a, sl, sp, sj, r, x, ll, lp);
+      }
+      if (s1 == a.nbin && a.n > 0 && a.record_first) record();  // :66 slot 0
+    } else {                // :67-71 nskip steps, then a sample
+      const int64_t j = k - q.nseg_burn;
+      const int64_t slot0 = 1 + j * q.seg_slots;
+      const int64_t slot1 = (slot0 + q.seg_slots < a.n) ? slot0 + q.seg_slots : a.n;
+      if (a.nbin == 0 && j == 0 && a.n > 0 && a.record_first) record();  // no burn-in: slot 0 is the start point
+      if (out) out = a.samples + c + (slot0 - (a.record_first ? 0 : 1)) * sample_stride;
+      t = a.t0 + (uint64_t)(a.nbin + (slot0 - 1) * a.nskip);
+      for (int64_t slot = slot0; slot < slot1; ++slot) {
+        for (int64_t kk = 0; kk < a.nskip; ++kk, ++t) {
+          Rng r(a.key, P_MH, g, t, &a.rk);
+          nacc += mh_step<Like, Prior, Prop, D>(a, sl, sp, sj, r, x, ll, lp);
+        }
+        record();
+      }
+    }
+
+    const long long tp3 = clock64();
+    // ---- state back, group released for its next segment
+    if (live) {
+#pragma unroll
+      for (int i = 0; i < D; ++i)
+        if (i < dd) a.state[(int64_t)i * C + c] = x[i];
+      a.state[(int64_t)dd * C + c] = ll;
+      a.state[(int64_t)(dd + 1) * C + c] = lp;
+      if (a.accept && nacc) atomicAdd(a.accept + c, nacc);
+    }
+    __threadfence();
+    __syncwarp();
+    if (lane == 0 && k + 1 < q.nseg) {
+      q.seg_next[grp] = k + 1;
+      __threadfence();
+      const unsigned t2 = atomicAdd(&q.ctr[1], 1u);
+      volatile unsigned long long *slot2 = q.ring + (t2 & (q.cap - 1u));
+      const long long t_begin = clock64();
+      while (*slot2 != 0ull) {
+        __nanosleep(64);
+        if (clock64() - t_begin > kQueueWaitCycles) __trap();
+      }
+      *slot2 = (((unsigned long long)t2 + 1ull) << 32) | grp;
+    }
+    __syncwarp();
+    if (q.prof && lane == 0) {
+      long long *pr = q.prof + (size_t)blockIdx.x * 4;
+      pr[0] += tp1 - tp0; pr[1] += tp2 - tp1; pr[2] += tp3 - tp2; pr[3] += clock64() - tp3;
+    }
+  }
+}
+
+}  // namespace mg

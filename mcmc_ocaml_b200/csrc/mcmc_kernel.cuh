@@ -6,12 +6,85 @@
 #include "common.cuh"
 #include "host_plugins.hpp"
 #include "mcmc_kernel_dev.cuh"
+#include "mcmc_balanced.cuh"
+
+#include <algorithm>
+#include <cstdlib>
+#include <cstdio>
+#include <vector>
 
 namespace mg {
 
+// Steps per task of the balanced kernel: long enough that the state round trip
+// (2 x (D+2) doubles per chain) and the queue traffic vanish, short enough that
+// a run has many tasks per group to even out.
+constexpr int64_t kSegSteps = 128;
+
 template <class Like, class Prior, class Prop, int D>
 static int launch_mh(mg_ctx *ctx, const MhArgs<Like, Prior, Prop, D> &a) {
-  const int64_t grid = (a.C + MH_BLOCK - 1) / MH_BLOCK;
+  const int64_t ngroups = (a.C + MH_BLOCK - 1) / MH_BLOCK;
+  const int64_t total_steps = a.nbin + (a.n > 0 ? (a.n - 1) * a.nskip : 0);
+  static const bool want_balanced = [] { const char *e = getenv("MCMC_GPU_MH_BALANCED"); return e ? atoi(e) != 0 : true; }();
+  // Dynamic hand-out pays when the warps do not divide evenly over the schedulers.  The persistent grid holds the
+  // largest whole number of warps per scheduler that the ensemble can keep busy all the time (no warp ever waits for
+  // work until the tail: a polling warp on a saturated scheduler is starved by the arbiter and picks its group up late).
+  const int64_t nsched = (int64_t)ctx->sm_count * 4;
+  if (want_balanced && total_steps >= 4 * kSegSteps && ngroups > nsched && ngroups < (1ll << 30)) {
+    int occ = 0;
+    MG_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, mh_balanced_kernel<Like, Prior, Prop, D>, MH_BLOCK, 0));
+    int64_t grid = std::min<int64_t>((int64_t)std::max(occ, 1) * ctx->sm_count, (ngroups / nsched) * nsched);
+    if (const char *e = getenv("MCMC_GPU_MH_GRID")) grid = std::max(1, atoi(e));
+    if (grid != ngroups) {
+    MhQueue q;
+    q.seg_steps = kSegSteps;
+    if (const char *e = getenv("MCMC_GPU_MH_SEG")) q.seg_steps = std::max(1, atoi(e));
+    const int64_t nrec = a.n > 1 ? a.n - 1 : 0;   // slots 1 .. n-1
+    int64_t nseg;
+    for (;; q.seg_steps *= 2) {
+      q.seg_slots = std::max<int64_t>(1, q.seg_steps / a.nskip);
+      q.nseg_burn = (int32_t)((a.nbin + q.seg_steps - 1) / q.seg_steps);
+      nseg = q.nseg_burn + (nrec + q.seg_slots - 1) / q.seg_slots;
+      if (ngroups * nseg + grid < 0xFFFFFFF0ll) break;
+    }
+    q.nseg = (int32_t)nseg;
+    q.ngroups = (uint32_t)ngroups;
+    q.total = (uint32_t)(ngroups * nseg);
+    if (getenv("MCMC_GPU_DEBUG")) fprintf(stderr, "mh_balanced: occ %d grid %lld groups %lld seg %lld nseg %d\n", occ, (long long)grid, (long long)ngroups, (long long)q.seg_steps, q.nseg);
+    q.cap = 1u;
+    while (q.cap < 2u * q.ngroups) q.cap <<= 1;
+    DevBuf<unsigned long long> ring;
+    DevBuf<unsigned int> ctr;
+    DevBuf<int32_t> seg_next;
+    MG_CUDA(ctx, ring.alloc(q.cap, ctx->stream));
+    MG_CUDA(ctx, ctr.alloc(2, ctx->stream));
+    MG_CUDA(ctx, seg_next.alloc(q.ngroups, ctx->stream));
+    q.ring = ring.get(); q.ctr = ctr.get(); q.seg_next = seg_next.get();
+    DevBuf<long long> prof;
+    q.prof = nullptr;
+    if (getenv("MCMC_GPU_DEBUG")) {
+      MG_CUDA(ctx, prof.alloc((size_t)grid * 4, ctx->stream));
+      MG_CUDA(ctx, cudaMemsetAsync(prof.get(), 0, sizeof(long long) * grid * 4, ctx->stream));
+      q.prof = prof.get();
+    }
+    mh_queue_init_kernel<<<(q.cap + 255u) / 256u, 256, 0, ctx->stream>>>(q);
+    MG_CHECK_LAUNCH(ctx);
+    time_begin(ctx);
+    mh_balanced_kernel<Like, Prior, Prop, D><<<(unsigned)grid, MH_BLOCK, 0, ctx->stream>>>(a, q);
+    MG_CHECK_LAUNCH(ctx);
+    time_end(ctx);
+    if (q.prof) {
+      std::vector<long long> h((size_t)grid * 4);
+      MG_CUDA(ctx, cudaMemcpyAsync(h.data(), q.prof, sizeof(long long) * grid * 4, cudaMemcpyDeviceToHost, ctx->stream));
+      MG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+      double sum[4] = {0, 0, 0, 0}, mx[4] = {0, 0, 0, 0};
+      for (int64_t w = 0; w < grid; ++w) for (int i = 0; i < 4; ++i) { sum[i] += (double)h[w * 4 + i]; mx[i] = std::max(mx[i], (double)h[w * 4 + i]); }
+      fprintf(stderr, "mh_balanced: mean cycles/warp wait %.3g load %.3g step %.3g release %.3g | max %.3g %.3g %.3g %.3g\n",
+              sum[0] / grid, sum[1] / grid, sum[2] / grid, sum[3] / grid, mx[0], mx[1], mx[2], mx[3]);
+    }
+    return MG_OK;  // queue buffers are freed stream-ordered after the kernel
+    }
+  }
+  const int64_t grid = ngroups;
   time_begin(ctx);
   mh_ensemble_kernel<Like, Prior, Prop, D><<<(unsigned)grid, MH_BLOCK, 0, ctx->stream>>>(a);
   MG_CHECK_LAUNCH(ctx);

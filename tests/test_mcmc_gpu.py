@@ -208,3 +208,18 @@ def test_combine_jump_proposals(ctx, og):
     assert np.array_equal(got.block[:, :D, :], want[:, :D, :])    # symmetric components: log q = log(sum p) = 0 terms cancel exactly
     with pytest.raises(InvalidArgument):
         mcmc.mcmc_array(10, like, prior, P.Proposal(5, 1, [2.0, 1.0, 0.0, 2.0]), [0.0], ctx=ctx)   # truncated block
+
+
+@pytest.mark.parametrize("D,nbin,nskip,n", [(10, 100, 3, 200), (10, 0, 1, 600), (3, 700, 2, 1), (12, 130, 1, 520)])
+def test_balanced_kernel_bit_exact(ctx, og, D, nbin, nskip, n):
+    """Ensembles of more than one warp per scheduler and >= 512 steps take the
+    dynamically balanced kernel (csrc/mcmc_balanced.cuh): the run of each group of
+    32 chains is cut into segments handed out through a device-side queue.  The
+    chains must not notice: same values as the oracle, ragged last group included."""
+    mu, like, prior, prop = corr_model(D)
+    C = 592 * 32 + 1000 + 7                      # 624 groups: one more than the schedulers, last one ragged
+    ctx.set_seed(0xBA1A)
+    got = mcmc.mcmc_array(n, like, prior, prop, mu, nchains=C, nbin=nbin, nskip=nskip, ctx=ctx)
+    want, acc, rej = og.mcmc_array(0xBA1A, 0, n, like, prior, prop, mu, nchains=C, nbin=nbin, nskip=nskip, nthreads=16)
+    assert np.array_equal(got.block, want)
+    assert np.array_equal(got.accept, acc) and np.array_equal(got.reject, rej)
