@@ -1,5 +1,7 @@
 // host_plugins.hpp -- host-side validation / upload of plugin specs.
 #pragma once
+#include <cmath>
+#include <vector>
 #include "common.cuh"
 #include "models.cuh"
 
@@ -76,8 +78,18 @@ inline int validate_proposal(mg_ctx *ctx, const mg_proposal *f, int dim) {
 struct DevLogFn {
   DevBuf<double> buf;
   DynFnParams params{};
+  // Values that depend on the parameters only are evaluated here, once, and appended after the nparams user values
+  // (models.cuh reads them at p + np): log sigma of SHELL, log sigma_i of GAUSS_DIAG and GAUSS_MIX.
   cudaError_t upload_from(const mg_logfn *f, cudaStream_t s) {
-    cudaError_t e = upload(buf, f->params, (size_t)f->nparams, s);
+    std::vector<double> blob(f->params, f->params + f->nparams);
+    const int d = f->dim;
+    if (f->kind == MG_FN_SHELL) blob.push_back(std::log(f->params[d + 1]));
+    else if (f->kind == MG_FN_GAUSS_DIAG) for (int i = 0; i < d; ++i) blob.push_back(std::log(f->params[d + i]));
+    else if (f->kind == MG_FN_GAUSS_MIX) {
+      const int K = (int)f->params[0];
+      for (int i = 0; i < d; ++i) blob.push_back(std::log(f->params[1 + K * d + i]));
+    }
+    cudaError_t e = upload(buf, blob.data(), blob.size(), s);   // pageable source: staged before the call returns
     params.kind = f->kind; params.dim = f->dim; params.scale = f->scale;
     params.p = buf.get(); params.np = f->nparams;
     return e;

@@ -209,12 +209,13 @@ struct DynFnParams {
 };
 
 template <int DMAX>
-__device__ __forceinline__ double dyn_log_multi_gaussian(const double *mu, const double *sigma,
+__device__ __forceinline__ double dyn_log_multi_gaussian(const double *mu, const double *sigma, const double *log_sigma,
                                                          const double (&x)[DMAX], int d) {
+  // log sigma_i does not depend on x: it is evaluated once on the host (host_plugins.hpp appends it to the blob)
   double result = 0.0;  // stats.ml:103-108
 #pragma unroll (DMAX <= 16 ? DMAX : 1)
   for (int i = 0; i < DMAX; ++i)
-    if (i < d) result = result + log_gaussian(__ldg(mu + i), __ldg(sigma + i), x[i]);
+    if (i < d) result = result + log_gaussian_ls(__ldg(mu + i), __ldg(sigma + i), __ldg(log_sigma + i), x[i]);
   return result + 0.0;
 }
 
@@ -228,20 +229,24 @@ struct DynFn {
       case MG_FN_ZERO: return 0.0;
       case MG_FN_CONST: return __ldg(p);
       case MG_FN_BOX_CLOSED: {  // bin/gaussian_cauchy_efficiency.ml:60-67
-        bool out = false;
+        // no short circuit: the 2 d bounds are independent loads and the comparisons combine bitwise
+        // (same truth value; a short-circuit chain serialises the loads behind the predicates)
+        int out = 0;
 #pragma unroll (DMAX <= 16 ? DMAX : 1)
         for (int i = 0; i < DMAX; ++i)
-          if (i < d) out = out || (x[i] < __ldg(p + i)) || (x[i] > __ldg(p + d + i));
-        return out ? neg_inf() : __ldg(p + 2 * d);
+          if (i < d) { const double lo = __ldg(p + i), hi = __ldg(p + d + i); out |= (int)(x[i] < lo) | (int)(x[i] > hi); }
+        const double inside = __ldg(p + 2 * d);
+        return out ? neg_inf() : inside;
       }
       case MG_FN_BOX_OPEN: {  // test/nested_test.ml:24-28
-        bool in = true;
+        int in = 1;
 #pragma unroll (DMAX <= 16 ? DMAX : 1)
         for (int i = 0; i < DMAX; ++i)
-          if (i < d) in = in && (x[i] > __ldg(p + i)) && (x[i] < __ldg(p + d + i));
-        return in ? __ldg(p + 2 * d) : neg_inf();
+          if (i < d) { const double lo = __ldg(p + i), hi = __ldg(p + d + i); in &= (int)(x[i] > lo) & (int)(x[i] < hi); }
+        const double inside = __ldg(p + 2 * d);
+        return in ? inside : neg_inf();
       }
-      case MG_FN_GAUSS_DIAG: return dyn_log_multi_gaussian<DMAX>(p, p + d, x, d);
+      case MG_FN_GAUSS_DIAG: return dyn_log_multi_gaussian<DMAX>(p, p + d, p + f.np, x, d);
       case MG_FN_GAUSS_CORR: {
         const double *mu = p, *L = p + d;
         double z[DMAX];
@@ -277,12 +282,12 @@ struct DynFn {
 #pragma unroll (DMAX <= 16 ? DMAX : 1)
         for (int i = 0; i < DMAX; ++i)
           if (i < d) { const double dx = x[i] - __ldg(p + i); s = s + dx * dx; }
-        return log_gaussian(__ldg(p + d), __ldg(p + d + 1), sqrt(s));
+        return log_gaussian_ls(__ldg(p + d), __ldg(p + d + 1), __ldg(p + f.np), sqrt(s));  // [np] = log sigma (host)
       }
       case MG_FN_GAUSS_MIX: {  // test/nested_test.ml:47-53
         const int K = (int)__ldg(p);
         double tot = 0.0;
-        for (int k = 0; k < K; ++k) tot = tot + exp(dyn_log_multi_gaussian<DMAX>(p + 1 + k * d, p + 1 + K * d, x, d));
+        for (int k = 0; k < K; ++k) tot = tot + exp(dyn_log_multi_gaussian<DMAX>(p + 1 + k * d, p + 1 + K * d, p + f.np, x, d));
         return log(tot);
       }
     }

@@ -19,6 +19,8 @@
 #include "radix_sort.cuh"
 #include "reduce_sum.cuh"
 
+#include <cuda_pipeline.h>
+
 #include <algorithm>
 #include <cmath>
 
@@ -53,55 +55,184 @@ __global__ void nest_init_kernel(NestArgs a, double *__restrict__ x_out, double 
   lp_out[i] = DynFn::eval<DMAX>(a.prior, nullptr, x, a.D);
 }
 
-// draw_new_live_point (nested.ml:50-74), one thread per replacement chain
-template <int DMAX>
-__global__ void nest_replace_kernel(NestArgs a) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= a.K) return;
-  const uint64_t rid = (uint64_t)(a.R + j);
-  Rng rs(a.key, P_NEST_START, rid, 0);
-  // livepts.(Random.int nlive) (:63); with K > 1 the start must satisfy the common threshold
-  const int start = (a.K - 1) + (int)rs.below((uint64_t)(a.nlive - a.K + 1));
-  double x[DMAX], y[DMAX];
-#pragma unroll (DMAX <= 16 ? DMAX : 1)
-  for (int d = 0; d < DMAX; ++d) x[d] = (d < a.D) ? a.live_x[(int64_t)start * a.D + d] : 0.0;
+// draw_new_live_point (nested.ml:50-74) in two kernels.
+//
+// A step of the constrained chain is: a differential-evolution proposal (two
+// live-point indices, a scale that is 1 or a Gaussian draw -- mcmc.ml:198-218),
+// the likelihood of the proposed point, and the accept test.  Only the last
+// two depend on the chain's state; the proposal's random part does not.  With
+// one batch of K chains the kernel is latency-bound (K = 8,192 is 256 warps
+// on 592 schedulers, nmcmc strictly sequential steps), so what counts is the
+// length of the dependent path per step.  nest_propose_kernel therefore draws
+// the random part of every (chain, step) up front, one thread each, at full
+// occupancy; nest_replace_kernel then walks the steps with the two live rows
+// of step s+1 already in flight while step s computes, leaving
+// y = x + delta, the log-likelihood and the comparison on the critical path.
+// Same Philox stream, same draw order per (chain, step), same arithmetic:
+// output identical to the single-kernel form.
+constexpr int NEST_BLOCK = 32;   // threads per CTA of nest_replace_kernel
+constexpr int kSR = 4;           // stages of the proposal-scalar ring (step s reads s and s+1, writes s+2)
+// doubles per staged live row: 16-byte aligned and an odd number of 16-byte units when D % 4 == 0 (conflict-free
+// 128-bit reads by the row's owner); odd D: an odd number of doubles
+__host__ __device__ constexpr int nest_row_stride(int D) { return (D % 2 == 0) ? D + 2 : (D | 1); }
+
+struct NestProp {
+  int32_t *i0, *j0;   // [S][K] live-set rows x, y of the proposal  (mcmc.ml:201-202)
+  double *ds;         // [S][K] scale d                             (:209-213)
+  double *u;          // [S][K] Random.float 1.0 of the accept test (mcmc.ml:47)
+};
+
+__global__ void nest_propose_kernel(NestArgs a, NestProp p, int s0, int S) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)S * a.K) return;
+  const int s = (int)(idx / a.K), j = (int)(idx % a.K);
+  Rng r(a.key, P_NEST_MCMC, (uint64_t)(a.R + j), (uint64_t)(s0 + s));
+  const uint64_t n = (uint64_t)a.nlive;
+  const uint64_t i0 = r.below(n);
+  uint64_t j0;
+  do { j0 = r.below(n); } while (j0 == i0);
+  double dscale;
+  if (a.mode_hop != 0.0 && r.uniform() < a.mode_hop) dscale = 1.0;
+  else dscale = draw_gaussian(r, 0.0, a.de_sigma);
+  p.i0[idx] = (int32_t)i0; p.j0[idx] = (int32_t)j0; p.ds[idx] = dscale; p.u[idx] = r.uniform();
+}
+
+// chain_x [DMAX][K], chain_cl [K]: chain state between launches when nmcmc is walked in several chunks.
+// kFull: the run-time dimension equals DMAX, every `d < D` guard folds away.
+//
+// One warp per CTA, one thread per chain.  The two live rows a step needs are gathered by the WARP, not by the
+// thread: consecutive lanes copy consecutive 16-byte (8-byte when D is odd) pieces of a row straight into shared
+// memory with cp.async, so a 128-byte row costs one line request instead of sixteen 8-byte requests from one lane
+// (thread-per-row loads kept the L1 tag stage busy for ~1,000 cycles per step and every later load queued behind
+// them).  Rows of step s+1 and scalars of step s+2 are in flight while step s computes.
+template <int DMAX, bool kFull>
+__global__ void nest_replace_kernel(NestArgs a, NestProp p, int s0, int s1, int first, int last, double *chain_x,
+                                    double *chain_cl) {
+  extern __shared__ __align__(16) double s_rows[];            // [2 stages][2 * NEST_BLOCK rows][RS]
+  __shared__ int32_t s_i0[kSR][NEST_BLOCK], s_j0[kSR][NEST_BLOCK];
+  __shared__ double s_ds[kSR][NEST_BLOCK], s_u[kSR][NEST_BLOCK];
+  const int tx = threadIdx.x;
+  const int K = a.K;
+  const int jr = blockIdx.x * NEST_BLOCK + tx;
+  const bool live = jr < K;
+  const int j = live ? jr : K - 1;     // the whole warp takes part in the row copies; spare lanes shadow the last chain
+  const int D = kFull ? DMAX : a.D;
+  const bool vec = (D % 2) == 0;       // 16-byte pieces need even D (row starts are then 16-byte aligned)
+  const int RS = nest_row_stride(D);   // doubles per staged row
   const double thr = a.threshold;
   auto mcmc_logl = [&](const double (&pt)[DMAX]) {           // :54-59
-    const double l = DynFn::eval<DMAX>(a.like, nullptr, pt, a.D);
-    return (l >= thr) ? DynFn::eval<DMAX>(a.prior, nullptr, pt, a.D) : neg_inf();
+    // both evaluated (they are pure and independent), then selected: nothing waits behind a branch
+    const double l = DynFn::eval<DMAX>(a.like, nullptr, pt, D);
+    const double pr = DynFn::eval<DMAX>(a.prior, nullptr, pt, D);
+    return (l >= thr) ? pr : neg_inf();
   };
-  double cl = mcmc_logl(x);
-  const double cp = 0.0;                                     // mcmc_logp, :60
-  for (int s = 0; s < a.nmcmc; ++s) {                        // :65-67
-    Rng r(a.key, P_NEST_MCMC, rid, (uint64_t)s);
-    // differential_evolution_proposal (mcmc.ml:198-218)
-    const uint64_t n = (uint64_t)a.nlive;
-    const uint64_t i0 = r.below(n);
-    uint64_t j0;
-    do { j0 = r.below(n); } while (j0 == i0);
-    double dscale;
-    if (a.mode_hop != 0.0 && r.uniform() < a.mode_hop) dscale = 1.0;
-    else dscale = draw_gaussian(r, 0.0, a.de_sigma);
-    const double *px = a.live_x + (int64_t)i0 * a.D, *py = a.live_x + (int64_t)j0 * a.D;
+  double x[DMAX], y[DMAX], delta[DMAX];
+  double cl;
+  if (first) {
+    Rng rs(a.key, P_NEST_START, (uint64_t)(a.R + j), 0);
+    // livepts.(Random.int nlive) (:63); with K > 1 the start must satisfy the common threshold
+    const int start = (a.K - 1) + (int)rs.below((uint64_t)(a.nlive - a.K + 1));
 #pragma unroll (DMAX <= 16 ? DMAX : 1)
-    for (int d = 0; d < DMAX; ++d) y[d] = (d < a.D) ? x[d] + dscale * (__ldg(py + d) - __ldg(px + d)) : 0.0;
+    for (int d = 0; d < DMAX; ++d) x[d] = (d < D) ? a.live_x[(int64_t)start * D + d] : 0.0;
+    cl = mcmc_logl(x);
+  } else {
+#pragma unroll (DMAX <= 16 ? DMAX : 1)
+    for (int d = 0; d < DMAX; ++d) x[d] = (d < D) ? chain_x[(int64_t)d * K + j] : 0.0;
+    cl = chain_cl[j];
+  }
+  const double cp = 0.0;                                     // mcmc_logp, :60
+  const int S = s1 - s0;
+  auto fetch_scalars = [&](int t) {    // own column of the scalar ring
+    if (t < S) {
+      const int64_t q = (int64_t)t * K + j;
+      const int st = t % kSR;
+      __pipeline_memcpy_async(&s_i0[st][tx], p.i0 + q, 4);
+      __pipeline_memcpy_async(&s_j0[st][tx], p.j0 + q, 4);
+      __pipeline_memcpy_async(&s_ds[st][tx], p.ds + q, 8);
+      __pipeline_memcpy_async(&s_u[st][tx], p.u + q, 8);
+    }
+  };
+  auto fetch_rows = [&](int t) {       // rows x (0..31) and y (32..63) of all the warp's chains for step t
+    if (t < S) {
+      const int st = t % kSR;
+      double *dst = s_rows + (size_t)(t & 1) * (2 * NEST_BLOCK) * RS;
+      if (vec) {
+        const int cpr = D / 2;         // 16-byte pieces per row
+#pragma unroll (kFull && DMAX <= 16 ? DMAX : 1)
+        for (int it = 0; it < 2 * cpr; ++it) {
+          const int c = tx + it * NEST_BLOCK;
+          const int row = c / cpr, k = c - row * cpr;
+          const int idx = (row < NEST_BLOCK) ? s_i0[st][row] : s_j0[st][row - NEST_BLOCK];
+          __pipeline_memcpy_async(dst + (size_t)row * RS + 2 * k, a.live_x + (int64_t)idx * D + 2 * k, 16);
+        }
+      } else {
+        for (int c = tx; c < 2 * NEST_BLOCK * D; c += NEST_BLOCK) {
+          const int row = c / D, k = c - row * D;
+          const int idx = (row < NEST_BLOCK) ? s_i0[st][row] : s_j0[st][row - NEST_BLOCK];
+          __pipeline_memcpy_async(dst + (size_t)row * RS + k, a.live_x + (int64_t)idx * D + k, 8);
+        }
+      }
+    }
+  };
+  // prologue: scalars of steps 0 and 1, then rows of step 0
+  fetch_scalars(0); fetch_scalars(1);
+  __pipeline_commit();
+  __pipeline_wait_prior(0);
+  __syncwarp();
+  fetch_rows(0);
+  __pipeline_commit();
+  for (int s = 0; s < S; ++s) {                              // :65-67
+    __pipeline_wait_prior(0);          // rows of step s, scalars of step s+1
+    __syncwarp();
+    // delta = d * (y_row - x_row), mcmc.ml:214-216; own rows out of the staging buffer
+    const int st = s % kSR;
+    const double ds = s_ds[st][tx], u_cur = s_u[st][tx];
+    {
+      const double *rx = s_rows + (size_t)(s & 1) * (2 * NEST_BLOCK) * RS + (size_t)tx * RS;
+      const double *ry = rx + (size_t)NEST_BLOCK * RS;
+      if (kFull) {
+        const double2 *rx2 = reinterpret_cast<const double2 *>(rx), *ry2 = reinterpret_cast<const double2 *>(ry);
+#pragma unroll (DMAX <= 16 ? DMAX / 2 : 1)
+        for (int d = 0; d < DMAX / 2; ++d) {
+          const double2 vx = rx2[d], vy = ry2[d];
+          delta[2 * d] = ds * (vy.x - vx.x); delta[2 * d + 1] = ds * (vy.y - vx.y);
+        }
+      } else {
+#pragma unroll (DMAX <= 16 ? DMAX : 1)
+        for (int d = 0; d < DMAX; ++d) delta[d] = (d < D) ? ds * (ry[d] - rx[d]) : 0.0;
+      }
+    }
+    fetch_rows(s + 1);                 // into the other stage: its last readers passed the barrier above
+    fetch_scalars(s + 2);
+    __pipeline_commit();
     // make_mcmc_sampler (mcmc.ml:37-56) with the closures of :54-61
+#pragma unroll (DMAX <= 16 ? DMAX : 1)
+    for (int d = 0; d < DMAX; ++d) y[d] = (d < D) ? x[d] + delta[d] : 0.0;
     const double start_log_post = cl + cp;
     const double proposed_like = mcmc_logl(y);
     const double proposed_log_posterior = proposed_like + 0.0;
     const double log_accept_prob = proposed_log_posterior - start_log_post + 0.0 - 0.0;
-    if (log_u_less_than(r.uniform(), log_accept_prob)) {
+    if (log_u_less_than(u_cur, log_accept_prob)) {
 #pragma unroll (DMAX <= 16 ? DMAX : 1)
       for (int d = 0; d < DMAX; ++d) x[d] = y[d];
       cl = proposed_like;
     }
   }
-  const double nl = DynFn::eval<DMAX>(a.like, nullptr, x, a.D);   // :68-69
-  const double np = DynFn::eval<DMAX>(a.prior, nullptr, x, a.D);
+  __pipeline_wait_prior(0);
+  if (!live) return;
+  if (!last) {
+#pragma unroll (DMAX <= 16 ? DMAX : 1)
+    for (int d = 0; d < DMAX; ++d)
+      if (d < D) chain_x[(int64_t)d * K + j] = x[d];
+    chain_cl[j] = cl;
+    return;
+  }
+  const double nl = DynFn::eval<DMAX>(a.like, nullptr, x, D);   // :68-69
+  const double np = DynFn::eval<DMAX>(a.prior, nullptr, x, D);
   if (!(nl >= thr)) *a.fail = 1;                                   // :70-72
 #pragma unroll (DMAX <= 16 ? DMAX : 1)
   for (int d = 0; d < DMAX; ++d)
-    if (d < a.D) a.fresh_x[(int64_t)j * a.D + d] = x[d];
+    if (d < D) a.fresh_x[(int64_t)j * D + d] = x[d];
   a.fresh_ll[j] = nl; a.fresh_lp[j] = np;
 }
 
@@ -330,6 +461,14 @@ extern "C" int mg_nested_evidence(mg_ctx *ctx, const mg_logfn *like, const mg_lo
   MG_CUDA(ctx, keys.alloc(nlive, s)); MG_CUDA(ctx, order.alloc(nlive, s));
   MG_CUDA(ctx, d_fail.alloc(1, s));
   MG_CUDA(ctx, cudaMemsetAsync(d_fail.get(), 0, sizeof(int), s));
+  // proposals of one chunk of steps for all K chains (24 B each): at most ~200 MB
+  const int chunk = std::max(1, std::min(std::max(cfg->nmcmc, 1), std::max(16, (1 << 23) / K)));
+  DevBuf<int32_t> pi0, pj0;
+  DevBuf<double> pds, pu, chain_x, chain_cl;
+  MG_CUDA(ctx, pi0.alloc((size_t)chunk * K, s)); MG_CUDA(ctx, pj0.alloc((size_t)chunk * K, s));
+  MG_CUDA(ctx, pds.alloc((size_t)chunk * K, s)); MG_CUDA(ctx, pu.alloc((size_t)chunk * K, s));
+  MG_CUDA(ctx, chain_x.alloc((size_t)64 * K, s)); MG_CUDA(ctx, chain_cl.alloc(K, s));
+  NestProp prop{pi0.get(), pj0.get(), pds.get(), pu.get()};
 
   NestArgs a{};
   a.like = dl.params; a.prior = dp.params; a.plo = d_plo.get(); a.phi = d_phi.get();
@@ -347,6 +486,27 @@ extern "C" int mg_nested_evidence(mg_ctx *ctx, const mg_logfn *like, const mg_lo
     else if (D <= 16) KERNEL<16><<<GRID, BLOCK, 0, s>>>(__VA_ARGS__);                \
     else if (D <= 32) KERNEL<32><<<GRID, BLOCK, 0, s>>>(__VA_ARGS__);                \
     else KERNEL<64><<<GRID, BLOCK, 0, s>>>(__VA_ARGS__);                             \
+  } while (0)
+
+  const size_t row_smem = (size_t)2 * 2 * NEST_BLOCK * nest_row_stride(D) * sizeof(double);
+#define MG_NEST_CASE2(KERNEL, DM, GRID, BLOCK, ...)                                  \
+  do {                                                                               \
+    if (D == DM) {                                                                   \
+      if (row_smem > 48 * 1024) MG_CUDA(ctx, cudaFuncSetAttribute(KERNEL<DM, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)row_smem)); \
+      KERNEL<DM, true><<<GRID, BLOCK, row_smem, s>>>(__VA_ARGS__);                   \
+    } else {                                                                         \
+      if (row_smem > 48 * 1024) MG_CUDA(ctx, cudaFuncSetAttribute(KERNEL<DM, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)row_smem)); \
+      KERNEL<DM, false><<<GRID, BLOCK, row_smem, s>>>(__VA_ARGS__);                  \
+    }                                                                                \
+  } while (0)
+#define MG_NEST_DISPATCH2(KERNEL, GRID, BLOCK, ...)                                  \
+  do {                                                                               \
+    if (D <= 2) MG_NEST_CASE2(KERNEL, 2, GRID, BLOCK, __VA_ARGS__);                  \
+    else if (D <= 4) MG_NEST_CASE2(KERNEL, 4, GRID, BLOCK, __VA_ARGS__);             \
+    else if (D <= 8) MG_NEST_CASE2(KERNEL, 8, GRID, BLOCK, __VA_ARGS__);             \
+    else if (D <= 16) MG_NEST_CASE2(KERNEL, 16, GRID, BLOCK, __VA_ARGS__);           \
+    else if (D <= 32) MG_NEST_CASE2(KERNEL, 32, GRID, BLOCK, __VA_ARGS__);           \
+    else MG_NEST_CASE2(KERNEL, 64, GRID, BLOCK, __VA_ARGS__);                        \
   } while (0)
 
   int cur = 0;
@@ -371,7 +531,7 @@ extern "C" int mg_nested_evidence(mg_ctx *ctx, const mg_logfn *like, const mg_lo
   int64_t R = 0;
   std::vector<double> h_low(K);
   double h_edge[2];
-  const int rblock = 64;
+  const int rblock = NEST_BLOCK;
   time_begin(ctx);
   for (;;) {
     if (R + K + nlive > cap) return set_err(ctx, MG_EFAIL, "nested_evidence: max_points too small");
@@ -380,8 +540,19 @@ extern "C" int mg_nested_evidence(mg_ctx *ctx, const mg_logfn *like, const mg_lo
     MG_CUDA(ctx, cudaStreamSynchronize(s));
     a.live_x = lx[cur].get(); a.live_ll = lll[cur].get(); a.live_lp = llp[cur].get();
     a.R = R; a.threshold = h_low[K - 1];
-    MG_NEST_DISPATCH(nest_replace_kernel, (K + rblock - 1) / rblock, rblock, a);
-    MG_CHECK_LAUNCH(ctx);
+    for (int s0 = 0;;) {
+      const int s1 = std::min(cfg->nmcmc, s0 + chunk);
+      if (s1 > s0) {
+        const int64_t np_ = (int64_t)(s1 - s0) * K;
+        nest_propose_kernel<<<(unsigned)((np_ + 255) / 256), 256, 0, s>>>(a, prop, s0, s1 - s0);
+        MG_CHECK_LAUNCH(ctx);
+      }
+      MG_NEST_DISPATCH2(nest_replace_kernel, (K + rblock - 1) / rblock, rblock, a, prop, s0, s1, s0 == 0 ? 1 : 0,
+                        s1 >= cfg->nmcmc ? 1 : 0, chain_x.get(), chain_cl.get());
+      MG_CHECK_LAUNCH(ctx);
+      if (s1 >= cfg->nmcmc) break;
+      s0 = s1;
+    }
     // retired_pt :: retired_pts (:137)
     MG_CUDA(ctx, cudaMemcpyAsync(rx.get() + R * D, lx[cur].get(), sizeof(double) * K * D, cudaMemcpyDeviceToDevice, s));
     MG_CUDA(ctx, cudaMemcpyAsync(rll.get() + R, lll[cur].get(), sizeof(double) * K, cudaMemcpyDeviceToDevice, s));
