@@ -22,7 +22,10 @@
 #include <cuda_pipeline.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 
 namespace mg {
 
@@ -463,12 +466,26 @@ extern "C" int mg_nested_evidence(mg_ctx *ctx, const mg_logfn *like, const mg_lo
   MG_CUDA(ctx, cudaMemsetAsync(d_fail.get(), 0, sizeof(int), s));
   // proposals of one chunk of steps for all K chains (24 B each): at most ~200 MB
   const int chunk = std::max(1, std::min(std::max(cfg->nmcmc, 1), std::max(16, (1 << 23) / K)));
-  DevBuf<int32_t> pi0, pj0;
-  DevBuf<double> pds, pu, chain_x, chain_cl;
-  MG_CUDA(ctx, pi0.alloc((size_t)chunk * K, s)); MG_CUDA(ctx, pj0.alloc((size_t)chunk * K, s));
-  MG_CUDA(ctx, pds.alloc((size_t)chunk * K, s)); MG_CUDA(ctx, pu.alloc((size_t)chunk * K, s));
+  // two sets: when a batch is one chunk, the draws of batch b+1 are made on the second stream while the chains of
+  // batch b run (the draws do not depend on the live set; the chain kernel leaves most of the machine idle)
+  const bool overlap = chunk >= cfg->nmcmc && cfg->nmcmc > 0;
+  DevBuf<int32_t> pi0[2], pj0[2];
+  DevBuf<double> pds[2], pu[2], chain_x, chain_cl;
+  NestProp prop2[2];
+  for (int b = 0; b < (overlap ? 2 : 1); ++b) {
+    MG_CUDA(ctx, pi0[b].alloc((size_t)chunk * K, s)); MG_CUDA(ctx, pj0[b].alloc((size_t)chunk * K, s));
+    MG_CUDA(ctx, pds[b].alloc((size_t)chunk * K, s)); MG_CUDA(ctx, pu[b].alloc((size_t)chunk * K, s));
+    prop2[b] = NestProp{pi0[b].get(), pj0[b].get(), pds[b].get(), pu[b].get()};
+  }
   MG_CUDA(ctx, chain_x.alloc((size_t)64 * K, s)); MG_CUDA(ctx, chain_cl.alloc(K, s));
-  NestProp prop{pi0.get(), pj0.get(), pds.get(), pu.get()};
+  cudaEvent_t ev_drawn[2] = {nullptr, nullptr}, ev_used[2] = {nullptr, nullptr};
+  // declared after the buffers: runs first on any exit and drains the second stream before they are released
+  struct EvGuard { cudaEvent_t *a, *b; cudaStream_t aux; ~EvGuard() { cudaStreamSynchronize(aux); for (int i = 0; i < 2; ++i) { if (a[i]) cudaEventDestroy(a[i]); if (b[i]) cudaEventDestroy(b[i]); } } } ev_guard{ev_drawn, ev_used, ctx->aux};
+  if (overlap)
+    for (int b = 0; b < 2; ++b) {
+      MG_CUDA(ctx, cudaEventCreateWithFlags(&ev_drawn[b], cudaEventDisableTiming));
+      MG_CUDA(ctx, cudaEventCreateWithFlags(&ev_used[b], cudaEventDisableTiming));
+    }
 
   NestArgs a{};
   a.like = dl.params; a.prior = dp.params; a.plo = d_plo.get(); a.phi = d_phi.get();
@@ -533,14 +550,40 @@ extern "C" int mg_nested_evidence(mg_ctx *ctx, const mg_logfn *like, const mg_lo
   double h_edge[2];
   const int rblock = NEST_BLOCK;
   time_begin(ctx);
+  const bool dbg = getenv("MCMC_GPU_DEBUG") != nullptr;
+  double t_chain = 0, t_sort = 0, t_rest = 0; int nb = 0;
+  auto now = [&]() { cudaStreamSynchronize(s); return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
   for (;;) {
+    double tA = dbg ? now() : 0;
     if (R + K + nlive > cap) return set_err(ctx, MG_EFAIL, "nested_evidence: max_points too small");
     // threshold = ll of the K-th lowest live point; the K lowest are retired
     MG_CUDA(ctx, cudaMemcpyAsync(h_low.data(), lll[cur].get(), sizeof(double) * K, cudaMemcpyDeviceToHost, s));
     MG_CUDA(ctx, cudaStreamSynchronize(s));
     a.live_x = lx[cur].get(); a.live_ll = lll[cur].get(); a.live_lp = llp[cur].get();
     a.R = R; a.threshold = h_low[K - 1];
+    if (overlap) {
+      const int64_t np_ = (int64_t)cfg->nmcmc * K;
+      const int b = (int)((R / K) & 1);
+      if (R == 0) {   // first batch: its draws on the main stream
+        nest_propose_kernel<<<(unsigned)((np_ + 255) / 256), 256, 0, s>>>(a, prop2[0], 0, cfg->nmcmc);
+        MG_CHECK_LAUNCH(ctx);
+      } else {
+        MG_CUDA(ctx, cudaStreamWaitEvent(s, ev_drawn[b], 0));
+      }
+      MG_NEST_DISPATCH2(nest_replace_kernel, (K + rblock - 1) / rblock, rblock, a, prop2[b], 0, cfg->nmcmc, 1, 1,
+                        chain_x.get(), chain_cl.get());
+      MG_CHECK_LAUNCH(ctx);
+      MG_CUDA(ctx, cudaEventRecord(ev_used[b], s));
+      // draws of the next batch (ids R+K ..) into the other set, once the chains that read it have finished
+      NestArgs an = a; an.R = R + K;
+      if (R > 0) MG_CUDA(ctx, cudaStreamWaitEvent(ctx->aux, ev_used[1 - b], 0));
+      else { cudaEvent_t e0; MG_CUDA(ctx, cudaEventCreateWithFlags(&e0, cudaEventDisableTiming)); MG_CUDA(ctx, cudaEventRecord(e0, s)); MG_CUDA(ctx, cudaStreamWaitEvent(ctx->aux, e0, 0)); cudaEventDestroy(e0); }
+      nest_propose_kernel<<<(unsigned)((np_ + 255) / 256), 256, 0, ctx->aux>>>(an, prop2[1 - b], 0, cfg->nmcmc);
+      MG_CHECK_LAUNCH(ctx);
+      MG_CUDA(ctx, cudaEventRecord(ev_drawn[1 - b], ctx->aux));
+    } else
     for (int s0 = 0;;) {
+      const NestProp &prop = prop2[0];
       const int s1 = std::min(cfg->nmcmc, s0 + chunk);
       if (s1 > s0) {
         const int64_t np_ = (int64_t)(s1 - s0) * K;
@@ -553,6 +596,7 @@ extern "C" int mg_nested_evidence(mg_ctx *ctx, const mg_logfn *like, const mg_lo
       if (s1 >= cfg->nmcmc) break;
       s0 = s1;
     }
+    double tB = dbg ? now() : 0;
     // retired_pt :: retired_pts (:137)
     MG_CUDA(ctx, cudaMemcpyAsync(rx.get() + R * D, lx[cur].get(), sizeof(double) * K * D, cudaMemcpyDeviceToDevice, s));
     MG_CUDA(ctx, cudaMemcpyAsync(rll.get() + R, lll[cur].get(), sizeof(double) * K, cudaMemcpyDeviceToDevice, s));
@@ -561,8 +605,11 @@ extern "C" int mg_nested_evidence(mg_ctx *ctx, const mg_logfn *like, const mg_lo
     MG_CUDA(ctx, cudaMemcpyAsync(lx[cur].get(), fx.get(), sizeof(double) * K * D, cudaMemcpyDeviceToDevice, s));
     MG_CUDA(ctx, cudaMemcpyAsync(lll[cur].get(), fll.get(), sizeof(double) * K, cudaMemcpyDeviceToDevice, s));
     MG_CUDA(ctx, cudaMemcpyAsync(llp[cur].get(), flp.get(), sizeof(double) * K, cudaMemcpyDeviceToDevice, s));
+    double tC = dbg ? now() : 0;
     if ((rc = sort_live(cur, 1 - cur))) return rc;
     cur = 1 - cur;
+    double tD = dbg ? now() : 0;
+    if (dbg) { t_chain += tB - tA; t_rest += tC - tB; t_sort += tD - tC; ++nb; }
     // running tracker (:138-141), quirk F5d kept: log_dv = log_vol +. vol_fraction
     for (int j = 0; j < K; ++j) {
       const double vol_fraction = 1.0 / (double)(nlive - j);
@@ -581,7 +628,9 @@ extern "C" int mg_nested_evidence(mg_ctx *ctx, const mg_logfn *like, const mg_lo
     const double log_live_estimate = log_vol + h_edge[0];
     if (log_live_estimate - h_log_sum_logs(log_int, log_live_estimate) <= std::log(cfg->epsrel)) break;
   }
+  if (overlap) { MG_CUDA(ctx, cudaStreamWaitEvent(s, ev_drawn[(int)((R / K) & 1)], 0)); }   // the draws made ahead for a batch that never ran
   time_end(ctx);
+  if (dbg) fprintf(stderr, "nested: %d batches; per batch: chains %.3f ms, copies %.3f ms, sort %.3f ms\n", nb, 1e3 * t_chain / nb, 1e3 * t_rest / nb, 1e3 * t_sort / nb);
   const int64_t n = R + nlive;
   if (n > cap) return set_err(ctx, MG_EFAIL, "nested_evidence: max_points too small");
   // all points ascending in ll: retired (in order) followed by the sorted live set (:143)

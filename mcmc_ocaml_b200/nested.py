@@ -44,7 +44,8 @@ def nested_evidence(log_likelihood: LogFn, log_prior: LogFn, prior_low, prior_hi
                                          C.byref(lev), C.byref(ldev), C.byref(npts), _abi.ptr(pts), _abi.ptr(ll),
                                          _abi.ptr(lp), _abi.ptr(lw)))
     k = npts.value
-    return NestedOutput(lev.value, ldev.value, pts[:k].copy(), ll[:k].copy(), lp[:k].copy(), lw[:k].copy(), nlive, batch)
+    # views: the untouched tail of the max_points-sized buffers is never paged in
+    return NestedOutput(lev.value, ldev.value, pts[:k], ll[:k], lp[:k], lw[:k], nlive, batch)
 
 
 def evidence_error_and_weights(ll, nlive: int, batch: int = 1, *, ctx: Context | None = None):

@@ -43,7 +43,7 @@ def main():
            "likelihood_evals": nret * (a.nmcmc + 1), "evals_per_s": nret * (a.nmcmc + 1) / dt,
            "log_ev": res.log_evidence, "log_ev_analytic": logZ,
            "log_total_error": nested.log_total_error_estimate(res.log_evidence, res.log_delta_evidence, a.nlive),
-           "launches": ctx.launch_count - l0, "weights_sum": float(np.exp(res.log_weights).sum())}
+           "launches": ctx.launch_count - l0, "replacement_loop_seconds": ctx.last_kernel_ms * 1e-3, "weights_sum": float(np.exp(res.log_weights).sum())}
     print(json.dumps(out))
 
 
