@@ -394,6 +394,17 @@ int mg_stats_autocorrelation(mg_ctx *ctx, const double *x, int64_t n,
                              int32_t nslides, double *out_r,
                              double *out_length);
 
+/* Stats.draw_uniform a b / draw_gaussian mu sigma / draw_cauchy x0 gamma
+ * (stats.ml:126-128, 113-124 [Leva's ratio of uniforms], 89-91), n draws at
+ * once.  Draw i comes from the call's Philox stream; the reference's global
+ * Random stream is not reproduced, parity is in distribution (and value for
+ * value against the oracle, which addresses the same stream). */
+enum { MG_DRAW_UNIFORM = 0, MG_DRAW_GAUSSIAN = 1, MG_DRAW_CAUCHY = 2 };
+int mg_stats_draw(mg_ctx *ctx, int32_t kind, double a, double b, int64_t n,
+                  double *out);
+int mg_stats_draw_dev(mg_ctx *ctx, int32_t kind, double a, double b,
+                      int64_t n, double *d_out);
+
 /* ------------------------------------------------------------------ */
 /* Nested sampling                                                     */
 /* ------------------------------------------------------------------ */

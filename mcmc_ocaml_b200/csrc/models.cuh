@@ -71,6 +71,12 @@ __device__ __forceinline__ double draw_gaussian(R &r, double mu, double sigma) {
     return mu + sigma * v / u;
   }
 }
+// stats.ml:89-91
+template <class R>
+__device__ __forceinline__ double draw_cauchy(R &r, double x0, double gamma) {
+  const double p = r.uniform();
+  return x0 + gamma * tan(3.14159265358979323846 * (p - 0.5));
+}
 // stats.ml:126-128
 template <class R>
 __device__ __forceinline__ double draw_uniform(R &r, double a, double b) {

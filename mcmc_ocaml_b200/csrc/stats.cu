@@ -9,6 +9,8 @@
 // exact than the reference's own sequential sum.  Parity tolerance: 1e-12 rel.
 // All kernels are HBM-bound: 8 bytes read per element per pass.
 #include "common.cuh"
+#include "models.cuh"
+#include "rng.cuh"
 #include "reduce.cuh"
 
 namespace mg {
@@ -271,5 +273,48 @@ extern "C" int mg_stats_autocorrelation(mg_ctx *ctx, const double *x, int64_t n,
     for (int i = 1; i < nslides && out_r[i] > 0.0; ++i) L += 2.0 * out_r[i];
     *out_length = L;
   }
+  return MG_OK;
+}
+
+// ---------------------------------------------------------------------------
+// Stats.draw_uniform / draw_gaussian / draw_cauchy (stats.ml:89-91,113-128) in bulk: draw i of a call uses the
+// Philox stream (P_DRAW, i, 1) -- the reference's global Random stream is not reproduced.
+// ---------------------------------------------------------------------------
+namespace mg {
+__global__ void stats_draw_kernel(CallKey key, int kind, double a, double b, int64_t n, double *__restrict__ out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    Rng r(key, P_DRAW, (uint64_t)i, 1);
+    double v;
+    if (kind == MG_DRAW_UNIFORM) v = draw_uniform(r, a, b);
+    else if (kind == MG_DRAW_GAUSSIAN) v = draw_gaussian(r, a, b);
+    else v = draw_cauchy(r, a, b);
+    out[i] = v;
+  }
+}
+}  // namespace mg
+
+extern "C" int mg_stats_draw_dev(mg_ctx *ctx, int32_t kind, double a, double b, int64_t n, double *d_out) {
+  if (!ctx) return MG_EINVAL;
+  MG_REQUIRE(ctx, kind >= MG_DRAW_UNIFORM && kind <= MG_DRAW_CAUCHY, "stats_draw: unknown distribution %d", kind);
+  MG_REQUIRE(ctx, n >= 0 && (d_out || n == 0), "stats_draw: bad arguments");
+  MG_CUDA(ctx, cudaSetDevice(ctx->device));
+  const CallKey key = next_key(ctx);
+  if (n == 0) return MG_OK;
+  const int64_t blocks = std::min<int64_t>((n + 255) / 256, (int64_t)ctx->sm_count * 16);
+  stats_draw_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(key, kind, a, b, n, d_out);
+  MG_CHECK_LAUNCH(ctx);
+  return MG_OK;
+}
+
+extern "C" int mg_stats_draw(mg_ctx *ctx, int32_t kind, double a, double b, int64_t n, double *out) {
+  if (!ctx) return MG_EINVAL;
+  MG_REQUIRE(ctx, n >= 0 && (out || n == 0), "stats_draw: bad arguments");
+  MG_CUDA(ctx, cudaSetDevice(ctx->device));
+  DevBuf<double> d;
+  MG_CUDA(ctx, d.alloc((size_t)n, ctx->stream));
+  int rc = mg_stats_draw_dev(ctx, kind, a, b, n, d.get());
+  if (rc) return rc;
+  if (n) MG_CUDA(ctx, cudaMemcpyAsync(out, d.get(), sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
+  MG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return MG_OK;
 }

@@ -73,3 +73,59 @@ def sample_block_stats(samples_ptr: int, n: int, D: int, nchains: int, *, ctx: C
     ctx.check(ctx.lib.mg_stats_sample_block_dev(ctx.h, C.c_void_p(samples_ptr), C.c_int64(n), C.c_int32(D),
                                                 C.c_int64(nchains), _abi.ptr(m), _abi.ptr(s)))
     return m, s
+
+
+# --- draws and densities (stats.ml:89-128, 240-248) ------------------------------------------------------------
+
+DRAW_UNIFORM, DRAW_GAUSSIAN, DRAW_CAUCHY = 0, 1, 2
+
+
+def _draw(kind: int, a: float, b: float, n: int, ctx: Context | None) -> np.ndarray:
+    ctx = ctx or default_context()
+    out = np.empty(int(n))
+    ctx.check(ctx.lib.mg_stats_draw(ctx.h, C.c_int32(kind), C.c_double(a), C.c_double(b), C.c_int64(n), _abi.ptr(out)))
+    return out
+
+
+def draw_uniform(a: float, b: float, n: int = 1, *, ctx: Context | None = None) -> np.ndarray:
+    """``Stats.draw_uniform a b`` (stats.ml:126-128), n draws from the context's Philox stream."""
+    return _draw(DRAW_UNIFORM, a, b, n, ctx)
+
+
+def draw_gaussian(mu: float, sigma: float, n: int = 1, *, ctx: Context | None = None) -> np.ndarray:
+    """``Stats.draw_gaussian mu sigma`` (Leva's ratio of uniforms, stats.ml:113-124)."""
+    return _draw(DRAW_GAUSSIAN, mu, sigma, n, ctx)
+
+
+def draw_cauchy(x0: float, gamma: float, n: int = 1, *, ctx: Context | None = None) -> np.ndarray:
+    """``Stats.draw_cauchy x0 gamma`` (stats.ml:89-91)."""
+    return _draw(DRAW_CAUCHY, x0, gamma, n, ctx)
+
+
+def log_gaussian(mu, sigma, x):
+    """``Stats.log_gaussian`` (stats.ml:98-101) on the host; the device body is the GAUSS_DIAG plugin."""
+    dx = (np.asarray(x, dtype=np.float64) - mu) / sigma
+    return -0.91893853320467274178 - np.log(sigma) - 0.5 * dx * dx
+
+
+def log_cauchy(x0, gamma, x):
+    """``Stats.log_cauchy`` (stats.ml:93-96) on the host; the device body is the CAUCHY_DATA plugin."""
+    dx = (np.asarray(x, dtype=np.float64) - x0) / gamma
+    return 0.0 - np.log(np.pi * gamma) - np.log(1.0 + dx * dx)
+
+
+def log_multi_gaussian(mu, sigma, x) -> float:
+    """``Stats.log_multi_gaussian`` (stats.ml:103-108): sequential sum over the coordinates."""
+    result = 0.0
+    for m, s, v in zip(np.asarray(mu, dtype=np.float64), np.asarray(sigma, dtype=np.float64), np.asarray(x, dtype=np.float64)):
+        result = result + float(log_gaussian(m, s, v))
+    return result + 0.0
+
+
+def log_sum_logs(a: float, b: float) -> float:
+    """``Stats.log_sum_logs`` (stats.ml:240-248): log(e^a + e^b) without overflow."""
+    if a == -np.inf and b == -np.inf:
+        return -np.inf
+    if b > a:
+        a, b = b, a
+    return float(a + np.log1p(np.exp(b - a)))

@@ -649,6 +649,14 @@ void og_draw_gaussian(uint64_t seed, uint64_t epoch, double mu, double sigma, in
   CallKey ck = derive_key(seed, epoch);
   for (int64_t i = 0; i < n; ++i) { Rng r(ck, P_DRAW, (uint64_t)i, 1); out[i] = draw_gaussian(r, mu, sigma); }
 }
+// stats.ml:89-91,113-128 in bulk, kinds as include/mcmc_gpu.h MG_DRAW_*: 0 uniform a b, 1 gaussian mu sigma, 2 cauchy x0 gamma
+void og_stats_draw(uint64_t seed, uint64_t epoch, int32_t kind, double a, double b, int64_t n, double *out) {
+  CallKey ck = derive_key(seed, epoch);
+  for (int64_t i = 0; i < n; ++i) {
+    Rng r(ck, P_DRAW, (uint64_t)i, 1);
+    out[i] = kind == 0 ? draw_uniform(r, a, b) : kind == 1 ? draw_gaussian(r, a, b) : draw_cauchy(r, a, b);
+  }
+}
 // mcmc.ml:198-218 on a fixed sample table [n][D]; M proposals from `z`
 void og_de_proposals(uint64_t seed, uint64_t epoch, const double *table, int64_t n, int32_t D, double mode_hop,
                      const double *z, int64_t M, double *out) {

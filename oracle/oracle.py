@@ -198,6 +198,12 @@ def evidence_harmonic_mean(ll):
     return out[0], out[1]
 
 
+def stats_draw(seed, epoch, kind, a, b, n):
+    out = np.empty(n)
+    lib().og_stats_draw(U64(seed), U64(epoch), C.c_int32(kind), C.c_double(a), C.c_double(b), C.c_int64(n), ptr(out))
+    return out
+
+
 def harmonic_bootstrap(seed, epoch, ll, nbstrap):
     ll = as_f64(ll)
     out = np.empty(nbstrap)

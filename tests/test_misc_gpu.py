@@ -133,3 +133,22 @@ def test_radix_sort_sorted_and_stable(ctx):
         k = C.c_int64(-1)
         ctx.check(ctx.lib.mg_debug_sort_check(ctx.h, C.c_void_p(v.data_ptr()), C.c_int64(v.numel()), C.byref(k)))
         assert k.value == 0, v.numel()
+
+
+def test_bulk_draws_match_oracle(ctx, og):
+    """Stats.draw_uniform / draw_gaussian / draw_cauchy (stats.ml:89-91,113-128): same Philox stream on both sides."""
+    from mcmc_ocaml_b200 import stats
+    n = 200_000
+    for kind, fn, a, b in [(0, stats.draw_uniform, -2.0, 3.5), (1, stats.draw_gaussian, 0.7, 1.3), (2, stats.draw_cauchy, -1.0, 0.25)]:
+        ctx.set_seed(4242)
+        e0 = ctx.epoch
+        got = fn(a, b, n, ctx=ctx)
+        want = og.stats_draw(4242, e0, kind, a, b, n)
+        if kind == 2:   # tan: CUDA libm vs glibc
+            np.testing.assert_allclose(got, want, rtol=1e-9)
+        else:
+            assert np.array_equal(got, want)
+    g = stats.draw_gaussian(0.7, 1.3, n, ctx=ctx)
+    assert abs(g.mean() - 0.7) < 0.02 and abs(g.std() - 1.3) < 0.02       # test/stats_test.ml style moments
+    u = stats.draw_uniform(-2.0, 3.5, n, ctx=ctx)
+    assert u.min() >= -2.0 and u.max() < 3.5 and abs(u.mean() - 0.75) < 0.02

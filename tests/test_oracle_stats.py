@@ -65,3 +65,18 @@ def test_autocorrelation_unpinned(og):
     np.testing.assert_allclose(r, want, rtol=1e-13)
     golden = [1.0, -0.117926565125732, -0.043808623348460]
     assert not np.allclose(r, golden, rtol=1e-5)  # parity unpinned, documented in DESIGN.md
+
+
+def test_host_density_helpers_follow_the_reference():
+    """stats.ml:93-108,240-248 restated in numpy (mcmc_ocaml_b200.stats) against the C++ oracle's scalar functions."""
+    import ctypes as C
+    from mcmc_ocaml_b200 import stats
+    from oracle import oracle as og
+    L = og.lib()
+    for mu, sg, x in [(0.0, 1.0, 0.3), (1.5, 0.2, 1.1), (-3.0, 4.0, 10.0)]:
+        assert stats.log_gaussian(mu, sg, x) == L.og_log_gaussian(C.c_double(mu), C.c_double(sg), C.c_double(x))
+        assert abs(stats.log_cauchy(mu, sg, x) - L.og_log_cauchy(C.c_double(mu), C.c_double(sg), C.c_double(x))) < 1e-15
+    assert stats.log_sum_logs(-np.inf, -np.inf) == -np.inf
+    for a, b in [(0.0, 0.0), (-700.0, -705.0), (3.0, -np.inf), (-np.inf, 2.0)]:
+        assert abs(stats.log_sum_logs(a, b) - L.og_log_sum_logs(C.c_double(a), C.c_double(b))) < 1e-15
+    assert stats.log_multi_gaussian([0.0, 1.0], [1.0, 2.0], [0.5, 0.5]) == (stats.log_gaussian(0.0, 1.0, 0.5) + stats.log_gaussian(1.0, 2.0, 0.5)) + 0.0
