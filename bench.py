@@ -304,8 +304,9 @@ def main():
             "config": workload_config(Cn, T),
             "e2e": {"value": e2e_value, "unit": "chain-steps/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps,
-                    "call": "mg_mcmc_array_resident: pinned x0 -> device, MH kernel, sample block stays in HBM, "
-                            "Stats mean/std over the block, final states + counters + stats -> host"},
+                    "call": "mg_mcmc_array_resident: pinned x0 -> device, MH kernel (per-chain running moments kept in "
+                            "registers), sample block stays in HBM, Stats mean/std pooled from the chain moments, "
+                            "final states + counters + stats -> host"},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

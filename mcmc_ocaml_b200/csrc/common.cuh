@@ -26,6 +26,8 @@ struct mg_ctx {
   int64_t launches = 0;
   int64_t naccept = 0, nreject = 0;  // Mcmc.get_counters (mcmc.ml:27-35)
   int sm_count = 148;
+  double *mh_mom = nullptr;        // request: per-chain running moments from the next MH launch (mcmc_balanced.cuh)
+  bool mh_mom_done = false;        // answer: the launch produced them
   std::string err;
 };
 

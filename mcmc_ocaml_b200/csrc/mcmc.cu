@@ -60,6 +60,7 @@ int sample_block_stats(mg_ctx *ctx, const double *d_blk, int64_t n, int F, int64
 int moments_grid(mg_ctx *ctx, int64_t n);
 int sample_block_moments_async(mg_ctx *ctx, cudaStream_t st, const double *blk_base, const double *seg, int64_t n,
                                int F, int64_t C, int gx, double *partial);
+int chain_moments_finish(mg_ctx *ctx, cudaStream_t st, const double *mom, int F, int64_t C, int64_t n, double *d_out);
 int sample_block_moments_finish(mg_ctx *ctx, cudaStream_t st, const double *partial, int nseg, int gx, int F, double cnt,
                                 const double *blk_base, int64_t C, double *d_out);
 
@@ -208,6 +209,7 @@ extern "C" int mg_mcmc_array_resident(mg_ctx *ctx, const mg_logfn *like, const m
       if (!ctx->aux) MG_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->aux, cudaStreamNonBlocking));
     }
     int64_t done = 0;                                 // recorded samples after slot 0 handled so far
+    bool fused_stats = false;
     for (int k = 0; k < nseg; ++k) {
       const int64_t m = nrec / nseg + (k < nrec % nseg ? 1 : 0);
       mg_mcmc_cfg seg = *cfg;
@@ -215,9 +217,23 @@ extern "C" int mg_mcmc_array_resident(mg_ctx *ctx, const mg_logfn *like, const m
       seg.n = (n > 0) ? m + 1 : 0;
       const uint64_t t0 = (k == 0) ? 0 : (uint64_t)(cfg->nbin + done * cfg->nskip);
       double *dst = d_samples ? d_samples + (size_t)((k == 0) ? 0 : 1 + done) * F * C : nullptr;
-      if ((rc = mcmc_launch_segment(ctx, like, prior, prop, &seg, key, t0, k == 0 ? 1 : 0, d_state.get(), dst, d_acc.get())))
-        return rc;
-      if (want_stats) {
+      // one segment: ask the sampler for per-chain running moments (the balanced kernel provides them; any other
+      // path leaves mh_mom_done false and the block is read back below)
+      DevBuf<double> d_mom;
+      if (want_stats && nseg == 1) {
+        MG_CUDA(ctx, d_mom.alloc((size_t)3 * F * C, s));
+        MG_CUDA(ctx, cudaMemsetAsync(d_mom.get(), 0, sizeof(double) * 3 * F * C, s));
+        ctx->mh_mom = d_mom.get();
+      }
+      ctx->mh_mom_done = false;
+      rc = mcmc_launch_segment(ctx, like, prior, prop, &seg, key, t0, k == 0 ? 1 : 0, d_state.get(), dst, d_acc.get());
+      ctx->mh_mom = nullptr;
+      if (rc) return rc;
+      if (want_stats && ctx->mh_mom_done) {
+        if ((rc = chain_moments_finish(ctx, s, d_mom.get(), F, C, n, d_stats.get()))) return rc;
+        MG_CUDA(ctx, cudaMemcpyAsync(stats.data(), d_stats.get(), sizeof(double) * 2 * F, cudaMemcpyDeviceToHost, s));
+        fused_stats = true;
+      } else if (want_stats) {
         cudaEvent_t e;
         MG_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         evs.push_back(e);
@@ -229,7 +245,7 @@ extern "C" int mg_mcmc_array_resident(mg_ctx *ctx, const mg_logfn *like, const m
       }
       done += m;
     }
-    if (want_stats) {
+    if (want_stats && !fused_stats) {
       cudaEvent_t e;
       MG_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
       evs.push_back(e);

@@ -30,6 +30,9 @@ namespace mg {
 #ifndef MG_MHB_MAXNREG
 #define MG_MHB_MAXNREG(D) MG_MH_MAXNREG(D)
 #endif
+#ifndef MG_MHB_MOM_MAXNREG
+#define MG_MHB_MOM_MAXNREG(D) ((D) <= 10 ? 168 : 255)
+#endif
 
 struct MhQueue {
   unsigned long long *ring;  // [cap]: (ticket + 1) << 32 | group; 0 = empty
@@ -54,8 +57,12 @@ static __global__ void mh_queue_init_kernel(MhQueue q) {
   if (i == 0) { q.ctr[0] = 0u; q.ctr[1] = q.ngroups; }
 }
 
-template <class Like, class Prior, class Prop, int D>
-__global__ void __maxnreg__(MG_MHB_MAXNREG(D))
+// kMom: also accumulate, per chain, sum (v - pivot) and sum (v - pivot)^2 of every recorded field value, pivot =
+// the chain's own slot-0 sample -- Stats.multi_mean / multi_std of the block without reading the block back
+// (the finishing kernel pools the chains with the parallel-variance formula, stats.cu).  The accumulators live in
+// registers (three warps per scheduler leave room for 168), the pivots in shared memory.
+template <class Like, class Prior, class Prop, int D, bool kMom>
+__global__ void __maxnreg__(kMom ? MG_MHB_MOM_MAXNREG(D) : MG_MHB_MAXNREG(D))
 mh_balanced_kernel(const __grid_constant__ MhArgs<Like, Prior, Prop, D> a, const __grid_constant__ MhQueue q) {
   static_assert(MH_BLOCK == 32, "one warp per CTA");
   const int dd = Prop::kStaticDim ? D : a.d;
@@ -74,6 +81,7 @@ mh_balanced_kernel(const __grid_constant__ MhArgs<Like, Prior, Prop, D> a, const
   }
   const unsigned lane = threadIdx.x;
   const int64_t sample_stride = (int64_t)F * C;
+  __shared__ double s_piv[kMom ? (D + 2) * MH_BLOCK : 1];   // [field][lane]
   for (;;) {
     // ---- take a ticket and wait for its group
     const long long tp0 = clock64();
@@ -123,7 +131,23 @@ mh_balanced_kernel(const __grid_constant__ MhArgs<Like, Prior, Prop, D> a, const
     // slot j of the output holds the state after nbin + j * nskip steps (mcmc.ml:63-71); a continuation launch
     // (record_first == 0) owns slots 1.. only and its block starts at slot 1
     double *out = (a.samples && live) ? a.samples + c - (a.record_first ? 0 : sample_stride) : nullptr;
-    auto record = [&]() {
+    double m1[kMom ? D + 2 : 1], m2[kMom ? D + 2 : 1];
+    if (kMom) {
+#pragma unroll
+      for (int i = 0; i < D + 2; ++i) {
+        const bool on = i < dd + 2;
+        s_piv[i * MH_BLOCK + lane] = on ? __ldcg(a.mom + (int64_t)i * C + c) : 0.0;
+        m1[i] = on ? __ldcg(a.mom + (int64_t)(F + i) * C + c) : 0.0;
+        m2[i] = on ? __ldcg(a.mom + (int64_t)(2 * F + i) * C + c) : 0.0;
+      }
+    }
+    auto accumulate = [&](int i, double v, bool first) {
+      if (first) s_piv[i * MH_BLOCK + lane] = v;            // slot 0 is the pivot (deviation 0)
+      const double dv = v - s_piv[i * MH_BLOCK + lane];
+      m1[i] = m1[i] + dv;
+      m2[i] = fma(dv, dv, m2[i]);
+    };
+    auto record = [&](bool first) {
       if (out) {
 #pragma unroll
         for (int i = 0; i < D; ++i)
@@ -131,6 +155,13 @@ mh_balanced_kernel(const __grid_constant__ MhArgs<Like, Prior, Prop, D> a, const
         __stcs(out + (int64_t)dd * C, ll);
         __stcs(out + (int64_t)(dd + 1) * C, lp);
         out += sample_stride;
+      }
+      if (kMom) {
+#pragma unroll
+        for (int i = 0; i < D; ++i)
+          if (i < dd) accumulate(i, x[i], first);
+        accumulate(dd, ll, first);
+        accumulate(dd + 1, lp, first);
       }
     };
     const long long tp2 = clock64();
@@ -144,12 +175,12 @@ mh_balanced_kernel(const __grid_constant__ MhArgs<Like, Prior, Prop, D> a, const
         Rng r(a.key, P_MH, g, t, &a.rk);
         nacc += mh_step<Like, Prior, Prop, D>(a, sl, sp, sj, r, x, ll, lp);
       }
-      if (s1 == a.nbin && a.n > 0 && a.record_first) record();  // :66 slot 0
+      if (s1 == a.nbin && a.n > 0 && a.record_first) record(true);  // :66 slot 0
     } else {                // :67-71 nskip steps, then a sample
       const int64_t j = k - q.nseg_burn;
       const int64_t slot0 = 1 + j * q.seg_slots;
       const int64_t slot1 = (slot0 + q.seg_slots < a.n) ? slot0 + q.seg_slots : a.n;
-      if (a.nbin == 0 && j == 0 && a.n > 0 && a.record_first) record();  // no burn-in: slot 0 is the start point
+      if (a.nbin == 0 && j == 0 && a.n > 0 && a.record_first) record(true);  // no burn-in: slot 0 is the start point
       if (out) out = a.samples + c + (slot0 - (a.record_first ? 0 : 1)) * sample_stride;
       t = a.t0 + (uint64_t)(a.nbin + (slot0 - 1) * a.nskip);
       for (int64_t slot = slot0; slot < slot1; ++slot) {
@@ -157,7 +188,7 @@ mh_balanced_kernel(const __grid_constant__ MhArgs<Like, Prior, Prop, D> a, const
           Rng r(a.key, P_MH, g, t, &a.rk);
           nacc += mh_step<Like, Prior, Prop, D>(a, sl, sp, sj, r, x, ll, lp);
         }
-        record();
+        record(false);
       }
     }
 
@@ -170,6 +201,15 @@ mh_balanced_kernel(const __grid_constant__ MhArgs<Like, Prior, Prop, D> a, const
       a.state[(int64_t)dd * C + c] = ll;
       a.state[(int64_t)(dd + 1) * C + c] = lp;
       if (a.accept && nacc) atomicAdd(a.accept + c, nacc);
+      if (kMom) {
+#pragma unroll
+        for (int i = 0; i < D + 2; ++i)
+          if (i < dd + 2) {
+            a.mom[(int64_t)i * C + c] = s_piv[i * MH_BLOCK + lane];
+            a.mom[(int64_t)(F + i) * C + c] = m1[i];
+            a.mom[(int64_t)(2 * F + i) * C + c] = m2[i];
+          }
+      }
     }
     __threadfence();
     __syncwarp();

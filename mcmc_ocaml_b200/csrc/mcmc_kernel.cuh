@@ -31,7 +31,7 @@ static int launch_mh(mg_ctx *ctx, const MhArgs<Like, Prior, Prop, D> &a) {
   const int64_t nsched = (int64_t)ctx->sm_count * 4;
   if (want_balanced && total_steps >= 4 * kSegSteps && ngroups > nsched && ngroups < (1ll << 30)) {
     int occ = 0;
-    MG_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, mh_balanced_kernel<Like, Prior, Prop, D>, MH_BLOCK, 0));
+    MG_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, mh_balanced_kernel<Like, Prior, Prop, D, false>, MH_BLOCK, 0));
     int64_t grid = std::min<int64_t>((int64_t)std::max(occ, 1) * ctx->sm_count, (ngroups / nsched) * nsched);
     if (const char *e = getenv("MCMC_GPU_MH_GRID")) grid = std::max(1, atoi(e));
     if (grid != ngroups) {
@@ -68,8 +68,18 @@ static int launch_mh(mg_ctx *ctx, const MhArgs<Like, Prior, Prop, D> &a) {
     }
     mh_queue_init_kernel<<<(q.cap + 255u) / 256u, 256, 0, ctx->stream>>>(q);
     MG_CHECK_LAUNCH(ctx);
+    // running moments of the recorded samples (requested through the context by mg_mcmc_array_resident): the
+    // variant with the accumulators is a separate instantiation, the plain kernel does not pay for them
+    const bool with_mom = ctx->mh_mom != nullptr && a.t0 == 0 && a.record_first && a.samples != nullptr;
     time_begin(ctx);
-    mh_balanced_kernel<Like, Prior, Prop, D><<<(unsigned)grid, MH_BLOCK, 0, ctx->stream>>>(a, q);
+    if (with_mom) {
+      MhArgs<Like, Prior, Prop, D> am = a;
+      am.mom = ctx->mh_mom;
+      mh_balanced_kernel<Like, Prior, Prop, D, true><<<(unsigned)grid, MH_BLOCK, 0, ctx->stream>>>(am, q);
+      ctx->mh_mom_done = true;
+    } else {
+      mh_balanced_kernel<Like, Prior, Prop, D, false><<<(unsigned)grid, MH_BLOCK, 0, ctx->stream>>>(a, q);
+    }
     MG_CHECK_LAUNCH(ctx);
     time_end(ctx);
     if (q.prof) {
@@ -99,7 +109,7 @@ static void fill_common(A &a, const mg_mcmc_cfg *cfg, CallKey key, uint64_t t0, 
   a.nbin = cfg->nbin; a.nskip = cfg->nskip; a.n = cfg->n; a.key = key;
   a.t0 = t0; a.record_first = record_first; a.pad2 = 0;
   a.rk = make_round_keys(key);
-  a.state = d_state; a.samples = d_samples; a.accept = d_accept;
+  a.state = d_state; a.samples = d_samples; a.accept = d_accept; a.mom = nullptr;
 }
 
 }  // namespace mg

@@ -35,6 +35,7 @@ struct MhArgs {
   double *state;    // [D+2][C] in/out
   double *samples;  // [n][D+2][C] or null
   int32_t *accept;  // [C] accumulated, or null
+  double *mom;      // [3][D+2][C] per-chain pivot, sum (v - pivot), sum (v - pivot)^2 of the recorded samples, or null
 };
 
 // mcmc.ml:37-56 make_mcmc_sampler: one step.  Returns 1 on acceptance.

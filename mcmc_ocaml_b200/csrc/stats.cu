@@ -138,6 +138,37 @@ static int grid_for(mg_ctx *ctx, int64_t work_items) {
 
 int moments_grid(mg_ctx *ctx, int64_t n) { return grid_for(ctx, n); }
 
+// Pool the per-chain running moments of the balanced sampler (mcmc_balanced.cuh, kMom): chain c holds its pivot
+// p_c, S1_c = sum (v - p_c), S2_c = sum (v - p_c)^2 over its n recorded samples.  Chain mean m_c = p_c + S1_c / n,
+// chain M2_c = S2_c - S1_c^2 / n; pooled mean = sum_c m_c / C and M2 = sum_c M2_c + n sum_c (m_c - mean)^2
+// (the parallel-variance combination).  One CTA per field, compensated sums in a fixed order.
+__global__ void __launch_bounds__(RED_BLOCK)
+chain_moments_finish_kernel(const double *__restrict__ mom, int F, int64_t C, double n, double *__restrict__ out /* [2][F] */) {
+  const int f = blockIdx.x;
+  const double *piv = mom + (int64_t)f * C, *s1 = mom + (int64_t)(F + f) * C, *s2 = mom + (int64_t)(2 * F + f) * C;
+  Comp acc;
+  for (int64_t c = threadIdx.x; c < C; c += RED_BLOCK) acc.add(piv[c] + s1[c] / n);
+  const double mean = block_reduce_comp<RED_BLOCK>(acc) / (double)C;
+  __shared__ double s_mean;
+  if (threadIdx.x == 0) s_mean = mean;
+  __syncthreads();
+  const double mu = s_mean;
+  Comp m2;
+  for (int64_t c = threadIdx.x; c < C; c += RED_BLOCK) {
+    const double a = s1[c], mc = piv[c] + a / n, d = mc - mu;
+    m2.add(s2[c] - a * a / n);
+    m2.add(n * d * d);
+  }
+  const double M2 = block_reduce_comp<RED_BLOCK>(m2);
+  if (threadIdx.x == 0) { out[f] = mu; out[F + f] = sqrt(M2 / (n * (double)C - 1.0)); }   // stats.ml:85 (n - 1)
+}
+
+int chain_moments_finish(mg_ctx *ctx, cudaStream_t st, const double *mom, int F, int64_t C, int64_t n, double *d_out) {
+  chain_moments_finish_kernel<<<F, RED_BLOCK, 0, st>>>(mom, F, C, (double)n, d_out);
+  MG_CHECK_LAUNCH(ctx);
+  return MG_OK;
+}
+
 // partial moments of the samples [seg, seg + n) about the block's pivot, on stream `st`
 int sample_block_moments_async(mg_ctx *ctx, cudaStream_t st, const double *blk_base, const double *seg, int64_t n,
                                int F, int64_t C, int gx, double *partial) {

@@ -223,3 +223,37 @@ def test_balanced_kernel_bit_exact(ctx, og, D, nbin, nskip, n):
     want, acc, rej = og.mcmc_array(0xBA1A, 0, n, like, prior, prop, mu, nchains=C, nbin=nbin, nskip=nskip, nthreads=16)
     assert np.array_equal(got.block, want)
     assert np.array_equal(got.accept, acc) and np.array_equal(got.reject, rej)
+
+
+def test_resident_call_running_moments(ctx, og):
+    """Above one warp per scheduler the resident call takes Stats.multi_mean / multi_std from per-chain running
+    moments kept by the balanced sampler (pivot = each chain's slot-0 sample, pooled with the parallel-variance
+    formula) instead of reading the block back; same values as the oracle's pooled fold to 1e-12."""
+    import ctypes as C
+
+    import torch
+
+    from mcmc_ocaml_b200 import _abi
+    D, n = 10, 520
+    Cn = 592 * 32 + 1000 + 7
+    mu, like, prior, prop = corr_model(D)
+    F = D + 2
+    blk = torch.empty((n, F, Cn), dtype=torch.float64, device="cuda")
+    final = np.empty((Cn, F)); acc = np.empty(Cn, np.int64); rej = np.empty(Cn, np.int64)
+    mean = np.empty(F); std = np.empty(F)
+    cfg = _abi.mg_mcmc_cfg(Cn, D, 0, 7, 1, n, 0, 1, 0)
+    ls, ps, js = like.spec(), prior.spec(), prop.spec()
+    ctx.set_seed(78)
+    x0 = _abi.as_f64(mu)
+    ctx.check(ctx.lib.mg_mcmc_array_resident(ctx.h, C.byref(ls), C.byref(ps), C.byref(js), C.byref(cfg), _abi.ptr(x0),
+                                             C.c_void_p(blk.data_ptr()), _abi.ptr(final),
+                                             _abi.ptr(acc, _abi.c_int64_p), _abi.ptr(rej, _abi.c_int64_p),
+                                             _abi.ptr(mean), _abi.ptr(std)))
+    want, wacc, _ = og.mcmc_array(78, 0, n, like, prior, prop, mu, nchains=Cn, nbin=7, nskip=1, nthreads=16)
+    torch.cuda.synchronize()
+    got = blk.cpu().numpy()
+    assert np.array_equal(got, want)
+    assert np.array_equal(final, want[-1].T) and np.array_equal(acc, wacc)
+    pooled = want.transpose(0, 2, 1).reshape(-1, F)
+    np.testing.assert_allclose(mean, og.multi_mean(pooled), rtol=1e-12, atol=1e-13)
+    np.testing.assert_allclose(std, og.multi_std(pooled), rtol=1e-12, atol=1e-13)
