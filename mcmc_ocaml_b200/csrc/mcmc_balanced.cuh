@@ -81,6 +81,7 @@ mh_balanced_kernel(const __grid_constant__ MhArgs<Like, Prior, Prop, D> a, const
   }
   const unsigned lane = threadIdx.x;
   const int64_t sample_stride = (int64_t)F * C;
+  const uint32_t pitch32 = sample_pitch32(C, F);
   __shared__ double s_piv[kMom ? (D + 2) * MH_BLOCK : 1];   // [field][lane]
   for (;;) {
     // ---- take a ticket and wait for its group
@@ -149,11 +150,7 @@ mh_balanced_kernel(const __grid_constant__ MhArgs<Like, Prior, Prop, D> a, const
     };
     auto record = [&](bool first) {
       if (out) {
-#pragma unroll
-        for (int i = 0; i < D; ++i)
-          if (i < dd) __stcs(out + (int64_t)i * C, x[i]);
-        __stcs(out + (int64_t)dd * C, ll);
-        __stcs(out + (int64_t)(dd + 1) * C, lp);
+        store_sample<D>(out, pitch32, C, dd, x, ll, lp);
         out += sample_stride;
       }
       if (kMom) {

@@ -38,6 +38,35 @@ struct MhArgs {
   double *mom;      // [3][D+2][C] per-chain pivot, sum (v - pivot), sum (v - pivot)^2 of the recorded samples, or null
 };
 
+// Recording a sample: field i lives i * C doubles after field 0.  With the pitch of a field row in BYTES held as a
+// 32-bit value, every field address is one IMAD.WIDE.U32 (pitch * i + base) instead of a 64-bit multiply and add
+// per field (47 of the 59 instructions of a 12-field record were address arithmetic).  pitch32 == 0: the block is
+// too wide for that (C * 8 * (D + 2) >= 2^32), 64-bit path.
+template <int D>
+__device__ __forceinline__ void store_sample(double *out, uint32_t pitch32, int64_t C, int dd, const double (&x)[D],
+                                             double ll, double lp) {
+#ifdef MG_EXP_NOSTORE  /* timing experiment only (tools/mh_ablation.sh): one field instead of D + 2 */
+  __stcs(out, ll + lp + x[0]); return;
+#endif
+  if (pitch32) {
+    char *b = reinterpret_cast<char *>(out);
+#pragma unroll
+    for (int i = 0; i < D; ++i)
+      if (i < dd) __stcs(reinterpret_cast<double *>(b + (uint64_t)pitch32 * (uint32_t)i), x[i]);
+    __stcs(reinterpret_cast<double *>(b + (uint64_t)pitch32 * (uint32_t)dd), ll);
+    __stcs(reinterpret_cast<double *>(b + (uint64_t)pitch32 * (uint32_t)(dd + 1)), lp);
+  } else {
+#pragma unroll
+    for (int i = 0; i < D; ++i)
+      if (i < dd) __stcs(out + (int64_t)i * C, x[i]);
+    __stcs(out + (int64_t)dd * C, ll);
+    __stcs(out + (int64_t)(dd + 1) * C, lp);
+  }
+}
+__device__ __forceinline__ uint32_t sample_pitch32(int64_t C, int F) {
+  return ((uint64_t)C * 8ull * (uint64_t)F < (1ull << 32)) ? (uint32_t)(C * 8) : 0u;
+}
+
 // mcmc.ml:37-56 make_mcmc_sampler: one step.  Returns 1 on acceptance.
 template <class Like, class Prior, class Prop, int D, class RNG>
 __device__ __forceinline__ int mh_step(const MhArgs<Like, Prior, Prop, D> &a, const double *sl, const double *sp,
@@ -120,13 +149,10 @@ __device__ __forceinline__ void mh_ensemble_body(const MhArgs<Like, Prior, Prop,
   for (int64_t i = 0; i < a.nbin; ++i) nacc += step();  // :63-65
   double *out = (a.samples && live) ? a.samples + c : nullptr;
   const int64_t sample_stride = (int64_t)F * C;
+  const uint32_t pitch32 = sample_pitch32(C, F);
   auto record = [&]() {
     if (out) {
-#pragma unroll
-      for (int i = 0; i < D; ++i)
-        if (i < dd) __stcs(out + (int64_t)i * C, x[i]);
-      __stcs(out + (int64_t)dd * C, ll);
-      __stcs(out + (int64_t)(dd + 1) * C, lp);
+      store_sample<D>(out, pitch32, C, dd, x, ll, lp);
       out += sample_stride;
     }
   };

@@ -149,6 +149,9 @@ struct GaussCorr {
   template <int DD>
   static __device__ __forceinline__ double eval(const Params &, const double *s, const double (&x)[DD], int) {
     static_assert(DD == D, "GaussCorr: dimension mismatch");
+#ifdef MG_EXP_NOLIKE   /* timing experiment only (tools/mh_ablation.sh): a log-density of D adds */
+    { double q = lds1(s + kLogc); for (int j = 0; j < D; ++j) q = q - x[j]; return q; }
+#endif
     double z[D];
 #pragma unroll
     for (int j = 0; j < D; j += 2) {

@@ -52,8 +52,13 @@ inline RoundKeys make_round_keys(CallKey ck) {
 }
 __device__ __forceinline__ void philox4x32_10_rk(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
                                                  const RoundKeys &rk, uint32_t (&out)[4]) {
+#ifdef MG_EXP_ROUNDS   /* timing experiment only (tools/mh_ablation.sh): fewer rounds, NOT the shipped generator */
+  constexpr int kRounds = MG_EXP_ROUNDS;
+#else
+  constexpr int kRounds = 10;
+#endif
 #pragma unroll
-  for (int r = 0; r < 10; ++r) {
+  for (int r = 0; r < kRounds; ++r) {
     const uint64_t p0 = (uint64_t)MG_PHILOX_M0 * c0;
     const uint64_t p1 = (uint64_t)MG_PHILOX_M1 * c2;
     const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ rk.k[2 * r];
