@@ -23,6 +23,9 @@ external interp_jump_prob_raw :
   ctx -> tree -> int -> (float, float64_elt, c_layout) Array2.t -> (float, float64_elt, c_layout) Array1.t -> unit
   = "mcmcgpu_interp_jump_prob"
 external interp_draw_raw : ctx -> tree -> int -> (float, float64_elt, c_layout) Array2.t -> unit = "mcmcgpu_interp_draw"
+external stats_draw_raw : ctx -> int -> float -> float -> (float, float64_elt, c_layout) Array1.t -> unit = "mcmcgpu_stats_draw"
+external posterior_indices_raw :
+  ctx -> (float, float64_elt, c_layout) Array1.t -> (int64, int64_elt, c_layout) Array1.t -> unit = "mcmcgpu_nested_posterior_indices"
 external harmonic_raw : ctx -> (float, float64_elt, c_layout) Array1.t -> float = "mcmcgpu_evidence_harmonic_mean"
 external lebesgue_raw :
   ctx -> int -> float -> (float, float64_elt, c_layout) Array2.t -> (float, float64_elt, c_layout) Array1.t ->
@@ -84,3 +87,19 @@ module Evidence = struct
   let evidence_direct ctx ?(n = 64) samples =
     let pts, ll, lp = columns samples in direct_raw ctx n pts ll lp
 end
+
+(* Stats.draw_uniform / draw_gaussian / draw_cauchy (stats.ml:89-91,113-128): n draws from the context's stream *)
+let draw kind ctx a b n =
+  let out = Array1.create float64 c_layout n in
+  stats_draw_raw ctx kind a b out;
+  Array.init n (fun i -> out.{i})
+let draw_uniform ctx a b n = draw 0 ctx a b n
+let draw_gaussian ctx mu sigma n = draw 1 ctx mu sigma n
+let draw_cauchy ctx x0 gamma n = draw 2 ctx x0 gamma n
+
+(* Nested.posterior_samples n output (nested.ml:167-178): the sampled points *)
+let posterior_samples ctx n (pts : float array array) (log_wts : float array) =
+  let lw = Array1.of_array float64 c_layout log_wts in
+  let idx = Array1.create int64 c_layout n in
+  posterior_indices_raw ctx lw idx;
+  Array.init n (fun i -> pts.(Int64.to_int idx.{i}))

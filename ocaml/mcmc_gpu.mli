@@ -53,3 +53,12 @@ module Evidence : sig
   val evidence_lebesgue : ctx -> ?n:int -> ?eps:float -> float array Mcmc.mcmc_sample array -> float
   val evidence_direct : ctx -> ?n:int -> float array Mcmc.mcmc_sample array -> float
 end
+
+(** [Stats.draw_uniform a b], [draw_gaussian mu sigma], [draw_cauchy x0 gamma] (stats.ml:89-91,113-128),
+    [n] draws per call from the context's Philox stream. *)
+val draw_uniform : ctx -> float -> float -> int -> float array
+val draw_gaussian : ctx -> float -> float -> int -> float array
+val draw_cauchy : ctx -> float -> float -> int -> float array
+
+(** [Nested.posterior_samples n output] (nested.ml:167-178) given the points and their log weights. *)
+val posterior_samples : ctx -> int -> float array array -> float array -> float array array

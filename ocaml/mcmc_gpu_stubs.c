@@ -222,6 +222,27 @@ CAMLprim value mcmcgpu_stats_multi_std(value ctx, value xs, value mean_opt, valu
   CAMLreturn(Val_unit);
 }
 
+/* ---- Stats.draw_uniform / draw_gaussian / draw_cauchy (stats.ml:89-91,113-128), n draws per call ----------
+ * external stats_draw : ctx -> int -> float -> float -> (float, float64_elt, c_layout) Array1.t -> unit
+ * kind: 0 uniform a b | 1 gaussian mu sigma | 2 cauchy x0 gamma (MG_DRAW_*) */
+CAMLprim value mcmcgpu_stats_draw(value ctx, value kind, value a, value b, value out) {
+  CAMLparam5(ctx, kind, a, b, out);
+  mg_ctx *c = Ctx_val(ctx);
+  check(c, mg_stats_draw(c, Int_val(kind), Double_val(a), Double_val(b), Caml_ba_array_val(out)->dim[0],
+                         (double *)Caml_ba_data_val(out)));
+  CAMLreturn(Val_unit);
+}
+
+/* ---- Nested.posterior_samples (nested.ml:152-178): indices of n weighted draws ------------------------------
+ * external posterior_indices : ctx -> (float, float64_elt, c_layout) Array1.t -> (int64, int64_elt, c_layout) Array1.t -> unit */
+CAMLprim value mcmcgpu_nested_posterior_indices(value ctx, value logw, value out) {
+  CAMLparam3(ctx, logw, out);
+  mg_ctx *c = Ctx_val(ctx);
+  check(c, mg_nested_posterior_indices(c, (const double *)Caml_ba_data_val(logw), Caml_ba_array_val(logw)->dim[0],
+                                       Caml_ba_array_val(out)->dim[0], (int64_t *)Caml_ba_data_val(out)));
+  CAMLreturn(Val_unit);
+}
+
 /* ---- Mcmc.rjmcmc_array (mcmc.ml:121-139) -----------------------------------
  * type rj_model = { like : logfn; prior : logfn; prop : proposal; into : tree option;
  *                   into_gauss : (float, float64_elt, c_layout) Array1.t; nstop : int; p : float }
