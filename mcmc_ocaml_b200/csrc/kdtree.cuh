@@ -124,11 +124,12 @@ __device__ __forceinline__ double kd_jump_prob(const KdView &t, const KdScratch 
 // Interpolate_pdf.draw (interpolate_pdf.ml:114-133): pick a stored point,
 // locate its cell by descent, draw uniformly in the cell's box.  The result is
 // written to s.Q(.).  Returns false where the reference raises.
-__device__ __forceinline__ bool kd_draw(const KdView &t, const KdScratch &s, int nstop, Rng &r) {
+__device__ __forceinline__ bool kd_draw(const KdView &t, const KdScratch &s, int nstop, Rng &r, int32_t *node = nullptr) {
   const int64_t k = (int64_t)r.below((uint64_t)t.N);
   const double *p = t.pts + k * t.D;
   for (int d = 0; d < t.D; ++d) s.Q(d) = __ldg(p + d);
   const int32_t id = kd_descend(t, s, nstop);
+  if (node) *node = id;
   if (id < 0) return false;
   for (int d = 0; d < t.D; ++d) {  // random_in_volume :80-86
     const double lo = s.LO(d), hi = s.HI(d);

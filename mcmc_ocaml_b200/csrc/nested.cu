@@ -444,6 +444,7 @@ extern "C" int mg_nested_evidence(mg_ctx *ctx, const mg_logfn *like, const mg_lo
              "nested_evidence: run-time plugins are supported by mcmc_array and logfn_eval only");
   MG_CUDA(ctx, cudaSetDevice(ctx->device));
   cudaStream_t s = ctx->stream;
+  const double t_entry = std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
   DevLogFn dl, dp;
   MG_CUDA(ctx, dl.upload_from(like, s));
   MG_CUDA(ctx, dp.upload_from(prior, s));
@@ -553,6 +554,7 @@ extern "C" int mg_nested_evidence(mg_ctx *ctx, const mg_logfn *like, const mg_lo
   const bool dbg = getenv("MCMC_GPU_DEBUG") != nullptr;
   double t_chain = 0, t_sort = 0, t_rest = 0; int nb = 0;
   auto now = [&]() { cudaStreamSynchronize(s); return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  const double t_loop0 = dbg ? now() : 0;
   for (;;) {
     double tA = dbg ? now() : 0;
     if (R + K + nlive > cap) return set_err(ctx, MG_EFAIL, "nested_evidence: max_points too small");
@@ -630,6 +632,7 @@ extern "C" int mg_nested_evidence(mg_ctx *ctx, const mg_logfn *like, const mg_lo
   }
   if (overlap) { MG_CUDA(ctx, cudaStreamWaitEvent(s, ev_drawn[(int)((R / K) & 1)], 0)); }   // the draws made ahead for a batch that never ran
   time_end(ctx);
+  const double t_loop1 = dbg ? now() : 0;
   if (dbg) fprintf(stderr, "nested: %d batches; per batch: chains %.3f ms, copies %.3f ms, sort %.3f ms\n", nb, 1e3 * t_chain / nb, 1e3 * t_rest / nb, 1e3 * t_sort / nb);
   const int64_t n = R + nlive;
   if (n > cap) return set_err(ctx, MG_EFAIL, "nested_evidence: max_points too small");
@@ -645,6 +648,7 @@ extern "C" int mg_nested_evidence(mg_ctx *ctx, const mg_logfn *like, const mg_lo
   if (lp) MG_CUDA(ctx, cudaMemcpyAsync(lp, rlp.get(), sizeof(double) * n, cudaMemcpyDeviceToHost, s));
   MG_CUDA(ctx, cudaMemcpyAsync(logw, d_w.get(), sizeof(double) * n, cudaMemcpyDeviceToHost, s));
   MG_CUDA(ctx, cudaStreamSynchronize(s));
+  if (dbg) fprintf(stderr, "nested: setup %.3f s, loop %.3f s, weights + copy-out %.3f s\n", t_loop0 - t_entry, t_loop1 - t_loop0, now() - t_loop1);
   *npts = n;
   return MG_OK;
 }

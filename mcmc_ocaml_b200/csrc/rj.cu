@@ -2,10 +2,13 @@
 // of independent two-model reversible-jump chains, one thread per chain.
 //
 // A chain's state is (model, x[Dmax], ll, lp) in registers.  Cross-model
-// proposals are Interpolate_pdf draws (two kd-tree descents per cross-model
-// step: one to draw into the target model, one to evaluate the reverse jump
-// density of the current point, test/mcmc_test.ml:175-178); the descent keeps
-// its box in shared memory (kdtree.cuh).  Traffic per step: 1 byte (model) or
+// proposals are Interpolate_pdf draws.  The reference descends a kd-tree three
+// times per cross-model step (draw into the target model, density of the drawn
+// point, density of the current point for the reverse jump,
+// test/mcmc_test.ml:175-178); here the drawn point's density comes with its
+// draw and the current point's is kept until the point changes, so most
+// cross-model steps descend once.  The descent keeps its box in shared memory
+// (kdtree.cuh).  Traffic per step: 1 byte (model) or
 // 8 (Dmax+2) bytes (full sample) per recorded chain-step plus ~16 B per tree
 // level gathered through L2 -- latency-bound pointer chasing, not HBM-bound.
 #include "common.cuh"
@@ -37,12 +40,30 @@ struct RjArgs {
   int *fail;
 };
 
+// *lq / *lq_known: Interp.draw leaves the cell's box in the scratch.  When the drawn point lies strictly inside
+// it, Interp.jump_prob of that point descends to the same cell (at every ancestor the point is inside the child on
+// the path and, where the path goes right, strictly beyond the split), so its value -- count / (volume * N), the
+// same expression as kd_jump_prob -- is taken here and the second descent is skipped.  A point on the box
+// boundary (u = 0, or a degenerate cell) is left to the full descent.
 template <int DMAX>
-__device__ __forceinline__ bool rj_draw_into(const RjModelDev &m, const KdScratch &s, Rng &r, double (&y)[DMAX]) {
+__device__ __forceinline__ bool rj_draw_into(const RjModelDev &m, const KdScratch &s, Rng &r, double (&y)[DMAX],
+                                             double *lq, bool *lq_known) {
+  *lq_known = false;
   if (m.into_kind == MG_INTO_INTERP) {
-    if (!kd_draw(m.tree, s, m.nstop, r)) return false;
+    int32_t node;
+    if (!kd_draw(m.tree, s, m.nstop, r, &node)) return false;
+    bool inside = true;
 #pragma unroll (DMAX <= 16 ? DMAX : 1)
-    for (int i = 0; i < DMAX; ++i) y[i] = (i < m.D) ? s.Q(i) : 0.0;
+    for (int i = 0; i < DMAX; ++i) {
+      y[i] = (i < m.D) ? s.Q(i) : 0.0;
+      if (i < m.D) inside = inside && (s.LO(i) < y[i]) && (y[i] < s.HI(i));
+    }
+    if (inside) {
+      const double nobjs = (double)__ldg(m.tree.count + node);
+      const double v = kd_cell_volume(s, m.tree.D);
+      *lq = log(nobjs / (v * (double)m.tree.N));
+      *lq_known = true;
+    }
   } else {
 #pragma unroll (DMAX <= 16 ? DMAX : 1)
     for (int i = 0; i < DMAX; ++i)
@@ -92,9 +113,13 @@ __global__ void rj_ensemble_kernel(const __grid_constant__ RjArgs a) {
     double lp = DynFn::eval<DMAX>(a.m[model].prior, nullptr, x, a.m[model].D) + a.m[model].log_p;  // :128
     uint64_t t = 0;
     bool bad = false;
+    double lq_x = 0.0;          // log of the jump-in probability of the current point in its own model
+    bool lq_x_valid = false;
     auto step = [&]() {
       Rng r(a.key, P_RJ, g, t);
       ++t;
+      double fwd_lq = 0.0;
+      bool fwd_known = false;
       const double start_log_post = ll + lp;
       const RjModelDev &cm = a.m[model];
       int pmodel;
@@ -103,7 +128,7 @@ __global__ void rj_ensemble_kernel(const __grid_constant__ RjArgs a) {
         DynProp::propose<DMAX>(cm.prop, nullptr, r, x, y, cm.D);
       } else {                                // :97,102 jump into the other model
         pmodel = 1 - model;
-        if (!rj_draw_into<DMAX>(a.m[pmodel], s, r, y)) { bad = true; return; }
+        if (!rj_draw_into<DMAX>(a.m[pmodel], s, r, y, &fwd_lq, &fwd_known)) { bad = true; return; }
       }
       const RjModelDev &pm = a.m[pmodel];
       const double proposed_like = DynFn::eval<DMAX>(pm.like, nullptr, y, pm.D);                 // :113-115
@@ -114,12 +139,17 @@ __global__ void rj_ensemble_kernel(const __grid_constant__ RjArgs a) {
         log_forward_jump = pm.log_p + DynProp::log_q<DMAX>(pm.prop, nullptr, x, y, pm.D);
         log_backward_jump = cm.log_p + DynProp::log_q<DMAX>(cm.prop, nullptr, y, x, cm.D);
       } else {
-        log_forward_jump = pm.log_p + rj_log_into<DMAX>(pm, s, y);
-        log_backward_jump = cm.log_p + rj_log_into<DMAX>(cm, s, x);
+        if (!fwd_known) fwd_lq = rj_log_into<DMAX>(pm, s, y);
+        // log (jump into the current model at x) is a pure function of x: kept until x changes
+        if (!lq_x_valid) { lq_x = rj_log_into<DMAX>(cm, s, x); lq_x_valid = true; }
+        log_forward_jump = pm.log_p + fwd_lq;
+        log_backward_jump = cm.log_p + lq_x;
       }
       const double log_accept_prob =
           proposed_log_posterior - start_log_post + log_backward_jump - log_forward_jump;
       if (log_u_less_than(r.uniform(), log_accept_prob)) {
+        if (pmodel != model) { lq_x = fwd_lq; lq_x_valid = true; }   // the new point's own jump-in probability
+        else lq_x_valid = false;
         model = pmodel;
 #pragma unroll (DMAX <= 16 ? DMAX : 1)
         for (int i = 0; i < DMAX; ++i) x[i] = y[i];

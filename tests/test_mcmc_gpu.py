@@ -210,7 +210,7 @@ def test_combine_jump_proposals(ctx, og):
         mcmc.mcmc_array(10, like, prior, P.Proposal(5, 1, [2.0, 1.0, 0.0, 2.0]), [0.0], ctx=ctx)   # truncated block
 
 
-@pytest.mark.parametrize("D,nbin,nskip,n", [(10, 100, 3, 200), (10, 0, 1, 600), (3, 700, 2, 1), (12, 130, 1, 520)])
+@pytest.mark.parametrize("D,nbin,nskip,n", [(10, 100, 3, 200), (10, 0, 1, 600), (3, 700, 2, 1), (12, 130, 1, 520), (3, 50, 200, 6)])
 def test_balanced_kernel_bit_exact(ctx, og, D, nbin, nskip, n):
     """Ensembles of more than one warp per scheduler and >= 512 steps take the
     dynamically balanced kernel (csrc/mcmc_balanced.cuh): the run of each group of
