@@ -88,8 +88,16 @@ __device__ __forceinline__ double rj_log_into(const RjModelDev &m, const KdScrat
   return acc;
 }
 
+// Register cap: the step is bound by the latency of dependent tree-node loads, so resident warps count for more than
+// a few spilled values (tools/rj_regs_sweep.sh, config 5 (2,4)-D: 143 regs 1.35e9, 120: 1.69e9, 92: 1.95e9, 80: 2.07e9,
+// 64: 2.21e9 chain-steps/s).
+#ifndef MG_RJ_MAXNREG
+#define MG_RJ_MAXNREG(DMAX) ((DMAX) <= 8 ? 64 : ((DMAX) <= 16 ? 96 : 255))
+#endif
+
 template <int DMAX>
-__global__ void rj_ensemble_kernel(const __grid_constant__ RjArgs a) {
+__global__ void __maxnreg__(MG_RJ_MAXNREG(DMAX))
+rj_ensemble_kernel(const __grid_constant__ RjArgs a) {
   extern __shared__ double smem[];
   const KdScratch s = kd_scratch(smem, a.DT);
   const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
