@@ -133,8 +133,11 @@ __global__ void mark_side_kernel(BuildArrays a, const int32_t *__restrict__ list
 // already running.
 constexpr unsigned long long LB_AGG = 1ull << 62, LB_PREFIX = 2ull << 62, LB_MASK = 3ull << 62;
 
+#ifndef MG_PART_MINBLOCKS
+#define MG_PART_MINBLOCKS 5   /* 48 registers: 5 CTAs per SM; gather-latency bound (tools/part_occupancy_sweep.sh: 4 -> 5 CTAs, Lebesgue 73 -> 67 ms) */
+#endif
 template <bool VEC>
-__global__ void __launch_bounds__(SCAN_BLOCK)
+__global__ void __launch_bounds__(SCAN_BLOCK, MG_PART_MINBLOCKS)
 part_fused_kernel(BuildArrays a, const int32_t *__restrict__ lists_in, int32_t *__restrict__ lists_out,
                   const int32_t *__restrict__ seg_in, int32_t *__restrict__ seg_out,
                   const uint8_t *__restrict__ side, int32_t lb, int32_t le, int64_t ntiles,
