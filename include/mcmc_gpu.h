@@ -75,6 +75,12 @@ int mg_measure_store_gbs(mg_ctx *ctx, int64_t nbytes, int reps, double *out_gbs)
 /* diagnostic: stable radix sort of n float64 keys on the device (the sort
  * under Kd_tree and Evidence); counts order / stability violations. */
 int mg_debug_sort_check(mg_ctx *ctx, const double *d_x, int64_t n, int64_t *violations);
+/* diagnostic: the sampler's accept test  log u < delta  (mcmc.ml:47) for n host
+ * (u, delta) pairs, as the kernels decide it (single-precision estimate with an
+ * error bound, float64 log on near-ties) and by the float64 comparison alone;
+ * out_fast[i], out_exact[i] in {0, 1}.  The two must agree everywhere. */
+int mg_debug_accept_test(mg_ctx *ctx, const double *u, const double *delta, int64_t n,
+                         uint8_t *out_fast, uint8_t *out_exact);
 
 /* device / pinned memory helpers for callers without their own allocator */
 int mg_malloc_device(mg_ctx *ctx, int64_t nbytes, void **out);

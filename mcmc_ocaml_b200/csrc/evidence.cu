@@ -97,16 +97,26 @@ __global__ void lex_order_check_kernel(const double *__restrict__ pts, const int
   }
 }
 
-// survivors in REVERSED order: dst = K-1-rank
+// survivors in REVERSED order: dst = K-1-rank.  One warp per 32 candidate rows: the row ids are read coalesced and
+// broadcast, each row is then copied by consecutive lanes (a row is D contiguous doubles on both sides).
 __global__ void gather_kernel(const double *__restrict__ pts, const double *__restrict__ ll,
                               const double *__restrict__ lp, const int32_t *__restrict__ order,
                               const int32_t *__restrict__ keep, const int32_t *__restrict__ rank, int64_t m, int64_t K,
                               int D, double *__restrict__ spts, double *__restrict__ sll, double *__restrict__ slp) {
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (int64_t)gridDim.x * blockDim.x) {
-    if (!keep[i]) continue;
-    const int64_t dst = K - 1 - rank[i], src = order[i];
-    for (int d = 0; d < D; ++d) spts[dst * D + d] = pts[src * D + d];
-    sll[dst] = ll[src]; slp[dst] = lp[src];
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t i0 = warp * 32; i0 < m; i0 += nwarps * 32) {
+    const int64_t i = i0 + lane;
+    const bool k = (i < m) && keep[i] != 0;
+    const int64_t dst = k ? K - 1 - rank[i] : 0, src = k ? order[i] : 0;
+    if (k) { sll[dst] = ll[src]; slp[dst] = lp[src]; }
+    const unsigned mask = __ballot_sync(0xffffffffu, k);
+    for (unsigned rem = mask; rem; rem &= rem - 1) {
+      const int r = __ffs(rem) - 1;
+      const int64_t rs = __shfl_sync(0xffffffffu, src, r), rd = __shfl_sync(0xffffffffu, dst, r);
+      for (int d = lane; d < D; d += 32) spts[rd * D + d] = pts[rs * D + d];
+    }
   }
 }
 

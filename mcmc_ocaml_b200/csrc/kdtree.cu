@@ -33,13 +33,29 @@ __global__ void check_finite_kernel(const double *__restrict__ x, int64_t n, int
     if (x[i] != x[i]) *flag = 1;
 }
 
-// keys[d][i] = ordered(pts[i][d]), vals[d][i] = i; row D of vals = identity
-__global__ void make_keys_kernel(const double *__restrict__ pts, int64_t N, int D, uint64_t *__restrict__ keys,
-                                 int32_t *__restrict__ vals) {
-  const int d = blockIdx.y;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x) {
-    if (d < D) keys[(int64_t)d * N + i] = f64_to_ordered(pts[i * D + d]);
-    vals[(int64_t)d * N + i] = (int32_t)i;
+// keys[d][i] = ordered(pts[i][d]), vals[d][i] = i; row D of vals = identity.  A CTA transposes a tile of
+// MK_TILE points through shared memory: the rows are read as one contiguous chunk, each dimension's keys are
+// written as one contiguous run (a thread-per-(d, i) kernel reads with a stride of D doubles).
+constexpr int MK_TILE = 128;
+__global__ void __launch_bounds__(KB)
+make_keys_kernel(const double *__restrict__ pts, int64_t N, int D, uint64_t *__restrict__ keys,
+                 int32_t *__restrict__ vals) {
+  extern __shared__ double mk_tile[];            // [MK_TILE][DP], DP odd: conflict-free column reads
+  const int DP = D | 1;
+  for (int64_t i0 = (int64_t)blockIdx.x * MK_TILE; i0 < N; i0 += (int64_t)gridDim.x * MK_TILE) {
+    const int cnt = (int)((N - i0 < MK_TILE) ? N - i0 : MK_TILE);
+    const double *src = pts + i0 * D;
+    for (int k = threadIdx.x; k < cnt * D; k += KB) { const int r = k / D, c = k - r * D; mk_tile[r * DP + c] = src[k]; }
+    __syncthreads();
+    for (int k = threadIdx.x; k < D * MK_TILE; k += KB) {
+      const int d = k / MK_TILE, r = k - d * MK_TILE;
+      if (r < cnt) {
+        keys[(int64_t)d * N + i0 + r] = f64_to_ordered(mk_tile[r * DP + d]);
+        vals[(int64_t)d * N + i0 + r] = (int32_t)(i0 + r);
+      }
+    }
+    for (int r = threadIdx.x; r < cnt; r += KB) vals[(int64_t)D * N + i0 + r] = (int32_t)(i0 + r);
+    __syncthreads();
   }
 }
 
@@ -282,7 +298,10 @@ int build_tree(mg_ctx *ctx, const double *d_pts, int64_t N, int D, const double 
   {
     DevBuf<uint64_t> keys;
     MG_CUDA(ctx, keys.alloc((size_t)D * N, s));
-    make_keys_kernel<<<dim3(grid1d(ctx, N), NL), KB, 0, s>>>(d_pts, N, D, keys.get(), listsA.get());
+    const size_t mk_smem = (size_t)MK_TILE * (D | 1) * sizeof(double);
+    if (mk_smem > 48 * 1024)
+      MG_CUDA(ctx, cudaFuncSetAttribute(make_keys_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mk_smem));
+    make_keys_kernel<<<grid1d(ctx, (N + MK_TILE - 1) / MK_TILE * KB), KB, mk_smem, s>>>(d_pts, N, D, keys.get(), listsA.get());
     MG_CHECK_LAUNCH(ctx);
     int rc = radix_sort_pairs(ctx, keys.get(), listsA.get(), N, D);
     if (rc) return rc;

@@ -103,3 +103,35 @@ extern "C" int mg_remove_repeat_samples(mg_ctx *ctx, const double *rows, int64_t
   return MG_OK;
 }
 
+// ---- diagnostic: accept-test prefilter against the plain float64 comparison --------------------------------
+namespace mg {
+__global__ void accept_test_kernel(const double *__restrict__ u, const double *__restrict__ delta, int64_t n,
+                                   uint8_t *__restrict__ fast, uint8_t *__restrict__ exact) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    fast[i] = log_u_less_than(u[i], delta[i]) ? 1 : 0;
+    exact[i] = (log(u[i]) < delta[i]) ? 1 : 0;
+  }
+}
+}  // namespace mg
+
+extern "C" int mg_debug_accept_test(mg_ctx *ctx, const double *u, const double *delta, int64_t n, uint8_t *out_fast,
+                                    uint8_t *out_exact) {
+  if (!ctx) return MG_EINVAL;
+  MG_REQUIRE(ctx, u && delta && out_fast && out_exact && n >= 0, "debug_accept_test: bad arguments");
+  MG_CUDA(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t s = ctx->stream;
+  DevBuf<double> du, dd;
+  DevBuf<uint8_t> df, de;
+  MG_CUDA(ctx, upload(du, u, (size_t)n, s));
+  MG_CUDA(ctx, upload(dd, delta, (size_t)n, s));
+  MG_CUDA(ctx, df.alloc((size_t)n + 1, s));
+  MG_CUDA(ctx, de.alloc((size_t)n + 1, s));
+  if (n) {
+    accept_test_kernel<<<(unsigned)std::min<int64_t>((n + 255) / 256, 4096), 256, 0, s>>>(du.get(), dd.get(), n, df.get(), de.get());
+    MG_CHECK_LAUNCH(ctx);
+    MG_CUDA(ctx, cudaMemcpyAsync(out_fast, df.get(), (size_t)n, cudaMemcpyDeviceToHost, s));
+    MG_CUDA(ctx, cudaMemcpyAsync(out_exact, de.get(), (size_t)n, cudaMemcpyDeviceToHost, s));
+  }
+  MG_CUDA(ctx, cudaStreamSynchronize(s));
+  return MG_OK;
+}

@@ -19,6 +19,9 @@
 
 namespace mg {
 
+#ifndef MG_RS_MINBLOCKS
+#define MG_RS_MINBLOCKS 4
+#endif
 constexpr int RS_BLOCK = 256;
 constexpr int RS_WARPS = RS_BLOCK / 32;
 constexpr int RS_ROUNDS = 8;                       // 32 keys per warp per round
@@ -65,7 +68,7 @@ rs_hist_kernel(const uint64_t *__restrict__ keys, int64_t n, int64_t ntiles, int
 constexpr size_t RS_SCATTER_SMEM = (size_t)RS_TILE * (sizeof(uint64_t) + sizeof(int32_t)) +
                                    (size_t)(RS_WARPS * RS_RADIX + 2 * RS_RADIX) * sizeof(int);
 
-static __global__ void __launch_bounds__(RS_BLOCK)
+static __global__ void __launch_bounds__(RS_BLOCK, MG_RS_MINBLOCKS)
 rs_scatter_kernel(const uint64_t *__restrict__ keys_in, const int32_t *__restrict__ vals_in, int64_t n,
                   int64_t ntiles, int shift, const int32_t *__restrict__ offs /* scanned hist */,
                   uint64_t *__restrict__ keys_out, int32_t *__restrict__ vals_out) {

@@ -152,3 +152,28 @@ def test_bulk_draws_match_oracle(ctx, og):
     assert abs(g.mean() - 0.7) < 0.02 and abs(g.std() - 1.3) < 0.02       # test/stats_test.ml style moments
     u = stats.draw_uniform(-2.0, 3.5, n, ctx=ctx)
     assert u.min() >= -2.0 and u.max() < 3.5 and abs(u.mean() - 0.75) < 0.02
+
+
+def test_accept_prefilter_decides_like_float64(ctx):
+    """rng.cuh log_u_less_than: the single-precision estimate may only decide when it cannot be wrong.  Thresholds
+    are placed at log u +- k ulps, +- 1e-7 .. 1e-3 relative (inside and outside the tolerance band), and at the
+    special values; the fast decision must equal the float64 comparison in every case."""
+    rng = np.random.default_rng(5)
+    base = np.concatenate([rng.random(200_000), rng.random(50_000) * 1e-3, 1.0 - rng.random(50_000) * 1e-9,
+                           np.array([0.0, 5e-324, 1e-310, 1e-40, 1e-31, 1e-30, 1e-29, 2.0 ** -52, 0.5, 1.0 - 2.0 ** -53])])
+    with np.errstate(divide="ignore"):
+        lg = np.log(base)
+    us, ds = [], []
+    for rel in [0.0, 1e-16, 1e-12, 1e-9, 1e-7, 3e-6, 1e-5, 3e-5, 1e-4, 1e-3, 0.1]:
+        for sign in (-1.0, 1.0):
+            us.append(base); ds.append(lg + sign * rel * (1.0 + np.abs(lg)))
+    for k in (-2, -1, 1, 2):
+        us.append(base); ds.append(np.nextafter(lg, np.inf * k) if abs(k) == 1 else np.nextafter(np.nextafter(lg, np.inf * k), np.inf * k))
+    for special in (np.inf, -np.inf, np.nan, 0.0, -1e308, 1e308, -745.0, -800.0):
+        us.append(base); ds.append(np.full(base.size, special))
+    u = np.ascontiguousarray(np.concatenate(us)); d = np.ascontiguousarray(np.concatenate(ds))
+    fast = np.empty(u.size, np.uint8); exact = np.empty(u.size, np.uint8)
+    ctx.check(ctx.lib.mg_debug_accept_test(ctx.h, _abi.ptr(u), _abi.ptr(d), C.c_int64(u.size),
+                                           fast.ctypes.data_as(C.c_void_p), exact.ctypes.data_as(C.c_void_p)))
+    assert np.array_equal(fast, exact)
+    assert 0 < exact.sum() < exact.size
