@@ -239,6 +239,70 @@ __global__ void nest_replace_kernel(NestArgs a, NestProp p, int s0, int s1, int 
   a.fresh_ll[j] = nl; a.fresh_lp[j] = np;
 }
 
+// ---- replace_live_point for a batch (nested.ml:26-43) without re-sorting the whole live set -------------------
+// The survivors [K, nlive) are already ascending; the K new points are sorted by one CTA (bitonic network on
+// (ordered ll, j): stable) and merged by rank: a new point lands before survivors of equal ll (the reference's
+// bubble-up stops at `>` not `>=`, :36), new points of equal ll keep their order j.  Two launches per batch
+// instead of the ~40 of a full radix sort.
+constexpr int NEST_SORT_MAX = 8192;
+
+__global__ void __launch_bounds__(1024)
+nest_sort_fresh_kernel(const double *__restrict__ fll, int K, int P /* pow2 >= K */, uint64_t *__restrict__ skey,
+                       int32_t *__restrict__ sidx) {
+  extern __shared__ __align__(16) unsigned char nsf_smem[];
+  uint64_t *key = reinterpret_cast<uint64_t *>(nsf_smem);
+  int32_t *idx = reinterpret_cast<int32_t *>(key + P);
+  for (int i = threadIdx.x; i < P; i += blockDim.x) {
+    key[i] = (i < K) ? f64_to_ordered(fll[i]) : ~0ull;
+    idx[i] = (i < K) ? i : 0x7FFFFFFF;
+  }
+  __syncthreads();
+  for (int k = 2; k <= P; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < P; i += blockDim.x) {
+        const int l = i ^ j;
+        if (l > i) {
+          const bool up = (i & k) == 0;
+          const uint64_t ka = key[i], kb = key[l];
+          const int32_t ia = idx[i], ib = idx[l];
+          const bool a_gt_b = (ka > kb) || (ka == kb && ia > ib);
+          if (a_gt_b == up) { key[i] = kb; key[l] = ka; idx[i] = ib; idx[l] = ia; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  for (int i = threadIdx.x; i < K; i += blockDim.x) { skey[i] = key[i]; sidx[i] = idx[i]; }
+}
+
+__global__ void nest_merge_kernel(const double *__restrict__ ox, const double *__restrict__ oll,
+                                  const double *__restrict__ olp,            // old live set: [0,K) retired, [K,nlive) survivors
+                                  const double *__restrict__ fx, const double *__restrict__ fll,
+                                  const double *__restrict__ flp,            // the K new points
+                                  const uint64_t *__restrict__ skey, const int32_t *__restrict__ sidx, int nlive, int K,
+                                  int D, double *__restrict__ nx, double *__restrict__ nll, double *__restrict__ nlp) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= nlive) return;
+  const int ns = nlive - K;
+  const double *srow; double ll, lp; int rank;
+  if (e < K) {                       // new point at sorted position e: survivors strictly below it come first
+    const uint64_t k = skey[e];
+    int lo = 0, hi = ns;
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (f64_to_ordered(oll[K + mid]) < k) lo = mid + 1; else hi = mid; }
+    const int j = sidx[e];
+    rank = e + lo; srow = fx + (int64_t)j * D; ll = fll[j]; lp = flp[j];
+  } else {                           // survivor a: new points with ll <= its own come first
+    const int a = e - K;
+    const uint64_t k = f64_to_ordered(oll[e]);
+    int lo = 0, hi = K;
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (skey[mid] <= k) lo = mid + 1; else hi = mid; }
+    rank = a + lo; srow = ox + (int64_t)e * D; ll = oll[e]; lp = olp[e];
+  }
+  nll[rank] = ll; nlp[rank] = lp;
+  double *drow = nx + (int64_t)rank * D;
+  for (int d = 0; d < D; ++d) drow[d] = srow[d];
+}
+
 __global__ void nest_keys_kernel(const double *__restrict__ ll, int n, uint64_t *__restrict__ keys, int32_t *__restrict__ vals) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) { keys[i] = f64_to_ordered(ll[i]); vals[i] = i; }
@@ -463,6 +527,10 @@ extern "C" int mg_nested_evidence(mg_ctx *ctx, const mg_logfn *like, const mg_lo
   const int64_t cap = cfg->max_points;
   MG_CUDA(ctx, rx.alloc((size_t)cap * D, s)); MG_CUDA(ctx, rll.alloc(cap, s)); MG_CUDA(ctx, rlp.alloc(cap, s));
   MG_CUDA(ctx, keys.alloc(nlive, s)); MG_CUDA(ctx, order.alloc(nlive, s));
+  DevBuf<uint64_t> skey; DevBuf<int32_t> sidx;
+  MG_CUDA(ctx, skey.alloc(K, s)); MG_CUDA(ctx, sidx.alloc(K, s));
+  if (K <= NEST_SORT_MAX && K > 4096)
+    MG_CUDA(ctx, cudaFuncSetAttribute(nest_sort_fresh_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, NEST_SORT_MAX * 12));
   MG_CUDA(ctx, d_fail.alloc(1, s));
   MG_CUDA(ctx, cudaMemsetAsync(d_fail.get(), 0, sizeof(int), s));
   // proposals of one chunk of steps for all K chains (24 B each): at most ~200 MB
@@ -603,12 +671,23 @@ extern "C" int mg_nested_evidence(mg_ctx *ctx, const mg_logfn *like, const mg_lo
     MG_CUDA(ctx, cudaMemcpyAsync(rx.get() + R * D, lx[cur].get(), sizeof(double) * K * D, cudaMemcpyDeviceToDevice, s));
     MG_CUDA(ctx, cudaMemcpyAsync(rll.get() + R, lll[cur].get(), sizeof(double) * K, cudaMemcpyDeviceToDevice, s));
     MG_CUDA(ctx, cudaMemcpyAsync(rlp.get() + R, llp[cur].get(), sizeof(double) * K, cudaMemcpyDeviceToDevice, s));
-    // replace_live_point (:26-43): new points take the vacated front slots, then a stable sort
-    MG_CUDA(ctx, cudaMemcpyAsync(lx[cur].get(), fx.get(), sizeof(double) * K * D, cudaMemcpyDeviceToDevice, s));
-    MG_CUDA(ctx, cudaMemcpyAsync(lll[cur].get(), fll.get(), sizeof(double) * K, cudaMemcpyDeviceToDevice, s));
-    MG_CUDA(ctx, cudaMemcpyAsync(llp[cur].get(), flp.get(), sizeof(double) * K, cudaMemcpyDeviceToDevice, s));
     double tC = dbg ? now() : 0;
-    if ((rc = sort_live(cur, 1 - cur))) return rc;
+    if (K <= NEST_SORT_MAX) {
+      // replace_live_point (:26-43): sort the K new points, merge them into the (sorted) survivors
+      int P = 1; while (P < K) P <<= 1;
+      nest_sort_fresh_kernel<<<1, 1024, (size_t)P * 12, s>>>(fll.get(), K, P, skey.get(), sidx.get());
+      MG_CHECK_LAUNCH(ctx);
+      nest_merge_kernel<<<(nlive + 255) / 256, 256, 0, s>>>(lx[cur].get(), lll[cur].get(), llp[cur].get(), fx.get(), fll.get(),
+                                                           flp.get(), skey.get(), sidx.get(), nlive, K, D, lx[1 - cur].get(),
+                                                           lll[1 - cur].get(), llp[1 - cur].get());
+      MG_CHECK_LAUNCH(ctx);
+    } else {
+      // new points take the vacated front slots, then a stable sort of the whole set
+      MG_CUDA(ctx, cudaMemcpyAsync(lx[cur].get(), fx.get(), sizeof(double) * K * D, cudaMemcpyDeviceToDevice, s));
+      MG_CUDA(ctx, cudaMemcpyAsync(lll[cur].get(), fll.get(), sizeof(double) * K, cudaMemcpyDeviceToDevice, s));
+      MG_CUDA(ctx, cudaMemcpyAsync(llp[cur].get(), flp.get(), sizeof(double) * K, cudaMemcpyDeviceToDevice, s));
+      if ((rc = sort_live(cur, 1 - cur))) return rc;
+    }
     cur = 1 - cur;
     double tD = dbg ? now() : 0;
     if (dbg) { t_chain += tB - tA; t_rest += tC - tB; t_sort += tD - tC; ++nb; }
