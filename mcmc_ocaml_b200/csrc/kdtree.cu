@@ -174,7 +174,7 @@ part_fused_kernel(BuildArrays a, const int32_t *__restrict__ lists_in, int32_t *
     const int4 *lp = reinterpret_cast<const int4 *>(list + base), *sp = reinterpret_cast<const int4 *>(seg_in + base);
 #pragma unroll
     for (int v = 0; v < SCAN_ITEMS / 4; ++v) {
-      const int4 li = __ldg(lp + v), si = __ldg(sp + v);
+      const int4 li = __ldcs(lp + v), si = __ldg(sp + v);   // lists stream through (evict first): keep L2 for side[] and seg[]
       ix[4 * v] = li.x; ix[4 * v + 1] = li.y; ix[4 * v + 2] = li.z; ix[4 * v + 3] = li.w;
       nd[4 * v] = si.x; nd[4 * v + 1] = si.y; nd[4 * v + 2] = si.z; nd[4 * v + 3] = si.w;
     }
@@ -183,7 +183,7 @@ part_fused_kernel(BuildArrays a, const int32_t *__restrict__ lists_in, int32_t *
     for (int k = 0; k < SCAN_ITEMS; ++k) {
       const int64_t p = base + k;
       ix[k] = 0; nd[k] = -1;
-      if (p < a.N) { ix[k] = list[p]; nd[k] = seg_in[p]; }
+      if (p < a.N) { ix[k] = __ldcs(list + p); nd[k] = seg_in[p]; }
     }
   }
   int acc = 0;
@@ -235,14 +235,14 @@ part_fused_kernel(BuildArrays a, const int32_t *__restrict__ lists_in, int32_t *
     const int64_t p = base + k;
     if (p < a.N) {
       if (nd[k] < 0) {                       // element of a node that does not split at this level
-        out[p] = ix[k];
+        __stcs(out + p, ix[k]);
         if (l == 0) seg_out[p] = -1 - nd[k];
       } else {
         const int32_t id = nd[k];
         const int32_t b = a.begin[id], sp = a.spos[id];
         const int32_t r = E - ebegin[id - lb];            // right-goers in [b, p)
         const int64_t dst = f[k] ? (int64_t)sp + r : (int64_t)b + (p - b) - r;
-        out[dst] = ix[k];
+        __stcs(out + dst, ix[k]);
         if (l == 0) seg_out[p] = (p < sp) ? a.left[id] : a.left[id] + 1;
       }
     }
