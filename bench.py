@@ -326,7 +326,7 @@ def main():
                 torch.cuda.empty_cache()
                 sys.path.insert(0, os.path.join(ROOT, "tools"))
                 import bench_evidence
-                ev = bench_evidence.run(bench_evidence._Args(reps=2, device=local_rank), ctx=ctx)
+                ev = bench_evidence.run(bench_evidence._Args(reps=3, device=local_rank), ctx=ctx)
                 out["evidence"] = {
                     "workload": "cfg3: Weinberg (Lebesgue) kd-tree evidence + harmonic mean, 1e7 synthetic 20-D "
                                 "posterior samples, device resident, one GPU",
