@@ -534,7 +534,8 @@ extern "C" int mg_nested_evidence(mg_ctx *ctx, const mg_logfn *like, const mg_lo
   MG_CUDA(ctx, d_fail.alloc(1, s));
   MG_CUDA(ctx, cudaMemsetAsync(d_fail.get(), 0, sizeof(int), s));
   // proposals of one chunk of steps for all K chains (24 B each): at most ~200 MB
-  const int chunk = std::max(1, std::min(std::max(cfg->nmcmc, 1), std::max(16, (1 << 23) / K)));
+  int chunk = std::max(1, std::min(std::max(cfg->nmcmc, 1), std::max(16, (1 << 23) / K)));
+  if (const char *e = getenv("MCMC_GPU_NEST_CHUNK")) chunk = std::max(1, std::min(chunk, atoi(e)));   // tests: force the multi-chunk path
   // two sets: when a batch is one chunk, the draws of batch b+1 are made on the second stream while the chains of
   // batch b run (the draws do not depend on the live set; the chain kernel leaves most of the machine idle)
   const bool overlap = chunk >= cfg->nmcmc && cfg->nmcmc > 0;

@@ -31,7 +31,7 @@ def test_harmonic_mean(ctx, og):
         assert got == pytest.approx(seq, rel=1e-11)         # vs the reference's left-to-right sum
 
 
-@pytest.mark.parametrize("D,n,nb", [(2, 10000, 64), (2, 3000, 16), (5, 20000, 64), (20, 30000, 64), (1, 5000, 32)])
+@pytest.mark.parametrize("D,n,nb", [(2, 10000, 64), (2, 3000, 16), (5, 20000, 64), (20, 30000, 64), (1, 5000, 32), (40, 6000, 64)])
 def test_lebesgue_matches_oracle(ctx, og, D, n, nb):
     pts, ll, lp = mh_samples(ctx, 100 + D, D, n)            # MH output: ~50 % exact repeats
     for eps in (0.1, 0.2, 1e9):

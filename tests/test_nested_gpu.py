@@ -28,6 +28,35 @@ def test_point_for_point_vs_oracle(ctx, og, batch):
     np.testing.assert_allclose(g.log_weights, o["logw"], rtol=0, atol=1e-10)
 
 
+@pytest.mark.parametrize("D,nlive,batch,nmcmc,kind", [(3, 300, 40, 25, "diag"), (16, 400, 70, 20, "shell"), (5, 256, 33, 30, "shell"),
+                                                      (20, 300, 64, 12, "diag"), (4, 200, 1, 40, "shell")])
+def test_point_for_point_more_shapes(ctx, og, D, nlive, batch, nmcmc, kind):
+    """odd and even D, D == DMAX and D < DMAX, batches that are not a multiple of the warp, closed box prior"""
+    like = P.gauss_diag(np.full(D, 0.5), np.linspace(0.05, 0.2, D)) if kind == "diag" else P.shell(np.full(D, 0.5), 0.3, 0.05)
+    prior = P.box(np.zeros(D), np.ones(D), 0.0)
+    ctx.set_seed(1000 + D)
+    g = nested.nested_evidence(like, prior, np.zeros(D), np.ones(D), nlive=nlive, nmcmc=nmcmc, batch=batch, ctx=ctx)
+    o = og.nested_evidence(1000 + D, 0, like, prior, np.zeros(D), np.ones(D), nlive=nlive, nmcmc=nmcmc, batch=batch)
+    assert len(g.log_likelihood) == len(o["ll"])
+    assert np.array_equal(g.points, o["pts"])
+    np.testing.assert_allclose(g.log_likelihood, o["ll"], rtol=1e-13, atol=1e-13)
+    assert g.log_evidence == pytest.approx(o["log_ev"], abs=1e-10)
+
+
+def test_chunked_chain_walk(ctx, og, monkeypatch):
+    """nmcmc walked in several chunks (proposal buffer smaller than nmcmc x K): chain state parked in global memory"""
+    D = 6
+    like = P.shell(np.full(D, 0.5), 0.3, 0.05)
+    prior = P.box(np.zeros(D), np.ones(D), 0.0)
+    ctx.set_seed(77)
+    whole = nested.nested_evidence(like, prior, np.zeros(D), np.ones(D), nlive=200, nmcmc=50, batch=24, ctx=ctx)
+    monkeypatch.setenv("MCMC_GPU_NEST_CHUNK", "7")
+    ctx.set_seed(77)
+    parts = nested.nested_evidence(like, prior, np.zeros(D), np.ones(D), nlive=200, nmcmc=50, batch=24, ctx=ctx)
+    assert np.array_equal(whole.points, parts.points) and np.array_equal(whole.log_likelihood, parts.log_likelihood)
+    assert whole.log_evidence == parts.log_evidence
+
+
 def test_weights_deterministic_parity(ctx, og):
     """N5: evidence_error_and_weights given identical inputs, K = 1 and batched"""
     rng = np.random.default_rng(3)
