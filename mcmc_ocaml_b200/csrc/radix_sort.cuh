@@ -88,12 +88,18 @@ rs_scatter_kernel(const uint64_t *__restrict__ keys_in, const int32_t *__restric
   const int64_t wbase = tile0 + (int64_t)w * (32 * RS_ROUNDS);
   const int nvalid = (int)((n - tile0 < RS_TILE) ? (n - tile0) : RS_TILE);
   uint64_t key[RS_ROUNDS];
+  int32_t val[RS_ROUNDS];
   int rank[RS_ROUNDS];
+#pragma unroll
+  for (int r = 0; r < RS_ROUNDS; ++r) {   // all the tile's loads in flight before the first ranking round
+    const int64_t i = wbase + r * 32 + lane;
+    key[r] = (i < n) ? __ldcs(ksrc + i) : ~0ull;
+    val[r] = (i < n) ? __ldcs(vsrc + i) : 0;
+  }
 #pragma unroll
   for (int r = 0; r < RS_ROUNDS; ++r) {
     const int64_t i = wbase + r * 32 + lane;
     const bool valid = i < n;
-    key[r] = valid ? ksrc[i] : ~0ull;
     const int d = (int)((key[r] >> shift) & 0xFF);
     const unsigned peers = __match_any_sync(0xffffffffu, valid ? d : 256);
     const int before = __popc(peers & ((1u << lane) - 1u));
@@ -124,7 +130,7 @@ rs_scatter_kernel(const uint64_t *__restrict__ keys_in, const int32_t *__restric
       const int d = (int)((key[r] >> shift) & 0xFF);
       const int pos = dbase[d] + cnt[w][d] + rank[r];
       skeys[pos] = key[r];
-      svals[pos] = vsrc[i];
+      svals[pos] = val[r];
     }
   }
   __syncthreads();
