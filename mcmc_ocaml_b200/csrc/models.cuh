@@ -231,157 +231,83 @@ __device__ __forceinline__ double dyn_log_multi_gaussian(const double *mu, const
 struct DynFn {
   typedef DynFnParams Params;
   static constexpr int kSmem = 0;
-  // NP points evaluated side by side inside ONE switch: with NP = 2 the two dependent chains sit in the same
-  // straight-line code and interleave (the nested-sampling chain kernel is latency bound and runs two chains
-  // per thread); NP = 1 is the plain form.
-  template <int DMAX, int NP>
-  static __device__ __forceinline__ void rawn(const Params &f, const double (&x)[NP][DMAX], int d, double (&out)[NP]) {
+  template <int DMAX>
+  static __device__ __forceinline__ double raw(const Params &f, const double (&x)[DMAX], int d) {
     const double *p = f.p;
     switch (f.kind) {
-      case MG_FN_ZERO:
-#pragma unroll
-        for (int c = 0; c < NP; ++c) out[c] = 0.0;
-        return;
-      case MG_FN_CONST:
-#pragma unroll
-        for (int c = 0; c < NP; ++c) out[c] = __ldg(p);
-        return;
+      case MG_FN_ZERO: return 0.0;
+      case MG_FN_CONST: return __ldg(p);
       case MG_FN_BOX_CLOSED: {  // bin/gaussian_cauchy_efficiency.ml:60-67
         // no short circuit: the 2 d bounds are independent loads and the comparisons combine bitwise
         // (same truth value; a short-circuit chain serialises the loads behind the predicates)
-        int o[NP];
-#pragma unroll
-        for (int c = 0; c < NP; ++c) o[c] = 0;
+        int out = 0;
 #pragma unroll (DMAX <= 16 ? DMAX : 1)
         for (int i = 0; i < DMAX; ++i)
-          if (i < d) {
-            const double lo = __ldg(p + i), hi = __ldg(p + d + i);
-#pragma unroll
-            for (int c = 0; c < NP; ++c) o[c] |= (int)(x[c][i] < lo) | (int)(x[c][i] > hi);
-          }
+          if (i < d) { const double lo = __ldg(p + i), hi = __ldg(p + d + i); out |= (int)(x[i] < lo) | (int)(x[i] > hi); }
         const double inside = __ldg(p + 2 * d);
-#pragma unroll
-        for (int c = 0; c < NP; ++c) out[c] = o[c] ? neg_inf() : inside;
-        return;
+        return out ? neg_inf() : inside;
       }
       case MG_FN_BOX_OPEN: {  // test/nested_test.ml:24-28
-        int in[NP];
-#pragma unroll
-        for (int c = 0; c < NP; ++c) in[c] = 1;
+        int in = 1;
 #pragma unroll (DMAX <= 16 ? DMAX : 1)
         for (int i = 0; i < DMAX; ++i)
-          if (i < d) {
-            const double lo = __ldg(p + i), hi = __ldg(p + d + i);
-#pragma unroll
-            for (int c = 0; c < NP; ++c) in[c] &= (int)(x[c][i] > lo) & (int)(x[c][i] < hi);
-          }
+          if (i < d) { const double lo = __ldg(p + i), hi = __ldg(p + d + i); in &= (int)(x[i] > lo) & (int)(x[i] < hi); }
         const double inside = __ldg(p + 2 * d);
-#pragma unroll
-        for (int c = 0; c < NP; ++c) out[c] = in[c] ? inside : neg_inf();
-        return;
+        return in ? inside : neg_inf();
       }
-      case MG_FN_GAUSS_DIAG:
-#pragma unroll
-        for (int c = 0; c < NP; ++c) out[c] = dyn_log_multi_gaussian<DMAX>(p, p + d, p + f.np, x[c], d);
-        return;
+      case MG_FN_GAUSS_DIAG: return dyn_log_multi_gaussian<DMAX>(p, p + d, p + f.np, x, d);
       case MG_FN_GAUSS_CORR: {
         const double *mu = p, *L = p + d;
-#pragma unroll
-        for (int c = 0; c < NP; ++c) {
-          double z[DMAX];
+        double z[DMAX];
 #pragma unroll (DMAX <= 16 ? DMAX : 1)
-          for (int j = 0; j < DMAX; ++j) z[j] = (j < d) ? x[c][j] - __ldg(mu + j) : 0.0;
-          double q = 0.0;
+        for (int j = 0; j < DMAX; ++j) z[j] = (j < d) ? x[j] - __ldg(mu + j) : 0.0;
+        double q = 0.0;
 #pragma unroll (DMAX <= 16 ? DMAX : 1)
-          for (int i = 0; i < DMAX; ++i) {
-            if (i < d) {
-              double y = __ldg(L + i * (i + 1) / 2) * z[0];
+        for (int i = 0; i < DMAX; ++i) {
+          if (i < d) {
+            double y = __ldg(L + i * (i + 1) / 2) * z[0];
 #pragma unroll (DMAX <= 16 ? DMAX : 1)
-              for (int j = 1; j < DMAX; ++j)
-                if (j <= i) y = fma(__ldg(L + i * (i + 1) / 2 + j), z[j], y);
-              q = fma(y, y, q);
-            }
+            for (int j = 1; j < DMAX; ++j)
+              if (j <= i) y = fma(__ldg(L + i * (i + 1) / 2 + j), z[j], y);
+            q = fma(y, y, q);
           }
-          out[c] = fma(-0.5, q, __ldg(p + d + d * (d + 1) / 2));
         }
-        return;
+        return fma(-0.5, q, __ldg(p + d + d * (d + 1) / 2));
       }
       case MG_FN_GAUSS_DATA: {  // bin/gaussian_cauchy_efficiency.ml:69-77
-        double ls[NP], sum[NP];
-#pragma unroll
-        for (int c = 0; c < NP; ++c) { ls[c] = log(x[c][1]); sum[c] = 0.0; }
-        for (int64_t i = 0; i < f.np; ++i) {
-          const double v = __ldg(p + i);
-#pragma unroll
-          for (int c = 0; c < NP; ++c) sum[c] = sum[c] + log_gaussian_ls(x[c][0], x[c][1], ls[c], v);
-        }
-#pragma unroll
-        for (int c = 0; c < NP; ++c) out[c] = sum[c] + 0.0;
-        return;
+        const double mu = x[0], sigma = x[1], ls = log(sigma);
+        double sum = 0.0;
+        for (int64_t i = 0; i < f.np; ++i) sum = sum + log_gaussian_ls(mu, sigma, ls, __ldg(p + i));
+        return sum + 0.0;
       }
       case MG_FN_CAUCHY_DATA: {  // bin/gaussian_cauchy_efficiency.ml:79-87
-        double lg[NP], sum[NP];
-#pragma unroll
-        for (int c = 0; c < NP; ++c) { lg[c] = log(MG_PI * x[c][1]); sum[c] = 0.0; }
-        for (int64_t i = 0; i < f.np; ++i) {
-          const double v = __ldg(p + i);
-#pragma unroll
-          for (int c = 0; c < NP; ++c) sum[c] = sum[c] + log_cauchy_lg(x[c][0], x[c][1], lg[c], v);
-        }
-#pragma unroll
-        for (int c = 0; c < NP; ++c) out[c] = sum[c] + 0.0;
-        return;
+        const double x0 = x[0], gamma = x[1], lg = log(MG_PI * gamma);
+        double sum = 0.0;
+        for (int64_t i = 0; i < f.np; ++i) sum = sum + log_cauchy_lg(x0, gamma, lg, __ldg(p + i));
+        return sum + 0.0;
       }
       case MG_FN_SHELL: {
-        double s[NP];
-#pragma unroll
-        for (int c = 0; c < NP; ++c) s[c] = 0.0;
+        double s = 0.0;
 #pragma unroll (DMAX <= 16 ? DMAX : 1)
         for (int i = 0; i < DMAX; ++i)
-          if (i < d) {
-            const double ci = __ldg(p + i);
-#pragma unroll
-            for (int c = 0; c < NP; ++c) { const double dx = x[c][i] - ci; s[c] = s[c] + dx * dx; }
-          }
-        const double mu = __ldg(p + d), sigma = __ldg(p + d + 1), lsig = __ldg(p + f.np);   // [np] = log sigma (host)
-#pragma unroll
-        for (int c = 0; c < NP; ++c) out[c] = log_gaussian_ls(mu, sigma, lsig, sqrt(s[c]));
-        return;
+          if (i < d) { const double dx = x[i] - __ldg(p + i); s = s + dx * dx; }
+        return log_gaussian_ls(__ldg(p + d), __ldg(p + d + 1), __ldg(p + f.np), sqrt(s));  // [np] = log sigma (host)
       }
       case MG_FN_GAUSS_MIX: {  // test/nested_test.ml:47-53
         const int K = (int)__ldg(p);
-#pragma unroll
-        for (int c = 0; c < NP; ++c) {
-          double tot = 0.0;
-          for (int k = 0; k < K; ++k) tot = tot + exp(dyn_log_multi_gaussian<DMAX>(p + 1 + k * d, p + 1 + K * d, p + f.np, x[c], d));
-          out[c] = log(tot);
-        }
-        return;
+        double tot = 0.0;
+        for (int k = 0; k < K; ++k) tot = tot + exp(dyn_log_multi_gaussian<DMAX>(p + 1 + k * d, p + 1 + K * d, p + f.np, x, d));
+        return log(tot);
       }
     }
     // kinds >= MG_FN_USER: functions registered with mg_plugin_register_source; they
     // exist only in kernels compiled at run time (jit.cu), where MG_USER_EVAL is defined
-#pragma unroll
-    for (int c = 0; c < NP; ++c) out[c] = MG_USER_EVAL(f.kind, x[c], d, p, f.np);
-  }
-  template <int DMAX>
-  static __device__ __forceinline__ double raw(const Params &f, const double (&x)[DMAX], int d) {
-    double o[1];
-    rawn<DMAX, 1>(f, reinterpret_cast<const double (&)[1][DMAX]>(x), d, o);
-    return o[0];
+    return MG_USER_EVAL(f.kind, x, d, p, f.np);
   }
   template <int DMAX>
   static __device__ __forceinline__ double eval(const Params &f, const double *, const double (&x)[DMAX], int d) {
     const double v = raw<DMAX>(f, x, d);
     return f.scale == 1.0 ? v : f.scale * v;
-  }
-  template <int DMAX, int NP>
-  static __device__ __forceinline__ void evaln(const Params &f, const double (&x)[NP][DMAX], int d, double (&out)[NP]) {
-    rawn<DMAX, NP>(f, x, d, out);
-    if (f.scale != 1.0) {
-#pragma unroll
-      for (int c = 0; c < NP; ++c) out[c] = f.scale * out[c];
-    }
   }
 };
 
