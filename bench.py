@@ -266,6 +266,7 @@ def main():
     e1.record(stream)
     barrier()
     e2e_ms = max(e0.elapsed_time(e1), 1e3 * (time.perf_counter() - t0))
+    e2e_kernel_ms = ctx.last_kernel_ms   # the sampler launch inside the last call (library events)
     t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -303,7 +304,7 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(Cn, T),
             "e2e": {"value": e2e_value, "unit": "chain-steps/s", "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps,
+                    "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps, "sampler_kernel_ms_in_call": e2e_kernel_ms,
                     "call": "mg_mcmc_array_resident: pinned x0 -> device, MH kernel (per-chain running moments kept in "
                             "registers), sample block stays in HBM, Stats mean/std pooled from the chain moments, "
                             "final states + counters + stats -> host"},
