@@ -141,19 +141,19 @@ cell_terms_kernel(const KdNode *__restrict__ nodes, const int32_t *__restrict__ 
     if (nodes[id].left >= 0 || cnt >= nmax) continue;   // not (length_at_least nmax objs) -> [c]
     const int b = begin[id];
     // bounds_of_objects (kd_tree.ml:96-110) + bounds_volume (:177-182, product in dimension order)
+    // Lane d owns dimension d (d + 32, ... beyond 32): every point is one coalesced row read, no reduction across
+    // lanes; the extents are then multiplied in dimension order.
     double v = 1.0;
-    for (int d = 0; d < D; ++d) {
+    for (int d0 = 0; d0 < D; d0 += 32) {
+      const int d = d0 + lane;
       double lo = __longlong_as_double(0x7FF0000000000000ll), hi = -lo;
-      for (int k = lane; k < cnt; k += 32) {
-        const double c = pts[(int64_t)perm[b + k] * D + d];
-        lo = fmin(lo, c); hi = fmax(hi, c);
+      for (int k = 0; k < cnt; ++k) {
+        const int64_t row = (int64_t)__ldg(perm + b + k) * D;
+        if (d < D) { const double c = pts[row + d]; lo = fmin(lo, c); hi = fmax(hi, c); }
       }
-#pragma unroll
-      for (int off = 16; off > 0; off >>= 1) {
-        lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, off));
-        hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, off));
-      }
-      v = v * (hi - lo);
+      const double ext = hi - lo;
+      const int nd = (D - d0 < 32) ? D - d0 : 32;
+      for (int i = 0; i < nd; ++i) v = v * __shfl_sync(0xffffffffu, ext, i);
     }
     v = v + 0.0;
     for (int k = lane; k < cnt; k += 32) {
