@@ -67,6 +67,34 @@ def gather_ensemble_stats(n_samples: int, mean: np.ndarray, std: np.ndarray, acc
     return dict(n=n, mean=mu, std=sd, accept=int(g[:, 1].sum()), reject=int(g[:, 2].sum()))
 
 
+def combine_harmonic(counts, evidences) -> float:
+    """Harmonic-mean evidence of pooled samples from per-rank shards (evidence.ml:101-107): shard r reports
+    n_r and Z_r = n_r / sum_i 1/L_i, so the pooled estimate is (sum n_r) / sum_r (n_r / Z_r), summed in rank order."""
+    n, inv = 0.0, 0.0
+    for c, z in zip(counts, evidences):
+        if c > 0:
+            n += float(c)
+            inv += float(c) / float(z)
+    return n / inv
+
+
+def harmonic_mean_sharded(log_likelihoods_shard, ctx=None, device=None) -> float:
+    """``Evidence.evidence_harmonic_mean`` over samples sharded across ranks: each rank reduces its own shard on
+    its GPU, the (count, estimate) pairs are all-gathered and combined in rank order."""
+    from . import evidence
+    ll = np.asarray(log_likelihoods_shard, dtype=np.float64)
+    z = evidence.evidence_harmonic_mean(ll=ll, ctx=ctx) if ll.size else 0.0
+    g = all_gather_array(np.array([float(ll.size), z]), device)
+    return combine_harmonic(g[:, 0], g[:, 1])
+
+
+def combine_model_counts(counts_a_b, device=None):
+    """``Mcmc.rjmcmc_model_counts`` / ``rjmcmc_evidence_ratio`` (mcmc.ml:141-153) of an ensemble sharded across ranks."""
+    g = all_gather_array(np.asarray(counts_a_b, dtype=np.float64), device)
+    na, nb = int(g[:, 0].sum()), int(g[:, 1].sum())
+    return na, nb, (na / nb if nb else float("inf"))
+
+
 def broadcast_tree(tree, src: int = 0, ctx=None):
     """Replicate a KdTree built on rank `src` to every rank: one broadcast of
     the serialised device blob.  Returns the local KdTree."""

@@ -30,6 +30,15 @@ def test_combine_moments_matches_pooled():
     np.testing.assert_allclose(sd, allx.std(0, ddof=1), rtol=1e-13)
 
 
+def test_combine_harmonic_matches_pooled():
+    rng = np.random.default_rng(2)
+    ll = rng.normal(-3.0, 1.0, 5000)
+    pooled = ll.size / np.sum(1.0 / np.exp(ll))
+    parts = [ll[:1234], ll[1234:1235], ll[1235:]]
+    z = D.combine_harmonic([p.size for p in parts], [p.size / np.sum(1.0 / np.exp(p)) for p in parts])
+    assert abs(z - pooled) <= 1e-13 * pooled
+
+
 def _worker(rank, world, port, q):
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -40,6 +49,8 @@ def _worker(rank, world, port, q):
     x = np.random.default_rng(5).normal(1.0, 3.0, (1001, 3))[b:e]       # this rank's shard of a common data set
     res = D.gather_ensemble_stats(len(x), x.mean(0), x.std(0, ddof=1), accept=10 * (rank + 1), reject=5)
     g = D.all_gather_array(np.array([float(rank), rng.random()]))
+    na, nb, ratio = D.combine_model_counts([100 * (rank + 1), 50])
+    assert (na, nb, ratio) == (300, 100, 3.0)
     q.put((rank, res["n"], res["mean"], res["std"], res["accept"], res["reject"], g[:, 0].tolist()))
     dist.barrier()
     dist.destroy_process_group()

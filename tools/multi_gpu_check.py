@@ -65,16 +65,22 @@ def main():
     s = mcmc.mcmc_array(n, like, prior, prop, mu, nchains=ce - cb, chain_offset=cb, nbin=20, ctx=ctx)
     pooled = s.block.transpose(0, 2, 1).reshape(-1, Dd + 2)
     res = D.gather_ensemble_stats(pooled.shape[0], pooled.mean(0), pooled.std(0, ddof=1), int(s.accept.sum()), int(s.reject.sum()), device=dev)
+    # ---- 3. harmonic-mean evidence of the pooled chains from per-rank shards ---
+    z_sharded = D.harmonic_mean_sharded(pooled[:, Dd], ctx=ctx, device=dev)
     if rank == 0:
         ctx.set_seed(99)
         ref = mcmc.mcmc_array(n, like, prior, prop, mu, nchains=C, chain_offset=0, nbin=20, ctx=ctx)
+        from mcmc_ocaml_b200 import evidence
+        z_all = evidence.evidence_harmonic_mean(ll=ref.block[:, Dd, :].reshape(-1), ctx=ctx)
+        out["harmonic_sharded_rel_err"] = float(abs(z_sharded - z_all) / abs(z_all))
         rp = ref.block.transpose(0, 2, 1).reshape(-1, Dd + 2)
         out["ensemble_mean_err"] = float(np.max(np.abs(res["mean"] - rp.mean(0))))
         out["ensemble_std_err"] = float(np.max(np.abs(res["std"] - rp.std(0, ddof=1))))
         out["accept_equal"] = bool(res["accept"] == int(ref.accept.sum()))
         out["shard_chains_bit_exact"] = bool(np.array_equal(ref.block[:, :, cb:ce], s.block))
         out["ok"] = bool(out.get("sharded_density_bit_exact") and out["accept_equal"] and out["shard_chains_bit_exact"]
-                         and out["ensemble_mean_err"] < 1e-12 and out["ensemble_std_err"] < 1e-12)
+                         and out["ensemble_mean_err"] < 1e-12 and out["ensemble_std_err"] < 1e-12
+                         and out["harmonic_sharded_rel_err"] < 1e-12)
         print(json.dumps(out))
     if world > 1:
         dist.barrier()
