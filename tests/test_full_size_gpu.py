@@ -106,3 +106,13 @@ def test_config2_full_size_posterior(ctx):
     # slot 0 is the start, the block statistics agree with torch's own reduction over the resident block
     assert torch.equal(blk[0, :D, 0].cpu(), torch.as_tensor(mu))
     np.testing.assert_allclose(mean[3], float(blk[:, 3, :].mean()), rtol=1e-12)
+    np.testing.assert_allclose(std[3], float(blk[:, 3, :].std()), rtol=1e-10)
+    np.testing.assert_allclose(mean[D], float(blk[:, D, :].mean()), rtol=1e-12)
+    # the full-length chains themselves: 24 chains spread over the ensemble (first, ragged middle, last) are bit-identical
+    # to the oracle's run of the same global chain ids (the balanced kernel hands their 79 segments to different warps)
+    from oracle import oracle as og
+    for c0 in (0, 31337, Cn - 8):
+        want, wacc, _ = og.mcmc_array(0x5EED0001, 0, n, like, prior, prop, mu, nchains=8, chain_offset=c0, nthreads=8)
+        got = blk[:, :, c0:c0 + 8].cpu().numpy()
+        assert np.array_equal(got, want)
+        assert np.array_equal(acc[c0:c0 + 8], wacc)
