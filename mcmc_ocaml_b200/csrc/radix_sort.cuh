@@ -24,7 +24,10 @@ namespace mg {
 #endif
 constexpr int RS_BLOCK = 256;
 constexpr int RS_WARPS = RS_BLOCK / 32;
-constexpr int RS_ROUNDS = 8;                       // 32 keys per warp per round
+#ifndef MG_RS_ROUNDS
+#define MG_RS_ROUNDS 8
+#endif
+constexpr int RS_ROUNDS = MG_RS_ROUNDS;             // 32 keys per warp per round
 constexpr int RS_TILE = RS_BLOCK * RS_ROUNDS;       // 4096 keys per CTA
 constexpr int RS_RADIX = 256;
 
