@@ -20,6 +20,9 @@
 // of 8 D-byte rows).  All kernels are HBM / L2-gather bound.
 #include "kdtree.cuh"
 
+#include <cstdlib>
+#include <vector>
+
 #include "common.cuh"
 #include "radix_sort.cuh"
 #include "scan.cuh"
@@ -56,6 +59,51 @@ make_keys_kernel(const double *__restrict__ pts, int64_t N, int D, uint64_t *__r
     }
     for (int r = threadIdx.x; r < cnt; r += KB) vals[(int64_t)D * N + i0 + r] = (int32_t)(i0 + r);
     __syncthreads();
+  }
+}
+
+// ---- sorting the D coordinate lists on a 32-bit window of the keys ------------------------------------------------
+// The tree needs the index lists only, not the sorted keys.  The coordinates of one dimension usually share their
+// top bytes (sign, most of the exponent), so the order is decided by the 32 bits below the highest byte that
+// varies: four radix passes over (4-byte key, 4-byte index) pairs instead of seven over (8-byte key, index) pairs.
+// Elements whose windows tie keep their input order (the passes are stable); tie_fix_kernel then orders each run of
+// equal windows by the full key (stable insertion, runs are a handful of elements for continuous data, equal full
+// keys -- duplicated samples -- stay in input order).  A run longer than KD_TIE_MAX raises a flag and the build
+// falls back to the 64-bit sort.
+constexpr int KD_TIE_MAX = 64;
+
+__global__ void make_key32_kernel(const uint64_t *__restrict__ keys, int64_t N, const int *__restrict__ shift /* [D] */,
+                                  uint32_t *__restrict__ key32) {
+  const int d = blockIdx.y;
+  const int sh = shift[d];
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x)
+    key32[(int64_t)d * N + i] = (uint32_t)(__ldcs(keys + (int64_t)d * N + i) >> sh);
+}
+
+__global__ void tie_fix_kernel(const uint32_t *__restrict__ key32 /* sorted */, int32_t *__restrict__ lists,
+                               const uint64_t *__restrict__ keys /* [D][N] by point id */, int64_t N,
+                               const int *__restrict__ shift, int *__restrict__ overflow) {
+  const int d = blockIdx.y;
+  if (shift[d] == 0) return;                      // the window holds every varying bit: ties are equal keys
+  const uint32_t *k32 = key32 + (int64_t)d * N;
+  int32_t *lst = lists + (int64_t)d * N;
+  const uint64_t *kf = keys + (int64_t)d * N;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint32_t k = k32[i];
+    if ((i > 0 && k32[i - 1] == k) || i + 1 >= N || k32[i + 1] != k) continue;   // not the head of a run
+    int L = 2;
+    while (i + L < N && L <= KD_TIE_MAX && k32[i + L] == k) ++L;
+    if (L > KD_TIE_MAX) { *overflow = 1; continue; }
+    int32_t id[KD_TIE_MAX];
+    uint64_t full[KD_TIE_MAX];
+    for (int j = 0; j < L; ++j) { id[j] = lst[i + j]; full[j] = kf[id[j]]; }
+    for (int j = 1; j < L; ++j) {                 // stable insertion sort by the full key
+      const uint64_t fk = full[j]; const int32_t fi = id[j];
+      int m = j - 1;
+      while (m >= 0 && full[m] > fk) { full[m + 1] = full[m]; id[m + 1] = id[m]; --m; }
+      full[m + 1] = fk; id[m + 1] = fi;
+    }
+    for (int j = 0; j < L; ++j) lst[i + j] = id[j];
   }
 }
 
@@ -303,8 +351,40 @@ int build_tree(mg_ctx *ctx, const double *d_pts, int64_t N, int D, const double 
       MG_CUDA(ctx, cudaFuncSetAttribute(make_keys_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mk_smem));
     make_keys_kernel<<<grid1d(ctx, (N + MK_TILE - 1) / MK_TILE * KB), KB, mk_smem, s>>>(d_pts, N, D, keys.get(), listsA.get());
     MG_CHECK_LAUNCH(ctx);
-    int rc = radix_sort_pairs(ctx, keys.get(), listsA.get(), N, D);
-    if (rc) return rc;
+    int rc;
+    bool sorted = false;
+    static const bool use32 = [] { const char *e = getenv("MCMC_GPU_SORT32"); return e ? atoi(e) != 0 : true; }();
+    if (use32 && N >= 65536) {
+      // 32-bit window under the highest varying byte of each dimension (see make_key32_kernel)
+      std::vector<unsigned char> cb;
+      if ((rc = radix_constant_bytes<uint64_t>(ctx, keys.get(), N, D, cb))) return rc;
+      std::vector<int> h_shift(D, 0);
+      for (int d = 0; d < D; ++d) {
+        int top = 0;
+        for (int p = 7; p >= 0; --p) if (!cb[(size_t)d * 8 + p]) { top = p; break; }
+        h_shift[d] = 8 * std::max(0, top - 3);
+      }
+      DevBuf<int> d_shift, d_over;
+      DevBuf<uint32_t> key32;
+      MG_CUDA(ctx, upload(d_shift, h_shift.data(), (size_t)D, s));
+      MG_CUDA(ctx, d_over.alloc(1, s));
+      MG_CUDA(ctx, cudaMemsetAsync(d_over.get(), 0, sizeof(int), s));
+      MG_CUDA(ctx, key32.alloc((size_t)D * N, s));
+      make_key32_kernel<<<dim3(grid1d(ctx, N), (unsigned)D), KB, 0, s>>>(keys.get(), N, d_shift.get(), key32.get());
+      MG_CHECK_LAUNCH(ctx);
+      if ((rc = radix_sort_pairs_t<uint32_t>(ctx, key32.get(), listsA.get(), N, D))) return rc;
+      tie_fix_kernel<<<dim3(grid1d(ctx, N), (unsigned)D), KB, 0, s>>>(key32.get(), listsA.get(), keys.get(), N, d_shift.get(), d_over.get());
+      MG_CHECK_LAUNCH(ctx);
+      int h_over = 0;
+      MG_CUDA(ctx, cudaMemcpyAsync(&h_over, d_over.get(), sizeof(int), cudaMemcpyDeviceToHost, s));
+      MG_CUDA(ctx, cudaStreamSynchronize(s));
+      sorted = (h_over == 0);
+      if (!sorted) {   // a long run of equal windows: start over with the full keys
+        make_keys_kernel<<<grid1d(ctx, (N + MK_TILE - 1) / MK_TILE * KB), KB, mk_smem, s>>>(d_pts, N, D, keys.get(), listsA.get());
+        MG_CHECK_LAUNCH(ctx);
+      }
+    }
+    if (!sorted && (rc = radix_sort_pairs(ctx, keys.get(), listsA.get(), N, D))) return rc;
   }
   const int64_t cap = 2 * N;
   MG_CUDA(ctx, nd_begin.alloc(cap, s)); MG_CUDA(ctx, nd_end.alloc(cap, s)); MG_CUDA(ctx, nd_dim.alloc(cap, s));

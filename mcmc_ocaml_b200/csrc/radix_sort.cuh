@@ -17,6 +17,8 @@
 #include "common.cuh"
 #include "scan.cuh"
 
+#include <vector>
+
 namespace mg {
 
 #ifndef MG_RS_MINBLOCKS
@@ -43,14 +45,15 @@ __host__ __device__ __forceinline__ uint64_t f64_to_ordered(double x) {
   return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
 }
 
+template <class KeyT>
 static __global__ void __launch_bounds__(RS_BLOCK)
-rs_hist_kernel(const uint64_t *__restrict__ keys, int64_t n, int64_t ntiles, int shift,
+rs_hist_kernel(const KeyT *__restrict__ keys, int64_t n, int64_t ntiles, int shift,
                int32_t *__restrict__ hist /* [nb][256][ntiles] */) {
   __shared__ int sh[RS_RADIX];
   const int64_t b = blockIdx.y, t = blockIdx.x;
   sh[threadIdx.x] = 0;
   __syncthreads();
-  const uint64_t *src = keys + b * n;
+  const KeyT *src = keys + b * n;
   const int64_t base = t * RS_TILE;
 #pragma unroll 4
   for (int k = 0; k < RS_ROUNDS; ++k) {
@@ -68,15 +71,18 @@ rs_hist_kernel(const uint64_t *__restrict__ keys, int64_t n, int64_t ntiles, int
 // out from there, so that every digit's run leaves as contiguous, coalesced
 // global stores (a direct scatter writes 8-byte keys to 256 different streams:
 // one 32-byte sector per key).
-constexpr size_t RS_SCATTER_SMEM = (size_t)RS_TILE * (sizeof(uint64_t) + sizeof(int32_t)) +
-                                   (size_t)(RS_WARPS * RS_RADIX + 2 * RS_RADIX) * sizeof(int);
+template <class KeyT>
+constexpr size_t rs_scatter_smem() {
+  return (size_t)RS_TILE * (sizeof(KeyT) + sizeof(int32_t)) + (size_t)(RS_WARPS * RS_RADIX + 2 * RS_RADIX) * sizeof(int);
+}
 
+template <class KeyT>
 static __global__ void __launch_bounds__(RS_BLOCK, MG_RS_MINBLOCKS)
-rs_scatter_kernel(const uint64_t *__restrict__ keys_in, const int32_t *__restrict__ vals_in, int64_t n,
+rs_scatter_kernel(const KeyT *__restrict__ keys_in, const int32_t *__restrict__ vals_in, int64_t n,
                   int64_t ntiles, int shift, const int32_t *__restrict__ offs /* scanned hist */,
-                  uint64_t *__restrict__ keys_out, int32_t *__restrict__ vals_out) {
+                  KeyT *__restrict__ keys_out, int32_t *__restrict__ vals_out) {
   extern __shared__ __align__(16) unsigned char rs_smem[];
-  uint64_t *skeys = reinterpret_cast<uint64_t *>(rs_smem);
+  KeyT *skeys = reinterpret_cast<KeyT *>(rs_smem);
   int32_t *svals = reinterpret_cast<int32_t *>(skeys + RS_TILE);
   int (*cnt)[RS_RADIX] = reinterpret_cast<int (*)[RS_RADIX]>(svals + RS_TILE);  // [RS_WARPS][RS_RADIX]
   int *dbase = &cnt[RS_WARPS][0];   // digit start inside the tile
@@ -85,18 +91,18 @@ rs_scatter_kernel(const uint64_t *__restrict__ keys_in, const int32_t *__restric
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int k = threadIdx.x; k < RS_WARPS * RS_RADIX; k += RS_BLOCK) (&cnt[0][0])[k] = 0;
   __syncthreads();
-  const uint64_t *ksrc = keys_in + b * n;
+  const KeyT *ksrc = keys_in + b * n;
   const int32_t *vsrc = vals_in + b * n;
   const int64_t tile0 = t * RS_TILE;
   const int64_t wbase = tile0 + (int64_t)w * (32 * RS_ROUNDS);
   const int nvalid = (int)((n - tile0 < RS_TILE) ? (n - tile0) : RS_TILE);
-  uint64_t key[RS_ROUNDS];
+  KeyT key[RS_ROUNDS];
   int32_t val[RS_ROUNDS];
   int rank[RS_ROUNDS];
 #pragma unroll
   for (int r = 0; r < RS_ROUNDS; ++r) {   // all the tile's loads in flight before the first ranking round
     const int64_t i = wbase + r * 32 + lane;
-    key[r] = (i < n) ? __ldcs(ksrc + i) : ~0ull;
+    key[r] = (i < n) ? __ldcs(ksrc + i) : (KeyT)~(KeyT)0;
     val[r] = (i < n) ? __ldcs(vsrc + i) : 0;
   }
 #pragma unroll
@@ -137,97 +143,120 @@ rs_scatter_kernel(const uint64_t *__restrict__ keys_in, const int32_t *__restric
     }
   }
   __syncthreads();
-  uint64_t *kdst = keys_out + b * n;
+  KeyT *kdst = keys_out + b * n;
   int32_t *vdst = vals_out + b * n;
   for (int i = threadIdx.x; i < nvalid; i += RS_BLOCK) {
-    const uint64_t k = skeys[i];
+    const KeyT k = skeys[i];
     const int64_t pos = (int64_t)gdelta[(int)((k >> shift) & 0xFF)] + i;
     kdst[pos] = k;
     vdst[pos] = svals[i];
   }
 }
 
-// all eight global digit histograms in one pass over the keys: [nb][8][256]
+// all global digit histograms (one per key byte) in one pass over the keys: [nb][sizeof(KeyT)][256]
+template <class KeyT>
 static __global__ void __launch_bounds__(RS_BLOCK)
-rs_prehist_kernel(const uint64_t *__restrict__ keys, int64_t n, unsigned int *__restrict__ ghist) {
-  __shared__ unsigned int sh[8][RS_RADIX];
+rs_prehist_kernel(const KeyT *__restrict__ keys, int64_t n, unsigned int *__restrict__ ghist) {
+  constexpr int NB = (int)sizeof(KeyT);
+  __shared__ unsigned int sh[NB][RS_RADIX];
   const int64_t b = blockIdx.y;
-  for (int k = threadIdx.x; k < 8 * RS_RADIX; k += RS_BLOCK) (&sh[0][0])[k] = 0u;
+  for (int k = threadIdx.x; k < NB * RS_RADIX; k += RS_BLOCK) (&sh[0][0])[k] = 0u;
   __syncthreads();
-  const uint64_t *src = keys + b * n;
+  const KeyT *src = keys + b * n;
   for (int64_t i = (int64_t)blockIdx.x * RS_BLOCK + threadIdx.x; i < n; i += (int64_t)gridDim.x * RS_BLOCK) {
-    const uint64_t k = src[i];
+    const KeyT k = src[i];
 #pragma unroll
-    for (int p = 0; p < 8; ++p) atomicAdd(&sh[p][(k >> (8 * p)) & 0xFF], 1u);
+    for (int p = 0; p < NB; ++p) atomicAdd(&sh[p][(k >> (8 * p)) & 0xFF], 1u);
   }
   __syncthreads();
-  for (int k = threadIdx.x; k < 8 * RS_RADIX; k += RS_BLOCK) {
+  for (int k = threadIdx.x; k < NB * RS_RADIX; k += RS_BLOCK) {
     const unsigned int v = (&sh[0][0])[k];
-    if (v) atomicAdd(ghist + b * 8 * RS_RADIX + k, v);
+    if (v) atomicAdd(ghist + b * NB * RS_RADIX + k, v);
   }
 }
 
+// const_byte[b][p] = 1 iff byte p of every key of row b is the same (a radix pass over it moves nothing)
+template <class KeyT>
+static inline int radix_constant_bytes(mg_ctx *ctx, const KeyT *d_keys, int64_t n, int64_t nb, std::vector<unsigned char> &const_byte) {
+  constexpr int NB = (int)sizeof(KeyT);
+  cudaStream_t s = ctx->stream;
+  DevBuf<unsigned int> ghist;
+  MG_CUDA(ctx, ghist.alloc((size_t)nb * NB * RS_RADIX, s));
+  MG_CUDA(ctx, cudaMemsetAsync(ghist.get(), 0, sizeof(unsigned int) * nb * NB * RS_RADIX, s));
+  int64_t gx = (n + RS_BLOCK * 8 - 1) / (RS_BLOCK * 8);
+  if (gx > (int64_t)ctx->sm_count * 8) gx = (int64_t)ctx->sm_count * 8;
+  rs_prehist_kernel<KeyT><<<dim3((unsigned)gx, (unsigned)nb), RS_BLOCK, 0, s>>>(d_keys, n, ghist.get());
+  MG_CHECK_LAUNCH(ctx);
+  std::vector<unsigned int> h((size_t)nb * NB * RS_RADIX);
+  MG_CUDA(ctx, cudaMemcpyAsync(h.data(), ghist.get(), sizeof(unsigned int) * h.size(), cudaMemcpyDeviceToHost, s));
+  MG_CUDA(ctx, cudaStreamSynchronize(s));
+  const_byte.assign((size_t)nb * NB, 0);
+  for (int64_t b = 0; b < nb; ++b)
+    for (int p = 0; p < NB; ++p)
+      for (int d = 0; d < RS_RADIX; ++d)
+        if (h[((size_t)b * NB + p) * RS_RADIX + d] == (unsigned int)n) { const_byte[(size_t)b * NB + p] = 1; break; }
+  return MG_OK;
+}
+
+template <class KeyT>
 struct RadixSortTemp {
-  DevBuf<uint64_t> keys_alt;
+  DevBuf<KeyT> keys_alt;
   DevBuf<int32_t> vals_alt, hist, scan_tmp, totals;
   std::vector<int32_t> h_hist;
 };
 
 // Sorts in place (result ends in d_keys / d_vals).  key_bits: number of
-// significant low bits (64 for doubles).  Returns MG_OK or an error.
-static inline int radix_sort_pairs(mg_ctx *ctx, uint64_t *d_keys, int32_t *d_vals, int64_t n, int64_t nb, int key_bits = 64) {
+// significant low bits (the key width by default).  Returns MG_OK or an error.
+template <class KeyT>
+static inline int radix_sort_pairs_t(mg_ctx *ctx, KeyT *d_keys, int32_t *d_vals, int64_t n, int64_t nb,
+                                     int key_bits = 8 * (int)sizeof(KeyT)) {
+  constexpr int NB = (int)sizeof(KeyT);
   if (n <= 1 || nb <= 0) return MG_OK;
   cudaStream_t s = ctx->stream;
   const int64_t ntiles = (n + RS_TILE - 1) / RS_TILE;
   const int64_t hist_n = RS_RADIX * ntiles;  // per batch row
   if (hist_n >= 2147483647LL) return set_err(ctx, MG_EINVAL, "radix sort: array too long");
-  RadixSortTemp tmp;
+  RadixSortTemp<KeyT> tmp;
   MG_CUDA(ctx, tmp.keys_alt.alloc((size_t)n * nb, s));
   MG_CUDA(ctx, tmp.vals_alt.alloc((size_t)n * nb, s));
   MG_CUDA(ctx, tmp.hist.alloc((size_t)hist_n * nb, s));
   MG_CUDA(ctx, tmp.scan_tmp.alloc((size_t)scan_tmp_elems(hist_n, nb), s));
-  uint64_t *kin = d_keys, *kout = tmp.keys_alt.get();
+  KeyT *kin = d_keys, *kout = tmp.keys_alt.get();
   int32_t *vin = d_vals, *vout = tmp.vals_alt.get();
   dim3 grid((unsigned)ntiles, (unsigned)nb);
   // a pass whose digit is the same for every key of every row moves nothing: find those up front
-  bool skip[8] = {false, false, false, false, false, false, false, false};
+  bool skip[NB];
+  for (int p = 0; p < NB; ++p) skip[p] = false;
   if (n >= 4 * RS_TILE) {
-    DevBuf<unsigned int> ghist;
-    MG_CUDA(ctx, ghist.alloc((size_t)nb * 8 * RS_RADIX, s));
-    MG_CUDA(ctx, cudaMemsetAsync(ghist.get(), 0, sizeof(unsigned int) * nb * 8 * RS_RADIX, s));
-    int64_t gx = (n + RS_BLOCK * 8 - 1) / (RS_BLOCK * 8);
-    if (gx > (int64_t)ctx->sm_count * 8) gx = (int64_t)ctx->sm_count * 8;
-    rs_prehist_kernel<<<dim3((unsigned)gx, (unsigned)nb), RS_BLOCK, 0, s>>>(d_keys, n, ghist.get());
-    MG_CHECK_LAUNCH(ctx);
-    std::vector<unsigned int> h((size_t)nb * 8 * RS_RADIX);
-    MG_CUDA(ctx, cudaMemcpyAsync(h.data(), ghist.get(), sizeof(unsigned int) * h.size(), cudaMemcpyDeviceToHost, s));
-    MG_CUDA(ctx, cudaStreamSynchronize(s));
-    for (int p = 0; p < 8; ++p) {
+    std::vector<unsigned char> cb;
+    int rc = radix_constant_bytes<KeyT>(ctx, d_keys, n, nb, cb);
+    if (rc) return rc;
+    for (int p = 0; p < NB; ++p) {
       bool all_const = true;
-      for (int64_t b = 0; b < nb && all_const; ++b) {
-        bool row_const = false;
-        for (int d = 0; d < RS_RADIX; ++d) if (h[((size_t)b * 8 + p) * RS_RADIX + d] == (unsigned int)n) { row_const = true; break; }
-        all_const = row_const;
-      }
+      for (int64_t b = 0; b < nb && all_const; ++b) all_const = cb[(size_t)b * NB + p] != 0;
       skip[p] = all_const;
     }
   }
-  MG_CUDA(ctx, cudaFuncSetAttribute(rs_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RS_SCATTER_SMEM));
+  MG_CUDA(ctx, cudaFuncSetAttribute(rs_scatter_kernel<KeyT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_scatter_smem<KeyT>()));
   for (int shift = 0; shift < key_bits; shift += 8) {
     if (skip[shift / 8]) continue;
-    rs_hist_kernel<<<grid, RS_BLOCK, 0, s>>>(kin, n, ntiles, shift, tmp.hist.get());
+    rs_hist_kernel<KeyT><<<grid, RS_BLOCK, 0, s>>>(kin, n, ntiles, shift, tmp.hist.get());
     MG_CHECK_LAUNCH(ctx);
     int rc = exclusive_scan_i32(ctx, tmp.hist.get(), tmp.hist.get(), hist_n, nb, tmp.scan_tmp.get(), nullptr);
     if (rc) return rc;
-    rs_scatter_kernel<<<grid, RS_BLOCK, RS_SCATTER_SMEM, s>>>(kin, vin, n, ntiles, shift, tmp.hist.get(), kout, vout);
+    rs_scatter_kernel<KeyT><<<grid, RS_BLOCK, rs_scatter_smem<KeyT>(), s>>>(kin, vin, n, ntiles, shift, tmp.hist.get(), kout, vout);
     MG_CHECK_LAUNCH(ctx);
     std::swap(kin, kout); std::swap(vin, vout);
   }
   if (kin != d_keys) {  // odd number of passes: copy back
-    MG_CUDA(ctx, cudaMemcpyAsync(d_keys, kin, sizeof(uint64_t) * n * nb, cudaMemcpyDeviceToDevice, s));
+    MG_CUDA(ctx, cudaMemcpyAsync(d_keys, kin, sizeof(KeyT) * n * nb, cudaMemcpyDeviceToDevice, s));
     MG_CUDA(ctx, cudaMemcpyAsync(d_vals, vin, sizeof(int32_t) * n * nb, cudaMemcpyDeviceToDevice, s));
   }
   return MG_OK;
+}
+
+static inline int radix_sort_pairs(mg_ctx *ctx, uint64_t *d_keys, int32_t *d_vals, int64_t n, int64_t nb, int key_bits = 64) {
+  return radix_sort_pairs_t<uint64_t>(ctx, d_keys, d_vals, n, nb, key_bits);
 }
 
 }  // namespace mg

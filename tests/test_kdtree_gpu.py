@@ -182,3 +182,27 @@ def test_blob_round_trip(ctx, og):
     i1 = interpolate_pdf.InterpPdf(None, None, None, tree=g)
     i2 = interpolate_pdf.InterpPdf(None, None, None, tree=g2)
     assert np.array_equal(i1.jump_prob(q), i2.jump_prob(q))
+
+
+@pytest.mark.parametrize("cluster,what", [(40, "tie runs fixed up"), (300, "long run: 64-bit fallback"), (0, "MH repeats")])
+def test_window_sort_ties(ctx, og, cluster, what):
+    """Builds of >= 65,536 points sort each coordinate on a 32-bit window of the keys and repair runs of equal
+    windows with the full keys (csrc/kdtree.cu tie_fix_kernel).  Wide-range data (windows truncate low mantissa
+    bits) with clusters of points that differ only BELOW the window, in scrambled order, plus exact duplicates:
+    the tree must still be the oracle's, object order included."""
+    rng = np.random.default_rng(4242 + cluster)
+    n, d = 70000, 3
+    if cluster == 0:
+        pts = mh_like(rng, n, d, repeat=0.4)
+        pts[:, 1] = pts[:, 1] * 1e3          # a second dimension with a wide exponent range
+    else:
+        pts = rng.random((n, d)) * np.array([1.0, 100.0, 1e-3])
+        for c in range(60):                  # clusters: same window, different low bits, shuffled
+            at = rng.integers(0, n - cluster)
+            centre = rng.random(d) * np.array([1.0, 100.0, 1e-3])
+            k = rng.permutation(cluster)[:, None] * np.array([2.0 ** -50, 2.0 ** -44, 2.0 ** -60])
+            pts[at:at + cluster] = centre * (1.0 + 0.0) + k * np.array([1.0, 1.0, 1.0])
+        pts[1000:1010] = pts[1000]           # exact duplicates inside the data
+    lo = pts.min(0) - 1.0
+    hi = pts.max(0) + 1.0
+    assert_same_tree(kd_tree.KdTree(pts, lo, hi, ctx=ctx), og.Tree(pts, lo, hi))
