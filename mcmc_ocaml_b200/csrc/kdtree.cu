@@ -20,6 +20,7 @@
 // of 8 D-byte rows).  All kernels are HBM / L2-gather bound.
 #include "kdtree.cuh"
 
+#include <cmath>
 #include <cstdlib>
 #include <vector>
 
@@ -357,13 +358,25 @@ int build_tree(mg_ctx *ctx, const double *d_pts, int64_t N, int D, const double 
     if (use32 && N >= 65536) {
       // 32-bit window under the highest varying byte of each dimension (see make_key32_kernel)
       std::vector<unsigned char> cb;
-      if ((rc = radix_constant_bytes<uint64_t>(ctx, keys.get(), N, D, cb))) return rc;
+      std::vector<double> veff;
+      if ((rc = radix_constant_bytes<uint64_t>(ctx, keys.get(), N, D, cb, &veff))) return rc;
       std::vector<int> h_shift(D, 0);
+      bool window_ok = true;
       for (int d = 0; d < D; ++d) {
         int top = 0;
         for (int p = 7; p >= 0; --p) if (!cb[(size_t)d * 8 + p]) { top = p; break; }
         h_shift[d] = 8 * std::max(0, top - 3);
+        // Equal windows must be rare or the repair pass touches millions of runs.  Distinct windows are estimated
+        // from the byte histograms as the product of the effective number of values (n^2 / sum count^2) of the
+        // window's four bytes; N points then give ~N^2 / (2 distinct) tied pairs, accepted up to N / 16.  Coordinates whose sign or high exponent bits vary (top byte 7: only 20 mantissa bits are left in
+        // the window) fail this at 1e7 points and take the 64-bit sort.
+        if (h_shift[d] > 0) {
+          double distinct = 1.0;
+          for (int p = top - 3; p <= top; ++p) distinct *= veff[(size_t)d * 8 + p];
+          if ((double)N * (double)N / (2.0 * distinct) > (double)N / 16.0) window_ok = false;
+        }
       }
+      if (window_ok) {
       DevBuf<int> d_shift, d_over;
       DevBuf<uint32_t> key32;
       MG_CUDA(ctx, upload(d_shift, h_shift.data(), (size_t)D, s));
@@ -382,6 +395,7 @@ int build_tree(mg_ctx *ctx, const double *d_pts, int64_t N, int D, const double 
       if (!sorted) {   // a long run of equal windows: start over with the full keys
         make_keys_kernel<<<grid1d(ctx, (N + MK_TILE - 1) / MK_TILE * KB), KB, mk_smem, s>>>(d_pts, N, D, keys.get(), listsA.get());
         MG_CHECK_LAUNCH(ctx);
+      }
       }
     }
     if (!sorted && (rc = radix_sort_pairs(ctx, keys.get(), listsA.get(), N, D))) return rc;

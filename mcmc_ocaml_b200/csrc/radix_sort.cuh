@@ -177,7 +177,8 @@ rs_prehist_kernel(const KeyT *__restrict__ keys, int64_t n, unsigned int *__rest
 
 // const_byte[b][p] = 1 iff byte p of every key of row b is the same (a radix pass over it moves nothing)
 template <class KeyT>
-static inline int radix_constant_bytes(mg_ctx *ctx, const KeyT *d_keys, int64_t n, int64_t nb, std::vector<unsigned char> &const_byte) {
+static inline int radix_constant_bytes(mg_ctx *ctx, const KeyT *d_keys, int64_t n, int64_t nb, std::vector<unsigned char> &const_byte,
+                                       std::vector<double> *eff_values = nullptr /* [nb][bytes]: n^2 / sum count^2 */) {
   constexpr int NB = (int)sizeof(KeyT);
   cudaStream_t s = ctx->stream;
   DevBuf<unsigned int> ghist;
@@ -191,10 +192,17 @@ static inline int radix_constant_bytes(mg_ctx *ctx, const KeyT *d_keys, int64_t 
   MG_CUDA(ctx, cudaMemcpyAsync(h.data(), ghist.get(), sizeof(unsigned int) * h.size(), cudaMemcpyDeviceToHost, s));
   MG_CUDA(ctx, cudaStreamSynchronize(s));
   const_byte.assign((size_t)nb * NB, 0);
+  if (eff_values) eff_values->assign((size_t)nb * NB, 1.0);
   for (int64_t b = 0; b < nb; ++b)
-    for (int p = 0; p < NB; ++p)
-      for (int d = 0; d < RS_RADIX; ++d)
-        if (h[((size_t)b * NB + p) * RS_RADIX + d] == (unsigned int)n) { const_byte[(size_t)b * NB + p] = 1; break; }
+    for (int p = 0; p < NB; ++p) {
+      double sq = 0.0;
+      for (int d = 0; d < RS_RADIX; ++d) {
+        const unsigned int c = h[((size_t)b * NB + p) * RS_RADIX + d];
+        if (c == (unsigned int)n) const_byte[(size_t)b * NB + p] = 1;
+        sq += (double)c * (double)c;
+      }
+      if (eff_values && sq > 0.0) (*eff_values)[(size_t)b * NB + p] = (double)n * (double)n / sq;
+    }
   return MG_OK;
 }
 
