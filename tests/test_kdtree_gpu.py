@@ -184,7 +184,8 @@ def test_blob_round_trip(ctx, og):
     assert np.array_equal(i1.jump_prob(q), i2.jump_prob(q))
 
 
-@pytest.mark.parametrize("cluster,what", [(40, "tie runs fixed up"), (300, "long run: 64-bit fallback"), (0, "MH repeats")])
+@pytest.mark.parametrize("cluster,what", [(40, "tie runs fixed up"), (300, "long run: 64-bit fallback"), (0, "MH repeats"),
+                                          (-1, "both signs, zeros, denormals")])
 def test_window_sort_ties(ctx, og, cluster, what):
     """Builds of >= 65,536 points sort each coordinate on a 32-bit window of the keys and repair runs of equal
     windows with the full keys (csrc/kdtree.cu tie_fix_kernel).  Wide-range data (windows truncate low mantissa
@@ -192,7 +193,12 @@ def test_window_sort_ties(ctx, og, cluster, what):
     the tree must still be the oracle's, object order included."""
     rng = np.random.default_rng(4242 + cluster)
     n, d = 70000, 3
-    if cluster == 0:
+    if cluster == -1:
+        pts = rng.normal(0.0, 1.0, (n, d)) * np.array([1.0, 1e-300, 1e5])
+        pts[::97, 0] = 0.0
+        pts[::101, 0] = -0.0
+        pts[::89, 1] = 5e-324 * rng.integers(0, 50, len(pts[::89]))
+    elif cluster == 0:
         pts = mh_like(rng, n, d, repeat=0.4)
         pts[:, 1] = pts[:, 1] * 1e3          # a second dimension with a wide exponent range
     else:
