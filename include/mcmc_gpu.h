@@ -59,6 +59,10 @@ uint64_t mg_ctx_get_epoch(const mg_ctx *ctx);
 int mg_ctx_set_stream(mg_ctx *ctx, void *cuda_stream); /* NULL = own stream */
 void *mg_ctx_get_stream(const mg_ctx *ctx);
 int mg_ctx_sync(mg_ctx *ctx);
+/* Temporaries are taken from the device's stream-ordered memory pool and kept
+ * cached there between calls; this returns the cached memory to the driver
+ * (for processes that share the GPU with another allocator). */
+int mg_ctx_trim_pool(mg_ctx *ctx);
 /* Mcmc.reset_counters / Mcmc.get_counters (mcmc.ml:30-35). */
 int mg_reset_counters(mg_ctx *ctx);
 int mg_get_counters(mg_ctx *ctx, int64_t *naccept, int64_t *nreject);

@@ -64,6 +64,10 @@ class Context:
     def sync(self):
         self.check(self.lib.mg_ctx_sync(self.h))
 
+    def trim_pool(self):
+        """Hand the library's cached temporaries (stream-ordered pool) back to the driver."""
+        self.check(self.lib.mg_ctx_trim_pool(self.h))
+
     @property
     def launch_count(self) -> int:
         return int(self.lib.mg_ctx_launch_count(self.h))

@@ -63,6 +63,17 @@ extern "C" int mg_ctx_sync(mg_ctx *ctx) {
   MG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return MG_OK;
 }
+// The library's temporaries come from the device's stream-ordered pool and stay cached there between calls
+// (release threshold = unlimited, set in mg_ctx_create); this hands the cached memory back to the driver.
+extern "C" int mg_ctx_trim_pool(mg_ctx *ctx) {
+  if (!ctx) return MG_EINVAL;
+  MG_CUDA(ctx, cudaSetDevice(ctx->device));
+  MG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  cudaMemPool_t pool;
+  MG_CUDA(ctx, cudaDeviceGetDefaultMemPool(&pool, ctx->device));
+  MG_CUDA(ctx, cudaMemPoolTrimTo(pool, 0));
+  return MG_OK;
+}
 extern "C" int mg_reset_counters(mg_ctx *ctx) { if (!ctx) return MG_EINVAL; ctx->naccept = ctx->nreject = 0; return MG_OK; }
 extern "C" int mg_get_counters(mg_ctx *ctx, int64_t *naccept, int64_t *nreject) {
   if (!ctx) return MG_EINVAL;

@@ -177,3 +177,16 @@ def test_accept_prefilter_decides_like_float64(ctx):
                                            fast.ctypes.data_as(C.c_void_p), exact.ctypes.data_as(C.c_void_p)))
     assert np.array_equal(fast, exact)
     assert 0 < exact.sum() < exact.size
+
+
+def test_trim_pool_releases_cached_memory(ctx):
+    """mg_ctx_trim_pool: temporaries cached in the stream-ordered pool go back to the driver; results unchanged after"""
+    import torch
+    from mcmc_ocaml_b200 import evidence
+    ll = np.random.default_rng(0).normal(-3, 1, 2_000_000)
+    z0 = evidence.evidence_harmonic_mean(ll=ll, ctx=ctx)
+    free_cached, _ = torch.cuda.mem_get_info()
+    ctx.trim_pool()
+    free_trimmed, _ = torch.cuda.mem_get_info()
+    assert free_trimmed >= free_cached
+    assert evidence.evidence_harmonic_mean(ll=ll, ctx=ctx) == z0
