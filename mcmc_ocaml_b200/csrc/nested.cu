@@ -108,9 +108,14 @@ __global__ void nest_propose_kernel(NestArgs a, NestProp p, int s0, int S) {
 // memory with cp.async, so a 128-byte row costs one line request instead of sixteen 8-byte requests from one lane
 // (thread-per-row loads kept the L1 tag stage busy for ~1,000 cycles per step and every later load queued behind
 // them).  Rows of step s+1 and scalars of step s+2 are in flight while step s computes.
-template <int DMAX, bool kFull>
+// FAST (only with kFull): the plugin pair is known at compile time -- 1: Gaussian shell under a closed box, 2: under
+// an open box (BASELINE.json config 4 and the reference's nested tests) -- and its parameters live in registers: no
+// switch on the kind, no parameter loads in the step.  Same expressions as the SHELL / BOX cases of DynFn
+// (models.cuh), so the chains are the same.  FAST = 0: any registered plugin pair through DynFn.
+template <int DMAX, bool kFull, int FAST = 0>
 __global__ void nest_replace_kernel(NestArgs a, NestProp p, int s0, int s1, int first, int last, double *chain_x,
                                     double *chain_cl) {
+  static_assert(FAST == 0 || kFull, "the register-resident plugin pair needs D == DMAX");
   extern __shared__ __align__(16) double s_rows[];            // [2 stages][2 * NEST_BLOCK rows][RS]
   __shared__ int32_t s_i0[kSR][NEST_BLOCK], s_j0[kSR][NEST_BLOCK];
   __shared__ double s_ds[kSR][NEST_BLOCK], s_u[kSR][NEST_BLOCK];
@@ -123,10 +128,45 @@ __global__ void nest_replace_kernel(NestArgs a, NestProp p, int s0, int s1, int 
   const bool vec = (D % 2) == 0;       // 16-byte pieces need even D (row starts are then 16-byte aligned)
   const int RS = nest_row_stride(D);   // doubles per staged row
   const double thr = a.threshold;
+  // FAST: centre, (mu, sigma, log sigma) of the shell and the box in registers
+  double f_c[FAST ? DMAX : 1], f_lo[FAST ? DMAX : 1], f_hi[FAST ? DMAX : 1];
+  double f_mu = 0.0, f_sigma = 1.0, f_ls = 0.0, f_inside = 0.0;
+  if (FAST) {
+#pragma unroll
+    for (int d = 0; d < DMAX; ++d) {
+      f_c[d] = __ldg(a.like.p + d); f_lo[d] = __ldg(a.prior.p + d); f_hi[d] = __ldg(a.prior.p + DMAX + d);
+    }
+    f_mu = __ldg(a.like.p + DMAX); f_sigma = __ldg(a.like.p + DMAX + 1); f_ls = __ldg(a.like.p + a.like.np);
+    f_inside = __ldg(a.prior.p + 2 * DMAX);
+  }
+  auto like_of = [&](const double (&pt)[DMAX]) -> double {
+    if (FAST) {            // MG_FN_SHELL (models.cuh)
+      double s = 0.0;
+#pragma unroll
+      for (int i = 0; i < DMAX; ++i) { const double dx = pt[i] - f_c[i]; s = s + dx * dx; }
+      return log_gaussian_ls(f_mu, f_sigma, f_ls, sqrt(s));
+    }
+    return DynFn::eval<DMAX>(a.like, nullptr, pt, D);
+  };
+  auto prior_of = [&](const double (&pt)[DMAX]) -> double {
+    if (FAST == 1) {       // MG_FN_BOX_CLOSED
+      int out = 0;
+#pragma unroll
+      for (int i = 0; i < DMAX; ++i) out |= (int)(pt[i] < f_lo[i]) | (int)(pt[i] > f_hi[i]);
+      return out ? neg_inf() : f_inside;
+    }
+    if (FAST == 2) {       // MG_FN_BOX_OPEN
+      int in = 1;
+#pragma unroll
+      for (int i = 0; i < DMAX; ++i) in &= (int)(pt[i] > f_lo[i]) & (int)(pt[i] < f_hi[i]);
+      return in ? f_inside : neg_inf();
+    }
+    return DynFn::eval<DMAX>(a.prior, nullptr, pt, D);
+  };
   auto mcmc_logl = [&](const double (&pt)[DMAX]) {           // :54-59
     // both evaluated (they are pure and independent), then selected: nothing waits behind a branch
-    const double l = DynFn::eval<DMAX>(a.like, nullptr, pt, D);
-    const double pr = DynFn::eval<DMAX>(a.prior, nullptr, pt, D);
+    const double l = like_of(pt);
+    const double pr = prior_of(pt);
     return (l >= thr) ? pr : neg_inf();
   };
   double x[DMAX], y[DMAX], delta[DMAX];
@@ -230,8 +270,8 @@ __global__ void nest_replace_kernel(NestArgs a, NestProp p, int s0, int s1, int 
     chain_cl[j] = cl;
     return;
   }
-  const double nl = DynFn::eval<DMAX>(a.like, nullptr, x, D);   // :68-69
-  const double np = DynFn::eval<DMAX>(a.prior, nullptr, x, D);
+  const double nl = like_of(x);                                    // :68-69
+  const double np = prior_of(x);
   if (!(nl >= thr)) *a.fail = 1;                                   // :70-72
 #pragma unroll (DMAX <= 16 ? DMAX : 1)
   for (int d = 0; d < DMAX; ++d)
@@ -576,9 +616,16 @@ extern "C" int mg_nested_evidence(mg_ctx *ctx, const mg_logfn *like, const mg_lo
   } while (0)
 
   const size_t row_smem = (size_t)2 * 2 * NEST_BLOCK * nest_row_stride(D) * sizeof(double);
+  // the shell-in-a-box pair with its parameters in registers (see nest_replace_kernel, FAST)
+  const int fast = (like->kind == MG_FN_SHELL && like->scale == 1.0 && prior->scale == 1.0 && !getenv("MCMC_GPU_NEST_GENERIC"))
+                       ? (prior->kind == MG_FN_BOX_CLOSED ? 1 : (prior->kind == MG_FN_BOX_OPEN ? 2 : 0)) : 0;
 #define MG_NEST_CASE2(KERNEL, DM, GRID, BLOCK, ...)                                  \
   do {                                                                               \
-    if (D == DM) {                                                                   \
+    if (D == DM && DM <= 16 && fast == 1) {                                          \
+      KERNEL<(DM <= 16 ? DM : 2), true, 1><<<GRID, BLOCK, row_smem, s>>>(__VA_ARGS__); \
+    } else if (D == DM && DM <= 16 && fast == 2) {                                   \
+      KERNEL<(DM <= 16 ? DM : 2), true, 2><<<GRID, BLOCK, row_smem, s>>>(__VA_ARGS__); \
+    } else if (D == DM) {                                                            \
       if (row_smem > 48 * 1024) MG_CUDA(ctx, cudaFuncSetAttribute(KERNEL<DM, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)row_smem)); \
       KERNEL<DM, true><<<GRID, BLOCK, row_smem, s>>>(__VA_ARGS__);                   \
     } else {                                                                         \
