@@ -48,7 +48,7 @@ struct MhQueue {
   int64_t seg_slots;         // recorded samples per sampling segment (nskip steps each)
 };
 
-constexpr long long kQueueWaitCycles = 1ll << 33;  // ~4 s at 2 GHz
+constexpr long long kQueueWaitCycles = 1ll << 38;  // ~2 min at 2 GHz: far beyond any segment (a heavy data likelihood can take seconds), still finite
 
 static __global__ void mh_queue_init_kernel(MhQueue q) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
