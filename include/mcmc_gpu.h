@@ -351,6 +351,10 @@ int mg_rjmcmc_array(mg_ctx *ctx, const mg_rj_model *A, const mg_rj_model *B,
                     const mg_rjmcmc_cfg *cfg, const double *a0,
                     const double *b0, uint8_t *out_model, double *out_samples,
                     int64_t out_counts[2]);
+/* Diagnostics of the last mg_rjmcmc_array call on this context: how many steps
+ * proposed a jump into the other model (mcmc.ml:97,102) and how many of those
+ * were accepted -- the mixing rate of the interpolated jumps. */
+int mg_rjmcmc_jump_counters(const mg_ctx *ctx, int64_t *proposed, int64_t *accepted);
 
 /* ------------------------------------------------------------------ */
 /* Evidence + Stats                                                    */

@@ -16,6 +16,12 @@ extern "C" int mg_ctx_create(int device, uint64_t seed, mg_ctx **out) {
   ctx->device = device; ctx->seed = seed; ctx->epoch = 0;
   if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return MG_ECUDA; }
   ctx->own_stream = true;
+  // the second stream (draw-ahead of Nested, Stats passes of the resident sampler) exists from the start, so that no
+  // path ever falls back to the legacy NULL stream (which would serialise with every blocking stream of the process)
+  if (cudaStreamCreateWithFlags(&ctx->aux, cudaStreamNonBlocking) != cudaSuccess) { cudaStreamDestroy(ctx->stream); delete ctx; return MG_ECUDA; }
+  if (cudaMalloc((void **)&ctx->d_devflag, 4 * sizeof(int)) != cudaSuccess || cudaMemset(ctx->d_devflag, 0, 4 * sizeof(int)) != cudaSuccess) {
+    cudaStreamDestroy(ctx->aux); cudaStreamDestroy(ctx->stream); delete ctx; return MG_ECUDA;
+  }
   cudaEventCreate(&ctx->ev0); cudaEventCreate(&ctx->ev1);
   cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
   // keep freed stream-ordered allocations cached in the pool between calls
@@ -35,6 +41,7 @@ extern "C" void mg_ctx_destroy(mg_ctx *ctx) {
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   if (ctx->aux) cudaStreamDestroy(ctx->aux);
+  if (ctx->d_devflag) cudaFree(ctx->d_devflag);
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -61,7 +68,7 @@ extern "C" int mg_ctx_sync(mg_ctx *ctx) {
   if (!ctx) return MG_EINVAL;
   MG_CUDA(ctx, cudaSetDevice(ctx->device));
   MG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  return MG_OK;
+  return poll_device_error(ctx);
 }
 // The library's temporaries come from the device's stream-ordered pool and stay cached there between calls
 // (release threshold = unlimited, set in mg_ctx_create); this hands the cached memory back to the driver.

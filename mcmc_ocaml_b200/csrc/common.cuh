@@ -25,11 +25,17 @@ struct mg_ctx {
   double last_kernel_ms = 0.0;
   int64_t launches = 0;
   int64_t naccept = 0, nreject = 0;  // Mcmc.get_counters (mcmc.ml:27-35)
+  int64_t rj_cross[2] = {0, 0};      // last mg_rjmcmc_array: cross-model proposals, of which accepted
   int sm_count = 148;
   double *mh_mom = nullptr;        // request: per-chain running moments from the next MH launch (mcmc_balanced.cuh)
   bool mh_mom_done = false;        // answer: the launch produced them
+  int *d_devflag = nullptr;        // device word set by a kernel whose bounded spin-wait ran out (MG_DEVERR_*)
+  int sticky = MG_OK;              // a device-side failure that every later call reports until mg_ctx_clear_error
   std::string err;
 };
+
+// codes a kernel leaves in mg_ctx::d_devflag instead of trapping (a trap poisons the CUDA context of the process)
+enum { MG_DEVERR_NONE = 0, MG_DEVERR_MH_QUEUE = 1, MG_DEVERR_KD_LOOKBACK = 2 };
 
 namespace mg {
 
@@ -73,6 +79,20 @@ struct DevBuf {
   ~DevBuf() { release(); }
   T *get() const { return p; }
 };
+
+// Read (and clear) the device error word after a synchronisation point.  A timed-out wait means the launch's
+// results are invalid; the CUDA context itself stays healthy, so the error is reported by the call that observes it.
+inline int poll_device_error(mg_ctx *ctx) {
+  if (!ctx->d_devflag) return MG_OK;
+  int h = 0;
+  if (cudaMemcpyAsync(&h, ctx->d_devflag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+      cudaStreamSynchronize(ctx->stream) != cudaSuccess)
+    return set_err(ctx, MG_ECUDA, "cuda: %s (reading the device error word)", cudaGetErrorString(cudaGetLastError()));
+  if (h == MG_DEVERR_NONE) return MG_OK;
+  cudaMemsetAsync(ctx->d_devflag, 0, sizeof(int), ctx->stream);
+  return set_err(ctx, MG_ECUDA, "cuda: device-side wait timed out (%s); the results of that launch are invalid, the context remains usable",
+                 h == MG_DEVERR_MH_QUEUE ? "Metropolis-Hastings task queue" : "kd-tree partition look-back");
+}
 
 inline void time_begin(mg_ctx *ctx) { cudaEventRecord(ctx->ev0, ctx->stream); }
 inline void time_end(mg_ctx *ctx) { cudaEventRecord(ctx->ev1, ctx->stream); ctx->ev_pending = true; }

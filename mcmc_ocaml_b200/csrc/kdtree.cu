@@ -114,6 +114,7 @@ struct BuildArrays {
   int D, min_split;
   int32_t *begin, *end, *dim, *left, *spos;
   double *split;
+  int *err;   // mg_ctx::d_devflag
 };
 
 __device__ __forceinline__ double key_at(const BuildArrays &a, const int32_t *lists, int d, int64_t pos) {
@@ -260,7 +261,10 @@ part_fused_kernel(BuildArrays a, const int32_t *__restrict__ lists_in, int32_t *
         unsigned spins = 0;
         do {
           v = *reinterpret_cast<volatile unsigned long long *>(st + k);
-          if (!(v & LB_MASK) && ++spins > (1u << 28)) __trap();
+          if (!(v & LB_MASK) && ((++spins & 1023u) == 0u)) {   // bounded wait: flag the context instead of trapping
+            if (spins > (1u << 28)) atomicExch(a.err, MG_DEVERR_KD_LOOKBACK);
+            if (*reinterpret_cast<volatile int *>(a.err) != 0) v = LB_PREFIX;   // give up: the build reports MG_ECUDA
+          }
         } while (!(v & LB_MASK));
       }
       const unsigned has_prefix = __ballot_sync(0xffffffffu, (v & LB_MASK) == LB_PREFIX);
@@ -413,7 +417,7 @@ int build_tree(mg_ctx *ctx, const double *d_pts, int64_t N, int D, const double 
   MG_CUDA(ctx, lb_ticket.alloc((size_t)NL, s));
   MG_CUDA(ctx, totals.alloc(2, s));
   BuildArrays a{d_pts, N, D, min_split, nd_begin.get(), nd_end.get(), nd_dim.get(), nd_left.get(), nd_spos.get(),
-                nd_split.get()};
+                nd_split.get(), ctx->d_devflag};
   {
     const int32_t zero = 0, n32 = (int32_t)N;
     MG_CUDA(ctx, cudaMemcpyAsync(nd_begin.get(), &zero, 4, cudaMemcpyHostToDevice, s));
@@ -493,6 +497,7 @@ int build_tree(mg_ctx *ctx, const double *d_pts, int64_t N, int D, const double 
   time_end(ctx);
   e = cudaStreamSynchronize(s);
   if (e != cudaSuccess) { cudaFreeAsync(t->d_blob, s); delete t; return set_err(ctx, MG_ECUDA, "cuda: %s (kd-tree build)", cudaGetErrorString(e)); }
+  if (int rc = poll_device_error(ctx)) { cudaFreeAsync(t->d_blob, s); delete t; return rc; }
   *out = t;
   return MG_OK;
 }
@@ -607,6 +612,19 @@ extern "C" int mg_kdtree_blob_dev(const mg_kdtree *t, void **d_blob) {
   *d_blob = t->d_blob;
   return MG_OK;
 }
+// A blob arrives from another process (NCCL broadcast): nothing in it is trusted before the kernels index with it.
+int mg::validate_blob_header(mg_ctx *ctx, const KdHeader &h) {
+  MG_REQUIRE(ctx, h.magic == KD_MAGIC, "kd-tree blob: bad magic");
+  MG_REQUIRE(ctx, h.D >= 1 && h.D <= 64 && h.N >= 1 && h.N < (1LL << 30), "kd-tree blob: bad N / D");
+  MG_REQUIRE(ctx, h.nnodes >= 1 && h.nnodes <= 2 * h.N, "kd-tree blob: bad node count");
+  const int64_t off[8] = {h.off_low, h.off_high, h.off_nodes, h.off_count, h.off_begin, h.off_perm, h.off_pts, h.nbytes};
+  const int64_t need[7] = {8LL * h.D, 8LL * h.D, 16 * h.nnodes, 4 * h.nnodes, 4 * h.nnodes, 4 * h.N, 8 * h.N * h.D};
+  MG_REQUIRE(ctx, off[0] >= (int64_t)sizeof(KdHeader), "kd-tree blob: sections overlap the header");
+  for (int i = 0; i < 7; ++i)
+    MG_REQUIRE(ctx, (off[i] & 255) == 0 && off[i] + need[i] <= off[i + 1], "kd-tree blob: section %d out of bounds or misaligned", i);
+  return MG_OK;
+}
+
 extern "C" int mg_kdtree_from_blob_dev(mg_ctx *ctx, const void *d_blob, int64_t nbytes, mg_kdtree **out) {
   if (!ctx) return MG_EINVAL;
   MG_REQUIRE(ctx, d_blob && out && nbytes >= (int64_t)sizeof(KdHeader), "kd-tree: bad blob");
@@ -615,12 +633,18 @@ extern "C" int mg_kdtree_from_blob_dev(mg_ctx *ctx, const void *d_blob, int64_t 
   MG_CUDA(ctx, cudaMemcpyAsync(&h, d_blob, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
   MG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   MG_REQUIRE(ctx, h.magic == KD_MAGIC && h.nbytes == nbytes, "kd-tree: blob header mismatch");
+  int rc = validate_blob_header(ctx, h);
+  if (rc) return rc;
   mg_kdtree *t = new mg_kdtree;
   t->ctx = ctx; t->h = h;
   cudaError_t e = cudaMallocAsync(&t->d_blob, (size_t)nbytes, ctx->stream);
   if (e != cudaSuccess) { delete t; return set_err(ctx, MG_ENOMEM, "cuda: %s", cudaGetErrorString(e)); }
-  MG_CUDA(ctx, cudaMemcpyAsync(t->d_blob, d_blob, (size_t)nbytes, cudaMemcpyDeviceToDevice, ctx->stream));
-  MG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  e = cudaMemcpyAsync(t->d_blob, d_blob, (size_t)nbytes, cudaMemcpyDeviceToDevice, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  if (e != cudaSuccess) {
+    cudaFreeAsync(t->d_blob, ctx->stream); delete t;
+    return set_err(ctx, MG_ECUDA, "cuda: %s (kd-tree from blob)", cudaGetErrorString(e));
+  }
   *out = t;
   return MG_OK;
 }

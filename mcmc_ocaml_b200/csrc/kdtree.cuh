@@ -33,6 +33,7 @@ struct KdHeader {
   int64_t off_low, off_high, off_nodes, off_count, off_begin, off_perm, off_pts;
 };
 constexpr uint64_t KD_MAGIC = 0x6b64747265653031ull;  // "kdtree01"
+int validate_blob_header(struct ::mg_ctx *ctx, const KdHeader &h);   // kdtree.cu
 
 struct KdView {
   const KdNode *nodes;

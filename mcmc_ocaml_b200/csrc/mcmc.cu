@@ -70,6 +70,13 @@ static int validate_cfg(mg_ctx *ctx, const mg_mcmc_cfg *cfg) {
   MG_REQUIRE(ctx, cfg->dim >= 1 && cfg->dim <= 64, "mcmc_array: dim must be in 1..64");
   MG_REQUIRE(ctx, cfg->nbin >= 0 && cfg->nskip >= 1 && cfg->n >= 0, "mcmc_array: bad nbin/nskip/n");
   MG_REQUIRE(ctx, cfg->nchains / MH_BLOCK < 2147483647LL, "mcmc_array: too many chains for one launch");
+  // the Philox counter addresses (chain, step) with 48 + 40 bits (rng.cuh); accept counters are int32 per chain
+  MG_REQUIRE(ctx, cfg->chain_offset < (1ull << 48) && (uint64_t)cfg->nchains <= (1ull << 48) - cfg->chain_offset,
+             "mcmc_array: global chain ids must stay below 2^48");
+  {
+    const long double steps = (long double)cfg->nbin + (cfg->n > 0 ? (long double)(cfg->n - 1) * (long double)cfg->nskip : 0.0L);
+    MG_REQUIRE(ctx, steps < 2147483647.0L, "mcmc_array: more than 2^31 - 1 steps per chain in one call (cut the run into calls)");
+  }
   return MG_OK;
 }
 
@@ -156,6 +163,7 @@ extern "C" int mg_mcmc_array(mg_ctx *ctx, const mg_logfn *like, const mg_logfn *
   std::vector<int32_t> acc((size_t)C);
   MG_CUDA(ctx, cudaMemcpyAsync(acc.data(), d_acc.get(), sizeof(int32_t) * C, cudaMemcpyDeviceToHost, s));
   MG_CUDA(ctx, cudaStreamSynchronize(s));
+  if ((rc = poll_device_error(ctx))) return rc;
   const int64_t steps = cfg->nbin + (n > 0 ? (n - 1) * cfg->nskip : 0);
   for (int64_t c = 0; c < C; ++c) {
     ctx->naccept += acc[c]; ctx->nreject += steps - acc[c];
@@ -267,6 +275,7 @@ extern "C" int mg_mcmc_array_resident(mg_ctx *ctx, const mg_logfn *like, const m
   std::vector<int32_t> acc((size_t)C);
   MG_CUDA(ctx, cudaMemcpyAsync(acc.data(), d_acc.get(), sizeof(int32_t) * C, cudaMemcpyDeviceToHost, s));
   MG_CUDA(ctx, cudaStreamSynchronize(s));
+  if ((rc = poll_device_error(ctx))) return rc;
   const int64_t steps = cfg->nbin + (n > 0 ? (n - 1) * cfg->nskip : 0);
   for (int64_t c = 0; c < C; ++c) {
     ctx->naccept += acc[c]; ctx->nreject += steps - acc[c];

@@ -21,7 +21,9 @@
 // Progress: ticket k waits for the k-th push; pushes come from segments of
 // lower tickets, which are held by running warps and never wait once started,
 // so the scheme cannot deadlock even if part of the grid is not resident.
-// Every wait is bounded (clock64 budget); running out of it traps (the launch fails with a CUDA error).
+// Every wait is bounded (clock64 budget).  Running out of it does NOT trap (a trap poisons the CUDA context of the
+// whole process): the warp writes MG_DEVERR_MH_QUEUE into the context's device error word and leaves; every other
+// waiter polls that word and leaves too, and the host reports MG_ECUDA for the call (common.cuh poll_device_error).
 #pragma once
 #include "mcmc_kernel_dev.cuh"
 
@@ -46,8 +48,11 @@ struct MhQueue {
   int32_t nseg_burn;         // segments of seg_steps burn-in steps (the last one records slot 0)
   int64_t seg_steps;         // steps per burn-in segment
   int64_t seg_slots;         // recorded samples per sampling segment (nskip steps each)
+  long long wait_cycles;     // budget of one wait (kQueueWaitCycles; MCMC_GPU_WAIT_CYCLES overrides it for the tests)
+  int *err;                  // mg_ctx::d_devflag
 };
 
+constexpr int kDevErrMhQueue = 1;   // = MG_DEVERR_MH_QUEUE (common.cuh; checked where both are visible, mcmc_kernel.cuh)
 constexpr long long kQueueWaitCycles = 1ll << 38;  // ~2 min at 2 GHz: far beyond any segment (a heavy data likelihood can take seconds), still finite
 
 static __global__ void mh_queue_init_kernel(MhQueue q) {
@@ -101,7 +106,8 @@ mh_balanced_kernel(const __grid_constant__ MhArgs<Like, Prior, Prop, D> a, const
           if ((e >> 32) == want) break;
           __nanosleep(ns);
           if (ns < 2048) ns *= 2;
-          if (clock64() - t_begin > kQueueWaitCycles) __trap();
+          if (clock64() - t_begin > q.wait_cycles) atomicExch(q.err, kDevErrMhQueue);
+          if (*reinterpret_cast<volatile int *>(q.err) != 0) { e = ~0ull; break; }   // someone timed out: everybody leaves
         }
         if (e != ~0ull) *slot = 0ull;
         __threadfence();
@@ -216,11 +222,13 @@ mh_balanced_kernel(const __grid_constant__ MhArgs<Like, Prior, Prop, D> a, const
       const unsigned t2 = atomicAdd(&q.ctr[1], 1u);
       volatile unsigned long long *slot2 = q.ring + (t2 & (q.cap - 1u));
       const long long t_begin = clock64();
+      bool ok = true;
       while (*slot2 != 0ull) {
         __nanosleep(64);
-        if (clock64() - t_begin > kQueueWaitCycles) __trap();
+        if (clock64() - t_begin > q.wait_cycles) atomicExch(q.err, kDevErrMhQueue);
+        if (*reinterpret_cast<volatile int *>(q.err) != 0) { ok = false; break; }
       }
-      *slot2 = (((unsigned long long)t2 + 1ull) << 32) | grp;
+      if (ok) *slot2 = (((unsigned long long)t2 + 1ull) << 32) | grp;
     }
     __syncwarp();
     if (q.prof && lane == 0) {

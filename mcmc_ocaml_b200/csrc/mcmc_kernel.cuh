@@ -19,6 +19,7 @@ namespace mg {
 // (2 x (D+2) doubles per chain) and the queue traffic vanish, short enough that
 // a run has many tasks per group to even out.
 constexpr int64_t kSegSteps = 128;
+static_assert(kDevErrMhQueue == MG_DEVERR_MH_QUEUE, "device error codes out of sync");
 
 template <class Like, class Prior, class Prop, int D>
 static int launch_mh(mg_ctx *ctx, const MhArgs<Like, Prior, Prop, D> &a) {
@@ -30,8 +31,12 @@ static int launch_mh(mg_ctx *ctx, const MhArgs<Like, Prior, Prop, D> &a) {
   // work until the tail: a polling warp on a saturated scheduler is starved by the arbiter and picks its group up late).
   const int64_t nsched = (int64_t)ctx->sm_count * 4;
   if (want_balanced && total_steps >= 4 * kSegSteps && ngroups > nsched && ngroups < (1ll << 30)) {
+    // running moments requested (mg_mcmc_array_resident): that instantiation holds more registers per warp, so its
+    // own occupancy sizes the persistent grid
+    const bool with_mom = ctx->mh_mom != nullptr && a.t0 == 0 && a.record_first && a.samples != nullptr;
     int occ = 0;
-    MG_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, mh_balanced_kernel<Like, Prior, Prop, D, false>, MH_BLOCK, 0));
+    if (with_mom) MG_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, mh_balanced_kernel<Like, Prior, Prop, D, true>, MH_BLOCK, 0));
+    else MG_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, mh_balanced_kernel<Like, Prior, Prop, D, false>, MH_BLOCK, 0));
     int64_t grid = std::min<int64_t>((int64_t)std::max(occ, 1) * ctx->sm_count, (ngroups / nsched) * nsched);
     if (const char *e = getenv("MCMC_GPU_MH_GRID")) grid = std::max(1, atoi(e));
     if (grid != ngroups) {
@@ -59,6 +64,9 @@ static int launch_mh(mg_ctx *ctx, const MhArgs<Like, Prior, Prop, D> &a) {
     MG_CUDA(ctx, ctr.alloc(2, ctx->stream));
     MG_CUDA(ctx, seg_next.alloc(q.ngroups, ctx->stream));
     q.ring = ring.get(); q.ctr = ctr.get(); q.seg_next = seg_next.get();
+    q.err = ctx->d_devflag;
+    q.wait_cycles = kQueueWaitCycles;
+    if (const char *e = getenv("MCMC_GPU_WAIT_CYCLES")) q.wait_cycles = std::max(1ll, atoll(e));
     DevBuf<long long> prof;
     q.prof = nullptr;
     if (getenv("MCMC_GPU_DEBUG")) {
@@ -70,7 +78,6 @@ static int launch_mh(mg_ctx *ctx, const MhArgs<Like, Prior, Prop, D> &a) {
     MG_CHECK_LAUNCH(ctx);
     // running moments of the recorded samples (requested through the context by mg_mcmc_array_resident): the
     // variant with the accumulators is a separate instantiation, the plain kernel does not pay for them
-    const bool with_mom = ctx->mh_mom != nullptr && a.t0 == 0 && a.record_first && a.samples != nullptr;
     time_begin(ctx);
     if (with_mom) {
       MhArgs<Like, Prior, Prop, D> am = a;

@@ -3,13 +3,9 @@
 // proposal, all parameters in the kernel argument block (constant bank).
 // Compiled once per dimension (-DMG_SD=<D>), see csrc/Makefile.
 #include "mcmc_kernel.cuh"
-#include "mcmc_ws.cuh"
 
 #include <cstdlib>
 
-#ifndef MG_MH_WS_DEFAULT
-#define MG_MH_WS_DEFAULT 0
-#endif
 #ifndef MG_SD
 #error "compile with -DMG_SD=<dimension>"
 #endif
@@ -25,11 +21,6 @@ int MG_CAT(mh_static_gauss_, MG_SD)(mg_ctx *ctx, const mg_logfn *like, const mg_
   GaussCorr<D>::pack(like->params, like->params + D, like->params[D + D * (D + 1) / 2], a.like);
   BoxProp<D>::pack(prop->params, a.prop);
   fill_common(a, cfg, key, t0, record_first, d_state, d_samples, d_accept);
-#if MG_SD <= 10
-  // warp-specialised kernel (mcmc_ws.cuh); MCMC_GPU_MH_WS=0 selects the single-role kernel
-  static const bool use_ws = [] { const char *e = getenv("MCMC_GPU_MH_WS"); return e ? atoi(e) != 0 : MG_MH_WS_DEFAULT; }();
-  if (use_ws) return launch_mh_ws<D>(ctx, a);
-#endif
   return launch_mh(ctx, a);
 }
 }  // namespace mg

@@ -35,7 +35,7 @@ struct RjArgs {
   int32_t Dm, DT;            // max model dim; scratch dim (max tree dim)
   uint8_t *out_model;        // [n][C] or null
   double *out_samples;       // [n][Dm+2][C] or null
-  unsigned long long *counts;  // [3]: #A, #B, #accepted
+  unsigned long long *counts;  // [5]: #A, #B, #accepted, #cross-model proposals, #cross-model accepted
   const double *start;         // [2][64]: the start points a0, b0
   int *fail;
 };
@@ -102,7 +102,7 @@ rj_ensemble_kernel(const __grid_constant__ RjArgs a) {
   const KdScratch s = kd_scratch(smem, a.DT);
   const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const bool live = c < a.C;
-  unsigned na = 0, nb = 0, nacc = 0;
+  unsigned na = 0, nb = 0, nacc = 0, ncross = 0, ncross_acc = 0;
   if (live) {
     const uint64_t g = a.chain_offset + (uint64_t)c;
     const int64_t C = a.C;
@@ -155,8 +155,9 @@ rj_ensemble_kernel(const __grid_constant__ RjArgs a) {
       }
       const double log_accept_prob =
           proposed_log_posterior - start_log_post + log_backward_jump - log_forward_jump;
+      if (pmodel != model) ++ncross;
       if (log_u_less_than(r.uniform(), log_accept_prob)) {
-        if (pmodel != model) { lq_x = fwd_lq; lq_x_valid = true; }   // the new point's own jump-in probability
+        if (pmodel != model) { lq_x = fwd_lq; lq_x_valid = true; ++ncross_acc; }   // the new point's own jump-in probability
         else lq_x_valid = false;
         model = pmodel;
 #pragma unroll (DMAX <= 16 ? DMAX : 1)
@@ -190,11 +191,15 @@ rj_ensemble_kernel(const __grid_constant__ RjArgs a) {
     na += __shfl_down_sync(0xffffffffu, na, off);
     nb += __shfl_down_sync(0xffffffffu, nb, off);
     nacc += __shfl_down_sync(0xffffffffu, nacc, off);
+    ncross += __shfl_down_sync(0xffffffffu, ncross, off);
+    ncross_acc += __shfl_down_sync(0xffffffffu, ncross_acc, off);
   }
   if ((threadIdx.x & 31) == 0) {
     atomicAdd(a.counts + 0, (unsigned long long)na);
     atomicAdd(a.counts + 1, (unsigned long long)nb);
     atomicAdd(a.counts + 2, (unsigned long long)nacc);
+    atomicAdd(a.counts + 3, (unsigned long long)ncross);
+    atomicAdd(a.counts + 4, (unsigned long long)ncross_acc);
   }
 }
 
@@ -245,8 +250,8 @@ extern "C" int mg_rjmcmc_array(mg_ctx *ctx, const mg_rj_model *A, const mg_rj_mo
   for (int i = 0; i < A->like.dim; ++i) h_start[i] = a0[i];
   for (int i = 0; i < B->like.dim; ++i) h_start[64 + i] = b0[i];
   MG_CUDA(ctx, upload(d_start, h_start.data(), h_start.size(), s));
-  MG_CUDA(ctx, d_counts.alloc(4, s));
-  MG_CUDA(ctx, cudaMemsetAsync(d_counts.get(), 0, 4 * sizeof(unsigned long long), s));
+  MG_CUDA(ctx, d_counts.alloc(8, s));
+  MG_CUDA(ctx, cudaMemsetAsync(d_counts.get(), 0, 8 * sizeof(unsigned long long), s));
   MG_CUDA(ctx, d_fail.alloc(1, s));
   MG_CUDA(ctx, cudaMemsetAsync(d_fail.get(), 0, sizeof(int), s));
   for (int k = 0; k < 2; ++k) {
@@ -294,7 +299,7 @@ extern "C" int mg_rjmcmc_array(mg_ctx *ctx, const mg_rj_model *A, const mg_rj_mo
   if (out_model && n > 0) MG_CUDA(ctx, cudaMemcpyAsync(out_model, d_model.get(), (size_t)n * C, cudaMemcpyDeviceToHost, s));
   if (out_samples && n > 0)
     MG_CUDA(ctx, cudaMemcpyAsync(out_samples, d_samples.get(), sizeof(double) * (size_t)n * F * C, cudaMemcpyDeviceToHost, s));
-  unsigned long long cnt[3];
+  unsigned long long cnt[5];
   int h_fail = 0;
   MG_CUDA(ctx, cudaMemcpyAsync(cnt, d_counts.get(), sizeof cnt, cudaMemcpyDeviceToHost, s));
   MG_CUDA(ctx, cudaMemcpyAsync(&h_fail, d_fail.get(), sizeof(int), cudaMemcpyDeviceToHost, s));
@@ -303,5 +308,13 @@ extern "C" int mg_rjmcmc_array(mg_ctx *ctx, const mg_rj_model *A, const mg_rj_mo
   out_counts[0] = (int64_t)cnt[0]; out_counts[1] = (int64_t)cnt[1];
   const int64_t steps = C * (cfg->nbin + (n > 0 ? (n - 1) * cfg->nskip : 0));
   ctx->naccept += (int64_t)cnt[2]; ctx->nreject += steps - (int64_t)cnt[2];
+  ctx->rj_cross[0] = (int64_t)cnt[3]; ctx->rj_cross[1] = (int64_t)cnt[4];
+  return MG_OK;
+}
+
+extern "C" int mg_rjmcmc_jump_counters(const mg_ctx *ctx, int64_t *proposed, int64_t *accepted) {
+  if (!ctx) return MG_EINVAL;
+  if (proposed) *proposed = ctx->rj_cross[0];
+  if (accepted) *accepted = ctx->rj_cross[1];
   return MG_OK;
 }

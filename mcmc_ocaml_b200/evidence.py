@@ -18,7 +18,10 @@ def _unpack(samples, ll=None, lp=None):
     pts = _abi.as_f64(samples)
     if pts.ndim == 1:
         pts = pts.reshape(-1, 1)
-    return pts, _abi.as_f64(ll), _abi.as_f64(lp)
+    ll, lp = _abi.as_f64(ll), _abi.as_f64(lp)
+    if ll.ndim and lp.ndim and (ll.size != pts.shape[0] or lp.size != pts.shape[0]):   # the library reads N of each
+        raise _abi.InvalidArgument("evidence: log_likelihood / log_prior must have one entry per sample")
+    return pts, ll, lp
 
 
 def kd_tree_of_samples(samples, low, high, *, ctx: Context | None = None) -> KdTree:

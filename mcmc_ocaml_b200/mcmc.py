@@ -161,6 +161,7 @@ class RjSamples:
     model: np.ndarray | None      # uint8 [n][C], 0 = A, 1 = B
     block: np.ndarray | None      # [n][Dmax+2][C]
     counts: tuple[int, int]       # rjmcmc_model_counts over every recorded sample
+    cross: tuple[int, int] = (0, 0)   # steps that proposed a jump into the other model, of which accepted
 
 
 def rjmcmc_array(n: int, A: RjModel, B: RjModel, a0, b0, *, nbin: int = 0, nskip: int = 1, nchains: int = 1,
@@ -176,9 +177,13 @@ def rjmcmc_array(n: int, A: RjModel, B: RjModel, a0, b0, *, nbin: int = 0, nskip
     counts = (C.c_int64 * 2)()
     sa, sb = A.spec(), B.spec()
     a0, b0 = _abi.as_f64(a0), _abi.as_f64(b0)
+    if a0.size != A.like.dim or b0.size != B.like.dim:      # the library reads like.dim values from each
+        raise _abi.InvalidArgument("rjmcmc_array: start points must have the dimensions of their models")
     ctx.check(ctx.lib.mg_rjmcmc_array(ctx.h, C.byref(sa), C.byref(sb), C.byref(cfg), _abi.ptr(a0), _abi.ptr(b0),
                                       _abi.ptr(model, _abi.c_uint8_p), _abi.ptr(block), counts))
-    return RjSamples(model, block, (int(counts[0]), int(counts[1])))
+    cp, ca = C.c_int64(), C.c_int64()
+    ctx.lib.mg_rjmcmc_jump_counters(ctx.h, C.byref(cp), C.byref(ca))
+    return RjSamples(model, block, (int(counts[0]), int(counts[1])), (int(cp.value), int(ca.value)))
 
 
 def rjmcmc_model_counts(samples: RjSamples) -> tuple[int, int]:

@@ -31,6 +31,15 @@ using namespace og;
 static thread_local std::string g_err;
 static int fail(int code, const std::string &m) { g_err = m; return code; }
 
+// Diagnostic for the parity tests: the smallest |log u - log_accept_prob| over the accept tests (mcmc.ml:47)
+// since the last reset.  A GPU chain may legitimately leave the oracle's only at a step whose margin is a
+// near-tie (the two libms differ in the last ulp of a transcendental); the tests check exactly that.
+static thread_local double tl_margin = HUGE_VAL;
+static inline void note_margin(double log_u, double log_accept_prob) {
+  const double m = std::fabs(log_u - log_accept_prob);
+  if (m < tl_margin) tl_margin = m;   // NaN (inf - inf) never compares smaller: not a tie
+}
+
 // ===========================================================================
 // mcmc.ml
 // ===========================================================================
@@ -49,7 +58,9 @@ static inline bool mh_step(Rng &r, int D, double *x, double &ll, double &lp, dou
   double log_forward_jump = log_jump_prob(x, prop), log_backward_jump = log_jump_prob(prop, x);
   double log_accept_prob =
       proposed_log_posterior - start_log_post + log_backward_jump - log_forward_jump;
-  if (std::log(r.uniform()) < log_accept_prob) {  // strict <, :47
+  const double log_u = std::log(r.uniform());
+  note_margin(log_u, log_accept_prob);
+  if (log_u < log_accept_prob) {  // strict <, :47
     for (int i = 0; i < D; ++i) x[i] = prop[i];
     ll = proposed_like; lp = proposed_prior;
     return true;
@@ -61,8 +72,9 @@ static inline bool mh_step(Rng &r, int D, double *x, double &ll, double &lp, dou
 // written step-major: out[(s*(D+2) + f)*C + c].
 static void mcmc_chain(const CallKey &ck, const LogFn &like, const LogFn &prior,
                        const Proposal &prop, const mg_mcmc_cfg &cfg, const double *start,
-                       int64_t c, double *out, int64_t *acc, int64_t *rej) {
+                       int64_t c, double *out, int64_t *acc, int64_t *rej, double *margin = nullptr) {
   const int D = cfg.dim; const int64_t C = cfg.nchains; const int F = D + 2;
+  tl_margin = HUGE_VAL;
   const uint64_t g = cfg.chain_offset + (uint64_t)c;
   std::vector<double> x(start, start + D), p(D);
   double ll = like(x.data()), lp = prior(x.data());  // :59-61
@@ -72,6 +84,7 @@ static void mcmc_chain(const CallKey &ck, const LogFn &like, const LogFn &prior,
   auto J = [&](Rng &r, const double *a, double *b) { prop.propose(r, a, b); };
   auto Q = [&](const double *a, const double *b) { return prop.log_q(a, b); };
   auto record = [&](int64_t s) {
+    if (margin) { margin[s * C + c] = tl_margin; tl_margin = HUGE_VAL; }   // min over the steps leading to slot s
     if (!out) return;
     for (int f = 0; f < D; ++f) out[(s * F + f) * C + c] = x[f];
     out[(s * F + D) * C + c] = ll; out[(s * F + D + 1) * C + c] = lp;
@@ -132,8 +145,11 @@ struct RjState { int model; std::vector<double> x; };
 
 static int rj_chain(const CallKey &ck, const RjModel &A, const RjModel &B, const mg_rjmcmc_cfg &cfg,
                     const double *a0, const double *b0, int64_t c, uint8_t *out_model,
-                    double *out_samples, int64_t *na_out, int64_t *nb_out, int64_t *acc) {
+                    double *out_samples, int64_t *na_out, int64_t *nb_out, int64_t *acc, double *margin = nullptr,
+                    int64_t *cross = nullptr) {
   const int64_t C = cfg.nchains; const int Dm = std::max(A.D, B.D); const int F = Dm + 2;
+  tl_margin = HUGE_VAL;
+  int64_t ncross = 0, ncross_acc = 0;
   const uint64_t g = cfg.chain_offset + (uint64_t)c;
   const RjModel *M[2] = {&A, &B};
   const double log_p[2] = {std::log(A.p), std::log(B.p)};  // :91
@@ -170,13 +186,18 @@ static int rj_chain(const CallKey &ck, const RjModel &A, const RjModel &B, const
     double log_forward_jump = ljp(cur, prop), log_backward_jump = ljp(prop, cur);
     double log_accept_prob =
         proposed_log_posterior - start_log_post + log_backward_jump - log_forward_jump;
-    if (std::log(r.uniform()) < log_accept_prob) {
+    const double log_u = std::log(r.uniform());
+    note_margin(log_u, log_accept_prob);
+    if (prop.model != cur.model) ++ncross;
+    if (log_u < log_accept_prob) {
+      if (prop.model != cur.model) ++ncross_acc;
       cur.model = prop.model; cur.x = prop.x; ll = proposed_like; lp = proposed_prior; ++nacc;
     }
     ++t;
   };
   auto record = [&](int64_t s) {
     (cur.model == 0 ? na : nb)++;
+    if (margin) { margin[s * C + c] = tl_margin; tl_margin = HUGE_VAL; }
     if (out_model) out_model[s * C + c] = (uint8_t)cur.model;
     if (out_samples) {
       for (int f = 0; f < Dm; ++f) out_samples[(s * F + f) * C + c] = cur.x[f];
@@ -190,6 +211,7 @@ static int rj_chain(const CallKey &ck, const RjModel &A, const RjModel &B, const
     if (i % cfg.nskip == 0) record(i / cfg.nskip);
   }
   *na_out = na; *nb_out = nb; if (acc) *acc = nacc;
+  if (cross) { cross[0] = ncross; cross[1] = ncross_acc; }
   return bad ? 1 : 0;
 }
 
@@ -499,24 +521,32 @@ int og_logfn_eval(const mg_logfn *fn, const double *x, int64_t M, double *out) {
   OG_CATCH
 }
 
-int og_mcmc_array(uint64_t seed, uint64_t epoch, const mg_logfn *like, const mg_logfn *prior,
-                  const mg_proposal *prop, const mg_mcmc_cfg *cfg, const double *x0, double *out,
-                  int64_t *acc, int64_t *rej, int nthreads) {
+// margin: [n][C] or null -- min |log u - log_accept_prob| over the steps leading to each slot (test diagnostic)
+int og_mcmc_array_m(uint64_t seed, uint64_t epoch, const mg_logfn *like, const mg_logfn *prior,
+                    const mg_proposal *prop, const mg_mcmc_cfg *cfg, const double *x0, double *out,
+                    int64_t *acc, int64_t *rej, int nthreads, double *margin) {
   OG_TRY
   LogFn L(like), P(prior); Proposal J(prop);
   if (cfg->nskip < 1 || cfg->n < 0 || cfg->nbin < 0) return fail(MG_EINVAL, "mcmc_array: bad nbin/nskip/n");
   CallKey ck = derive_key(seed, epoch);
   parallel_for(cfg->nchains, nthreads, [&](int64_t c) {
     const double *s = cfg->x0_shared ? x0 : x0 + c * cfg->dim;
-    mcmc_chain(ck, L, P, J, *cfg, s, c, out, acc, rej);
+    mcmc_chain(ck, L, P, J, *cfg, s, c, out, acc, rej, margin);
   });
   return MG_OK;
   OG_CATCH
 }
+int og_mcmc_array(uint64_t seed, uint64_t epoch, const mg_logfn *like, const mg_logfn *prior,
+                  const mg_proposal *prop, const mg_mcmc_cfg *cfg, const double *x0, double *out,
+                  int64_t *acc, int64_t *rej, int nthreads) {
+  return og_mcmc_array_m(seed, epoch, like, prior, prop, cfg, x0, out, acc, rej, nthreads, nullptr);
+}
 
-int og_rjmcmc_array(uint64_t seed, uint64_t epoch, const mg_rj_model *A, const mg_rj_model *B,
-                    const mg_rjmcmc_cfg *cfg, const double *a0, const double *b0, uint8_t *out_model,
-                    double *out_samples, int64_t out_counts[2], int64_t *out_accept, int nthreads) {
+// margin: [n][C] or null (as og_mcmc_array_m); out_cross: {cross-model proposals, accepted} or null
+int og_rjmcmc_array_m(uint64_t seed, uint64_t epoch, const mg_rj_model *A, const mg_rj_model *B,
+                      const mg_rjmcmc_cfg *cfg, const double *a0, const double *b0, uint8_t *out_model,
+                      double *out_samples, int64_t out_counts[2], int64_t *out_accept, int nthreads,
+                      double *margin, int64_t *out_cross) {
   OG_TRY
   // mcmc.ml:90 assert(pa +. pb -. 1.0 < sqrt epsilon_float)  (one-sided)
   if (!(A->p + B->p - 1.0 < std::sqrt(2.220446049250313e-16))) return fail(MG_EFAIL, "Assert_failure mcmc.ml:90");
@@ -524,15 +554,26 @@ int og_rjmcmc_array(uint64_t seed, uint64_t epoch, const mg_rj_model *A, const m
   CallKey ck = derive_key(seed, epoch);
   std::vector<int64_t> na(cfg->nchains), nb(cfg->nchains), ac(cfg->nchains);
   std::vector<int> bad(cfg->nchains, 0);
+  std::vector<int64_t> cr((size_t)cfg->nchains * 2, 0);
   parallel_for(cfg->nchains, nthreads, [&](int64_t c) {
-    bad[c] = rj_chain(ck, a, b, *cfg, a0, b0, c, out_model, out_samples, &na[c], &nb[c], &ac[c]);
+    bad[c] = rj_chain(ck, a, b, *cfg, a0, b0, c, out_model, out_samples, &na[c], &nb[c], &ac[c], margin, &cr[2 * c]);
   });
-  int64_t ta = 0, tb = 0, tacc = 0;
-  for (int64_t c = 0; c < cfg->nchains; ++c) { ta += na[c]; tb += nb[c]; tacc += ac[c]; if (bad[c]) return fail(MG_EFAIL, "draw: empty tree"); }
+  int64_t ta = 0, tb = 0, tacc = 0, c0 = 0, c1 = 0;
+  for (int64_t c = 0; c < cfg->nchains; ++c) {
+    ta += na[c]; tb += nb[c]; tacc += ac[c]; c0 += cr[2 * c]; c1 += cr[2 * c + 1];
+    if (bad[c]) return fail(MG_EFAIL, "draw: empty tree");
+  }
   out_counts[0] = ta; out_counts[1] = tb;
   if (out_accept) *out_accept = tacc;
+  if (out_cross) { out_cross[0] = c0; out_cross[1] = c1; }
   return MG_OK;
   OG_CATCH
+}
+int og_rjmcmc_array(uint64_t seed, uint64_t epoch, const mg_rj_model *A, const mg_rj_model *B,
+                    const mg_rjmcmc_cfg *cfg, const double *a0, const double *b0, uint8_t *out_model,
+                    double *out_samples, int64_t out_counts[2], int64_t *out_accept, int nthreads) {
+  return og_rjmcmc_array_m(seed, epoch, A, B, cfg, a0, b0, out_model, out_samples, out_counts, out_accept, nthreads,
+                           nullptr, nullptr);
 }
 
 // ---- kd-tree / interpolate ------------------------------------------------

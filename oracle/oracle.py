@@ -89,7 +89,9 @@ def logfn_eval(fn, x):
 
 
 def mcmc_array(seed, epoch, n, like, prior, prop, start, *, nbin=0, nskip=1, nchains=None, chain_offset=0,
-               nthreads=1, record=True):
+               nthreads=1, record=True, margins=False):
+    """margins=True additionally returns [n][C]: the smallest |log u - log_accept_prob| over the steps leading to
+    each slot (the near-tie diagnostic of the parity tests)."""
     dim = like.dim
     x0 = as_f64(start)
     shared = x0.ndim == 1 and (nchains is None or x0.size == dim)
@@ -102,8 +104,12 @@ def mcmc_array(seed, epoch, n, like, prior, prop, start, *, nbin=0, nskip=1, nch
     acc = np.zeros(nchains, dtype=np.int64)
     rej = np.zeros(nchains, dtype=np.int64)
     ls, ps, js = like.spec(), prior.spec(), prop.spec()
-    _check(lib().og_mcmc_array(U64(seed), U64(epoch), C.byref(ls), C.byref(ps), C.byref(js), C.byref(cfg), ptr(x0),
-                               ptr(out), ptr(acc, _abi.c_int64_p), ptr(rej, _abi.c_int64_p), C.c_int(nthreads)))
+    mg = np.full((n, nchains), np.inf) if margins else None
+    _check(lib().og_mcmc_array_m(U64(seed), U64(epoch), C.byref(ls), C.byref(ps), C.byref(js), C.byref(cfg), ptr(x0),
+                                 ptr(out), ptr(acc, _abi.c_int64_p), ptr(rej, _abi.c_int64_p), C.c_int(nthreads),
+                                 ptr(mg)))
+    if margins:
+        return out, acc, rej, mg
     return out, acc, rej
 
 
@@ -177,7 +183,7 @@ def rj_model(like, prior, prop, p, *, tree=None, nstop=0, into_gauss=None):
 
 
 def rjmcmc_array(seed, epoch, n, A, B, a0, b0, *, nbin=0, nskip=1, nchains=1, chain_offset=0, nthreads=1,
-                 record_model=True, record_samples=False):
+                 record_model=True, record_samples=False, margins=False):
     (ma, ka), (mb, kb) = A, B
     dm = max(ma.like.dim, mb.like.dim)
     cfg = _abi.mg_rjmcmc_cfg(nchains, nbin, nskip, n, chain_offset, 0, 0)
@@ -186,9 +192,13 @@ def rjmcmc_array(seed, epoch, n, A, B, a0, b0, *, nbin=0, nskip=1, nchains=1, ch
     counts = (C.c_int64 * 2)()
     acc = C.c_int64()
     a0, b0 = as_f64(a0), as_f64(b0)
-    _check(lib().og_rjmcmc_array(U64(seed), U64(epoch), C.byref(ma), C.byref(mb), C.byref(cfg), ptr(a0), ptr(b0),
-                                 ptr(model, _abi.c_uint8_p), ptr(samples), counts, C.byref(acc), C.c_int(nthreads)))
-    return dict(model=model, samples=samples, counts=(counts[0], counts[1]), accept=acc.value)
+    mg = np.full((n, nchains), np.inf) if margins else None
+    cross = (C.c_int64 * 2)()
+    _check(lib().og_rjmcmc_array_m(U64(seed), U64(epoch), C.byref(ma), C.byref(mb), C.byref(cfg), ptr(a0), ptr(b0),
+                                   ptr(model, _abi.c_uint8_p), ptr(samples), counts, C.byref(acc), C.c_int(nthreads),
+                                   ptr(mg), cross))
+    return dict(model=model, samples=samples, counts=(counts[0], counts[1]), accept=acc.value, margins=mg,
+                cross=(cross[0], cross[1]))
 
 
 def evidence_harmonic_mean(ll):

@@ -1,5 +1,9 @@
-"""Parity at BASELINE.json's full sizes through size-independent properties
-(the oracle cannot run these sizes in seconds): configs 2 and 3 on one GPU."""
+"""Parity at BASELINE.json's sizes: config 3 EXACTLY against the oracle at 1e6 x 20 (and, with
+MCMC_GPU_FULL_PARITY=1 or tools/parity_full_size.py, at the full 1e7 x 20: ~6 minutes of single-threaded oracle; the
+committed record of that run is profiles/r02_parity_cfg3_1e7.json), plus size-independent properties at the full
+sizes of configs 2 and 3 on one GPU."""
+import os
+
 import ctypes as C
 import math
 
@@ -9,6 +13,18 @@ import pytest
 from mcmc_ocaml_b200 import _abi, evidence, kd_tree, plugins as P
 
 pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("N,dups", [(1_000_000, 0.0), (1_000_000, 0.3)] +
+                         ([(10_000_000, 0.0)] if os.environ.get("MCMC_GPU_FULL_PARITY") else []))
+def test_config3_exact_against_oracle(ctx, og, N, dups):
+    """kd-tree (full and Evidence's truncated one) array for array, point location and densities value for value,
+    Lebesgue / direct evidence to 1e-12 -- the GPU path against the oracle on config 3's data at 1e6 x 20."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import parity_full_size
+    out = parity_full_size.compare(N, 20, dups, ctx=ctx, og=og, nquery=50000)
+    assert out["tree_full"]["nlevels"] >= 20 and out["lebesgue"]["ncells"] > 1000
 
 
 def test_config3_tree_and_evidence_properties(ctx):

@@ -11,6 +11,7 @@ import numpy as np
 import pytest
 
 from mcmc_ocaml_b200 import InvalidArgument, mcmc, plugins as P
+from tests._parity import divergence_report
 
 pytestmark = pytest.mark.gpu
 
@@ -70,12 +71,13 @@ def test_data_likelihoods(ctx, og):
     for k, like in enumerate([P.gauss_data(DATA), P.cauchy_data(DATA)]):
         ctx.set_seed(20111104 + k)
         got = mcmc.mcmc_array(50, like, prior, prop, [0.0, 1.0], nchains=128, nbin=20, nskip=4, ctx=ctx)
-        want, acc, _ = og.mcmc_array(20111104 + k, 0, 50, like, prior, prop, [0.0, 1.0], nchains=128, nbin=20,
-                                     nskip=4, nthreads=8)
-        # transcendental log-likelihood: a last-ulp difference can flip one
-        # accept decision; require the overwhelming majority of chains identical
+        want, acc, _, mg = og.mcmc_array(20111104 + k, 0, 50, like, prior, prop, [0.0, 1.0], nchains=128, nbin=20,
+                                         nskip=4, nthreads=8, margins=True)
+        # transcendental log-likelihood: a last-ulp difference (CUDA libm vs glibc) can flip an accept decision
+        # ONLY at a near-tie of the accept test; any chain that leaves the oracle elsewhere fails the test
+        frac = divergence_report(got.block[:, :2, :], want[:, :2, :], mg, f"data likelihood {k}")
+        assert frac <= 0.01
         same = np.all(got.block[:, :2, :] == want[:, :2, :], axis=(0, 1))
-        assert same.mean() >= 0.98
         np.testing.assert_allclose(got.block[:, 2, same], want[:, 2, same], rtol=1e-12)
 
 
@@ -86,9 +88,8 @@ def test_asymmetric_proposals_hastings(ctx, og):
     for prop in (P.left_biased_proposal(sigma), P.indep_gauss_proposal([mu + 0.3], [2.0 * sigma])):
         ctx.set_seed(5)
         got = mcmc.mcmc_array(400, like, prior, prop, [mu], nchains=64, ctx=ctx)
-        want, acc, _ = og.mcmc_array(5, 0, 400, like, prior, prop, [mu], nchains=64, nthreads=8)
-        same = np.all(got.block[:, 0, :] == want[:, 0, :], axis=0)
-        assert same.mean() >= 0.95
+        want, acc, _, mg = og.mcmc_array(5, 0, 400, like, prior, prop, [mu], nchains=64, nthreads=8, margins=True)
+        assert divergence_report(got.block[:, 0, :], want[:, 0, :], mg, "asymmetric proposal") <= 0.02
 
 
 def test_sharding_is_rank_independent(ctx):
@@ -191,9 +192,8 @@ def test_combine_jump_proposals(ctx, og):
     like, prior = P.gauss_diag([0.0], [1.0]), P.zero(1)
     ctx.set_seed(17)
     got = mcmc.mcmc_array(300, like, prior, prop, [0.0], nchains=128, nskip=2, ctx=ctx)
-    want, acc, _ = og.mcmc_array(17, 0, 300, like, prior, prop, [0.0], nchains=128, nskip=2, nthreads=8)
-    same = np.all(got.block[:, 0, :] == want[:, 0, :], axis=0)
-    assert same.mean() >= 0.95                      # log / exp: CUDA libm vs glibc may flip a rare decision
+    want, acc, _, mg = og.mcmc_array(17, 0, 300, like, prior, prop, [0.0], nchains=128, nskip=2, nthreads=8, margins=True)
+    assert divergence_report(got.block[:, 0, :], want[:, 0, :], mg, "mixture proposal") <= 0.01   # near-ties only
     ctx.set_seed(18)
     r = mcmc.mcmc_array(250, like, prior, prop, [0.0], nchains=4096, nbin=50, nskip=5, ctx=ctx)
     x = r.block[:, 0, :].ravel()                    # 1.02e6 samples, as the reference test
@@ -261,8 +261,8 @@ def test_resident_call_running_moments(ctx, og):
 
 def test_balanced_kernel_dynamic_plugins_data_likelihood(ctx, og):
     """The balanced sampler through the dynamic plugins (data likelihood, box prior, uniform_wrapping): a
-    transcendental log-likelihood may flip a rare decision (CUDA libm vs glibc), so the overwhelming majority of
-    the 18,977 chains must be identical over 520 samples and the rest must still be valid chains."""
+    transcendental log-likelihood may flip a decision (CUDA libm vs glibc) only at a near-tie of the accept test:
+    every one of the 18,977 chains is either identical over 520 samples or first differs at such a tie."""
     from tests.golden.gc_data import DATA
     like = P.gauss_data(DATA[:16])
     prior = P.box([-1.0, 0.5], [1.0, 1.5], value=-0.693147)
@@ -270,9 +270,9 @@ def test_balanced_kernel_dynamic_plugins_data_likelihood(ctx, og):
     C, n = 592 * 32 + 33, 520
     ctx.set_seed(31)
     got = mcmc.mcmc_array(n, like, prior, prop, [0.0, 1.0], nchains=C, nbin=5, ctx=ctx)
-    want, acc, _ = og.mcmc_array(31, 0, n, like, prior, prop, [0.0, 1.0], nchains=C, nbin=5, nthreads=16)
+    want, acc, _, mg = og.mcmc_array(31, 0, n, like, prior, prop, [0.0, 1.0], nchains=C, nbin=5, nthreads=16, margins=True)
+    assert divergence_report(got.block[:, :2, :], want[:, :2, :], mg, "balanced kernel, data likelihood") <= 1e-3
     same = np.all(got.block[:, :2, :] == want[:, :2, :], axis=(0, 1))
-    assert same.mean() >= 0.98
     np.testing.assert_allclose(got.block[:, 2, same], want[:, 2, same], rtol=1e-12)
     assert np.array_equal(got.accept[same], acc[same])
     assert np.all(got.block[:, 0, :] >= -1.0) and np.all(got.block[:, 1, :] <= 1.5)

@@ -190,3 +190,52 @@ def test_trim_pool_releases_cached_memory(ctx):
     free_trimmed, _ = torch.cuda.mem_get_info()
     assert free_trimmed >= free_cached
     assert evidence.evidence_harmonic_mean(ll=ll, ctx=ctx) == z0
+
+
+def test_bounded_wait_reports_error_and_context_survives(ctx, og, monkeypatch):
+    """The balanced sampler's queue waits are bounded.  Running out of the budget must not trap (a trap poisons the
+    CUDA context of the whole process): the call returns MG_ECUDA (Failure "cuda: ...") and the SAME context then
+    runs the same ensemble correctly.  The time-out is provoked by a persistent grid four times larger than the
+    number of chain groups (the surplus warps must wait for the first segments to finish) and a budget of 1,000
+    cycles."""
+    D = 4
+    mu = np.arange(D) / 10.0
+    cov = 0.7 ** np.abs(np.subtract.outer(np.arange(D), np.arange(D)))
+    like, prior, prop = P.gauss_corr(mu, cov), P.zero(D), P.box_proposal(np.full(D, 0.5))
+    C_, n = 592 * 32 + 64, 600
+    monkeypatch.setenv("MCMC_GPU_MH_GRID", str(4 * (C_ // 32)))
+    monkeypatch.setenv("MCMC_GPU_WAIT_CYCLES", "1000")
+    ctx.set_seed(5)
+    with pytest.raises(Failure, match="timed out"):
+        mcmc.mcmc_array(n, like, prior, prop, mu, nchains=C_, ctx=ctx)
+    monkeypatch.delenv("MCMC_GPU_MH_GRID")
+    monkeypatch.delenv("MCMC_GPU_WAIT_CYCLES")
+    ctx.set_seed(5)
+    got = mcmc.mcmc_array(n, like, prior, prop, mu, nchains=C_, ctx=ctx)          # same context, healthy
+    want, acc, _ = og.mcmc_array(5, 0, n, like, prior, prop, mu, nchains=C_, nthreads=16)
+    assert np.array_equal(got.block, want) and np.array_equal(got.accept, acc)
+
+
+def test_blob_validation_rejects_corrupt_headers(ctx):
+    """mg_kdtree_from_blob_dev trusts nothing in a blob that arrived from another process"""
+    import torch
+
+    from mcmc_ocaml_b200 import InvalidArgument, kd_tree
+    pts = np.random.default_rng(1).random((500, 3))
+    t = kd_tree.KdTree(pts, np.zeros(3), np.ones(3), ctx=ctx)
+    p, nbytes = t.blob()
+    buf = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+    ctx.check(ctx.lib.mg_memcpy_d2d(ctx.h, C.c_void_p(buf.data_ptr()), C.c_void_p(p), C.c_int64(nbytes)))
+    good = buf.clone()
+    hdr = good[:128].cpu().numpy().copy()
+    i64 = hdr.view(np.int64)
+    # header layout (csrc/kdtree.cuh KdHeader): magic, N, nnodes, nbytes, (D, nlevels), (min_split, pad), off_*[7]
+    for field, value in ((1, 1 << 40), (2, 10 * 500), (6, 64), (10, nbytes + 256), (11, 8)):
+        bad = i64.copy(); bad[field] = value
+        b2 = good.clone(); b2[:128] = torch.as_tensor(bad.view(np.uint8), device="cuda")
+        torch.cuda.synchronize()
+        with pytest.raises(InvalidArgument):
+            kd_tree.KdTree.from_blob(b2.data_ptr(), nbytes, ctx=ctx)
+    torch.cuda.synchronize()
+    t2 = kd_tree.KdTree.from_blob(good.data_ptr(), nbytes, ctx=ctx)          # the untouched copy still loads
+    assert t2.nnodes == t.nnodes

@@ -135,3 +135,15 @@ def test_posterior_samples_match_oracle(ctx, og):
     counts = np.bincount(got, minlength=5000)
     top = np.argsort(lw)[-50:]
     assert counts[top].sum() / 2000 == pytest.approx(np.exp(lw[top]).sum(), abs=0.03)
+
+
+def test_nested_first_call_on_a_fresh_context(og):
+    """The draw-ahead of the next batch runs on the context's second stream, which exists from mg_ctx_create on:
+    nested_evidence as the very first call of a fresh context (no sampler call before it) gives the oracle's run."""
+    from mcmc_ocaml_b200 import Context
+    like = P.gauss_diag([0.5, 0.5], [0.1, 0.1])
+    with Context(0, 321) as c:
+        g = nested.nested_evidence(like, PRIOR, [0, 0], [1, 1], nlive=128, nmcmc=30, batch=16, ctx=c)
+    o = og.nested_evidence(321, 0, like, PRIOR, [0, 0], [1, 1], nlive=128, nmcmc=30, batch=16)
+    assert np.array_equal(g.points, o["pts"])
+    assert g.log_evidence == pytest.approx(o["log_ev"], abs=1e-11)

@@ -5,6 +5,7 @@ import pytest
 from scipy import stats
 
 from mcmc_ocaml_b200 import Failure, interpolate_pdf, mcmc, plugins as P
+from tests._parity import divergence_report
 
 pytestmark = pytest.mark.gpu
 
@@ -35,11 +36,12 @@ def test_tophat_interp_matches_oracle_and_known_ratio(ctx, og):
     oa = og.rj_model(like1, prior, prop, 0.5, tree=t1)
     ob = og.rj_model(like2, prior, prop, 0.5, tree=t2)
     o = og.rjmcmc_array(77, 0, 300, oa, ob, [0.5, 0.5], [0.5, 0.5], nskip=3, nbin=10, nchains=256, nthreads=8,
-                        record_samples=True)
+                        record_samples=True, margins=True)
+    # log(jump_prob): CUDA libm vs glibc may flip a decision only at a near-tie of the accept test
+    assert divergence_report(g.block[:, :2, :], o["samples"][:, :2, :], o["margins"], "RJ tophat") <= 0.01
     same = np.all(g.model == o["model"], axis=0)
-    assert same.mean() >= 0.97          # log(jump_prob): CUDA libm vs glibc may flip a rare decision
     assert np.array_equal(g.block[:, :2, same], o["samples"][:, :2, same])
-    assert abs(g.counts[0] - o["counts"][0]) <= 0.03 * 300 * 256
+    assert abs(g.counts[0] - o["counts"][0]) <= 0.01 * 300 * 256
     # (2) the reference's known answer: evidence ratio 4.0 +- 0.1 (mcmc_test.ml:181-182),
     # here with 4096 chains x 250 samples at nskip = 10 (1.02e6 samples, as the test's 1e6)
     ctx.set_seed(78)
@@ -72,8 +74,8 @@ def test_rjmcmc_gaussians_priors_recovered(ctx, og):
     ob = og.rj_model(g2.scaled(0.3), g2.scaled(0.7), P.indep_gauss_proposal([mu2], [s2]), 0.9, into_gauss=([mu2], [s2]))
     ctx.set_seed(6)
     g = mcmc.rjmcmc_array(100, A, B, [mu1], [mu2], nskip=2, nchains=128, ctx=ctx)
-    o = og.rjmcmc_array(6, 0, 100, oa, ob, [mu1], [mu2], nskip=2, nchains=128, nthreads=8)
-    assert np.all(g.model == o["model"], axis=0).mean() >= 0.95
+    o = og.rjmcmc_array(6, 0, 100, oa, ob, [mu1], [mu2], nskip=2, nchains=128, nthreads=8, margins=True)
+    assert divergence_report(g.model, o["model"], o["margins"], "RJ two Gaussians") <= 0.02
 
 
 def test_gaussian_vs_cauchy_config1(ctx, og):
@@ -111,3 +113,39 @@ def test_prior_assertion(ctx):
     B = mcmc.RjModel(g, P.zero(1), P.box_proposal([1.0]), 0.6, into_gauss=([0.0], [1.0]))
     with pytest.raises(Failure):          # assert (pa +. pb -. 1.0 < sqrt epsilon_float), mcmc.ml:90
         mcmc.rjmcmc_array(10, A, B, [0.0], [0.0], ctx=ctx)
+
+
+@pytest.mark.parametrize("dA,dB,nstop", [(8, 16, 0), (8, 16, 64), (3, 5, 0)])
+def test_high_dimensional_interp_jumps_match_oracle(ctx, og, dA, dB, nstop):
+    """BASELINE.json config 5's model pair at test size: isotropic Gaussian posteriors of dA and dB dimensions
+    (flat priors of density 1 and 1/2 on the unit box, so Z_A / Z_B = 2), trees of 1e5 posterior draws each,
+    interpolated jumps at leaf level (nstop = 0) and through the *_high_level forms.  Chain for chain against the
+    oracle on the same Philox stream; a chain may leave the oracle only at a near-tie of the accept test."""
+    import math
+    s, ntree = 0.05, 100_000
+    rng = np.random.default_rng(dA * 100 + dB)
+    gm, om = [], []
+    for d, logc in ((dA, 0.0), (dB, -math.log(2.0))):
+        pts = rng.normal(0.5, s, (ntree, d)).clip(0.0, 1.0)
+        lo, hi = np.zeros(d), np.ones(d)
+        like = P.gauss_diag(np.full(d, 0.5), np.full(d, s))
+        prior = P.box(lo, hi, logc)
+        prop = P.wrap_proposal(lo, hi, np.full(d, 2.0 * s / math.sqrt(d)))
+        gm.append(mcmc.RjModel(like, prior, prop, 0.5, interp=interpolate_pdf.InterpPdf(pts, lo, hi, ctx=ctx), nstop=nstop))
+        om.append(og.rj_model(like, prior, prop, 0.5, tree=og.Tree(pts, lo, hi), nstop=nstop))
+    a0, b0 = np.full(dA, 0.5), np.full(dB, 0.5)
+    C, n = 512, 120
+    ctx.set_seed(4242)
+    g = mcmc.rjmcmc_array(n, gm[0], gm[1], a0, b0, nskip=2, nbin=5, nchains=C, record_samples=True, ctx=ctx)
+    o = og.rjmcmc_array(4242, 0, n, om[0], om[1], a0, b0, nskip=2, nbin=5, nchains=C, nthreads=8, record_samples=True,
+                        margins=True)
+    Dm = max(dA, dB)
+    frac = divergence_report(np.concatenate([g.block[:, :Dm, :], g.model[:, None, :].astype(float)], axis=1),
+                             np.concatenate([o["samples"][:, :Dm, :], o["model"][:, None, :].astype(float)], axis=1),
+                             o["margins"], f"RJ ({dA},{dB})-D nstop={nstop}")
+    assert frac <= 0.01
+    same = np.all(g.model == o["model"], axis=0)
+    np.testing.assert_allclose(g.block[:, Dm, same], o["samples"][:, Dm, same], rtol=1e-12, atol=1e-12)   # ll
+    if frac == 0.0:
+        assert g.counts == o["counts"] and g.cross == o["cross"]
+    assert g.cross[0] > 0.4 * C * (n - 1) * 2          # half of the steps propose a jump into the other model

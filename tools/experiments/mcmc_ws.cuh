@@ -1,3 +1,6 @@
+// RECORDED NEGATIVE EXPERIMENT (round 1), kept out of the product build: a warp-specialised variant of the MH sampler
+// (producer warps generate the Philox uniforms into shared memory, consumer warps run the float64 step).  Slower than
+// the single-role kernel on B200 (profiles/r01_mh_ncu_summary.md); not compiled into libmcmcgpu.so.
 // mcmc_ws.cuh -- warp-specialised form of the Metropolis-Hastings ensemble
 // kernel for the static plugins (GAUSS_CORR likelihood, flat prior, box
 // proposal).  Same arithmetic, same Philox stream and same results as
