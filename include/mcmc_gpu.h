@@ -42,6 +42,7 @@ enum {
 
 typedef struct mg_ctx mg_ctx;
 typedef struct mg_kdtree mg_kdtree;
+typedef struct mg_comm mg_comm;
 
 /* ------------------------------------------------------------------ */
 /* context                                                             */
@@ -458,6 +459,72 @@ int mg_nested_posterior_indices(mg_ctx *ctx, const double *logw, int64_t npts,
                                 int64_t n, int64_t *out_idx);
 /* Nested.log_total_error_estimate (nested.ml:148-150) */
 double mg_nested_log_total_error(double log_ev, double log_dev, int32_t nlive);
+
+/* ------------------------------------------------------------------ */
+/* Several GPUs of one box: one process (one context) per GPU, NCCL     */
+/* ------------------------------------------------------------------ */
+/* The reference is single-threaded; what it computes shards naturally
+ * (SURVEY.md 8e): chains and queries are independent, a kd-tree is built on
+ * one rank and replicated, per-rank statistics and per-cell evidence terms are
+ * gathered and combined in a fixed order.  NCCL is loaded at run time
+ * (libnccl.so.2); without it only the entry points below fail (MG_EFAIL).
+ * Every entry point here is COLLECTIVE: all ranks of the communicator call it. */
+#define MG_COMM_ID_BYTES 128
+/* ncclGetUniqueId: called by one rank, which hands the 128 bytes to the others
+ * through any channel of the host program (a file, a socket, MPI, ...). */
+int mg_comm_get_unique_id(uint8_t id[MG_COMM_ID_BYTES]);
+/* ncclCommInitRank on the context's device; nranks == 1 needs no NCCL. */
+int mg_comm_create(mg_ctx *ctx, int32_t nranks, int32_t rank,
+                   const uint8_t id[MG_COMM_ID_BYTES], mg_comm **out);
+void mg_comm_destroy(mg_comm *comm);
+int32_t mg_comm_rank(const mg_comm *comm);
+int32_t mg_comm_size(const mg_comm *comm);
+int mg_comm_nccl_version(int32_t *version);
+int mg_comm_barrier(mg_comm *comm);
+/* device time (ms, CUDA events on the context's stream) this rank spent in the
+ * NCCL calls of the last collective entry point. */
+double mg_comm_last_collective_ms(const mg_comm *comm);
+/* ncclAllGather of a small host record: recv[nranks][nbytes] in rank order. */
+int mg_comm_allgather(mg_comm *comm, const void *send, void *recv, int64_t nbytes);
+/* Interp.make on `root`, used everywhere: ONE ncclBroadcast of the tree's
+ * contiguous device blob, from the builder's blob straight into the receivers'
+ * (no staging copy).  tree: the root's tree (ignored elsewhere, may be NULL).
+ * *out: on the root `tree` itself, on the other ranks a new tree (destroy it). */
+int mg_kdtree_broadcast(mg_comm *comm, mg_kdtree *tree, int32_t root,
+                        mg_kdtree **out);
+/* Evidence.evidence_lebesgue / evidence_direct (evidence.ml:148-221) with the
+ * kd-cells shared out: `root` holds the samples (device pointers; ignored on
+ * the other ranks), does the global steps (sort, prefix cut, de-duplication,
+ * tree), the tree is broadcast, every rank integrates a contiguous range of
+ * nodes, the per-node terms are all-gathered and summed by the same
+ * deterministic reduction everywhere: *out is bit-identical on every rank and
+ * to the single-GPU call. */
+int mg_evidence_lebesgue_sharded(mg_comm *comm, int32_t root, const double *d_pts,
+                                 const double *d_ll, const double *d_lp,
+                                 int64_t N, int32_t D, int32_t n, double eps,
+                                 double *out);
+int mg_evidence_direct_sharded(mg_comm *comm, int32_t root, const double *d_pts,
+                               const double *d_ll, const double *d_lp, int64_t N,
+                               int32_t D, int32_t n, double *out);
+/* Evidence.evidence_harmonic_mean over samples sharded across the ranks
+ * (d_ll_shard: this rank's log-likelihoods, device). */
+int mg_evidence_harmonic_mean_sharded(mg_comm *comm, const double *d_ll_shard,
+                                      int64_t n_shard, double *out);
+/* Mcmc.rjmcmc_array with the cfg->nchains chains cut into one contiguous range
+ * per rank (global chain ids: results do not depend on the number of ranks);
+ * out_counts = rjmcmc_model_counts over ALL ranks; out_model / out_samples get
+ * this rank's chains only, which *shard_begin / *shard_count identify. */
+int mg_rjmcmc_array_sharded(mg_comm *comm, const mg_rj_model *A,
+                            const mg_rj_model *B, const mg_rjmcmc_cfg *cfg,
+                            const double *a0, const double *b0,
+                            uint8_t *out_model, double *out_samples,
+                            int64_t out_counts[2], int64_t *shard_begin,
+                            int64_t *shard_count);
+/* Stats.multi_mean / multi_std of samples held by several ranks, pooled from
+ * each rank's (count, mean[F], std[F]) in rank order. */
+int mg_comm_pool_moments(mg_comm *comm, int64_t n_local, const double *mean_local,
+                         const double *std_local, int32_t F, int64_t *n_total,
+                         double *out_mean, double *out_std);
 
 /* ------------------------------------------------------------------ */
 /* Read_write: the text format of the reference's tools (host only)    */

@@ -129,16 +129,18 @@ template <int MODE>
 __global__ void __launch_bounds__(EB)
 cell_terms_kernel(const KdNode *__restrict__ nodes, const int32_t *__restrict__ count, const int32_t *__restrict__ begin,
                   const int32_t *__restrict__ perm, const double *__restrict__ pts, const double *__restrict__ ll,
-                  const double *__restrict__ lp, int64_t nnodes, int D, int nmax, double *__restrict__ partial,
+                  const double *__restrict__ lp, int64_t node0, int64_t node1, int D, int nmax, double *__restrict__ terms,
                   unsigned long long *__restrict__ ncells) {
   extern __shared__ double sh[];  // [warps][nmax] scratch values
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = EB / 32;
   double *vals = sh + (size_t)w * nmax;
-  Comp acc;
   unsigned cells = 0;
-  for (int64_t id = (int64_t)blockIdx.x * nw + w; id < nnodes; id += (int64_t)gridDim.x * nw) {
+  // terms[id] for the nodes [node0, node1) (a rank's share of the tree): the cell's term, 0.0 for a node that is
+  // not one of collect_subvolumes' cells.  The terms are summed afterwards in node order by ONE deterministic
+  // reduction over the whole array, so the result does not depend on how the nodes were spread over ranks.
+  for (int64_t id = node0 + (int64_t)blockIdx.x * nw + w; id < node1; id += (int64_t)gridDim.x * nw) {
     const int cnt = count[id];
-    if (nodes[id].left >= 0 || cnt >= nmax) continue;   // not (length_at_least nmax objs) -> [c]
+    if (nodes[id].left >= 0 || cnt >= nmax) { if (lane == 0) terms[id] = 0.0; continue; }   // not (length_at_least nmax objs) -> [c]
     const int b = begin[id];
     // bounds_of_objects (kd_tree.ml:96-110) + bounds_volume (:177-182, product in dimension order)
     // Lane d owns dimension d (d + 32, ... beyond 32): every point is one coalesced row read, no reduction across
@@ -190,10 +192,8 @@ cell_terms_kernel(const KdNode *__restrict__ nodes, const int32_t *__restrict__ 
       term = v * post;
     }
     __syncwarp();
-    if (lane == 0) { acc.add(term); ++cells; }
+    if (lane == 0) { terms[id] = term; ++cells; }
   }
-  const double t = block_reduce_comp<EB>(acc);
-  if (threadIdx.x == 0) partial[blockIdx.x] = t;
   if (lane == 0 && cells) atomicAdd(ncells, (unsigned long long)cells);
 }
 
@@ -225,44 +225,64 @@ static int compact_reversed(mg_ctx *ctx, const double *d_pts, const double *d_ll
   return MG_OK;
 }
 
-// tree of the survivors (not split below nmax) and the sum of the per-cell terms
+// per-cell terms of the nodes [node0, node1) of a tree that was not split below nmax objects
+template <int MODE>
+int cell_terms_range(mg_ctx *ctx, const mg_kdtree *t, const double *sll, const double *slp, int nmax, int64_t node0,
+                     int64_t node1, double *d_terms, unsigned long long *d_ncells) {
+  if (node1 <= node0) return MG_OK;
+  cudaStream_t s = ctx->stream;
+  const char *blob = (const char *)t->d_blob;
+  const unsigned g = egrid(ctx, node1 - node0, EB / 32);
+  const size_t smem = (size_t)(EB / 32) * (nmax > 0 ? nmax : 1) * sizeof(double);
+  if (smem > 48 * 1024) MG_CUDA(ctx, cudaFuncSetAttribute(cell_terms_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cell_terms_kernel<MODE><<<g, EB, smem, s>>>((const KdNode *)(blob + t->h.off_nodes), (const int32_t *)(blob + t->h.off_count),
+                                              (const int32_t *)(blob + t->h.off_begin), (const int32_t *)(blob + t->h.off_perm),
+                                              (const double *)(blob + t->h.off_pts), sll, slp, node0, node1, t->h.D, nmax, d_terms, d_ncells);
+  MG_CHECK_LAUNCH(ctx);
+  return MG_OK;
+}
+template int cell_terms_range<0>(mg_ctx *, const mg_kdtree *, const double *, const double *, int, int64_t, int64_t, double *, unsigned long long *);
+template int cell_terms_range<1>(mg_ctx *, const mg_kdtree *, const double *, const double *, int, int64_t, int64_t, double *, unsigned long long *);
+
+// the sum of the terms of all nodes, in node order: one deterministic compensated reduction (fixed grid for a given
+// node count), the same on every rank and for every way the terms were produced
+int sum_terms(mg_ctx *ctx, const double *d_terms, int64_t nn, double *out) {
+  return reduce_sum(ctx, nn, [d_terms] __device__(int64_t i) { return d_terms[i]; }, out);
+}
+
+// tree of the survivors (not split below nmax)
+static int survivors_tree(mg_ctx *ctx, const Survivors &sv, int D, int nmax, mg_kdtree **t) {
+  std::vector<double> zeros(D, 0.0);
+  // The root box (bounds_of_objects, evidence.ml:164,206) does not influence
+  // any split nor the tight per-cell volumes, so it is not computed.
+  return build_tree(ctx, sv.pts.get(), sv.K, D, zeros.data(), zeros.data(), nmax < 2 ? 2 : nmax, t);
+}
+
+// tree of the survivors and the sum of the per-cell terms
 template <int MODE>
 static int integrate_cells(mg_ctx *ctx, const Survivors &sv, int D, int nmax, double *out, int64_t *ncells_out) {
   cudaStream_t s = ctx->stream;
-  std::vector<double> zeros(D, 0.0);
   mg_kdtree *t = nullptr;
-  // The root box (bounds_of_objects, evidence.ml:164,206) does not influence
-  // any split nor the tight per-cell volumes, so it is not computed.
-  int rc = build_tree(ctx, sv.pts.get(), sv.K, D, zeros.data(), zeros.data(), nmax < 2 ? 2 : nmax, &t);
+  int rc = survivors_tree(ctx, sv, D, nmax, &t);
   if (rc) return rc;
-  const char *blob = (const char *)t->d_blob;
   const int64_t nn = t->h.nnodes;
-  const unsigned g = egrid(ctx, nn, EB / 32);
-  DevBuf<double> partial;
+  DevBuf<double> terms;
   DevBuf<unsigned long long> ncells;
-  cudaError_t e = partial.alloc(g, s);
+  cudaError_t e = terms.alloc((size_t)nn, s);
   if (e == cudaSuccess) e = ncells.alloc(1, s);
   if (e == cudaSuccess) e = cudaMemsetAsync(ncells.get(), 0, 8, s);
   if (e != cudaSuccess) { mg_kdtree_destroy(t); return set_err(ctx, MG_ECUDA, "cuda: %s", cudaGetErrorString(e)); }
-  const size_t smem = (size_t)(EB / 32) * (nmax > 0 ? nmax : 1) * sizeof(double);
-  if (smem > 48 * 1024) cudaFuncSetAttribute(cell_terms_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  cell_terms_kernel<MODE><<<g, EB, smem, s>>>((const KdNode *)(blob + t->h.off_nodes), (const int32_t *)(blob + t->h.off_count),
-                                              (const int32_t *)(blob + t->h.off_begin), (const int32_t *)(blob + t->h.off_perm),
-                                              sv.pts.get(), sv.ll.get(), sv.lp.get(), nn, D, nmax, partial.get(), ncells.get());
-  ctx->launches++;
-  std::vector<double> h(g);
+  rc = cell_terms_range<MODE>(ctx, t, sv.ll.get(), sv.lp.get(), nmax, 0, nn, terms.get(), ncells.get());
+  if (rc == MG_OK) rc = sum_terms(ctx, terms.get(), nn, out);
   unsigned long long nc = 0;
-  e = cudaGetLastError();
-  if (e == cudaSuccess) e = cudaMemcpyAsync(h.data(), partial.get(), sizeof(double) * g, cudaMemcpyDeviceToHost, s);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(&nc, ncells.get(), 8, cudaMemcpyDeviceToHost, s);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  if (rc == MG_OK && ncells_out) {
+    e = cudaMemcpyAsync(&nc, ncells.get(), 8, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) rc = set_err(ctx, MG_ECUDA, "cuda: %s (evidence cells)", cudaGetErrorString(e));
+    *ncells_out = (int64_t)nc;
+  }
   mg_kdtree_destroy(t);
-  if (e != cudaSuccess) return set_err(ctx, MG_ECUDA, "cuda: %s (evidence cells)", cudaGetErrorString(e));
-  Comp acc;
-  for (unsigned b = 0; b < g; ++b) acc.add(h[b]);
-  *out = acc.value();
-  if (ncells_out) *ncells_out = (int64_t)nc;
-  return MG_OK;
+  return rc;
 }
 
 }  // namespace mg
@@ -291,10 +311,10 @@ extern "C" int mg_evidence_harmonic_mean(mg_ctx *ctx, const double *ll, int64_t 
   return mg_evidence_harmonic_mean_dev(ctx, d_ll.get(), N, out);
 }
 
-extern "C" int mg_evidence_lebesgue_dev(mg_ctx *ctx, const double *d_pts, const double *d_ll, const double *d_lp,
-                                        int64_t N, int32_t D, int32_t n, double eps, double *out) {
-  if (!ctx) return MG_EINVAL;
-  MG_REQUIRE(ctx, d_pts && d_ll && d_lp && out, "evidence_lebesgue: null argument");
+// evidence.ml:202-205: the kept prefix, its mean 1/L, and the survivors of remove_dups_rev (reversed)
+static int lebesgue_prepare(mg_ctx *ctx, const double *d_pts, const double *d_ll, const double *d_lp, int64_t N, int32_t D,
+                            int32_t n, double eps, Survivors &sv, double *mean_il_out) {
+  MG_REQUIRE(ctx, d_pts && d_ll && d_lp, "evidence_lebesgue: null argument");
   MG_REQUIRE(ctx, N >= 1, "bounds_of_objects: no objects");
   MG_REQUIRE(ctx, D >= 1 && D <= 64 && n >= 1 && N < (1LL << 30), "evidence_lebesgue: bad sizes");
   MG_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -348,19 +368,28 @@ extern "C" int mg_evidence_lebesgue_dev(mg_ctx *ctx, const double *d_pts, const 
   MG_CUDA(ctx, keep.alloc(m, s));
   keep_ll_kernel<<<egrid(ctx, m), EB, 0, s>>>(d_ll, order.get(), m, keep.get());
   MG_CHECK_LAUNCH(ctx);
-  Survivors sv;
   if ((rc = compact_reversed(ctx, d_pts, d_ll, d_lp, order.get(), keep.get(), m, D, sv))) return rc;
-  order.release(); keep.release();
-  double pm = 0.0;
+  *mean_il_out = mean_il;
+  return MG_OK;
+}
+
+extern "C" int mg_evidence_lebesgue_dev(mg_ctx *ctx, const double *d_pts, const double *d_ll, const double *d_lp,
+                                        int64_t N, int32_t D, int32_t n, double eps, double *out) {
+  if (!ctx) return MG_EINVAL;
+  MG_REQUIRE(ctx, out != nullptr, "evidence_lebesgue: null argument");
+  Survivors sv;
+  double mean_il = 0.0, pm = 0.0;
+  int rc = lebesgue_prepare(ctx, d_pts, d_ll, d_lp, N, D, n, eps, sv, &mean_il);
+  if (rc) return rc;
   if ((rc = integrate_cells<0>(ctx, sv, D, n, &pm, nullptr))) return rc;
   *out = pm / mean_il;  // :221
   return MG_OK;
 }
 
-extern "C" int mg_evidence_direct_dev(mg_ctx *ctx, const double *d_pts, const double *d_ll, const double *d_lp,
-                                      int64_t N, int32_t D, int32_t n, double *out) {
-  if (!ctx) return MG_EINVAL;
-  MG_REQUIRE(ctx, d_pts && d_ll && d_lp && out, "evidence_direct: null argument");
+// evidence.ml:143-146,162-163: the samples sorted by coordinates with duplicates dropped (reversed)
+static int direct_prepare(mg_ctx *ctx, const double *d_pts, const double *d_ll, const double *d_lp, int64_t N, int32_t D,
+                          int32_t n, Survivors &sv) {
+  MG_REQUIRE(ctx, d_pts && d_ll && d_lp, "evidence_direct: null argument");
   MG_REQUIRE(ctx, N >= 1, "bounds_of_objects: no objects");
   MG_REQUIRE(ctx, D >= 1 && D <= 64 && n >= 1 && N < (1LL << 30), "evidence_direct: bad sizes");
   MG_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -401,10 +430,111 @@ extern "C" int mg_evidence_direct_dev(mg_ctx *ctx, const double *d_pts, const do
   MG_CUDA(ctx, keep.alloc(N, s));
   keep_rows_kernel<<<egrid(ctx, N), EB, 0, s>>>(d_pts, order.get(), N, D, keep.get());
   MG_CHECK_LAUNCH(ctx);
+  return compact_reversed(ctx, d_pts, d_ll, d_lp, order.get(), keep.get(), N, D, sv);
+}
+
+extern "C" int mg_evidence_direct_dev(mg_ctx *ctx, const double *d_pts, const double *d_ll, const double *d_lp,
+                                      int64_t N, int32_t D, int32_t n, double *out) {
+  if (!ctx) return MG_EINVAL;
+  MG_REQUIRE(ctx, out != nullptr, "evidence_direct: null argument");
   Survivors sv;
-  if ((rc = compact_reversed(ctx, d_pts, d_ll, d_lp, order.get(), keep.get(), N, D, sv))) return rc;
-  order.release(); keep.release();
+  int rc = direct_prepare(ctx, d_pts, d_ll, d_lp, N, D, n, sv);
+  if (rc) return rc;
   return integrate_cells<1>(ctx, sv, D, n, out, nullptr);
+}
+
+// ---- the same over the GPUs of one box (evidence.ml:148-221) -----------------------------------------
+// The global steps (sort, prefix cut, de-duplication, tree of the survivors) run on `root`, which holds the samples;
+// the tree blob and the survivors' ll / lp are replicated with NCCL broadcasts; the tree's nodes are cut into
+// contiguous ranges, one per rank, each rank evaluates the cell terms of its range; the per-node terms are
+// all-gathered (ncclAllGather, in place) and every rank runs the SAME deterministic reduction over the complete
+// array -- the result is bit-identical on every rank and to the single-GPU call.
+struct mg_comm;
+namespace mg {
+int comm_broadcast_dev(mg_comm *c, void *d_buf, size_t nbytes, int root);
+int comm_allgather_dev(mg_comm *c, const void *d_send, void *d_recv, size_t nbytes_per_rank);
+}
+extern "C" int mg_kdtree_broadcast(mg_comm *c, mg_kdtree *tree, int32_t root, mg_kdtree **out);
+extern "C" int32_t mg_comm_rank(const mg_comm *c);
+extern "C" int32_t mg_comm_size(const mg_comm *c);
+mg_ctx *mg_comm_ctx(const mg_comm *c);   // comm.cu
+
+static int evidence_sharded(mg_comm *c, int which, int32_t root, const double *d_pts, const double *d_ll, const double *d_lp,
+                            int64_t N, int32_t D, int32_t n, double eps, double *out) {
+  if (!c) return MG_EINVAL;
+  mg_ctx *ctx = mg_comm_ctx(c);
+  const int R = mg_comm_size(c), rank = mg_comm_rank(c);
+  MG_REQUIRE(ctx, out && root >= 0 && root < R && n >= 1, "evidence (sharded): bad arguments");
+  MG_CUDA(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t s = ctx->stream;
+  int rc = MG_OK;
+  Survivors sv;
+  double head[2] = {0.0, 0.0};        // {mean 1/L of the kept prefix, status of the root's preparation}
+  mg_kdtree *t_root = nullptr, *t = nullptr;
+  if (rank == root) {
+    double mean_il = 1.0;
+    rc = which == 0 ? lebesgue_prepare(ctx, d_pts, d_ll, d_lp, N, D, n, eps, sv, &mean_il)
+                    : direct_prepare(ctx, d_pts, d_ll, d_lp, N, D, n, sv);
+    if (rc == MG_OK) rc = survivors_tree(ctx, sv, D, n, &t_root);
+    head[0] = mean_il; head[1] = (double)rc;
+  }
+  // the root's status travels first, so that a failure there ends the call on every rank instead of a hang
+  DevBuf<double> d_head;
+  MG_CUDA(ctx, d_head.alloc(2, s));
+  if (rank == root) MG_CUDA(ctx, cudaMemcpyAsync(d_head.get(), head, sizeof head, cudaMemcpyHostToDevice, s));
+  int rc2 = comm_broadcast_dev(c, d_head.get(), sizeof head, root);
+  if (rc2) { if (t_root) mg_kdtree_destroy(t_root); return rc2; }
+  MG_CUDA(ctx, cudaMemcpyAsync(head, d_head.get(), sizeof head, cudaMemcpyDeviceToHost, s));
+  MG_CUDA(ctx, cudaStreamSynchronize(s));
+  if (head[1] != 0.0) {
+    if (t_root) mg_kdtree_destroy(t_root);
+    return rank == root ? rc : set_err(ctx, (int)head[1], "evidence (sharded): the root rank failed to prepare the samples");
+  }
+  if ((rc = mg_kdtree_broadcast(c, t_root, root, &t))) { if (t_root) mg_kdtree_destroy(t_root); return rc; }
+  const int64_t K = t->h.N, nn = t->h.nnodes;
+  // survivors' ll and lp (the points travel inside the tree blob)
+  DevBuf<double> r_ll, r_lp;
+  const double *sll = sv.ll.get(), *slp = sv.lp.get();
+  if (rank != root) {
+    cudaError_t e = r_lp.alloc((size_t)K, s);
+    if (e == cudaSuccess && which == 1) e = r_ll.alloc((size_t)K, s);
+    if (e != cudaSuccess) { mg_kdtree_destroy(t); return set_err(ctx, MG_ENOMEM, "cuda: %s", cudaGetErrorString(e)); }
+    sll = r_ll.get(); slp = r_lp.get();
+  }
+  rc = comm_broadcast_dev(c, (void *)slp, sizeof(double) * (size_t)K, root);
+  if (rc == MG_OK && which == 1) rc = comm_broadcast_dev(c, (void *)sll, sizeof(double) * (size_t)K, root);
+  // my range of nodes; slices of equal length so that the gathered slices ARE the node-ordered array
+  const int64_t slice = (nn + R - 1) / R;
+  const int64_t n0 = std::min<int64_t>(nn, (int64_t)rank * slice), n1 = std::min<int64_t>(nn, n0 + slice);
+  DevBuf<double> terms;
+  DevBuf<unsigned long long> ncells;
+  if (rc == MG_OK) {
+    cudaError_t e = terms.alloc((size_t)slice * R, s);
+    if (e == cudaSuccess) e = ncells.alloc(1, s);
+    if (e == cudaSuccess) e = cudaMemsetAsync(ncells.get(), 0, 8, s);
+    if (e == cudaSuccess) e = cudaMemsetAsync(terms.get() + (size_t)rank * slice, 0, sizeof(double) * (size_t)slice, s);
+    if (e != cudaSuccess) rc = set_err(ctx, MG_ENOMEM, "cuda: %s", cudaGetErrorString(e));
+  }
+  if (rc == MG_OK)
+    rc = which == 0 ? cell_terms_range<0>(ctx, t, sll, slp, n, n0, n1, terms.get(), ncells.get())
+                    : cell_terms_range<1>(ctx, t, sll, slp, n, n0, n1, terms.get(), ncells.get());
+  if (rc == MG_OK) rc = comm_allgather_dev(c, terms.get() + (size_t)rank * slice, terms.get(), sizeof(double) * (size_t)slice);
+  double total = 0.0;
+  if (rc == MG_OK) rc = sum_terms(ctx, terms.get(), nn, &total);
+  if (t != t_root) mg_kdtree_destroy(t);
+  if (t_root) mg_kdtree_destroy(t_root);
+  if (rc) return rc;
+  *out = which == 0 ? total / head[0] : total;
+  return MG_OK;
+}
+
+extern "C" int mg_evidence_lebesgue_sharded(mg_comm *c, int32_t root, const double *d_pts, const double *d_ll,
+                                            const double *d_lp, int64_t N, int32_t D, int32_t n, double eps, double *out) {
+  return evidence_sharded(c, 0, root, d_pts, d_ll, d_lp, N, D, n, eps, out);
+}
+extern "C" int mg_evidence_direct_sharded(mg_comm *c, int32_t root, const double *d_pts, const double *d_ll,
+                                          const double *d_lp, int64_t N, int32_t D, int32_t n, double *out) {
+  return evidence_sharded(c, 1, root, d_pts, d_ll, d_lp, N, D, n, 0.0, out);
 }
 
 static int evidence_host(mg_ctx *ctx, int which, const double *pts, const double *ll, const double *lp, int64_t N,

@@ -24,6 +24,7 @@ def main():
     ap.add_argument("--db", type=int, default=4)
     ap.add_argument("--ntree", type=int, default=10_000_000)
     ap.add_argument("--ratio", type=float, default=2.0)
+    ap.add_argument("--nstop", type=int, default=0, help="> 0: the *_high_level jumps (cells of <= nstop objects)")
     a = ap.parse_args()
     import numpy as np
     import torch
@@ -47,7 +48,7 @@ def main():
         like = P.gauss_diag(np.full(d, 0.5), np.full(d, s))
         prior = P.box(np.zeros(d), np.ones(d), logc)
         prop = P.wrap_proposal(np.zeros(d), np.ones(d), np.full(d, 2.0 * s / math.sqrt(d)))
-        models.append(mcmc.RjModel(like, prior, prop, 0.5, interp=interp))
+        models.append(mcmc.RjModel(like, prior, prop, 0.5, interp=interp, nstop=a.nstop))
     A, B = models
     a0, b0 = np.full(a.da, 0.5), np.full(a.db, 0.5)
     mcmc.rjmcmc_array(2, A, B, a0, b0, nskip=10, nchains=a.chains, record_model=False, ctx=ctx)   # warm-up
@@ -60,6 +61,9 @@ def main():
     out["counts"] = r.counts
     out["ratio"] = r.counts[0] / max(1, r.counts[1])
     out["expected_ratio"] = a.ratio
+    out["nstop"] = a.nstop
+    out["cross_model_proposals"], out["cross_model_accepted"] = r.cross
+    out["cross_model_accept_rate"] = r.cross[1] / max(1, r.cross[0])
     acc, rej = ctx.get_counters()
     out["accept_rate"] = acc / max(1, acc + rej)
     print(json.dumps(out))
