@@ -51,12 +51,20 @@ def _worker(rank, world, port, q):
     g = D.all_gather_array(np.array([float(rank), rng.random()]))
     na, nb, ratio = D.combine_model_counts([100 * (rank + 1), 50])
     assert (na, nb, ratio) == (300, 100, 3.0)
+    # the 128-byte NCCL id of the C-ABI communicator travels from rank 0 to the others through the host program's
+    # own channel (mcmc_ocaml_b200/comm.py): here a gloo broadcast and a file
+    from mcmc_ocaml_b200 import comm as CM
+    make = lambda: bytes((7 * i + 3) % 256 for i in range(CM.ID_BYTES))
+    assert CM.exchange_id_torch(make if rank == 0 else (lambda: b""), rank) == make()
+    path = os.path.join(os.environ["MG_TEST_TMP"], "nccl_id.bin")
+    assert CM.exchange_id_file(make if rank == 0 else (lambda: b""), rank, path) == make()
     q.put((rank, res["n"], res["mean"], res["std"], res["accept"], res["reject"], g[:, 0].tolist()))
     dist.barrier()
     dist.destroy_process_group()
 
 
-def test_gloo_world2_gather_and_combine():
+def test_gloo_world2_gather_and_combine(tmp_path, monkeypatch):
+    monkeypatch.setenv("MG_TEST_TMP", str(tmp_path))
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
