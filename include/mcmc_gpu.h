@@ -72,6 +72,12 @@ int64_t mg_ctx_launch_count(const mg_ctx *ctx);
 /* duration in ms of the dominant kernel of the last sampling / build call,
  * from CUDA events recorded on the context's stream around that launch. */
 double mg_ctx_last_kernel_ms(const mg_ctx *ctx);
+/* the dominant kernel of the last sampling / build / evidence call: its
+ * (demangled) name, how many times the call launched it and the mean duration
+ * of a launch in ms (CUDA event pairs on the context's stream around EVERY
+ * launch).  bench.py derives roofline.achieved from these. */
+int mg_ctx_last_kernel_stats(mg_ctx *ctx, char *name, int64_t name_cap,
+                             int64_t *launches, double *mean_ms);
 
 /* diagnostics: device microbenchmarks for the roofline denominators that
  * MEASURED_PEAKS.json lacks (FP64 FMA TFLOP/s; streaming-store GB/s). */

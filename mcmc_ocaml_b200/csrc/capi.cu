@@ -1,6 +1,8 @@
 // capi.cu -- context management and memory helpers of the C ABI.
 #include "common.cuh"
 
+#include <cxxabi.h>
+
 using namespace mg;
 
 extern "C" int mg_abi_version(void) { return MG_ABI_VERSION; }
@@ -38,6 +40,7 @@ extern "C" void mg_ctx_destroy(mg_ctx *ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  for (cudaEvent_t e : ctx->kt_ev) if (e) cudaEventDestroy(e);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   if (ctx->aux) cudaStreamDestroy(ctx->aux);
@@ -100,6 +103,37 @@ extern "C" double mg_ctx_last_kernel_ms(const mg_ctx *c) {
     ctx->ev_pending = false;
   }
   return ctx->last_kernel_ms;
+}
+
+// name / launches / mean duration of the dominant kernel of the last call (events around every launch)
+extern "C" int mg_ctx_last_kernel_stats(mg_ctx *ctx, char *name, int64_t name_cap, int64_t *launches, double *mean_ms) {
+  if (!ctx) return MG_EINVAL;
+  MG_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (ctx->kt_launches < 0) {
+    double tot = 0.0;
+    for (int i = 0; i < ctx->kt_used; ++i) {
+      float ms = 0.f;
+      if (cudaEventSynchronize(ctx->kt_ev[2 * i + 1]) == cudaSuccess &&
+          cudaEventElapsedTime(&ms, ctx->kt_ev[2 * i], ctx->kt_ev[2 * i + 1]) == cudaSuccess) tot += ms;
+    }
+    ctx->kt_launches = ctx->kt_used;
+    ctx->kt_mean_ms = ctx->kt_used ? tot / ctx->kt_used : 0.0;
+    ctx->kt_name.clear();
+    const char *mangled = nullptr;
+    if (ctx->kt_func && cudaFuncGetName(&mangled, ctx->kt_func) == cudaSuccess && mangled) {
+      int status = 0;
+      char *dem = abi::__cxa_demangle(mangled, nullptr, nullptr, &status);
+      ctx->kt_name = (status == 0 && dem) ? dem : mangled;
+      free(dem);
+      const size_t paren = ctx->kt_name.find('(');            // drop the parameter list
+      if (paren != std::string::npos) ctx->kt_name.resize(paren);
+      if (ctx->kt_name.rfind("void ", 0) == 0) ctx->kt_name.erase(0, 5);
+    }
+  }
+  if (name && name_cap > 0) { strncpy(name, ctx->kt_name.c_str(), (size_t)name_cap - 1); name[name_cap - 1] = 0; }
+  if (launches) *launches = ctx->kt_launches;
+  if (mean_ms) *mean_ms = ctx->kt_mean_ms;
+  return MG_OK;
 }
 
 extern "C" int mg_malloc_device(mg_ctx *ctx, int64_t nbytes, void **out) {

@@ -29,6 +29,14 @@ struct mg_ctx {
   int sm_count = 148;
   double *mh_mom = nullptr;        // request: per-chain running moments from the next MH launch (mcmc_balanced.cuh)
   bool mh_mom_done = false;        // answer: the launch produced them
+  // per-launch timing of the dominant kernel of the last call (bench.py roofline): event pairs on the context's
+  // stream around EVERY launch of that kernel, collected lazily by mg_ctx_last_kernel_stats
+  std::vector<cudaEvent_t> kt_ev;
+  int kt_used = 0;
+  const void *kt_func = nullptr;
+  std::string kt_name;
+  double kt_mean_ms = 0.0;
+  int64_t kt_launches = 0;
   int *d_devflag = nullptr;        // device word set by a kernel whose bounded spin-wait ran out (MG_DEVERR_*)
   int sticky = MG_OK;              // a device-side failure that every later call reports until mg_ctx_clear_error
   std::string err;
@@ -93,6 +101,18 @@ inline int poll_device_error(mg_ctx *ctx) {
   return set_err(ctx, MG_ECUDA, "cuda: device-side wait timed out (%s); the results of that launch are invalid, the context remains usable",
                  h == MG_DEVERR_MH_QUEUE ? "Metropolis-Hastings task queue" : "kd-tree partition look-back");
 }
+
+// kernel-timer helpers: kt_reset names the kernel (host address of the __global__ function), kt_start / kt_stop
+// bracket one launch
+inline void kt_reset(mg_ctx *ctx, const void *func) { ctx->kt_used = 0; ctx->kt_func = func; ctx->kt_launches = -1; }
+inline void kt_start(mg_ctx *ctx) {
+  if ((size_t)(2 * ctx->kt_used + 2) > ctx->kt_ev.size()) {
+    const size_t want = ctx->kt_ev.size() + 64;
+    while (ctx->kt_ev.size() < want) { cudaEvent_t e = nullptr; cudaEventCreate(&e); ctx->kt_ev.push_back(e); }
+  }
+  cudaEventRecord(ctx->kt_ev[2 * ctx->kt_used], ctx->stream);
+}
+inline void kt_stop(mg_ctx *ctx) { cudaEventRecord(ctx->kt_ev[2 * ctx->kt_used + 1], ctx->stream); ctx->kt_used++; ctx->kt_launches = -1; }
 
 inline void time_begin(mg_ctx *ctx) { cudaEventRecord(ctx->ev0, ctx->stream); }
 inline void time_end(mg_ctx *ctx) { cudaEventRecord(ctx->ev1, ctx->stream); ctx->ev_pending = true; }

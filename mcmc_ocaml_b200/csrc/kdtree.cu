@@ -323,6 +323,11 @@ static inline unsigned grid1d(mg_ctx *ctx, int64_t n, int block = KB) {
 }
 static inline int64_t align256(int64_t x) { return (x + 255) & ~255LL; }
 
+int build_tree_v2(mg_ctx *ctx, const double *d_pts, int64_t N, int D, const double *low, const double *high, int min_split,
+                  mg_kdtree **out);   // kdtree_build2.cu
+static int build_tree_v1(mg_ctx *ctx, const double *d_pts, int64_t N, int D, const double *low, const double *high,
+                         int min_split, mg_kdtree **out);
+
 int build_tree(mg_ctx *ctx, const double *d_pts, int64_t N, int D, const double *low, const double *high,
                       int min_split, mg_kdtree **out) {
   cudaStream_t s = ctx->stream;
@@ -340,7 +345,20 @@ int build_tree(mg_ctx *ctx, const double *d_pts, int64_t N, int D, const double 
   MG_CUDA(ctx, cudaMemcpyAsync(&h_flag, d_flag.get(), sizeof(int), cudaMemcpyDeviceToHost, s));
   MG_CUDA(ctx, cudaStreamSynchronize(s));
   MG_REQUIRE(ctx, h_flag == 0, "kd-tree: NaN coordinate");
+  // MCMC_GPU_KD_BUILD=1 keeps the first builder (presorted index lists); the default is the second one (key columns
+  // moved level by level, subtrees finished in shared memory), which hands inputs it is not made for back to the first
+  static const int which = [] { const char *e = getenv("MCMC_GPU_KD_BUILD"); return e ? atoi(e) : 2; }();
+  if (which != 1) {
+    const int rc = build_tree_v2(ctx, d_pts, N, D, low, high, min_split, out);
+    if (rc != MG_V2_FALLBACK) return rc;
+    if (getenv("MCMC_GPU_DEBUG")) fprintf(stderr, "kd-tree: second builder handed the input back (ties / depth), first builder runs\n");
+  }
+  return build_tree_v1(ctx, d_pts, N, D, low, high, min_split, out);
+}
 
+static int build_tree_v1(mg_ctx *ctx, const double *d_pts, int64_t N, int D, const double *low, const double *high,
+                         int min_split, mg_kdtree **out) {
+  cudaStream_t s = ctx->stream;
   time_begin(ctx);
   const int NL = D + 1;  // D sorted lists + the input-order list
   DevBuf<int32_t> listsA, listsB, segA, segB, nd_begin, nd_end, nd_dim, nd_left, nd_spos, flags, scans, tsum, totals;

@@ -34,6 +34,7 @@ struct KdHeader {
 };
 constexpr uint64_t KD_MAGIC = 0x6b64747265653031ull;  // "kdtree01"
 int validate_blob_header(struct ::mg_ctx *ctx, const KdHeader &h);   // kdtree.cu
+constexpr int MG_V2_FALLBACK = -1000;   // build_tree_v2: this input is for the first builder (not an error)
 
 struct KdView {
   const KdNode *nodes;

@@ -79,6 +79,9 @@ static int launch_mh(mg_ctx *ctx, const MhArgs<Like, Prior, Prop, D> &a) {
     // running moments of the recorded samples (requested through the context by mg_mcmc_array_resident): the
     // variant with the accumulators is a separate instantiation, the plain kernel does not pay for them
     time_begin(ctx);
+    kt_reset(ctx, with_mom ? (const void *)mh_balanced_kernel<Like, Prior, Prop, D, true>
+                           : (const void *)mh_balanced_kernel<Like, Prior, Prop, D, false>);
+    kt_start(ctx);
     if (with_mom) {
       MhArgs<Like, Prior, Prop, D> am = a;
       am.mom = ctx->mh_mom;
@@ -87,6 +90,7 @@ static int launch_mh(mg_ctx *ctx, const MhArgs<Like, Prior, Prop, D> &a) {
     } else {
       mh_balanced_kernel<Like, Prior, Prop, D, false><<<(unsigned)grid, MH_BLOCK, 0, ctx->stream>>>(a, q);
     }
+    kt_stop(ctx);
     MG_CHECK_LAUNCH(ctx);
     time_end(ctx);
     if (q.prof) {
@@ -103,7 +107,10 @@ static int launch_mh(mg_ctx *ctx, const MhArgs<Like, Prior, Prop, D> &a) {
   }
   const int64_t grid = ngroups;
   time_begin(ctx);
+  kt_reset(ctx, (const void *)mh_ensemble_kernel<Like, Prior, Prop, D>);
+  kt_start(ctx);
   mh_ensemble_kernel<Like, Prior, Prop, D><<<(unsigned)grid, MH_BLOCK, 0, ctx->stream>>>(a);
+  kt_stop(ctx);
   MG_CHECK_LAUNCH(ctx);
   time_end(ctx);
   return MG_OK;
