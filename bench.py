@@ -1,28 +1,33 @@
 #!/usr/bin/env python
-"""bench.py -- headline benchmark of the sampling path (BASELINE.json config 2).
+"""bench.py -- BASELINE.json's metric on B200: chain-steps/s and evidence samples/s at 1/2/4/8 GPUs, next to the
+reference's CPU path timed on the box's host cores.
 
-Workload ("step" = one pass of the hot path over one batch): 65,536
-independent Metropolis-Hastings chains on a 10-D correlated Gaussian
-(mu_i = i/10, Sigma_ij = 0.7^|i-j|), box proposal h = 0.5, flat prior,
-10,000 steps per chain, every step recorded (nskip = 1) into a
-[n][D+2][C] float64 sample block in HBM (62.9 GB per pass per GPU).
-Metric: chain-steps/s, whole job over all GPUs (weak scaling: every rank
-runs its own 65,536 chains with global chain ids rank*C ...).
+Headline workload ("step" = one pass of the hot path over one batch), BASELINE.json config 2: 65,536 independent
+Metropolis-Hastings chains per GPU on a 10-D correlated Gaussian (mu_i = i/10, Sigma_ij = 0.7^|i-j|), box proposal
+h = 0.5, flat prior, 10,000 steps per chain, every step recorded (nskip = 1) into a [n][D+2][C] float64 sample block
+in HBM (62.9 GB per pass per GPU).  Weak scaling: every rank runs its own 65,536 chains with global chain ids.
 
-  value  device-resident: state and sample block live in HBM, one kernel.
-  e2e    the C-ABI call mg_mcmc_array_resident with HOST buffers: start
-         points copied from pinned host memory, the sample block kept in HBM
-         for the GPU consumers that follow, and final states + accept counts
-         + per-field mean/std over all 6.6e8 recorded samples read back.
-  --impl reference   the CPU restatement of the OCaml reference
-         (oracle/, the OCaml toolchain does not exist in this image) on all
-         host threads, on a bounded sample of the same workload.
+  value       device-resident: state and sample block live in HBM, one kernel per pass.
+  e2e         the C-ABI call mg_mcmc_array_resident with HOST buffers (pinned start points in; final states,
+              counters and Stats mean / std of the 6.6e8 recorded samples out; the block stays in HBM for the GPU
+              consumers that follow it); `e2e.mcmc_array_host` adds the plain Mcmc.mcmc_array-shaped call whose
+              samples all return to the host (nskip = 100).
+  evidence    the metric's second half, config 3: Weinberg (Lebesgue) kd-tree evidence of 1e7 synthetic 20-D
+              posterior samples -- device-resident value, roofline of its dominant kernel, host-buffer e2e, CPU
+              baseline; with --gpus N the kd-cells are shared out over the ranks (mg_evidence_lebesgue_sharded).
+  rjmcmc      config 5 (2-D vs 4-D): kd-trees of 1e7 posterior draws built on rank 0, replicated with one NCCL
+              broadcast each (mg_kdtree_broadcast), 1M reversible-jump chains shared out over the ranks.
+  --impl reference   the CPU restatement of the OCaml reference (oracle/; no OCaml toolchain exists in this image)
+              on all host threads, on a bounded sample of the headline workload.
+Every multi-GPU step goes through the C ABI's communicator (mg_comm_*, NCCL); torch.distributed only launches the
+ranks, carries the 128-byte NCCL id and takes the max of the timings.
 """
 from __future__ import annotations
 
 import argparse
 import ctypes as C
 import json
+import math
 import os
 import subprocess
 import sys
@@ -39,6 +44,7 @@ NCHAINS = 65536
 NSTEPS = 10000          # steps per chain per pass; n = NSTEPS + 1 samples, nskip = 1
 SEED = 0x5EED0001
 BYTES_PER_STEP = 8 * (D + 2)   # one recorded sample per chain-step at nskip = 1
+EV_N, EV_D = 10_000_000, 20    # config 3
 
 
 def model():
@@ -106,25 +112,77 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def kernel_stats(ctx):
+    """(name, launches, mean ms) of the dominant kernel of the last call: CUDA events around every launch, in the
+    library (mg_ctx_last_kernel_stats)."""
+    buf = C.create_string_buffer(512)
+    n, ms = C.c_int64(), C.c_double()
+    ctx.lib.mg_ctx_last_kernel_stats(ctx.h, buf, C.c_int64(512), C.byref(n), C.byref(ms))
+    return buf.value.decode(), int(n.value), float(ms.value)
+
+
+def traffic_of(kernel_name):
+    """dram bytes per launch from the round's committed `ncu --set full` capture, only if it is of THIS kernel."""
+    p = os.path.join(ROOT, "profiles", "r02", "ncu_traffic.json")
+    try:
+        rec = json.load(open(p))
+        for r in rec.get("kernels", []):
+            if kernel_name.startswith(r["kernel_prefix"]):
+                return r["dram_bytes_per_launch"], r.get("source")
+    except Exception:
+        pass
+    return None, None
+
+
 def cpu_reference(nthreads, target_seconds=12.0):
     """Time the CPU restatement on a bounded sample of the workload."""
     from oracle import oracle as og
     mu, like, prior, prop = model()
     og.lib()
-    # calibrate: one short run, then size the sample for ~target_seconds
     c0, n0 = max(nthreads * 4, 8), 201
     t = time.perf_counter()
     og.mcmc_array(SEED, 0, n0, like, prior, prop, mu, nchains=c0, nthreads=nthreads, record=False)
     dt = time.perf_counter() - t
     rate = c0 * (n0 - 1) / dt
-    # the sample keeps the real chain length (1e4 steps) and bounds the number of chains
-    steps = NSTEPS
+    steps = NSTEPS    # the sample keeps the real chain length (1e4 steps) and bounds the number of chains
     chains = int(max(nthreads, min(NCHAINS, rate * target_seconds / steps)))
     chains = max(nthreads, (chains // nthreads) * nthreads)
     t = time.perf_counter()
     og.mcmc_array(SEED, 1, steps + 1, like, prior, prop, mu, nchains=chains, nthreads=nthreads, record=True)
     dt = time.perf_counter() - t
     return chains * steps / dt, f"{chains} chains x {steps} steps of the same model, samples recorded, {nthreads} threads"
+
+
+def evidence_data_host(N, Dd, seed=12345):
+    rng = np.random.default_rng(seed)
+    x = rng.normal(0.5, 0.05, (N, Dd))
+    ll = (-0.91893853320467274178 - math.log(0.05) - 0.5 * ((x - 0.5) / 0.05) ** 2).sum(1)
+    return x, ll, np.zeros(N)
+
+
+def cpu_evidence_baseline(budget_s=25.0):
+    """The oracle's evidence_lebesgue (single thread: the reference is single-threaded and its list-based kd-tree
+    cannot be run in parallel) at growing N x 20 until the time budget; the figure at 1e7 is an EXTRAPOLATION."""
+    from oracle import oracle as og
+    rows, t_used = [], 0.0
+    for N in (10_000, 100_000, 1_000_000):
+        x, ll, lp = evidence_data_host(N, EV_D)
+        t = time.perf_counter()
+        og.evidence_lebesgue(x, ll, lp, n=64, eps=0.1)
+        dt = time.perf_counter() - t
+        rows.append({"N": N, "seconds": dt, "samples_per_s": N / dt})
+        t_used += dt
+        if t_used > budget_s:
+            break
+    last = rows[-1]
+    # cost ~ N log2 N: scale the largest measured run to 1e7
+    scale = (EV_N * math.log2(EV_N)) / (last["N"] * math.log2(last["N"]))
+    return {"value": last["samples_per_s"], "unit": "evidence samples/s", "cores": 1, "kind": "port",
+            "sample": f"oracle evidence_lebesgue (n=64, eps=0.1) on {last['N']} x {EV_D} samples of the same distribution, 1 thread",
+            "runs": rows,
+            "extrapolated_1e7_seconds": last["seconds"] * scale,
+            "extrapolated_1e7_samples_per_s": EV_N / (last["seconds"] * scale),
+            "note": "C++ restatement of farr/mcmc-ocaml (oracle/), not OCaml; the 1e7 figure is an N log N extrapolation"}
 
 
 def run_reference(args, rank, world):
@@ -141,16 +199,181 @@ def run_reference(args, rank, world):
         vals.append(v)
     wall = time.perf_counter() - t0
     v = float(np.mean(vals))
-    print(json.dumps({
+    out = {
         "impl": "reference", "metric": "chain-steps/sec", "value": v, "unit": "chain-steps/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / max(1, args.steps),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": dict(workload_config(args.chains, args.chain_steps),
-                       note="CPU arm: each step is a bounded sample of this workload, see cpu_baseline.sample"),
+        "config": workload_config(args.chains, args.chain_steps),
         "cpu_baseline": {"value": v, "unit": "chain-steps/s", "cores": nthreads, "kind": "port", "sample": sample,
-                         "note": "C++ restatement of farr/mcmc-ocaml (oracle/), not OCaml: no OCaml toolchain here"},
+                         "note": "C++ restatement of farr/mcmc-ocaml (oracle/), not OCaml: no OCaml toolchain here; "
+                                 "each step is a bounded sample of the workload in `config`"},
         "e2e": {"value": v, "unit": "chain-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }))
+    }
+    if not args.no_evidence:
+        out["evidence"] = {"cpu_baseline": cpu_evidence_baseline(20.0)}
+    print(json.dumps(out))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def leg_evidence(args, ctx, comm, dev, rank, world, peak):
+    """config 3: Lebesgue evidence of EV_N x EV_D samples held by rank 0."""
+    import torch
+    import torch.distributed as dist
+
+    from mcmc_ocaml_b200 import evidence
+    N, Dd = args.ev_n, EV_D
+    out = {"workload": f"cfg3: Weinberg (Lebesgue) kd-tree evidence (n=64, eps=0.1) + harmonic mean of {N} synthetic "
+                       f"{Dd}-D posterior samples (x ~ N(0.5, 0.05^2 I), ll = log_multi_gaussian, lp = 0)",
+           "metric": "evidence samples/s", "N": N, "D": Dd, "n_gpus": world}
+    if rank == 0:
+        g = torch.Generator(device=dev); g.manual_seed(12345)
+        x = torch.empty((N, Dd), dtype=torch.float64, device=dev).normal_(0.5, 0.05, generator=g)
+        ll = (-0.91893853320467274178 - math.log(0.05) - 0.5 * ((x - 0.5) / 0.05) ** 2).sum(1)
+        lp = torch.zeros(N, dtype=torch.float64, device=dev)
+        torch.cuda.synchronize(dev)
+        ptrs = (x.data_ptr(), ll.data_ptr(), lp.data_ptr())
+    else:
+        ptrs = (0, 0, 0)
+
+    def call():
+        if world > 1:
+            return comm.evidence_lebesgue(*ptrs, N, Dd, n=64, eps=0.1, root=0)
+        return evidence.evidence_lebesgue_dev(*ptrs, N, Dd, n=64, eps=0.1, ctx=ctx)
+
+    def sync_all():
+        if world > 1:
+            comm.barrier()
+        ctx.sync()
+
+    for _ in range(2):
+        z = call()
+    reps, ts = 5, []
+    l0 = ctx.launch_count
+    for _ in range(reps):
+        sync_all(); t = time.perf_counter(); z = call(); ctx.sync(); ts.append(time.perf_counter() - t)
+    launches = (ctx.launch_count - l0) // reps
+    kname, kn, kms = kernel_stats(ctx)
+    tt = torch.tensor([float(np.mean(ts))], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    mean_s = float(tt.item())
+    out.update({"value": N / mean_s, "unit": "evidence samples/s", "seconds": mean_s, "best_seconds": float(np.min(ts)),
+                "lebesgue_Z": z, "gpu_launches_per_call": int(launches),
+                "scaling": "strong (one data set; sort, prefix cut and tree on rank 0, kd-cells shared out)" if world > 1 else "n/a"})
+    if rank == 0:
+        # roofline of the dominant kernel: SURVEY.md 8d, one level of a row-permuting build moves (2*8*D + 16) N bytes
+        per_launch = (2 * 8 * Dd + 16) * N
+        ach = per_launch / (kms * 1e-3) / 1e9 if kms > 0 else None
+        tr, tr_src = traffic_of(kname)
+        out["roofline"] = {"bound": "hbm", "kernel": kname, "launches_per_call": kn, "kernel_ms": kms,
+                           "bytes_per_launch": per_launch, "bytes_per_sample_per_level": 2 * 8 * Dd + 16,
+                           "achieved": ach, "peak": peak, "unit": "GB/s", "frac": (ach / peak) if ach else None,
+                           "traffic": tr, "traffic_source": tr_src,
+                           "whole_call_frac_of_hbm": ((2 * 8 * Dd + 16) * N * 18 + 8 * (Dd + 2) * N) / mean_s / 1e9 / peak,
+                           "whole_call_bytes": "SURVEY 8d: 18 levels x (2*8*D+16) N + one 8 (D+2) N pass"}
+        if world == 1:
+            # the other estimators and the Interpolate_pdf kernels on the same data
+            t = time.perf_counter(); zh = evidence.evidence_harmonic_mean_dev(ptrs[1], N, ctx=ctx); out["harmonic_s"] = time.perf_counter() - t
+            evidence.evidence_direct_dev(*ptrs, N, Dd, n=64, ctx=ctx)
+            t = time.perf_counter(); zd = evidence.evidence_direct_dev(*ptrs, N, Dd, n=64, ctx=ctx); out["direct_s"] = time.perf_counter() - t
+            out["direct_Z"], out["harmonic_Z"] = zd, zh
+            from mcmc_ocaml_b200 import kd_tree
+            lo, hi = np.zeros(Dd), np.ones(Dd)
+            kd_tree.KdTree.from_device(ptrs[0], N, Dd, lo, hi, ctx=ctx).close()
+            t = time.perf_counter(); tr_ = kd_tree.KdTree.from_device(ptrs[0], N, Dd, lo, hi, ctx=ctx); out["kdtree_full_build_s"] = time.perf_counter() - t
+            out["kdtree_nodes"], out["kdtree_levels"] = tr_.nnodes, tr_.nlevels
+            out["kdtree_full_frac_of_hbm"] = ((2 * 8 * Dd + 16) * N * 25) / out["kdtree_full_build_s"] / 1e9 / peak
+            tr_.close()
+            # e2e: the C-ABI call with pinned HOST buffers (1.76 GB host -> device inside the timed region)
+            xh = torch.empty((N, Dd), dtype=torch.float64).pin_memory(); xh.copy_(x)
+            llh = torch.empty(N, dtype=torch.float64).pin_memory(); llh.copy_(ll)
+            lph = torch.zeros(N, dtype=torch.float64).pin_memory()
+            torch.cuda.synchronize(dev)
+            zc = C.c_double()
+
+            def host_call():
+                ctx.check(ctx.lib.mg_evidence_lebesgue(ctx.h, C.c_void_p(xh.data_ptr()), C.c_void_p(llh.data_ptr()),
+                                                       C.c_void_p(lph.data_ptr()), C.c_int64(N), C.c_int32(Dd), C.c_int32(64),
+                                                       C.c_double(0.1), C.byref(zc)))
+            host_call()
+            te = []
+            for _ in range(3):
+                t = time.perf_counter(); host_call(); te.append(time.perf_counter() - t)
+            out["e2e"] = {"value": N / float(np.mean(te)), "unit": "evidence samples/s", "seconds": float(np.mean(te)),
+                          "h2d_bytes_per_step": N * (Dd + 2) * 8, "d2h_bytes_per_step": 8,
+                          "call": "mg_evidence_lebesgue with pinned host pts / ll / lp", "same_result": bool(zc.value == z)}
+            del xh, llh, lph
+        del x, ll, lp
+        torch.cuda.empty_cache()
+    ctx.trim_pool()
+    return out
+
+
+def leg_rjmcmc(args, ctx, comm, dev, rank, world):
+    """config 5 at (2,4)-D: trees on rank 0, one broadcast each, chains shared out."""
+    import torch
+    import torch.distributed as dist
+
+    from mcmc_ocaml_b200 import interpolate_pdf, kd_tree, mcmc, plugins as P
+    chains, steps, ntree, s = args.rj_chains, 1000, args.rj_ntree, 0.05
+    out = {"workload": f"cfg5: {chains} two-model RJMCMC chains x {steps} steps (2-D vs 4-D isotropic Gaussian posteriors, "
+                       f"Z_A / Z_B = 2), interpolated jumps from kd-trees of {ntree} posterior draws each",
+           "metric": "chain-steps/s", "n_gpus": world}
+    models, bcast, builds = [], [], []
+    for d, logc in ((2, 0.0), (4, -math.log(2.0))):
+        tree = None
+        if rank == 0:
+            g = torch.Generator(device=dev); g.manual_seed(d)
+            pts = torch.empty((ntree, d), dtype=torch.float64, device=dev).normal_(0.5, s, generator=g).clamp_(0.0, 1.0)
+            torch.cuda.synchronize(dev)
+            kd_tree.KdTree.from_device(pts.data_ptr(), ntree, d, np.zeros(d), np.ones(d), ctx=ctx).close()   # warm (pool growth)
+            t = time.perf_counter()
+            tree = kd_tree.KdTree.from_device(pts.data_ptr(), ntree, d, np.zeros(d), np.ones(d), ctx=ctx)
+            builds.append(time.perf_counter() - t)
+            del pts
+        if world > 1:
+            tms = []
+            local = None
+            for rep in range(3):            # first broadcast warms NCCL up; steady state = the later ones
+                if local is not None and rank != 0:
+                    local.close()
+                comm.barrier(); t = time.perf_counter()
+                local = comm.broadcast_tree(tree, 0); ctx.sync()
+                tms.append(time.perf_counter() - t)
+            nbytes = local.blob()[1]
+            bcast.append({"blob_GB": nbytes / 1e9, "first_s": tms[0], "steady_s": min(tms[1:]),
+                          "steady_GBps": nbytes / min(tms[1:]) / 1e9, "device_ms": comm.last_collective_ms})
+            tree = local
+        interp = interpolate_pdf.InterpPdf(None, None, None, tree=tree)
+        like = P.gauss_diag(np.full(d, 0.5), np.full(d, s))
+        prior = P.box(np.zeros(d), np.ones(d), logc)
+        prop = P.wrap_proposal(np.zeros(d), np.ones(d), np.full(d, 2.0 * s / math.sqrt(d)))
+        models.append(mcmc.RjModel(like, prior, prop, 0.5, interp=interp))
+    A, B = models
+    a0, b0 = np.full(2, 0.5), np.full(4, 0.5)
+    ctx.set_seed(20111104)
+    comm.rjmcmc_array(2, A, B, a0, b0, nskip=10, nchains=chains)          # warm-up
+    ts = []
+    for rep in range(2):
+        ctx.set_seed(20111104)
+        if world > 1:
+            comm.barrier()
+        t = time.perf_counter()
+        r = comm.rjmcmc_array(steps // 10 + 1, A, B, a0, b0, nskip=10, nchains=chains)
+        ts.append(time.perf_counter() - t)
+    tt = torch.tensor([min(ts)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    sec = float(tt.item())
+    out.update({"value": chains * steps / sec, "unit": "chain-steps/s", "seconds": sec, "kernel_ms_this_rank": ctx.last_kernel_ms,
+                "counts": list(r.counts), "ratio": r.counts[0] / max(1, r.counts[1]), "expected_ratio": 2.0,
+                "cross_model_accept_rate": r.cross[1] / max(1, r.cross[0]), "scaling": "strong (chains shared out)",
+                "tree_build_s_rank0": builds, "tree_broadcast": bcast})
+    for m in models:
+        if m.interp is not None and m.interp.tree is not None:
+            m.interp.tree.close()
+    ctx.trim_pool()
+    return out
 
 
 def main():
@@ -161,8 +384,12 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--chains", type=int, default=NCHAINS)
     ap.add_argument("--chain-steps", type=int, default=NSTEPS)
-    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline legs")
     ap.add_argument("--no-evidence", action="store_true", help="skip the config-3 evidence leg")
+    ap.add_argument("--no-rjmcmc", action="store_true", help="skip the config-5 reversible-jump leg")
+    ap.add_argument("--ev-n", type=int, default=EV_N)
+    ap.add_argument("--rj-chains", type=int, default=1_000_000)
+    ap.add_argument("--rj-ntree", type=int, default=10_000_000)
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -175,7 +402,7 @@ def main():
     import torch
     import torch.distributed as dist
 
-    from mcmc_ocaml_b200 import Context, _abi
+    from mcmc_ocaml_b200 import Context, _abi, comm as CM
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -191,6 +418,7 @@ def main():
     torch.cuda.set_stream(stream)
     ctx.set_stream(stream.cuda_stream)   # time with torch events on the launching stream
     lib = ctx.lib
+    comm = CM.Comm.from_torch(ctx)       # the C ABI's own NCCL communicator (id carried by torch.distributed)
 
     # device-resident buffers (sized for 180 GB HBM: 62.9 GB sample block)
     state = torch.empty((F, Cn), dtype=torch.float64, device=dev)
@@ -228,10 +456,10 @@ def main():
     barrier()
     total_ms = e0.elapsed_time(e1)
     launches = ctx.launch_count - l0
-    # average launch duration of the dominant kernel: CUDA events on the
-    # launching stream around every launch of the timed region
+    # average launch duration of the dominant kernel: CUDA events on the launching stream around every launch of
+    # the timed region (torch events here, the library's own events around the last launch as a cross-check)
     k_ms = float(np.mean([marks[i].elapsed_time(marks[i + 1]) for i in range(args.steps)]))
-    k_ms_lib = ctx.last_kernel_ms     # the library's own events around the last launch
+    k_name, k_n, k_ms_lib = kernel_stats(ctx)
     t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -275,25 +503,37 @@ def main():
     h2d = Cn * D * 8
     d2h = Cn * F * 8 + Cn * 4 + 2 * F * 8
 
-    # gather a physics check from every rank (NCCL all_gather of a few bytes)
-    acc_rate = torch.tensor([float(acc_h.sum()) / float(acc_h.sum() + rej_h.sum())], dtype=torch.float64, device=dev)
-    rates = [torch.zeros_like(acc_rate) for _ in range(world)]
-    if world > 1:
-        dist.all_gather(rates, acc_rate)
-    else:
-        rates = [acc_rate]
+    # statistics of the whole job, gathered through the C ABI (ncclAllGather inside mg_comm_*)
+    ntot, pmean, pstd = comm.pool_moments(n * Cn, mean_h, std_h)
+    accs = comm.allgather(np.array([float(acc_h.sum()), float(rej_h.sum())]))
+    rates = [float(a / (a + r)) for a, r in accs]
 
+    # ---- e2e of the plain Mcmc.mcmc_array-shaped call: every recorded sample returns to the host --------------------
+    host_e2e = None
+    if world == 1 and Cn == NCHAINS:
+        n_h, nskip_h = T // 100 + 1, 100
+        out_h = torch.empty((n_h, F, Cn), dtype=torch.float64).pin_memory()
+        cfg_h = _abi.mg_mcmc_cfg(Cn, D, 0, 0, nskip_h, n_h, 0, 0, 0)
+
+        def step_host():
+            ctx.check(lib.mg_mcmc_array(ctx.h, C.byref(ls), C.byref(ps), C.byref(js), C.byref(cfg_h), C.c_void_p(x0.data_ptr()),
+                                        C.c_void_p(out_h.data_ptr()), C.c_void_p(acc_h.data_ptr()), C.c_void_p(rej_h.data_ptr())))
+        step_host()
+        th = []
+        for _ in range(3):
+            t0 = time.perf_counter(); step_host(); th.append(time.perf_counter() - t0)
+        host_e2e = {"value": Cn * (n_h - 1) * nskip_h / float(np.mean(th)), "unit": "chain-steps/s", "seconds": float(np.mean(th)),
+                    "call": f"mg_mcmc_array, nskip={nskip_h}, n={n_h}: pinned x0 in, all {n_h} x {F} x {Cn} recorded values out",
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": n_h * F * Cn * 8 + 2 * Cn * 8,
+                    "sampler_kernel_ms_in_call": ctx.last_kernel_ms}
+        del out_h
+
+    out = None
+    peaks, peak_kind = measured_peaks()
+    peak = float(peaks.get("hbm_gbs", 6650.0))
     if rank == 0:
-        peaks, peak_kind = measured_peaks()
-        peak = float(peaks.get("hbm_gbs", 6650.0))
         achieved = BYTES_PER_STEP * Cn * T / (k_ms * 1e-3) / 1e9
-        traffic = None
-        tp = os.path.join(ROOT, "profiles", "mh_traffic.json")
-        if os.path.exists(tp):
-            try:
-                traffic = json.load(open(tp)).get("dram_bytes_per_launch")
-            except Exception:
-                traffic = None
+        traffic, traffic_src = traffic_of(k_name)
         fp64 = C.c_double(0.0)
         store = C.c_double(0.0)
         lib.mg_measure_fp64_tflops(ctx.h, 3, C.byref(fp64))
@@ -307,44 +547,55 @@ def main():
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps, "sampler_kernel_ms_in_call": e2e_kernel_ms,
                     "call": "mg_mcmc_array_resident: pinned x0 -> device, MH kernel (per-chain running moments kept in "
                             "registers), sample block stays in HBM, Stats mean/std pooled from the chain moments, "
-                            "final states + counters + stats -> host"},
+                            "final states + counters + stats -> host",
+                    "mcmc_array_host": host_e2e},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": f"{peak_kind} hbm_gbs (burst copy)",
-                         "kernel": "mh_balanced_kernel<GaussCorr<10>,ZeroFn,BoxProp<10>,10>",
+                         "traffic": traffic, "traffic_source": traffic_src, "peak_source": f"{peak_kind} hbm_gbs (burst copy)",
+                         "kernel": k_name, "kernel_source": "mg_ctx_last_kernel_stats (cudaFuncGetName of the launched function)",
                          "kernel_ms": k_ms, "kernel_ms_last_launch_lib_events": k_ms_lib, "bytes_per_chain_step": BYTES_PER_STEP,
                          "store_only_peak_gbs": store.value, "fp64_fma_tflops_measured": fp64.value,
                          "fp64_flops_per_chain_step": D * D + 8 * D + 3,
                          "fp64_tflops_achieved": (D * D + 8 * D + 3) * Cn * T / (k_ms * 1e-3) / 1e12},
-            "accept_rate_per_rank": [float(r.item()) for r in rates],
-            "posterior_mean_err_max": float(np.max(np.abs(mean_h[:D] - mu))),
+            "accept_rate_per_rank": rates,
+            "pooled_samples": ntot,
+            "posterior_mean_err_max": float(np.max(np.abs(pmean[:D] - mu))),
+            "posterior_std_err_max": float(np.max(np.abs(pstd[:D] - 1.0))),
         }
-        if world == 1 and not args.no_evidence:
-            # second metric of BASELINE.json: evidence samples/s (config 3 on this GPU)
-            try:
-                del samples
-                torch.cuda.empty_cache()
-                sys.path.insert(0, os.path.join(ROOT, "tools"))
-                import bench_evidence
-                ev = bench_evidence.run(bench_evidence._Args(reps=3, device=local_rank), ctx=ctx)
-                out["evidence"] = {
-                    "workload": "cfg3: Weinberg (Lebesgue) kd-tree evidence + harmonic mean, 1e7 synthetic 20-D "
-                                "posterior samples, device resident, one GPU",
-                    "lebesgue_samples_per_s": ev["lebesgue_samples_per_s"], "lebesgue_s": ev["lebesgue_s"],
-                    "harmonic_s": ev["harmonic_s"], "direct_s": ev["direct_s"],
-                    "kdtree_full_build_s": ev.get("tree_full_s"), "kdtree_nodes": ev.get("tree_full_nodes"),
-                    "interp_jump_prob_per_s": ev.get("jump_prob_queries_per_s"), "interp_draw_per_s": ev.get("draw_per_s")}
-            except Exception as e:  # the headline line must still be printed
+    # ---- the other half of the metric and config 5, at the same number of GPUs ----------------------------------------
+    del samples, state
+    torch.cuda.empty_cache()
+    ctx.trim_pool()
+    if not args.no_evidence:
+        try:
+            ev = leg_evidence(args, ctx, comm, dev, rank, world, peak)
+            if rank == 0:
+                out["evidence"] = ev
+        except Exception as e:  # the headline line must still be printed
+            if rank == 0:
                 out["evidence"] = {"error": repr(e)}
+    if not args.no_rjmcmc:
+        try:
+            rj = leg_rjmcmc(args, ctx, comm, dev, rank, world)
+            if rank == 0:
+                out["rjmcmc"] = rj
+        except Exception as e:
+            if rank == 0:
+                out["rjmcmc"] = {"error": repr(e)}
+    if rank == 0:
         if world == 1 and not args.no_cpu:
             nthreads = os.cpu_count() or 1
             v, sample = cpu_reference(nthreads, 12.0)
             out["cpu_baseline"] = {"value": v, "unit": "chain-steps/s", "cores": nthreads, "kind": "port",
                                    "sample": sample,
                                    "note": "C++ restatement of farr/mcmc-ocaml (oracle/), not OCaml"}
+            if "evidence" in out and "error" not in out["evidence"]:
+                out["evidence"]["cpu_baseline"] = cpu_evidence_baseline(20.0)
         print(json.dumps(out))
+    comm.close()
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 

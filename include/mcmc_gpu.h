@@ -109,7 +109,9 @@ int mg_memcpy_d2d(mg_ctx *ctx, void *dst_dev, const void *src_dev, int64_t nbyte
  * cross to the GPU, so the GPU path takes *registered plugins*: a kind id
  * plus a float64 parameter blob.  Built-in kinds cover the models the
  * reference ships in bin/ and test/.  User kinds are added at run time with
- * mg_plugin_register_source (NVRTC, inlined into the sampler kernel). */
+ * mg_plugin_register_source (NVRTC, inlined into the sampler kernels) and are
+ * accepted wherever a log_likelihood / log_prior is: mg_mcmc_array*,
+ * mg_rjmcmc_array*, mg_nested_evidence, mg_logfn_eval. */
 
 enum {
   /* 0.0 */
@@ -171,7 +173,15 @@ enum {
    * chosen with probability weight / sum; log q is the log-sum-exp over ALL
    * components (Mcmc.log_sum_logs, mcmc.ml:155-163). */
   MG_PROP_MIXTURE = 5,
-  MG_PROP_NKINDS = 6
+  /* Mcmc.differential_evolution_proposal ?mode_hopping_frac to_float from_float
+   * samples (mcmc.ml:198-218; mcmc.mli:215-218): params: mode_hopping_frac, M,
+   * samples[M][D] (the `value`s of the 'a mcmc_sample array, M >= 2).
+   * z' = z + d (y - x), x = samples.(i), y = samples.(j), i <> j drawn with
+   * Random.int; d = 1 with probability mode_hopping_frac, else
+   * Stats.draw_gaussian 0 (2.38 / sqrt (2 D)) (the code, not the doc: SURVEY
+   * F5b).  Symmetric: log q = 0. */
+  MG_PROP_DE = 6,
+  MG_PROP_NKINDS = 7
 };
 
 typedef struct {
@@ -452,6 +462,13 @@ int mg_nested_evidence(mg_ctx *ctx, const mg_logfn *like, const mg_logfn *prior,
                        const mg_nested_cfg *cfg, double *log_ev,
                        double *log_dev, int64_t *npts, double *pts, double *ll,
                        double *lp, double *logw);
+/* ?observer (nested.ml:123-125,136): called on the calling thread with every
+ * retired point, in retirement order (K calls after each batch of K), before
+ * nested_evidence returns.  fn = NULL removes it.  The library and the plugins
+ * may NOT be re-entered from the callback. */
+typedef void (*mg_nested_observer)(void *user, const double *value, int32_t dim,
+                                   double log_likelihood, double log_prior);
+int mg_nested_set_observer(mg_ctx *ctx, mg_nested_observer fn, void *user);
 /* Nested.evidence_error_and_weights generalised to K-at-a-time shrinkage
  * (nested.ml:81-120 when batch = 1).  ll: host [n] ascending. */
 int mg_nested_weights(mg_ctx *ctx, const double *ll, int64_t n, int32_t nlive,

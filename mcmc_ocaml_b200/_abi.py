@@ -20,7 +20,7 @@ MG_OK, MG_EINVAL, MG_EFAIL, MG_ECUDA, MG_ENOMEM = 0, 1, 2, 3, 4
 FN_ZERO, FN_CONST, FN_BOX_CLOSED, FN_BOX_OPEN, FN_GAUSS_DIAG, FN_GAUSS_CORR = 0, 1, 2, 3, 4, 5
 FN_GAUSS_DATA, FN_CAUCHY_DATA, FN_SHELL, FN_GAUSS_MIX = 6, 7, 8, 9
 # proposal kinds
-PROP_BOX, PROP_WRAP, PROP_INDEP_GAUSS, PROP_LEFT_BIASED, PROP_ONE_SIDED, PROP_MIXTURE = 0, 1, 2, 3, 4, 5
+PROP_BOX, PROP_WRAP, PROP_INDEP_GAUSS, PROP_LEFT_BIASED, PROP_ONE_SIDED, PROP_MIXTURE, PROP_DE = 0, 1, 2, 3, 4, 5, 6
 # into-model proposal kinds
 INTO_INTERP, INTO_INDEP_GAUSS = 0, 1
 LAYOUT_STEP_MAJOR, LAYOUT_CHAIN_MAJOR = 0, 1

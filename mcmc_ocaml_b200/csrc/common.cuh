@@ -37,6 +37,8 @@ struct mg_ctx {
   std::string kt_name;
   double kt_mean_ms = 0.0;
   int64_t kt_launches = 0;
+  mg_nested_observer nest_observer = nullptr;   // Nested ?observer (nested.ml:123-125)
+  void *nest_observer_user = nullptr;
   int *d_devflag = nullptr;        // device word set by a kernel whose bounded spin-wait ran out (MG_DEVERR_*)
   int sticky = MG_OK;              // a device-side failure that every later call reports until mg_ctx_clear_error
   std::string err;

@@ -66,6 +66,12 @@ inline int validate_proposal(mg_ctx *ctx, const mg_proposal *f, int dim) {
       }
       need = k; break;
     }
+    case MG_PROP_DE: {       // mode_hopping_frac, M, samples[M][D]
+      if (f->nparams < 2 || !f->params) return set_err(ctx, MG_EINVAL, "differential_evolution_proposal: no samples");
+      const double M = f->params[1];
+      if (!(M >= 2.0) || M != (double)(int64_t)M || M > 1e12) return set_err(ctx, MG_EINVAL, "differential_evolution_proposal: need at least two samples");
+      need = 2 + (int64_t)M * dim; break;
+    }
     default: return set_err(ctx, MG_EINVAL, "jump_proposal: unknown kind %d", f->kind);
   }
   if (f->nparams != need || !f->params)

@@ -19,6 +19,8 @@
 #include "common.cuh"
 #include "host_plugins.hpp"
 #include "mcmc_kernel.cuh"
+#include "nested_kernel_dev.cuh"
+#include "rj_kernel_dev.cuh"
 
 #include "build/embedded_headers.inc"
 
@@ -52,6 +54,7 @@ struct Api {
   CUresult_t (*cuModuleLoadData)(CUmodule_t *, const void *);
   CUresult_t (*cuModuleGetFunction)(CUfunction_t *, CUmodule_t, const char *);
   CUresult_t (*cuLaunchKernel)(CUfunction_t, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, void *, void **, void **);
+  CUresult_t (*cuFuncSetAttribute)(CUfunction_t, int, int);
 };
 static Api &api() {
   static Api a;
@@ -68,6 +71,7 @@ static Api &api() {
     MG_BIND(hn, nvrtcGetProgramLog); MG_BIND(hn, nvrtcGetCUBINSize); MG_BIND(hn, nvrtcGetCUBIN);
     MG_BIND(hn, nvrtcDestroyProgram);
     MG_BIND(hc, cuModuleLoadData); MG_BIND(hc, cuModuleGetFunction); MG_BIND(hc, cuLaunchKernel);
+    MG_BIND(hc, cuFuncSetAttribute);
 #undef MG_BIND
     a.ok = true;
   });
@@ -76,7 +80,7 @@ static Api &api() {
 
 struct JitKey { int device, dmax; size_t version; bool operator<(const JitKey &o) const {
   return device != o.device ? device < o.device : dmax != o.dmax ? dmax < o.dmax : version < o.version; } };
-struct JitMod { CUmodule_t mod = nullptr; CUfunction_t mh = nullptr, eval = nullptr; };
+struct JitMod { CUmodule_t mod = nullptr; CUfunction_t mh = nullptr, eval = nullptr, rj = nullptr, nest_init = nullptr, nest_replace = nullptr; };
 static std::map<JitKey, JitMod> g_mods;
 
 static const char *kPrelude =
@@ -100,7 +104,14 @@ static std::string make_source(const std::vector<UserFn> &fns, int dmax) {
        "extern \"C\" __global__ void mg_user_eval(mg::DynFnParams f, const double *x, long long M, double *out) {\n"
        "  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;\n  if (i >= M) return;\n"
        "  double v[" << dmax << "];\n  for (int d = 0; d < " << dmax << "; ++d) v[d] = (d < f.dim) ? x[i * f.dim + d] : 0.0;\n"
-       "  out[i] = mg::DynFn::eval<" << dmax << ">(f, nullptr, v, f.dim);\n}\n";
+       "  out[i] = mg::DynFn::eval<" << dmax << ">(f, nullptr, v, f.dim);\n}\n"
+       // Mcmc.rjmcmc_array and Nested.nested_evidence with the user functions as log_likelihood / log_prior
+       "#include \"rj_kernel_dev.cuh\"\n#include \"nested_kernel_dev.cuh\"\n"
+       "extern \"C\" __global__ void __maxnreg__(255) mg_user_rj(const __grid_constant__ mg::RjArgs a) {\n  mg::rj_ensemble_body<" << dmax << ">(a);\n}\n"
+       "extern \"C\" __global__ void mg_user_nest_init(mg::NestArgs a, double *x, double *ll, double *lp) {\n"
+       "  mg::nest_init_body<" << dmax << ">(a, x, ll, lp);\n}\n"
+       "extern \"C\" __global__ void mg_user_nest_replace(mg::NestArgs a, mg::NestProp p, int s0, int s1, int first, int last, double *cx, double *ccl) {\n"
+       "  mg::nest_replace_simple_body<" << dmax << ">(a, p, s0, s1, first, last, cx, ccl);\n}\n";
   return s.str();
 }
 
@@ -133,7 +144,9 @@ static int get_module(mg_ctx *ctx, int dmax, JitMod *out) {
   MG_CUDA(ctx, cudaSetDevice(ctx->device));
   MG_CUDA(ctx, cudaFree(0));  // make sure the primary context is current
   if (a.cuModuleLoadData(&m.mod, cubin.data())) return set_err(ctx, MG_ECUDA, "cuda: cuModuleLoadData failed for the plugin module");
-  if (a.cuModuleGetFunction(&m.mh, m.mod, "mg_user_mh") || a.cuModuleGetFunction(&m.eval, m.mod, "mg_user_eval"))
+  if (a.cuModuleGetFunction(&m.mh, m.mod, "mg_user_mh") || a.cuModuleGetFunction(&m.eval, m.mod, "mg_user_eval") ||
+      a.cuModuleGetFunction(&m.rj, m.mod, "mg_user_rj") || a.cuModuleGetFunction(&m.nest_init, m.mod, "mg_user_nest_init") ||
+      a.cuModuleGetFunction(&m.nest_replace, m.mod, "mg_user_nest_replace"))
     return set_err(ctx, MG_ECUDA, "cuda: plugin module lacks its entry points");
   g_mods[key] = m;
   *out = m;
@@ -172,6 +185,43 @@ int jit_logfn_eval(mg_ctx *ctx, const DynFnParams &f, const double *d_x, int64_t
   if (api().cuLaunchKernel(m.eval, (unsigned)((M + 127) / 128), 1, 1, 128, 1, 1, 0, ctx->stream, params, nullptr))
     return set_err(ctx, MG_ECUDA, "cuda: launch of the plugin evaluation kernel failed");
   ctx->launches++;
+  return MG_OK;
+}
+
+// Mcmc.rjmcmc_array with user-registered log-densities (called from mg_rjmcmc_array)
+int jit_launch_rj(mg_ctx *ctx, const RjArgs &a, int Dm, unsigned grid, unsigned block, size_t smem) {
+  JitMod m;
+  int rc = get_module(ctx, dmax_for(Dm), &m);
+  if (rc) return rc;
+  if (smem > 48 * 1024 && api().cuFuncSetAttribute(m.rj, 8 /* MAX_DYNAMIC_SHARED_SIZE_BYTES */, (int)smem))
+    return set_err(ctx, MG_ECUDA, "cuda: cannot size the shared memory of the plugin reversible-jump kernel");
+  RjArgs aa = a;
+  void *params[] = {&aa};
+  if (api().cuLaunchKernel(m.rj, grid, 1, 1, block, 1, 1, (unsigned)smem, ctx->stream, params, nullptr))
+    return set_err(ctx, MG_ECUDA, "cuda: launch of the plugin reversible-jump kernel failed");
+  return MG_OK;
+}
+
+// Nested.nested_evidence with user-registered log-densities (called from mg_nested_evidence)
+int jit_launch_nest_init(mg_ctx *ctx, int D, const NestArgs &a, double *x_out, double *ll_out, double *lp_out) {
+  JitMod m;
+  int rc = get_module(ctx, dmax_for(D), &m);
+  if (rc) return rc;
+  NestArgs aa = a;
+  void *params[] = {&aa, &x_out, &ll_out, &lp_out};
+  if (api().cuLaunchKernel(m.nest_init, (unsigned)((a.nlive + 127) / 128), 1, 1, 128, 1, 1, 0, ctx->stream, params, nullptr))
+    return set_err(ctx, MG_ECUDA, "cuda: launch of the plugin nested-initialisation kernel failed");
+  return MG_OK;
+}
+int jit_launch_nest_replace(mg_ctx *ctx, int D, const NestArgs &a, const NestProp &p, int s0, int s1, int first, int last,
+                            double *chain_x, double *chain_cl) {
+  JitMod m;
+  int rc = get_module(ctx, dmax_for(D), &m);
+  if (rc) return rc;
+  NestArgs aa = a; NestProp pp = p;
+  void *params[] = {&aa, &pp, &s0, &s1, &first, &last, &chain_x, &chain_cl};
+  if (api().cuLaunchKernel(m.nest_replace, (unsigned)((a.K + 63) / 64), 1, 1, 64, 1, 1, 0, ctx->stream, params, nullptr))
+    return set_err(ctx, MG_ECUDA, "cuda: launch of the plugin nested-replacement kernel failed");
   return MG_OK;
 }
 

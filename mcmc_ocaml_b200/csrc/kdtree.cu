@@ -360,6 +360,7 @@ static int build_tree_v1(mg_ctx *ctx, const double *d_pts, int64_t N, int D, con
                          int min_split, mg_kdtree **out) {
   cudaStream_t s = ctx->stream;
   time_begin(ctx);
+  kt_reset(ctx, N % 4 == 0 ? (const void *)part_fused_kernel<true> : (const void *)part_fused_kernel<false>);
   const int NL = D + 1;  // D sorted lists + the input-order list
   DevBuf<int32_t> listsA, listsB, segA, segB, nd_begin, nd_end, nd_dim, nd_left, nd_spos, flags, scans, tsum, totals;
   DevBuf<double> nd_split;
@@ -475,12 +476,14 @@ static int build_tree_v1(mg_ctx *ctx, const double *d_pts, int64_t N, int D, con
     dim3 pgrid((unsigned)ntiles, (unsigned)NL);
     MG_CUDA(ctx, cudaMemsetAsync(lb_status.get(), 0, sizeof(unsigned long long) * NL * ntiles, s));
     MG_CUDA(ctx, cudaMemsetAsync(lb_ticket.get(), 0, sizeof(unsigned int) * NL, s));
+    kt_start(ctx);
     if (N % 4 == 0)
       part_fused_kernel<true><<<pgrid, SCAN_BLOCK, 0, s>>>(a, lin, lout, sin, sout, side.get(), (int32_t)lb, (int32_t)le,
                                                            ntiles, lb_status.get(), lb_ticket.get(), scans.get() + nlvl);
     else
       part_fused_kernel<false><<<pgrid, SCAN_BLOCK, 0, s>>>(a, lin, lout, sin, sout, side.get(), (int32_t)lb, (int32_t)le,
                                                             ntiles, lb_status.get(), lb_ticket.get(), scans.get() + nlvl);
+    kt_stop(ctx);
     MG_CHECK_LAUNCH(ctx);
     std::swap(lin, lout); std::swap(sin, sout);
     lb = le; le = nnodes + 2 * nsplit; nnodes = le;

@@ -13,7 +13,9 @@
 // from the root box and the (dim, split) pairs on the path, exactly as
 // split_bounds (kd_tree.ml:112-118) builds them.
 #pragma once
+#ifndef __CUDACC_RTC__
 #include <cstdint>
+#endif
 
 #include "models.cuh"
 
@@ -33,7 +35,9 @@ struct KdHeader {
   int64_t off_low, off_high, off_nodes, off_count, off_begin, off_perm, off_pts;
 };
 constexpr uint64_t KD_MAGIC = 0x6b64747265653031ull;  // "kdtree01"
+#ifndef __CUDACC_RTC__
 int validate_blob_header(struct ::mg_ctx *ctx, const KdHeader &h);   // kdtree.cu
+#endif
 constexpr int MG_V2_FALLBACK = -1000;   // build_tree_v2: this input is for the first builder (not an error)
 
 struct KdView {
@@ -63,7 +67,9 @@ __device__ __forceinline__ KdScratch kd_scratch(double *smem_base, int D) {
   s.hi = s.lo + (size_t)D * blockDim.x;
   return s;
 }
+#ifndef __CUDACC_RTC__
 inline size_t kd_scratch_bytes(int D, int block) { return (size_t)3 * D * block * sizeof(double); }
+#endif
 
 // find_cell (interpolate_pdf.ml:101-109) / the *_high_level descents
 // (:121-133,144-159).  The query is in s.Q(.).  Go left iff the point lies in
@@ -142,6 +148,7 @@ __device__ __forceinline__ bool kd_draw(const KdView &t, const KdScratch &s, int
 
 }  // namespace mg
 
+#ifndef __CUDACC_RTC__
 // host-side handle
 struct mg_kdtree {
   mg_ctx *ctx = nullptr;
@@ -160,3 +167,4 @@ struct mg_kdtree {
     return v;
   }
 };
+#endif  // !__CUDACC_RTC__

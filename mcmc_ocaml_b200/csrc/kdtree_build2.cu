@@ -392,7 +392,10 @@ v2_children_kernel(V2Top t, int L) {
 // bounds_of_objects) are reduced from it, so the next level needs no pass of its own over the data.
 constexpr unsigned long long V2_AGG = 1ull << 62, V2_PRE = 2ull << 62, V2_MSK = 3ull << 62;
 
-__global__ void __launch_bounds__(V2_TB)
+#ifndef MG_V2_SCATTER_MINBLOCKS
+#define MG_V2_SCATTER_MINBLOCKS 3
+#endif
+__global__ void __launch_bounds__(V2_TB, MG_V2_SCATTER_MINBLOCKS)
 v2_scatter_kernel(V2Top t, int L, const uint64_t *__restrict__ Kin, uint64_t *__restrict__ Kout,
                   const int32_t *__restrict__ perm_in, int32_t *__restrict__ perm_out, const int32_t *__restrict__ seg_in,
                   int32_t *__restrict__ seg_out, unsigned long long *__restrict__ status, unsigned int *__restrict__ ticket,
@@ -400,9 +403,9 @@ v2_scatter_kernel(V2Top t, int L, const uint64_t *__restrict__ Kin, uint64_t *__
   const V2Level lv = t.info->lvl[L];
   __shared__ unsigned int s_tile;
   __shared__ int s_base;
-  __shared__ uint64_t sk[V2_TILE];       // one column of the tile in destination order
-  __shared__ int32_t sdst[V2_TILE];      // destination of every compact slot
-  __shared__ int32_t schild[V2_TILE];    // child node of every compact slot, relative to the next level (-1: none)
+  __shared__ uint64_t sk0[V2_TILE], sk1[V2_TILE];   // two columns of the tile in destination order
+  int32_t *sdst = reinterpret_cast<int32_t *>(sk1);  // first: destination of every compact slot ...
+  int32_t *schild = sdst + V2_TILE;                  // ... and its child node relative to the next level (-1: none)
   if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
   __syncthreads();
   const int64_t tile = s_tile;
@@ -521,31 +524,40 @@ v2_scatter_kernel(V2Top t, int L, const uint64_t *__restrict__ Kin, uint64_t *__
     if (jq == V2_ITEMS - 1) cB = bch[q];
   }
   if (cA < 0) { cA = cB; }
-  for (int d = 0; d < t.D; ++d) {
-    uint64_t key[V2_ITEMS];
-    v2_load8(Kin + (int64_t)d * t.N, base, t.N, vec, key);
+  __syncthreads();                            // sdst / schild are in registers now: their memory becomes the second column buffer
+  for (int d0 = 0; d0 < t.D; d0 += 2) {       // two columns per barrier pair
+    const bool two = d0 + 1 < t.D;
+    uint64_t key[V2_ITEMS], key2[V2_ITEMS];
+    v2_load8(Kin + (int64_t)d0 * t.N, base, t.N, vec, key);
+    if (two) v2_load8(Kin + (int64_t)(d0 + 1) * t.N, base, t.N, vec, key2);
 #pragma unroll
-    for (int k = 0; k < V2_ITEMS; ++k) if (ci[k] >= 0) sk[ci[k]] = key[k];
+    for (int k = 0; k < V2_ITEMS; ++k) if (ci[k] >= 0) { sk0[ci[k]] = key[k]; if (two) sk1[ci[k]] = key2[k]; }
     __syncthreads();
-    uint64_t *co = Kout + (int64_t)d * t.N;
 #pragma unroll
-    for (int q = 0; q < V2_ITEMS; ++q)
-      if (odst[q] >= 0) __stcs(co + odst[q], sk[q * V2_TB + threadIdx.x]);
-    // bounds of the children (the next level's bounds_of_objects)
-    uint64_t mnA = ~0ull, mxA = 0ull, mnB = ~0ull, mxB = 0ull;
+    for (int h = 0; h < 2; ++h) {
+      if (h == 1 && !two) break;
+      const int d = d0 + h;
+      const uint64_t *sk = h == 0 ? sk0 : sk1;
+      uint64_t *co = Kout + (int64_t)d * t.N;
 #pragma unroll
-    for (int q = 0; q < V2_ITEMS; ++q) {
-      const int c = bch[q];
-      if (c < 0) continue;
-      const uint64_t x = sk[lpos0 + ((q + threadIdx.x) & (V2_ITEMS - 1))];
-      if (c == cA) { mnA = x < mnA ? x : mnA; mxA = x > mxA ? x : mxA; }
-      else if (c == cB) { mnB = x < mnB ? x : mnB; mxB = x > mxB ? x : mxB; }
-      else { atomicMin((unsigned long long *)lo_next + (int64_t)c * t.D + d, (unsigned long long)x);
-             atomicMax((unsigned long long *)hi_next + (int64_t)c * t.D + d, (unsigned long long)x); }
+      for (int q = 0; q < V2_ITEMS; ++q)
+        if (odst[q] >= 0) __stcs(co + odst[q], sk[q * V2_TB + threadIdx.x]);
+      // bounds of the children (the next level's bounds_of_objects)
+      uint64_t mnA = ~0ull, mxA = 0ull, mnB = ~0ull, mxB = 0ull;
+#pragma unroll
+      for (int q = 0; q < V2_ITEMS; ++q) {
+        const int c = bch[q];
+        if (c < 0) continue;
+        const uint64_t x = sk[lpos0 + ((q + threadIdx.x) & (V2_ITEMS - 1))];
+        if (c == cA) { mnA = x < mnA ? x : mnA; mxA = x > mxA ? x : mxA; }
+        else if (c == cB) { mnB = x < mnB ? x : mnB; mxB = x > mxB ? x : mxB; }
+        else { atomicMin((unsigned long long *)lo_next + (int64_t)c * t.D + d, (unsigned long long)x);
+               atomicMax((unsigned long long *)hi_next + (int64_t)c * t.D + d, (unsigned long long)x); }
+      }
+      warp_minmax_flush(cA < 0 ? -1 : cA * t.D, mnA, mxA, lo_next + d, hi_next + d);
+      if (__any_sync(0xffffffffu, cB >= 0 && cB != cA))
+        warp_minmax_flush((cB < 0 || cB == cA) ? -1 : cB * t.D, mnB, mxB, lo_next + d, hi_next + d);
     }
-    warp_minmax_flush(cA < 0 ? -1 : cA * t.D, mnA, mxA, lo_next + d, hi_next + d);
-    if (__any_sync(0xffffffffu, cB >= 0 && cB != cA))
-      warp_minmax_flush((cB < 0 || cB == cA) ? -1 : cB * t.D, mnB, mxB, lo_next + d, hi_next + d);
     __syncthreads();
   }
 }
@@ -573,21 +585,22 @@ struct V2Bottom {
   int *overflow;
 };
 
-template <int NMAX>
+template <int NMAX, int BT>
 constexpr size_t v2_bottom_smem(int D) {
-  return (size_t)D * NMAX * 2 /* ranks */ + (size_t)NMAX * 8 /* sort keys */ + (size_t)NMAX * 2 * 9 /* sidx, ids x2, cur b/e, next b/e, spl, sps */ + 64;
+  return (size_t)D * NMAX * 8 /* key columns */ + (size_t)(BT / 32) * 256 * 4 /* per-warp histograms */ +
+         (size_t)NMAX * 2 * 8 /* ids x2, cur b/e, next b/e, spl, sps */ + 64;
 }
 
+// One CTA per subtree; the subtree's key columns live in shared memory, one warp works on one node at a time.
 template <int NMAX, int BT>
 __global__ void __launch_bounds__(BT)
 v2_bottom_kernel(V2Bottom a) {
   extern __shared__ __align__(16) unsigned char v2_smem[];
-  uint64_t *skey = reinterpret_cast<uint64_t *>(v2_smem);                 // [NMAX]
-  uint16_t *R = reinterpret_cast<uint16_t *>(skey + NMAX);                // [D][NMAX] dense ranks by local id
-  uint16_t *sidx = R + (size_t)a.D * NMAX;                                // [NMAX]
-  uint16_t *ids0 = sidx + NMAX, *ids1 = ids0 + NMAX;                      // local ids in node order (ping-pong)
-  uint16_t *cb0 = ids1 + NMAX, *ce0 = cb0 + NMAX, *cb1 = ce0 + NMAX, *ce1 = cb1 + NMAX;   // level nodes: begin / end
-  uint16_t *spl = ce1 + NMAX, *sps = spl + NMAX;                          // is_split / local split position
+  uint64_t *skeys = reinterpret_cast<uint64_t *>(v2_smem);                    // [D][NMAX] keys by local id
+  uint32_t *hist_all = reinterpret_cast<uint32_t *>(skeys + (size_t)a.D * NMAX);   // [warps][256]
+  uint16_t *ids0 = reinterpret_cast<uint16_t *>(hist_all + (BT / 32) * 256), *ids1 = ids0 + NMAX;   // local ids in node order
+  uint16_t *cb0 = ids1 + NMAX, *ce0 = cb0 + NMAX, *cb1 = ce0 + NMAX, *ce1 = cb1 + NMAX;              // level nodes: begin / end
+  uint16_t *spl = ce1 + NMAX, *sps = spl + NMAX;                              // is_split / local split position
   __shared__ int s_scan[BT / 32], s_tot;
   const V2Level lv = a.info->lvl[a.L0];
   const int s = blockIdx.x;
@@ -596,144 +609,247 @@ v2_bottom_kernel(V2Bottom a) {
   const int32_t b = a.nb[g], e = a.ne[g];
   const int n = e - b;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = BT / 32;
+  const unsigned full = 0xffffffffu, lt = (1u << lane) - 1u;
   int32_t *cnt = a.cnt + (size_t)s * V2_MAXL;
   if (n > NMAX || n <= 0) { if (tid == 0) { *a.overflow = 1; a.depth[s] = 0; } return; }
-  int P = 32; while (P < n) P <<= 1;
-  // ---- dense ranks of every column --------------------------------------------------------------------------------
   for (int d = 0; d < a.D; ++d) {
     const uint64_t *col = a.K + (int64_t)d * a.N + b;
-    for (int j = tid; j < P; j += BT) { skey[j] = j < n ? col[j] : ~0ull; sidx[j] = (uint16_t)j; }
-    __syncthreads();
-    for (int k = 2; k <= P; k <<= 1) {
-      for (int j = k >> 1; j > 0; j >>= 1) {
-        for (int q = tid; q < (P >> 1); q += BT) {
-          const int i = 2 * j * (q / j) + (q % j), l = i + j;
-          const bool up = (i & k) == 0;
-          const uint64_t x = skey[i], y = skey[l];
-          if ((x > y) == up && x != y) { skey[i] = y; skey[l] = x; const uint16_t u = sidx[i]; sidx[i] = sidx[l]; sidx[l] = u; }
-        }
-        __syncthreads();
-      }
-    }
-    // rank[k] = number of distinct keys before position k (block-wide inclusive scan of "differs from predecessor")
-    const int per = (P + BT - 1) / BT;
-    const int k0 = tid * per;
-    int cntl = 0;
-    for (int k = k0; k < k0 + per && k < n; ++k) cntl += (k > 0 && skey[k] != skey[k - 1]) ? 1 : 0;
-    int incl = cntl;
-#pragma unroll
-    for (int off = 1; off < 32; off <<= 1) { const int x = __shfl_up_sync(0xffffffffu, incl, off); if (lane >= off) incl += x; }
-    if (lane == 31) s_scan[warp] = incl;
-    __syncthreads();
-    if (warp == 0) {
-      int x = lane < nwarps ? s_scan[lane] : 0, xi = x;
-#pragma unroll
-      for (int off = 1; off < 32; off <<= 1) { const int y = __shfl_up_sync(0xffffffffu, xi, off); if (lane >= off) xi += y; }
-      if (lane < nwarps) s_scan[lane] = xi - x;
-    }
-    __syncthreads();
-    int run = incl - cntl + s_scan[warp];
-    for (int k = k0; k < k0 + per && k < n; ++k) {
-      run += (k > 0 && skey[k] != skey[k - 1]) ? 1 : 0;
-      R[(size_t)d * NMAX + sidx[k]] = (uint16_t)run;
-    }
-    __syncthreads();
+    for (int j = tid; j < n; j += BT) skeys[(size_t)d * NMAX + j] = col[j];
   }
-  // ---- levels of the subtree, one warp per node ----------------------------------------------------------------------
   for (int j = tid; j < n; j += BT) ids0[j] = (uint16_t)j;
   if (tid == 0) { cb0[0] = 0; ce0[0] = (uint16_t)n; }
   __syncthreads();
   uint16_t *ids = ids0, *idn = ids1, *cb = cb0, *ce = ce0, *nb_ = cb1, *ne_ = ce1;
+  uint32_t *h = hist_all + warp * 256;
+  uint64_t *cand = reinterpret_cast<uint64_t *>(h);      // the same 1 KB holds up to 32 candidate keys
   int cur_n = 1, lbase = 0, l = 0;
   const int64_t gbase = 2 * (int64_t)b;
-  const uint64_t *Kb = a.K + b;
+  constexpr int kLaneDimMax = 128;     // nodes up to this size: one lane per dimension walks the node's points
+  constexpr int kTinyMax = 8;          // nodes up to this size: one thread per node
+  uint64_t *pair_lo = reinterpret_cast<uint64_t *>(hist_all), *pair_hi = pair_lo + (BT / 32) * 64;   // [warps][64] (aliases the histograms)
+  static_assert((BT / 32) * 64 * 16 <= (BT / 32) * 256 * 4, "pair bounds fit the histogram area");
   for (;;) {
     if (tid == 0) cnt[l] = cur_n;
+    // Large nodes exist only while the level has few nodes (at most one per warp): their bounds are then computed by
+    // ALL warps, one (node, dimension) pair at a time, instead of by the node's own warp alone.
+    const bool pair_mode = cur_n <= nwarps;
+    uint64_t pre_lo[2] = {~0ull, ~0ull}, pre_hi[2] = {0ull, 0ull};
+    bool have_pre = false;
+    if (pair_mode) {
+      for (int pair = warp; pair < cur_n * a.D; pair += nwarps) {
+        const int node = pair / a.D, d = pair - node * a.D;
+        const int nb0 = cb[node], ne0 = ce[node];
+        if (ne0 - nb0 <= kLaneDimMax) continue;
+        const uint64_t *col = skeys + (size_t)d * NMAX;
+        uint64_t mn = ~0ull, mx = 0ull;
+        for (int j = nb0 + lane; j < ne0; j += 32) { const uint64_t k = col[ids[j]]; mn = k < mn ? k : mn; mx = k > mx ? k : mx; }
+        mn = warp_min_u64(mn); mx = warp_max_u64(mx);
+        if (lane == 0) { pair_lo[node * 64 + d] = mn; pair_hi[node * 64 + d] = mx; }
+      }
+      __syncthreads();
+      if (warp < cur_n && ce[warp] - cb[warp] > kLaneDimMax) {
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          const int d = hh * 32 + lane;
+          if (d < a.D) { pre_lo[hh] = pair_lo[warp * 64 + d]; pre_hi[hh] = pair_hi[warp * 64 + d]; }
+        }
+        have_pre = true;
+      }
+      __syncthreads();          // the histogram area is free again
+    }
+    // Tiny nodes (the last levels of a full tree hold 7/8 of all nodes): one THREAD per node, everything in
+    // registers -- same rule, scalar code.
+    for (int node = tid; node < cur_n; node += BT) {
+      const int nb0 = cb[node], ne0 = ce[node], m = ne0 - nb0;
+      if (m > kTinyMax) continue;
+      int sd = -1; double split = 0.0; int spos = ne0;
+      uint16_t id[kTinyMax];
+#pragma unroll
+      for (int j = 0; j < kTinyMax; ++j) id[j] = j < m ? ids[nb0 + j] : (uint16_t)0;
+      if (m > 1 && m >= a.min_split) {                                // kd_tree.ml:157-158 (+ truncation)
+        double dx_max = neg_inf(); bool all_eq = true;
+        for (int d = 0; d < a.D; ++d) {                               // :96-110, :120-130
+          const uint64_t *col = skeys + (size_t)d * NMAX;
+          uint64_t mn = ~0ull, mx = 0ull;
+#pragma unroll
+          for (int j = 0; j < kTinyMax; ++j) if (j < m) { const uint64_t k = col[id[j]]; mn = k < mn ? k : mn; mx = k > mx ? k : mx; }
+          if (mn != mx) all_eq = false;
+          const double dx = ordered_to_f64(mx) - ordered_to_f64(mn);
+          if (dx > dx_max) { sd = d; dx_max = dx; }
+        }
+        if (all_eq) sd = -1;                                          // :159-160
+        if (sd >= 0) {
+          const uint64_t *col = skeys + (size_t)sd * NMAX;
+          uint64_t key[kTinyMax];
+#pragma unroll
+          for (int j = 0; j < kTinyMax; ++j) key[j] = j < m ? col[id[j]] : ~0ull;
+          uint64_t v = 0ull;                                          // the m/2-th order statistic (:162-167)
+#pragma unroll
+          for (int j = 0; j < kTinyMax; ++j) {
+            int r = 0;
+#pragma unroll
+            for (int i = 0; i < kTinyMax; ++i) r += (i < m && (key[i] < key[j] || (key[i] == key[j] && i < j))) ? 1 : 0;
+            if (j < m && r == m / 2) v = key[j];
+          }
+          int below = 0, eq = 0;
+#pragma unroll
+          for (int j = 0; j < kTinyMax; ++j) if (j < m) { below += key[j] < v; eq += key[j] == v; }
+          int cntL = below + eq;                                      // List.partition (<= pvt), :168
+          const bool fix = cntL == m;                                 // adjust_for_empty_split :150-152
+          if (fix) cntL = below;
+          spos = nb0 + cntL;
+          uint64_t ml = 0ull, mr = ~0ull;
+          int lc = 0, rc = 0;
+#pragma unroll
+          for (int j = 0; j < kTinyMax; ++j) {
+            if (j >= m) continue;
+            const bool left = fix ? (key[j] < v) : (key[j] <= v);
+            if (left) { ml = key[j] > ml ? key[j] : ml; idn[nb0 + lc++] = id[j]; }
+            else { mr = key[j] < mr ? key[j] : mr; idn[spos + rc++] = id[j]; }
+          }
+          split = 0.5 * (ordered_to_f64(ml) + ordered_to_f64(mr));    // split_bounds :113
+        }
+      }
+      if (sd < 0) {
+#pragma unroll
+        for (int j = 0; j < kTinyMax; ++j) if (j < m) idn[nb0 + j] = id[j];
+      }
+      spl[node] = sd >= 0 ? 1 : 0; sps[node] = (uint16_t)spos;
+      const int64_t gk = gbase + lbase + node;
+      a.l_dim[gk] = sd; a.l_split[gk] = split; a.l_begin[gk] = nb0; a.l_end[gk] = ne0; a.l_child[gk] = -1;
+    }
     for (int node = warp; node < cur_n; node += nwarps) {
       const int nb0 = cb[node], ne0 = ce[node], m = ne0 - nb0;
+      if (m <= kTinyMax) continue;                                    // done by its own thread above
       int sd = -1; double split = 0.0; int spos = ne0;
       if (m > 1 && m >= a.min_split) {                                // kd_tree.ml:157-158 (+ truncation)
-        // bounds (:96-110) as min / max of (rank << 16 | id); lane d keeps dimension d (and d + 32)
-        unsigned keep_mn[2] = {0xffffffffu, 0xffffffffu}, keep_mx[2] = {0u, 0u};
+        // bounds_of_objects (:96-110); lane d keeps dimension d (and d + 32)
+        uint64_t klo[2] = {~0ull, ~0ull}, khi[2] = {0ull, 0ull};
         bool all_eq = true;
-        for (int d = 0; d < a.D; ++d) {
-          const uint16_t *Rd = R + (size_t)d * NMAX;
-          unsigned mn = 0xffffffffu, mx = 0u;
-          for (int j = nb0 + lane; j < ne0; j += 32) {
-            const unsigned id = ids[j];
-            const unsigned p = ((unsigned)Rd[id] << 16) | id;
-            mn = p < mn ? p : mn; mx = p > mx ? p : mx;
+        if (have_pre) {
+          klo[0] = pre_lo[0]; klo[1] = pre_lo[1]; khi[0] = pre_hi[0]; khi[1] = pre_hi[1];
+        } else if (m <= kLaneDimMax) {
+          // small node: lane d walks the node's points along its own dimension(s); no cross-lane reduction
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            const int d = hh * 32 + lane;
+            if (hh * 32 >= a.D) break;
+            const uint64_t *col = skeys + (size_t)(d < a.D ? d : 0) * NMAX;
+            uint64_t mn = ~0ull, mx = 0ull;
+            for (int j = nb0; j < ne0; ++j) { const uint64_t k = col[ids[j]]; mn = k < mn ? k : mn; mx = k > mx ? k : mx; }
+            if (d < a.D) { klo[hh] = mn; khi[hh] = mx; }
           }
-          mn = __reduce_min_sync(0xffffffffu, mn); mx = __reduce_max_sync(0xffffffffu, mx);
-          if ((mn >> 16) != (mx >> 16)) all_eq = false;
-          if ((d & 31) == lane) { keep_mn[d >> 5] = mn; keep_mx[d >> 5] = mx; }
+        } else {
+          for (int d = 0; d < a.D; ++d) {
+            const uint64_t *col = skeys + (size_t)d * NMAX;
+            uint64_t mn = ~0ull, mx = 0ull;
+            for (int j = nb0 + lane; j < ne0; j += 32) { const uint64_t k = col[ids[j]]; mn = k < mn ? k : mn; mx = k > mx ? k : mx; }
+            mn = warp_min_u64(mn); mx = warp_max_u64(mx);
+            if ((d & 31) == lane) { klo[d >> 5] = mn; khi[d >> 5] = mx; }
+          }
+        }
+        {
+          const bool differs = (lane < a.D && klo[0] != khi[0]) || (lane + 32 < a.D && klo[1] != khi[1]);
+          all_eq = !__any_sync(full, differs);
         }
         if (!all_eq) {                                                // :159-160
-          // longest_dim (:120-130): first strictly largest spread, in float64 on the real values
+          // longest_dim (:120-130): first strictly largest spread, in float64
           double dx_best = neg_inf(); int d_best = -1;
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const int d = h * 32 + lane;
+          for (int hh = 0; hh < 2; ++hh) {
+            const int d = hh * 32 + lane;
             double dx = neg_inf(); bool ok = false;
-            if (d < a.D) {
-              const double lo = ordered_to_f64(Kb[(int64_t)d * a.N + (keep_mn[h] & 0xffffu)]);
-              const double hi = ordered_to_f64(Kb[(int64_t)d * a.N + (keep_mx[h] & 0xffffu)]);
-              dx = hi - lo; ok = dx > neg_inf();                      // NaN (inf - inf) never wins, as `dx > !dx_max`
-            }
+            if (d < a.D) { dx = ordered_to_f64(khi[hh]) - ordered_to_f64(klo[hh]); ok = dx > neg_inf(); }   // NaN never wins (`dx > !dx_max`)
             if (!ok) dx = neg_inf();
             double mxv = dx;
 #pragma unroll
-            for (int off = 16; off > 0; off >>= 1) { const double o = __shfl_xor_sync(0xffffffffu, mxv, off); mxv = o > mxv ? o : mxv; }
-            const unsigned who = __ballot_sync(0xffffffffu, ok && dx == mxv);
-            if (who && mxv > dx_best) { dx_best = mxv; d_best = h * 32 + __ffs(who) - 1; }
+            for (int off = 16; off > 0; off >>= 1) { const double o = __shfl_xor_sync(full, mxv, off); mxv = o > mxv ? o : mxv; }
+            const unsigned who = __ballot_sync(full, ok && dx == mxv);
+            if (who && mxv > dx_best) { dx_best = mxv; d_best = hh * 32 + __ffs(who) - 1; }
           }
           sd = d_best;
         }
         if (sd >= 0) {
-          const uint16_t *Rs = R + (size_t)sd * NMAX;
-          const unsigned pmn = __shfl_sync(0xffffffffu, keep_mn[sd >> 5], sd & 31), pmx = __shfl_sync(0xffffffffu, keep_mx[sd >> 5], sd & 31);
-          // the m/2-th order statistic (:162-167): smallest rank r with #(rank <= r) >= m/2 + 1
-          int rlo = (int)(pmn >> 16), rhi = (int)(pmx >> 16);
-          const int want = m / 2 + 1;
-          while (rlo < rhi) {
-            const int mid = (rlo + rhi) >> 1;
-            int c = 0;
-            for (int j = nb0 + lane; j < ne0; j += 32) c += (Rs[ids[j]] <= mid) ? 1 : 0;
-            c = __reduce_add_sync(0xffffffffu, c);
-            if (c >= want) rhi = mid; else rlo = mid + 1;
+          const uint64_t *col = skeys + (size_t)sd * NMAX;
+          const uint64_t lo = __shfl_sync(full, klo[sd >> 5], sd & 31), hi = __shfl_sync(full, khi[sd >> 5], sd & 31);
+          // the m/2-th order statistic (:162-167): MSB-first radix select below the bytes lo and hi share, finished
+          // by ranking once at most 32 candidates are left
+          int shift = ((63 - __clzll((long long)(lo ^ hi))) >> 3) << 3;
+          uint64_t prefix = shift >= 56 ? 0ull : (lo >> (shift + 8)) << (shift + 8);
+          int kth = m / 2, below_tot = 0, cnt_eq = 0, cand_n = m, cshift = 64;
+          uint64_t v = 0ull;
+          while (cand_n > 32 && cshift != 0) {
+            for (int q = lane; q < 256; q += 32) h[q] = 0u;
+            __syncwarp();
+            for (int j = nb0 + lane; j < ne0; j += 32) {
+              const uint64_t k = col[ids[j]];
+              if (shift >= 56 || ((k ^ prefix) >> (shift + 8)) == 0ull) atomicAdd(&h[(unsigned)(k >> shift) & 255u], 1u);
+            }
+            __syncwarp();
+            uint32_t c[8]; uint32_t sum = 0;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) { c[q] = h[lane * 8 + q]; sum += c[q]; }
+            uint32_t incl = sum;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) { const uint32_t x = __shfl_up_sync(full, incl, off); if (lane >= off) incl += x; }
+            const uint32_t excl = incl - sum;
+            const bool mine = (uint32_t)kth >= excl && (uint32_t)kth < incl;
+            const int src = __ffs(__ballot_sync(full, mine)) - 1;
+            int bin = 0; uint32_t below = 0, cn = 0;
+            if (mine) {
+              uint32_t run = excl;
+#pragma unroll
+              for (int q = 0; q < 8; ++q) { if ((uint32_t)kth >= run && (uint32_t)kth < run + c[q]) { bin = lane * 8 + q; below = run; cn = c[q]; } run += c[q]; }
+            }
+            bin = __shfl_sync(full, bin, src); below = __shfl_sync(full, below, src); cn = __shfl_sync(full, cn, src);
+            prefix |= (uint64_t)bin << shift;
+            kth -= (int)below; below_tot += (int)below; cand_n = (int)cn; cshift = shift; shift -= 8;
+            __syncwarp();
           }
-          const int rv = rlo;
-          int cle = 0, clt = 0;
-          for (int j = nb0 + lane; j < ne0; j += 32) { const int r = Rs[ids[j]]; cle += r <= rv; clt += r < rv; }
-          cle = __reduce_add_sync(0xffffffffu, cle); clt = __reduce_add_sync(0xffffffffu, clt);
-          const bool fix = (cle == m);                                // adjust_for_empty_split :150-152
-          const int cntL = fix ? clt : cle;
-          const int thr = fix ? rv - 1 : rv;                          // left <=> rank <= thr
+          if (cand_n > 32) { v = prefix; cnt_eq = cand_n; }          // every bit decided: cand_n copies of one key
+          else {
+            int pos = 0;
+            for (int j0 = nb0; j0 < ne0; j0 += 32) {
+              const int j = j0 + lane;
+              const uint64_t k = j < ne0 ? col[ids[j]] : 0ull;
+              const bool match = j < ne0 && (cshift >= 64 || ((k ^ prefix) >> cshift) == 0ull);
+              const unsigned mk = __ballot_sync(full, match);
+              if (match) cand[pos + __popc(mk & lt)] = k;
+              pos += __popc(mk);
+            }
+            __syncwarp();
+            const bool have = lane < cand_n;
+            const uint64_t mine = have ? cand[lane] : ~0ull;
+            int rank = 0;
+            for (int q = 0; q < cand_n; ++q) { const uint64_t o = __shfl_sync(full, mine, q); rank += (o < mine || (o == mine && q < lane)) ? 1 : 0; }
+            const int src = __ffs(__ballot_sync(full, have && rank == kth)) - 1;
+            v = __shfl_sync(full, mine, src < 0 ? 0 : src);
+            below_tot += __popc(__ballot_sync(full, have && mine < v));
+            cnt_eq = __popc(__ballot_sync(full, have && mine == v));
+            __syncwarp();
+          }
+          int cntL = below_tot + cnt_eq;                              // keys <= v   (List.partition (<= pvt), :168)
+          const bool fix = (cntL == m);                               // adjust_for_empty_split :150-152: L = {k < max}
+          if (fix) cntL = below_tot;
           spos = nb0 + cntL;
           // max L / min R (:170-171) and the stable partition (:168)
-          unsigned ml = 0u, mr = 0xffffffffu;
+          uint64_t ml = 0ull, mr = ~0ull;
           int lc = 0, rc = 0;
           for (int j0 = nb0; j0 < ne0; j0 += 32) {
             const int j = j0 + lane;
             const bool valid = j < ne0;
             const unsigned id = valid ? ids[j] : 0u;
-            const unsigned r = valid ? Rs[id] : 0u;
-            const bool left = valid && (int)r <= thr, right = valid && !left;
-            const unsigned p = (r << 16) | id;
-            if (left) ml = p > ml ? p : ml;
-            if (right) mr = p < mr ? p : mr;
-            const unsigned Lm = __ballot_sync(0xffffffffu, left), Rm = __ballot_sync(0xffffffffu, right);
-            const unsigned lt = (1u << lane) - 1u;
+            const uint64_t k = valid ? col[id] : 0ull;
+            const bool left = valid && (fix ? (k < v) : (k <= v)), right = valid && !left;
+            if (left) ml = k > ml ? k : ml;
+            if (right) mr = k < mr ? k : mr;
+            const unsigned Lm = __ballot_sync(full, left), Rm = __ballot_sync(full, right);
             if (left) idn[nb0 + lc + __popc(Lm & lt)] = (uint16_t)id;
             if (right) idn[spos + rc + __popc(Rm & lt)] = (uint16_t)id;
             lc += __popc(Lm); rc += __popc(Rm);
           }
-          ml = __reduce_max_sync(0xffffffffu, ml); mr = __reduce_min_sync(0xffffffffu, mr);
-          if (lane == 0) {
-            const double lt_bound = ordered_to_f64(Kb[(int64_t)sd * a.N + (ml & 0xffffu)]);
-            const double gt_bound = ordered_to_f64(Kb[(int64_t)sd * a.N + (mr & 0xffffu)]);
-            split = 0.5 * (lt_bound + gt_bound);                      // split_bounds :113
-          }
+          ml = warp_max_u64(ml); mr = warp_min_u64(mr);
+          split = 0.5 * (ordered_to_f64(ml) + ordered_to_f64(mr));    // split_bounds :113
         }
       }
       if (sd < 0) for (int j = nb0 + lane; j < ne0; j += 32) idn[j] = ids[j];
@@ -751,13 +867,13 @@ v2_bottom_kernel(V2Bottom a) {
       const int is = node < cur_n ? spl[node] : 0;
       int incl = is;
 #pragma unroll
-      for (int off = 1; off < 32; off <<= 1) { const int x = __shfl_up_sync(0xffffffffu, incl, off); if (lane >= off) incl += x; }
+      for (int off = 1; off < 32; off <<= 1) { const int x = __shfl_up_sync(full, incl, off); if (lane >= off) incl += x; }
       if (lane == 31) s_scan[warp] = incl;
       __syncthreads();
       if (warp == 0) {
         int x = lane < nwarps ? s_scan[lane] : 0, xi = x;
 #pragma unroll
-        for (int off = 1; off < 32; off <<= 1) { const int y = __shfl_up_sync(0xffffffffu, xi, off); if (lane >= off) xi += y; }
+        for (int off = 1; off < 32; off <<= 1) { const int y = __shfl_up_sync(full, xi, off); if (lane >= off) xi += y; }
         if (lane < nwarps) s_scan[lane] = xi - x;
         if (lane == nwarps - 1) s_tot = xi;
       }
@@ -843,7 +959,7 @@ static inline int64_t v2_align256(int64_t x) { return (x + 255) & ~255LL; }
 
 template <int NMAX, int BT>
 static int v2_launch_bottom(mg_ctx *ctx, const V2Bottom &a, int nsub, int D) {
-  const size_t smem = v2_bottom_smem<NMAX>(D);
+  const size_t smem = v2_bottom_smem<NMAX, BT>(D);
   MG_CUDA(ctx, cudaFuncSetAttribute(v2_bottom_kernel<NMAX, BT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   v2_bottom_kernel<NMAX, BT><<<(unsigned)nsub, BT, smem, ctx->stream>>>(a);
   MG_CHECK_LAUNCH(ctx);
@@ -854,7 +970,10 @@ static int v2_launch_bottom(mg_ctx *ctx, const V2Bottom &a, int nsub, int D) {
 int build_tree_v2(mg_ctx *ctx, const double *d_pts, int64_t N, int D, const double *low, const double *high, int min_split,
                   mg_kdtree **out) {
   cudaStream_t s = ctx->stream;
-  const int NMAX = (D <= 40) ? 2048 : 1024;
+  // the largest subtree whose key columns fit the shared memory of one SM
+  const size_t smem_cap = 224 * 1024;
+  const int NMAX = v2_bottom_smem<2048, 1024>(D) <= smem_cap ? 2048 : v2_bottom_smem<1024, 1024>(D) <= smem_cap ? 1024
+                   : v2_bottom_smem<512, 512>(D) <= smem_cap ? 512 : 256;
   if (N >= (1LL << 30)) return MG_V2_FALLBACK;
   int L0 = 0;
   { int64_t sz = N; while (sz > NMAX) { sz = sz / 2 + 1; ++L0; } }
@@ -964,7 +1083,8 @@ int build_tree_v2(mg_ctx *ctx, const double *d_pts, int64_t N, int D, const doub
     MG_CUDA(ctx, cudaMemcpyAsync(pout, pin, sizeof(int32_t) * N, cudaMemcpyDeviceToDevice, s));   // positions outside the subtrees
     a = V2Bottom{N, D, min_split, Lh, info.get(), nb.get(), ne.get(), Kin, pin, pout, l_dim.get(), l_child.get(), l_begin.get(),
                  l_end.get(), l_split.get(), cnt.get(), depth.get(), b_over.get()};
-    rc = NMAX == 2048 ? v2_launch_bottom<2048, 1024>(ctx, a, nsub, D) : v2_launch_bottom<1024, 512>(ctx, a, nsub, D);
+    rc = NMAX == 2048 ? v2_launch_bottom<2048, 1024>(ctx, a, nsub, D) : NMAX == 1024 ? v2_launch_bottom<1024, 1024>(ctx, a, nsub, D)
+         : NMAX == 512 ? v2_launch_bottom<512, 512>(ctx, a, nsub, D) : v2_launch_bottom<256, 256>(ctx, a, nsub, D);
     if (rc) return rc;
     v2_level_scan_kernel<<<V2_MAXL, 1024, 0, s>>>(cnt.get(), pre.get(), nsub, totals.get());
     MG_CHECK_LAUNCH(ctx);

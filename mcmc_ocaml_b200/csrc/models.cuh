@@ -358,6 +358,21 @@ struct DynProp {
       case MG_PROP_ONE_SIDED:    // test/mcmc_test.ml:186-189
         y[0] = x[0] + __ldg(p) * (__ldg(p + 1) * r.uniform());
         break;
+      case MG_PROP_DE: {         // differential_evolution_proposal, mcmc.ml:198-218
+        const double mode_hop = __ldg(p);
+        const uint64_t M = (uint64_t)__ldg(p + 1);
+        const uint64_t i = r.below(M);                                   // :201-202 pick_samples: i, then j <> i
+        uint64_t j;
+        do { j = r.below(M); } while (j == i);
+        double dd;
+        if (mode_hop != 0.0 && r.uniform() < mode_hop) dd = 1.0;           // :209-210
+        else dd = draw_gaussian(r, 0.0, 2.38 / sqrt(2.0 * (double)d));     // :212-213
+        const double *xs = p + 2 + i * (uint64_t)d, *ys = p + 2 + j * (uint64_t)d;
+#pragma unroll (DMAX <= 16 ? DMAX : 1)
+        for (int k = 0; k < DMAX; ++k)
+          if (k < d) y[k] = x[k] + dd * (__ldg(ys + k) - __ldg(xs + k));   // :215-217
+        break;
+      }
     }
   }
   template <int DMAX>

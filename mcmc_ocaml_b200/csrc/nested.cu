@@ -15,7 +15,7 @@
 // stays L2-resident; the DE proposal gathers two rows per step.
 #include "common.cuh"
 #include "host_plugins.hpp"
-#include "models.cuh"
+#include "nested_kernel_dev.cuh"
 #include "radix_sort.cuh"
 #include "reduce_sum.cuh"
 
@@ -29,34 +29,20 @@
 
 namespace mg {
 
-struct NestArgs {
-  DynFnParams like, prior;
-  const double *live_x, *live_ll, *live_lp;   // sorted ascending in ll
-  double *fresh_x, *fresh_ll, *fresh_lp;      // [K][D], [K], [K]
-  const double *plo, *phi;                    // prior box
-  CallKey key;
-  int64_t R;                                  // replacements done so far
-  double threshold, mode_hop, de_sigma;
-  int32_t D, nlive, K, nmcmc;
-  int *fail;
-};
-
-// draw_prior (nested_test.ml:34-35 style: per-dimension Stats.draw_uniform) + evaluation (:126-130)
 template <int DMAX>
 __global__ void nest_init_kernel(NestArgs a, double *__restrict__ x_out, double *__restrict__ ll_out,
                                  double *__restrict__ lp_out) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= a.nlive) return;
-  Rng r(a.key, P_NEST_INIT, (uint64_t)i, 0);
-  double x[DMAX];
-#pragma unroll (DMAX <= 16 ? DMAX : 1)
-  for (int d = 0; d < DMAX; ++d) x[d] = (d < a.D) ? draw_uniform(r, __ldg(a.plo + d), __ldg(a.phi + d)) : 0.0;
-#pragma unroll (DMAX <= 16 ? DMAX : 1)
-  for (int d = 0; d < DMAX; ++d)
-    if (d < a.D) x_out[(int64_t)i * a.D + d] = x[d];
-  ll_out[i] = DynFn::eval<DMAX>(a.like, nullptr, x, a.D);
-  lp_out[i] = DynFn::eval<DMAX>(a.prior, nullptr, x, a.D);
+  nest_init_body<DMAX>(a, x_out, ll_out, lp_out);
 }
+template <int DMAX>
+__global__ void nest_replace_simple_kernel(NestArgs a, NestProp p, int s0, int s1, int first, int last, double *chain_x,
+                                           double *chain_cl) {
+  nest_replace_simple_body<DMAX>(a, p, s0, s1, first, last, chain_x, chain_cl);
+}
+// user plugins: the two kernels above compiled at run time with the registered functions inlined (jit.cu)
+int jit_launch_nest_init(mg_ctx *ctx, int D, const NestArgs &a, double *x_out, double *ll_out, double *lp_out);
+int jit_launch_nest_replace(mg_ctx *ctx, int D, const NestArgs &a, const NestProp &p, int s0, int s1, int first, int last,
+                            double *chain_x, double *chain_cl);
 
 // draw_new_live_point (nested.ml:50-74) in two kernels.
 //
@@ -78,12 +64,6 @@ constexpr int kSR = 4;           // stages of the proposal-scalar ring (step s r
 // doubles per staged live row: 16-byte aligned and an odd number of 16-byte units when D % 4 == 0 (conflict-free
 // 128-bit reads by the row's owner); odd D: an odd number of doubles
 __host__ __device__ constexpr int nest_row_stride(int D) { return (D % 2 == 0) ? D + 2 : (D | 1); }
-
-struct NestProp {
-  int32_t *i0, *j0;   // [S][K] live-set rows x, y of the proposal  (mcmc.ml:201-202)
-  double *ds;         // [S][K] scale d                             (:209-213)
-  double *u;          // [S][K] Random.float 1.0 of the accept test (mcmc.ml:47)
-};
 
 __global__ void nest_propose_kernel(NestArgs a, NestProp p, int s0, int S) {
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -530,6 +510,12 @@ extern "C" int mg_nested_weights(mg_ctx *ctx, const double *ll, int64_t n, int32
   return MG_OK;
 }
 
+extern "C" int mg_nested_set_observer(mg_ctx *ctx, mg_nested_observer fn, void *user) {
+  if (!ctx) return MG_EINVAL;
+  ctx->nest_observer = fn; ctx->nest_observer_user = user;
+  return MG_OK;
+}
+
 extern "C" int mg_nested_evidence(mg_ctx *ctx, const mg_logfn *like, const mg_logfn *prior, const double *prior_lo,
                                   const double *prior_hi, const mg_nested_cfg *cfg, double *log_ev, double *log_dev,
                                   int64_t *npts, double *pts, double *ll, double *lp, double *logw) {
@@ -544,8 +530,8 @@ extern "C" int mg_nested_evidence(mg_ctx *ctx, const mg_logfn *like, const mg_lo
   int rc;
   if ((rc = validate_logfn(ctx, like, D, "log_likelihood"))) return rc;
   if ((rc = validate_logfn(ctx, prior, D, "log_prior"))) return rc;
-  MG_REQUIRE(ctx, like->kind < MG_FN_USER && prior->kind < MG_FN_USER,
-             "nested_evidence: run-time plugins are supported by mcmc_array and logfn_eval only");
+  const bool user = like->kind >= MG_FN_USER || prior->kind >= MG_FN_USER;   // kernels compiled at run time (jit.cu)
+  const bool simple = user || getenv("MCMC_GPU_NEST_SIMPLE") != nullptr;       // plain-load chain kernel (same chains)
   MG_CUDA(ctx, cudaSetDevice(ctx->device));
   cudaStream_t s = ctx->stream;
   const double t_entry = std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
@@ -644,8 +630,20 @@ extern "C" int mg_nested_evidence(mg_ctx *ctx, const mg_logfn *like, const mg_lo
   } while (0)
 
   int cur = 0;
-  MG_NEST_DISPATCH(nest_init_kernel, (nlive + 127) / 128, 128, a, lx[1].get(), lll[1].get(), llp[1].get());
+  if (user) { if ((rc = jit_launch_nest_init(ctx, D, a, lx[1].get(), lll[1].get(), llp[1].get()))) return rc; }
+  else MG_NEST_DISPATCH(nest_init_kernel, (nlive + 127) / 128, 128, a, lx[1].get(), lll[1].get(), llp[1].get());
   MG_CHECK_LAUNCH(ctx);
+  // the chain kernel of one chunk of steps: pipelined (built-in plugins), plain loads, or compiled at run time
+  auto launch_replace = [&](const NestProp &pp, int s0, int s1, int first, int last) -> int {
+    if (user) return jit_launch_nest_replace(ctx, D, a, pp, s0, s1, first, last, chain_x.get(), chain_cl.get());
+    if (simple) {
+      MG_NEST_DISPATCH(nest_replace_simple_kernel, (K + 63) / 64, 64, a, pp, s0, s1, first, last, chain_x.get(), chain_cl.get());
+      return MG_OK;
+    }
+    MG_NEST_DISPATCH2(nest_replace_kernel, (K + NEST_BLOCK - 1) / NEST_BLOCK, NEST_BLOCK, a, pp, s0, s1, first, last,
+                      chain_x.get(), chain_cl.get());
+    return MG_OK;
+  };
   // Array.fast_sort by log_likelihood (:132): stable radix sort + gather
   auto sort_live = [&](int from, int to) -> int {
     nest_keys_kernel<<<(nlive + 255) / 256, 256, 0, s>>>(lll[from].get(), nlive, keys.get(), order.get());
@@ -665,7 +663,6 @@ extern "C" int mg_nested_evidence(mg_ctx *ctx, const mg_logfn *like, const mg_lo
   int64_t R = 0;
   std::vector<double> h_low(K);
   double h_edge[2];
-  const int rblock = NEST_BLOCK;
   time_begin(ctx);
   const bool dbg = getenv("MCMC_GPU_DEBUG") != nullptr;
   double t_chain = 0, t_sort = 0, t_rest = 0; int nb = 0;
@@ -688,8 +685,7 @@ extern "C" int mg_nested_evidence(mg_ctx *ctx, const mg_logfn *like, const mg_lo
       } else {
         MG_CUDA(ctx, cudaStreamWaitEvent(s, ev_drawn[b], 0));
       }
-      MG_NEST_DISPATCH2(nest_replace_kernel, (K + rblock - 1) / rblock, rblock, a, prop2[b], 0, cfg->nmcmc, 1, 1,
-                        chain_x.get(), chain_cl.get());
+      if ((rc = launch_replace(prop2[b], 0, cfg->nmcmc, 1, 1))) return rc;
       MG_CHECK_LAUNCH(ctx);
       MG_CUDA(ctx, cudaEventRecord(ev_used[b], s));
       // draws of the next batch (ids R+K ..) into the other set, once the chains that read it have finished
@@ -708,8 +704,7 @@ extern "C" int mg_nested_evidence(mg_ctx *ctx, const mg_logfn *like, const mg_lo
         nest_propose_kernel<<<(unsigned)((np_ + 255) / 256), 256, 0, s>>>(a, prop, s0, s1 - s0);
         MG_CHECK_LAUNCH(ctx);
       }
-      MG_NEST_DISPATCH2(nest_replace_kernel, (K + rblock - 1) / rblock, rblock, a, prop, s0, s1, s0 == 0 ? 1 : 0,
-                        s1 >= cfg->nmcmc ? 1 : 0, chain_x.get(), chain_cl.get());
+      if ((rc = launch_replace(prop, s0, s1, s0 == 0 ? 1 : 0, s1 >= cfg->nmcmc ? 1 : 0))) return rc;
       MG_CHECK_LAUNCH(ctx);
       if (s1 >= cfg->nmcmc) break;
       s0 = s1;
@@ -719,6 +714,14 @@ extern "C" int mg_nested_evidence(mg_ctx *ctx, const mg_logfn *like, const mg_lo
     MG_CUDA(ctx, cudaMemcpyAsync(rx.get() + R * D, lx[cur].get(), sizeof(double) * K * D, cudaMemcpyDeviceToDevice, s));
     MG_CUDA(ctx, cudaMemcpyAsync(rll.get() + R, lll[cur].get(), sizeof(double) * K, cudaMemcpyDeviceToDevice, s));
     MG_CUDA(ctx, cudaMemcpyAsync(rlp.get() + R, llp[cur].get(), sizeof(double) * K, cudaMemcpyDeviceToDevice, s));
+    if (ctx->nest_observer) {   // ?observer (nested.ml:123-125,136): called with every retired point, in retirement order
+      std::vector<double> ox((size_t)K * D), oll(K), olp(K);
+      MG_CUDA(ctx, cudaMemcpyAsync(ox.data(), lx[cur].get(), sizeof(double) * K * D, cudaMemcpyDeviceToHost, s));
+      MG_CUDA(ctx, cudaMemcpyAsync(oll.data(), lll[cur].get(), sizeof(double) * K, cudaMemcpyDeviceToHost, s));
+      MG_CUDA(ctx, cudaMemcpyAsync(olp.data(), llp[cur].get(), sizeof(double) * K, cudaMemcpyDeviceToHost, s));
+      MG_CUDA(ctx, cudaStreamSynchronize(s));
+      for (int j = 0; j < K; ++j) ctx->nest_observer(ctx->nest_observer_user, ox.data() + (size_t)j * D, D, oll[j], olp[j]);
+    }
     double tC = dbg ? now() : 0;
     if (K <= NEST_SORT_MAX) {
       // replace_live_point (:26-43): sort the K new points, merge them into the (sorted) survivors

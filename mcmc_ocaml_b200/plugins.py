@@ -135,6 +135,20 @@ def combine_jump_proposals(props):
     return Proposal(_abi.PROP_MIXTURE, dim, blob)
 
 
+def differential_evolution_proposal(samples, mode_hopping_frac: float = 0.0) -> Proposal:
+    """``Mcmc.differential_evolution_proposal ?mode_hopping_frac to_float from_float samples`` (mcmc.ml:198-218,
+    mcmc.mli:215-218) with ``to_float`` = ``from_float`` = identity on ``float array``: ``samples`` are the
+    ``value``s [M][D] (or an ``McmcSamples``).  Symmetric; the scale of the ordinary mode is Gaussian with
+    sigma = 2.38 / sqrt(2 D), as coded (the .mli says uniform)."""
+    pts = samples.values() if hasattr(samples, "values") else _abi.as_f64(samples)
+    if pts.ndim == 1:
+        pts = pts.reshape(-1, 1)
+    if pts.shape[0] < 2:
+        raise _abi.InvalidArgument("differential_evolution_proposal: need at least two samples")
+    blob = np.concatenate([[float(mode_hopping_frac), float(pts.shape[0])], pts.ravel()])
+    return Proposal(_abi.PROP_DE, pts.shape[1], blob)
+
+
 def register_source(name: str, body: str, dim: int, params=(), *, ctx=None) -> LogFn:
     """Register a user log-density given as CUDA source (``mg_plugin_register_source``):
     ``body`` is the body of ``__device__ double f(const double* x, int dim, const double* p, long long np)``.

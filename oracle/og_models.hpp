@@ -243,6 +243,10 @@ struct Proposal {
         for (auto &x : w) x = x / ptot;
         need = (int64_t)k; break;
       }
+      case MG_PROP_DE: {       // mode_hopping_frac, M, samples[M][D]
+        if (p.size() < 2 || !(p[1] >= 2.0)) throw std::invalid_argument("differential_evolution_proposal: need at least two samples");
+        need = 2 + (int64_t)p[1] * D; break;
+      }
       default: throw std::invalid_argument("unknown proposal kind");
     }
     if ((int64_t)p.size() != need) throw std::invalid_argument("bad proposal nparams");
@@ -284,6 +288,18 @@ struct Proposal {
       case MG_PROP_ONE_SIDED:  // test/mcmc_test.ml:186-189
         y[0] = x[0] + p[0] * (p[1] * r.uniform());
         break;
+      case MG_PROP_DE: {       // differential_evolution_proposal, mcmc.ml:198-218
+        const double mode_hop = p[0];
+        const uint64_t M = (uint64_t)p[1];
+        uint64_t i = r.below(M), j;                              // :201-202
+        do { j = r.below(M); } while (j == i);
+        double d;
+        if (mode_hop != 0.0 && r.uniform() < mode_hop) d = 1.0;  // :209-210
+        else { double sigma = 2.38 / std::sqrt(2.0 * (double)D); d = draw_gaussian(r, 0.0, sigma); }   // :212-213
+        const double *xs = p.data() + 2 + i * (uint64_t)D, *ys = p.data() + 2 + j * (uint64_t)D;
+        for (int k = 0; k < D; ++k) y[k] = x[k] + d * (ys[k] - xs[k]);   // :215-217
+        break;
+      }
       case MG_PROP_MIXTURE: {  // mcmc.ml:168-176
         double prob = r.uniform();
         size_t c = 0;

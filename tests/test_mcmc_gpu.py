@@ -276,3 +276,30 @@ def test_balanced_kernel_dynamic_plugins_data_likelihood(ctx, og):
     np.testing.assert_allclose(got.block[:, 2, same], want[:, 2, same], rtol=1e-12)
     assert np.array_equal(got.accept[same], acc[same])
     assert np.all(got.block[:, 0, :] >= -1.0) and np.all(got.block[:, 1, :] <= 1.5)
+
+
+def test_differential_evolution_proposal(ctx, og):
+    """Mcmc.differential_evolution_proposal as a jump proposal of mcmc_array (mcmc.ml:198-218, mcmc.mli:215-218):
+    chains against the oracle on the same Philox stream, and the reference's own test (test/mcmc_test.ml:213-224):
+    with 100 % mode hopping the proposed displacements of N(10, 1) samples are N(0, sqrt 2)."""
+    rng = np.random.default_rng(11)
+    D = 3
+    table = rng.normal(0.5, 0.1, (5000, D))
+    prop = P.differential_evolution_proposal(table, mode_hopping_frac=0.1)
+    like, prior = P.gauss_diag(np.full(D, 0.5), np.full(D, 0.1)), P.box(np.zeros(D), np.ones(D), 0.0)
+    ctx.set_seed(2718)
+    got = mcmc.mcmc_array(150, like, prior, prop, np.full(D, 0.5), nchains=256, nbin=10, nskip=2, ctx=ctx)
+    want, acc, _, mg = og.mcmc_array(2718, 0, 150, like, prior, prop, np.full(D, 0.5), nchains=256, nbin=10, nskip=2,
+                                     nthreads=8, margins=True)
+    assert divergence_report(got.block[:, :D, :], want[:, :D, :], mg, "DE proposal") <= 0.02
+    x = got.block[20:, :D, :]
+    assert abs(x.mean() - 0.5) < 0.01 and abs(x.std() - 0.1) < 0.01          # it samples the target
+    # the reference's test: a flat target accepts every proposal, so sample 1 of every chain is one proposal from 0
+    samples = rng.normal(10.0, 1.0, (200000, 1))
+    hop = P.differential_evolution_proposal(samples, mode_hopping_frac=1.0)
+    ctx.set_seed(31415)
+    r = mcmc.mcmc_array(2, P.zero(1), P.zero(1), hop, [0.0], nchains=400000, ctx=ctx)
+    ps = r.block[1, 0, :]
+    assert abs(ps.mean()) < 1e-2 and abs(ps.std(ddof=1) - np.sqrt(2.0)) < 1e-2
+    with pytest.raises(InvalidArgument):
+        mcmc.mcmc_array(5, P.zero(1), P.zero(1), P.Proposal(6, 1, [0.0, 1.0, 0.5]), [0.0], ctx=ctx)    # one sample only
