@@ -34,6 +34,27 @@ external lebesgue_raw :
 external direct_raw :
   ctx -> int -> (float, float64_elt, c_layout) Array2.t -> (float, float64_elt, c_layout) Array1.t ->
   (float, float64_elt, c_layout) Array1.t -> float = "mcmcgpu_evidence_direct"
+type pinned_handle
+external pinned_raw : ctx -> int array -> (float, float64_elt, c_layout) Genarray.t * pinned_handle = "mcmcgpu_pinned_raw"
+external multi_mean_raw :
+  ctx -> (float, float64_elt, c_layout) Array2.t -> (float, float64_elt, c_layout) Array1.t -> unit = "mcmcgpu_stats_multi_mean"
+external multi_std_raw :
+  ctx -> (float, float64_elt, c_layout) Array2.t -> (float, float64_elt, c_layout) Array1.t ->
+  (float, float64_elt, c_layout) Array1.t -> unit = "mcmcgpu_stats_multi_std"
+(* the record the stub reads field by field (rj_of_value in mcmc_gpu_stubs.c) *)
+type rj_model_raw = {
+  r_like : logfn; r_prior : logfn; r_prop : proposal; r_into : tree option;
+  r_into_gauss : (float, float64_elt, c_layout) Array1.t; r_nstop : int; r_p : float }
+external rjmcmc_array_raw :
+  ctx -> rj_model_raw -> rj_model_raw -> int -> int -> int -> int -> (float, float64_elt, c_layout) Array1.t ->
+  (float, float64_elt, c_layout) Array1.t -> (int, int8_unsigned_elt, c_layout) Array2.t -> int * int
+  = "mcmcgpu_rjmcmc_array_bytecode" "mcmcgpu_rjmcmc_array_native"
+external nested_evidence_raw :
+  ctx -> logfn -> logfn -> (float, float64_elt, c_layout) Array1.t -> (float, float64_elt, c_layout) Array1.t ->
+  float -> int -> int -> float -> int -> (float, float64_elt, c_layout) Array2.t -> (float, float64_elt, c_layout) Array1.t ->
+  (float, float64_elt, c_layout) Array1.t -> (float, float64_elt, c_layout) Array1.t -> float * float * int
+  = "mcmcgpu_nested_evidence_bytecode" "mcmcgpu_nested_evidence_native"
+external log_total_error_estimate_raw : float -> float -> int -> float = "mcmcgpu_log_total_error_estimate"
 
 let create ?(device = 0) ?(seed = 0L) () = ctx_create device seed
 
@@ -49,6 +70,23 @@ let gaussian_data data = { kind = 6; dim = 2; scale = 1.0; params = ba1 data }
 let cauchy_data data = { kind = 7; dim = 2; scale = 1.0; params = ba1 data }
 let box_proposal h = { pkind = 0; pdim = Array.length h; pparams = ba1 h }
 let uniform_wrapping lo hi dx = { pkind = 1; pdim = Array.length lo; pparams = ba1 (Array.concat [lo; hi; dx]) }
+let independent_gaussian mu sigma = { pkind = 2; pdim = Array.length mu; pparams = ba1 (Array.append mu sigma) }
+(* Mcmc.differential_evolution_proposal ?mode_hopping_frac to_float from_float samples (mcmc.ml:198-218) with
+   to_float = from_float = identity: MG_PROP_DE, params = mode_hopping_frac, M, samples[M][D] *)
+let differential_evolution_proposal ?(mode_hopping_frac = 0.0) (samples : float array Mcmc.mcmc_sample array) =
+  let m = Array.length samples in
+  if m < 2 then invalid_arg "differential_evolution_proposal: need at least two samples";
+  let d = Array.length samples.(0).Mcmc.value in
+  let blob = Array.concat ([| mode_hopping_frac; float_of_int m |] :: Array.to_list (Array.map (fun s -> s.Mcmc.value) samples)) in
+  { pkind = 6; pdim = d; pparams = ba1 blob }
+
+(* Page-locked float64 Bigarrays: the view and the handle that owns the memory travel together. *)
+module Pinned = struct
+  type 'a t = { data : 'a; handle : pinned_handle }
+  let array1 ctx n = let g, h = pinned_raw ctx [| n |] in { data = array1_of_genarray g; handle = h }
+  let array2 ctx n d = let g, h = pinned_raw ctx [| n; d |] in { data = array2_of_genarray g; handle = h }
+  let array3 ctx a b c = let g, h = pinned_raw ctx [| a; b; c |] in { data = array3_of_genarray g; handle = h }
+end
 
 let mcmc_array ctx ?(nbin = 0) ?(nskip = 1) ?(nchains = 1) n like prior prop start =
   let d = like.dim in
@@ -87,6 +125,53 @@ module Evidence = struct
   let evidence_direct ctx ?(n = 64) samples =
     let pts, ll, lp = columns samples in direct_raw ctx n pts ll lp
 end
+
+(* Mcmc.rjmcmc_array (mcmc.ml:121-139; mcmc.mli:151-162) for [nchains] chains.  A model is its log-likelihood, log-prior,
+   in-model proposal, model prior and the proposal INTO it: an Interp.interp_pdf (Interp.draw / log (Interp.jump_prob ..),
+   test/mcmc_test.ml:175-178; ~nstop > 0 selects the *_high_level forms) or an independent Gaussian (mu, sigma). *)
+type rj_into = Into_interp of Interp.interp_pdf * int | Into_gaussian of float array * float array
+type rj_model = { rj_like : logfn; rj_prior : logfn; rj_prop : proposal; rj_into : rj_into; rj_p : float }
+let raw_of_model m =
+  match m.rj_into with
+  | Into_interp (ip, nstop) ->
+      { r_like = m.rj_like; r_prior = m.rj_prior; r_prop = m.rj_prop; r_into = Some ip.Interp.tree; r_into_gauss = ba1 [||];
+        r_nstop = nstop; r_p = m.rj_p }
+  | Into_gaussian (mu, sigma) ->
+      { r_like = m.rj_like; r_prior = m.rj_prior; r_prop = m.rj_prop; r_into = None; r_into_gauss = ba1 (Array.append mu sigma);
+        r_nstop = 0; r_p = m.rj_p }
+(* returns the model of every recorded sample ([n][nchains], 0 = A, 1 = B) and Mcmc.rjmcmc_model_counts *)
+let rjmcmc_array ctx ?(nbin = 0) ?(nskip = 1) ?(nchains = 1) n (ma : rj_model) (mb : rj_model) (a0 : float array) (b0 : float array) =
+  let model = Array2.create int8_unsigned c_layout n nchains in
+  let counts = rjmcmc_array_raw ctx (raw_of_model ma) (raw_of_model mb) nbin nskip n nchains (ba1 a0) (ba1 b0) model in
+  (model, counts)
+let rjmcmc_evidence_ratio (na, nb) = float_of_int na /. float_of_int nb     (* mcmc.ml:151-153 *)
+
+(* Stats.multi_mean / multi_std ?mean (stats.ml:58-87) *)
+let multi_mean ctx (xs : float array array) =
+  let out = Array1.create float64 c_layout (Array.length xs.(0)) in
+  multi_mean_raw ctx (ba2 xs) out;
+  Array.init (Array1.dim out) (fun i -> out.{i})
+let multi_std ctx ?mean (xs : float array array) =
+  let out = Array1.create float64 c_layout (Array.length xs.(0)) in
+  multi_std_raw ctx (ba2 xs) (match mean with None -> ba1 [||] | Some mu -> ba1 mu) out;
+  Array.init (Array1.dim out) (fun i -> out.{i})
+
+(* Nested.nested_evidence ?epsrel ?nmcmc ?nlive ?mode_hopping_frac (nested.ml:122-146; nested.mli:50-61) with draw_prior
+   uniform on [prior_low, prior_high]; ?batch live points are replaced per iteration (1 = the reference's schedule).
+   Result: 'a nested_output = (log_ev, log_dev, all points ascending in ll, log weights) (nested.ml:20). *)
+let nested_evidence ctx ?(epsrel = 0.01) ?(nmcmc = 1000) ?(nlive = 1000) ?(mode_hopping_frac = 0.1) ?(batch = 1)
+    ?max_points like prior prior_low prior_high =
+  let d = like.dim in
+  let cap = match max_points with Some c -> c | None -> nlive * 400 in
+  let pts = Array2.create float64 c_layout cap d and ll = Array1.create float64 c_layout cap
+  and lp = Array1.create float64 c_layout cap and lw = Array1.create float64 c_layout cap in
+  let log_ev, log_dev, n =
+    nested_evidence_raw ctx like prior (ba1 prior_low) (ba1 prior_high) epsrel nmcmc nlive mode_hopping_frac batch pts ll lp lw in
+  let samples = Array.init n (fun i ->
+      { Mcmc.value = Array.init d (fun k -> pts.{i, k});
+        like_prior = { Mcmc.log_likelihood = ll.{i}; log_prior = lp.{i} } }) in
+  (log_ev, log_dev, samples, Array.init n (fun i -> lw.{i}))
+let log_total_error_estimate log_ev log_dev nlive = log_total_error_estimate_raw log_ev log_dev nlive   (* nested.ml:148-150 *)
 
 (* Stats.draw_uniform / draw_gaussian / draw_cauchy (stats.ml:89-91,113-128): n draws from the context's stream *)
 let draw kind ctx a b n =

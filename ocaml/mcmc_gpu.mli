@@ -16,6 +16,8 @@ type logfn = { kind : int; dim : int; scale : float; params : (float, float64_el
 type proposal = { pkind : int; pdim : int; pparams : (float, float64_elt, c_layout) Array1.t }
 (** A jump proposal with its log jump probability (MG_PROP_* kinds). *)
 
+type pinned_handle
+
 val create : ?device:int -> ?seed:int64 -> unit -> ctx
 val set_seed : ctx -> int64 -> unit  (** [Random.init] *)
 
@@ -30,6 +32,19 @@ val box_prior : ?value:float -> float array -> float array -> logfn
 val flat : int -> logfn
 val box_proposal : float array -> proposal                    (* x_i + random_between (-h_i) h_i *)
 val uniform_wrapping : float array -> float array -> float array -> proposal  (* Mcmc.uniform_wrapping *)
+val independent_gaussian : float array -> float array -> proposal             (* test/mcmc_test.ml:119-127 *)
+val differential_evolution_proposal :
+  ?mode_hopping_frac:float -> float array Mcmc.mcmc_sample array -> proposal
+(** [Mcmc.differential_evolution_proposal] (mcmc.mli:215-218) with [to_float] = [from_float] = identity. *)
+
+(** Page-locked float64 Bigarrays (DMA at full PCIe rate for the host entry points).  Keep the record alive as long
+    as [data] is in use: the handle's finaliser frees the memory. *)
+module Pinned : sig
+  type 'a t = { data : 'a; handle : pinned_handle }
+  val array1 : ctx -> int -> (float, float64_elt, c_layout) Array1.t t
+  val array2 : ctx -> int -> int -> (float, float64_elt, c_layout) Array2.t t
+  val array3 : ctx -> int -> int -> int -> (float, float64_elt, c_layout) Array3.t t
+end
 
 val mcmc_array :
   ctx -> ?nbin:int -> ?nskip:int -> ?nchains:int -> int -> logfn -> logfn -> proposal -> float array ->
@@ -53,6 +68,31 @@ module Evidence : sig
   val evidence_lebesgue : ctx -> ?n:int -> ?eps:float -> float array Mcmc.mcmc_sample array -> float
   val evidence_direct : ctx -> ?n:int -> float array Mcmc.mcmc_sample array -> float
 end
+
+(** {2 Mcmc.rjmcmc_array (mcmc.mli:132-162)} *)
+type rj_into = Into_interp of Interp.interp_pdf * int | Into_gaussian of float array * float array
+(** how a chain proposes INTO a model: [Interp.draw] / [log (Interp.jump_prob ..)] ([int] > 0: the [*_high_level] forms
+    with that many objects per cell), or an independent Gaussian [(mu, sigma)] *)
+type rj_model = { rj_like : logfn; rj_prior : logfn; rj_prop : proposal; rj_into : rj_into; rj_p : float }
+val rjmcmc_array :
+  ctx -> ?nbin:int -> ?nskip:int -> ?nchains:int -> int -> rj_model -> rj_model -> float array -> float array ->
+  (int, int8_unsigned_elt, c_layout) Array2.t * (int * int)
+(** [rjmcmc_array ctx ?nbin ?nskip ?nchains n model_a model_b a b]: the model of every recorded sample ([n][nchains],
+    0 = A) and [Mcmc.rjmcmc_model_counts].  Raises [Failure] where the reference's [assert] on the priors fails. *)
+val rjmcmc_evidence_ratio : int * int -> float
+
+(** {2 Stats (stats.mli:41-55)} *)
+val multi_mean : ctx -> float array array -> float array
+val multi_std : ctx -> ?mean:float array -> float array array -> float array
+
+(** {2 Nested (nested.mli:50-69)} *)
+val nested_evidence :
+  ctx -> ?epsrel:float -> ?nmcmc:int -> ?nlive:int -> ?mode_hopping_frac:float -> ?batch:int -> ?max_points:int ->
+  logfn -> logfn -> float array -> float array ->
+  float * float * float array Mcmc.mcmc_sample array * float array
+(** ['a nested_output] of [Nested.nested_evidence] with [draw_prior] uniform on the box; [?batch] (default 1, the
+    reference's schedule) live points are replaced per iteration.  [Failure] as nested.ml:70-72. *)
+val log_total_error_estimate : float -> float -> int -> float
 
 (** [Stats.draw_uniform a b], [draw_gaussian mu sigma], [draw_cauchy x0 gamma] (stats.ml:89-91,113-128),
     [n] draws per call from the context's Philox stream. *)

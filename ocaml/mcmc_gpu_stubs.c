@@ -10,13 +10,14 @@
  *       -cclib -L../mcmc_ocaml_b200 -cclib -lmcmcgpu -a -o mcmc_gpu.cmxa
  *
  * Conventions: float64 Bigarray.Array{1,2,3} in c_layout carry all bulk data
- * (the host entry points copy to / from the device themselves; use
- * `Mcmc_gpu.pinned_*` allocators for pinned buffers); contexts and trees are
- * custom blocks with finalisers; every status other than MG_OK raises the
+ * (the host entry points copy to / from the device themselves; `Mcmc_gpu.Pinned`
+ * allocates page-locked ones, mcmcgpu_pinned_raw below); contexts, trees and pinned
+ * buffers are custom blocks with finalisers that share a reference-counted context; every status other than MG_OK raises the
  * exception the reference raises in the same situation:
  *   MG_EINVAL -> Invalid_argument, MG_EFAIL / MG_ECUDA / MG_ENOMEM -> Failure.
  * The runtime lock is released around every call that launches kernels.
  */
+#include <stdlib.h>
 #include <string.h>
 
 #include <caml/alloc.h>
@@ -29,12 +30,33 @@
 
 #include "mcmc_gpu.h"
 
-/* ---- handles ---------------------------------------------------------- */
-#define Ctx_val(v) (*((mg_ctx **)Data_custom_val(v)))
-#define Tree_val(v) (*((mg_kdtree **)Data_custom_val(v)))
+/* ---- handles ----------------------------------------------------------
+ * OCaml does not order finalisers: a tree (or a pinned buffer) may be finalised after the context it belongs to.
+ * Every handle therefore holds a reference on a small C box around the mg_ctx; the context is destroyed by whoever
+ * drops the last reference, so mg_kdtree_destroy / mg_free_pinned never see a dead context. */
+typedef struct { mg_ctx *ctx; long refs; } ctx_box;
+typedef struct { mg_kdtree *tree; ctx_box *box; } tree_box;
+typedef struct { void *ptr; ctx_box *box; } pinned_box;
+#define Box_val(v) (*((ctx_box **)Data_custom_val(v)))
+#define Ctx_val(v) (Box_val(v)->ctx)
+#define Treebox_val(v) ((tree_box *)Data_custom_val(v))
+#define Tree_val(v) (Treebox_val(v)->tree)
+#define Pinned_val(v) ((pinned_box *)Data_custom_val(v))
 
-static void ctx_finalize(value v) { if (Ctx_val(v)) { mg_ctx_destroy(Ctx_val(v)); Ctx_val(v) = NULL; } }
-static void tree_finalize(value v) { if (Tree_val(v)) { mg_kdtree_destroy(Tree_val(v)); Tree_val(v) = NULL; } }
+static void box_release(ctx_box *b) {
+  if (b && --b->refs == 0) { if (b->ctx) mg_ctx_destroy(b->ctx); free(b); }
+}
+static void ctx_finalize(value v) { box_release(Box_val(v)); Box_val(v) = NULL; }
+static void tree_finalize(value v) {
+  tree_box *t = Treebox_val(v);
+  if (t->tree) { mg_kdtree_destroy(t->tree); t->tree = NULL; }
+  box_release(t->box); t->box = NULL;
+}
+static void pinned_finalize(value v) {
+  pinned_box *p = Pinned_val(v);
+  if (p->ptr && p->box) { mg_free_pinned(p->box->ctx, p->ptr); p->ptr = NULL; }
+  box_release(p->box); p->box = NULL;
+}
 
 static struct custom_operations ctx_ops = {"mcmc_gpu.ctx", ctx_finalize, custom_compare_default, custom_hash_default,
                                            custom_serialize_default, custom_deserialize_default,
@@ -42,6 +64,9 @@ static struct custom_operations ctx_ops = {"mcmc_gpu.ctx", ctx_finalize, custom_
 static struct custom_operations tree_ops = {"mcmc_gpu.kdtree", tree_finalize, custom_compare_default,
                                             custom_hash_default, custom_serialize_default, custom_deserialize_default,
                                             custom_compare_ext_default, custom_fixed_length_default};
+static struct custom_operations pinned_ops = {"mcmc_gpu.pinned", pinned_finalize, custom_compare_default,
+                                              custom_hash_default, custom_serialize_default, custom_deserialize_default,
+                                              custom_compare_ext_default, custom_fixed_length_default};
 
 static void check(mg_ctx *ctx, int rc) {
   if (rc == MG_OK) return;
@@ -75,9 +100,32 @@ CAMLprim value mcmcgpu_ctx_create(value device, value seed) {
   mg_ctx *ctx = NULL;
   int rc = mg_ctx_create(Int_val(device), (uint64_t)Int64_val(seed), &ctx);
   if (rc != MG_OK) caml_failwith("cuda: cannot create a GPU context (no CPU fallback)");
-  v = caml_alloc_custom(&ctx_ops, sizeof(mg_ctx *), 0, 1);
-  Ctx_val(v) = ctx;
+  ctx_box *b = (ctx_box *)malloc(sizeof(ctx_box));
+  b->ctx = ctx; b->refs = 1;
+  v = caml_alloc_custom(&ctx_ops, sizeof(ctx_box *), 0, 1);
+  Box_val(v) = b;
   CAMLreturn(v);
+}
+
+/* ---- pinned float64 Bigarrays -------------------------------------------------------------------------------
+ * external pinned_raw : ctx -> int array (dims, 1..3) -> (float, float64_elt, c_layout) Genarray.t * pinned_handle
+ * The Bigarray is a view of page-locked host memory (mg_malloc_pinned): the host entry points then copy with DMA at
+ * full PCIe rate.  The handle's finaliser frees the memory; Mcmc_gpu.Pinned keeps handle and view together. */
+CAMLprim value mcmcgpu_pinned_raw(value ctx, value dims) {
+  CAMLparam2(ctx, dims);
+  CAMLlocal3(ba, h, r);
+  const int nd = (int)Wosize_val(dims);
+  if (nd < 1 || nd > 3) caml_invalid_argument("Mcmc_gpu.Pinned: 1 to 3 dimensions");
+  intnat d[3]; int64_t count = 1;
+  for (int i = 0; i < nd; ++i) { d[i] = Long_val(Field(dims, i)); if (d[i] < 0) caml_invalid_argument("Mcmc_gpu.Pinned: negative dimension"); count *= d[i]; }
+  void *p = NULL;
+  check(Ctx_val(ctx), mg_malloc_pinned(Ctx_val(ctx), count * (int64_t)sizeof(double), &p));
+  h = caml_alloc_custom(&pinned_ops, sizeof(pinned_box), 0, 1);
+  Pinned_val(h)->ptr = p; Pinned_val(h)->box = Box_val(ctx); Box_val(ctx)->refs++;
+  ba = caml_ba_alloc(CAML_BA_FLOAT64 | CAML_BA_C_LAYOUT | CAML_BA_EXTERNAL, nd, p, d);
+  r = caml_alloc_tuple(2);
+  Store_field(r, 0, ba); Store_field(r, 1, h);
+  CAMLreturn(r);
 }
 /* Random.init seed */
 CAMLprim value mcmcgpu_set_seed(value ctx, value seed) {
@@ -142,8 +190,8 @@ CAMLprim value mcmcgpu_interp_make(value ctx, value pts, value low, value high) 
   int rc = mg_kdtree_build(c, pp, N, D, pl, ph, 2, &t);
   caml_acquire_runtime_system();
   check(c, rc);
-  v = caml_alloc_custom(&tree_ops, sizeof(mg_kdtree *), 0, 1);
-  Tree_val(v) = t;
+  v = caml_alloc_custom(&tree_ops, sizeof(tree_box), 0, 1);
+  Treebox_val(v)->tree = t; Treebox_val(v)->box = Box_val(ctx); Box_val(ctx)->refs++;
   CAMLreturn(v);
 }
 /* Interpolate_pdf.jump_prob / jump_prob_high_level n (interpolate_pdf.ml:135-159) on a batch */

@@ -113,9 +113,42 @@ def test_runtime_plugin_matches_builtin(ctx, og):
     assert np.array_equal(eval_gpu(ctx, user, x), eval_gpu(ctx, builtin, x))
     with pytest.raises(InvalidArgument):                                        # does not compile
         P.register_source("broken", "return undefined_symbol;", 2, ctx=ctx)
-    from mcmc_ocaml_b200 import nested
-    with pytest.raises(InvalidArgument):                                        # not wired into Nested yet
-        nested.nested_evidence(banana, P.zero(2), [-1, -1], [1, 1], nlive=10, nmcmc=2, ctx=ctx)
+
+
+def test_runtime_plugins_in_rjmcmc_and_nested(ctx, og):
+    """User log-densities (NVRTC) as the closures of Mcmc.rjmcmc_array (mcmc.mli:132-140) and Nested.nested_evidence
+    (nested.mli:50-61): written with the built-in plugins' arithmetic they give the built-ins' runs value for value."""
+    from mcmc_ocaml_b200 import interpolate_pdf, nested
+    D = 3
+    mu, sig = [0.3, 0.5, 0.7], [0.1, 0.2, 0.05]
+    user = P.register_source("my_gaussian_again", GAUSS_BODY, D, np.concatenate([mu, sig]), ctx=ctx)
+    builtin = P.gauss_diag(mu, sig)
+    # ---- Nested: user likelihood under a built-in box prior, and the other way round
+    box_body = ("for (int i = 0; i < dim; ++i) { if (!(x[i] > p[i] && x[i] < p[dim + i])) return -__longlong_as_double(0x7FF0000000000000ll); }"
+                " return p[2 * dim];")
+    ubox = P.register_source("my_open_box", box_body, D, np.concatenate([np.zeros(D), np.ones(D), [0.0]]), ctx=ctx)
+    prior = P.box(np.zeros(D), np.ones(D), 0.0, closed=False)
+    runs = []
+    for like, pr in ((builtin, prior), (user, prior), (builtin, ubox), (user, ubox)):
+        ctx.set_seed(404)
+        runs.append(nested.nested_evidence(like, pr, np.zeros(D), np.ones(D), nlive=200, nmcmc=25, batch=32, ctx=ctx))
+    for r in runs[1:]:
+        assert np.array_equal(r.points, runs[0].points) and np.array_equal(r.log_likelihood, runs[0].log_likelihood)
+        assert r.log_evidence == runs[0].log_evidence
+    # ---- RJMCMC: user likelihood in model A
+    rng = np.random.default_rng(3)
+    pts = rng.normal(mu, sig, (20000, D)).clip(0.0, 1.0)
+    ip = interpolate_pdf.InterpPdf(pts, np.zeros(D), np.ones(D), ctx=ctx)
+    prop = P.wrap_proposal(np.zeros(D), np.ones(D), [0.05, 0.1, 0.03])
+    pb = P.box(np.zeros(D), np.ones(D), -0.7)
+    out = []
+    for like in (builtin, user):
+        A = mcmc.RjModel(like, P.box(np.zeros(D), np.ones(D), 0.0), prop, 0.5, interp=ip)
+        B = mcmc.RjModel(builtin, pb, prop, 0.5, interp=ip)
+        ctx.set_seed(505)
+        out.append(mcmc.rjmcmc_array(60, A, B, mu, mu, nskip=2, nbin=5, nchains=300, record_samples=True, ctx=ctx))
+    assert np.array_equal(out[0].model, out[1].model) and np.array_equal(out[0].block, out[1].block)
+    assert out[0].counts == out[1].counts and out[0].cross == out[1].cross and out[0].cross[1] > 0
 
 
 def test_radix_sort_sorted_and_stable(ctx):
@@ -239,3 +272,20 @@ def test_blob_validation_rejects_corrupt_headers(ctx):
     torch.cuda.synchronize()
     t2 = kd_tree.KdTree.from_blob(good.data_ptr(), nbytes, ctx=ctx)          # the untouched copy still loads
     assert t2.nnodes == t.nnodes
+
+
+def test_c_program_drives_the_abi():
+    """tests/c/test_capi.c: the call sequences of ocaml/mcmc_gpu_stubs.c (mg_mcmc_array, Interp, mg_rjmcmc_array,
+    Evidence, Stats, mg_nested_evidence) from plain C, no Python between the program and libmcmcgpu.so; checks the
+    reference's known answers (ratio 4.0 +- 0.1, nested evidence 1 within 2x its error)."""
+    import os
+    import subprocess
+    here = os.path.dirname(os.path.abspath(__file__))
+    exe = os.path.join(here, "c", "test_capi")
+    if not os.path.exists(exe):
+        subprocess.check_call(["gcc", "-O1", "-I" + os.path.join(here, "..", "include"), os.path.join(here, "c", "test_capi.c"),
+                               "-o", exe, "-L" + os.path.join(here, "..", "mcmc_ocaml_b200"), "-lmcmcgpu", "-lm",
+                               "-Wl,-rpath,$ORIGIN/../../mcmc_ocaml_b200"])
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.startswith("ok:")

@@ -147,3 +147,39 @@ def test_nested_first_call_on_a_fresh_context(og):
     o = og.nested_evidence(321, 0, like, PRIOR, [0, 0], [1, 1], nlive=128, nmcmc=30, batch=16)
     assert np.array_equal(g.points, o["pts"])
     assert g.log_evidence == pytest.approx(o["log_ev"], abs=1e-11)
+
+
+def test_plain_load_chain_kernel_equals_pipelined(ctx, monkeypatch):
+    """The chain kernel compiled at run time for user plugins (nested_kernel_dev.cuh: plain loads) and the pipelined
+    kernel of the built-in plugins read the same pre-drawn proposals and do the same arithmetic: same run."""
+    like = P.shell(np.full(5, 0.5), 0.3, 0.05)
+    prior = P.box(np.zeros(5), np.ones(5), 0.0)
+    ctx.set_seed(77)
+    a = nested.nested_evidence(like, prior, np.zeros(5), np.ones(5), nlive=300, nmcmc=40, batch=33, ctx=ctx)
+    monkeypatch.setenv("MCMC_GPU_NEST_SIMPLE", "1")
+    ctx.set_seed(77)
+    b = nested.nested_evidence(like, prior, np.zeros(5), np.ones(5), nlive=300, nmcmc=40, batch=33, ctx=ctx)
+    assert np.array_equal(a.points, b.points) and np.array_equal(a.log_likelihood, b.log_likelihood)
+    assert a.log_evidence == b.log_evidence and np.array_equal(a.log_weights, b.log_weights)
+
+
+def test_observer_sees_every_retired_point_in_order(ctx):
+    """?observer (nested.ml:123-125,136): called with each retired point, in retirement order"""
+    import ctypes as C
+    like = P.gauss_diag([0.5, 0.5], [0.1, 0.1])
+    seen = []
+    CB = C.CFUNCTYPE(None, C.c_void_p, C.POINTER(C.c_double), C.c_int32, C.c_double, C.c_double)
+
+    def cb(user, value, dim, ll, lp):
+        seen.append(([value[i] for i in range(dim)], ll, lp))
+    fn = CB(cb)
+    ctx.check(ctx.lib.mg_nested_set_observer(ctx.h, fn, None))
+    try:
+        ctx.set_seed(9)
+        r = nested.nested_evidence(like, PRIOR, [0, 0], [1, 1], nlive=100, nmcmc=20, batch=7, ctx=ctx)
+    finally:
+        ctx.check(ctx.lib.mg_nested_set_observer(ctx.h, None, None))
+    nret = len(r.log_likelihood) - 100
+    assert len(seen) == nret and nret > 0
+    assert np.array_equal(np.array([s[0] for s in seen]), r.points[:nret])
+    assert np.array_equal(np.array([s[1] for s in seen]), r.log_likelihood[:nret])
