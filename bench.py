@@ -61,7 +61,8 @@ def workload_config(Cn=NCHAINS, T=NSTEPS):
                         f"every sample recorded ([n][D+2][C] f64, {n * F * Cn * 8 / 1e9:.1f} GB/pass)",
             "chains_per_gpu": Cn, "dim": D, "steps_per_chain": T, "nskip": 1,
             "l2": "outputs (62.9 GB/pass) far exceed the 126 MB L2; no flush needed",
-            "rng": "Philox4x32-10, 52-bit uniforms, 6 blocks/step"}
+            "rng": "Philox4x32-10, 52 private bits per draw, 11 draws from 5 blocks (5 blocks per 10-D step)",
+            "stores": "recorded samples leave through the TMA: one cp.async.bulk.tensor.3d store per 4 samples of a warp"}
 
 
 def measured_peaks():
@@ -304,6 +305,28 @@ def leg_evidence(args, ctx, comm, dev, rank, world, peak):
                           "call": "mg_evidence_lebesgue with pinned host pts / ll / lp", "same_result": bool(zc.value == z)}
             del xh, llh, lph
         del x, ll, lp
+        torch.cuda.empty_cache()
+    if world > 1:
+        # weak scaling next to it: every rank integrates ITS OWN data set of N samples (e.g. one model per GPU), no
+        # collective on the data path; value = world * N / slowest rank
+        g2 = torch.Generator(device=dev); g2.manual_seed(1000 + rank)
+        x2 = torch.empty((N, Dd), dtype=torch.float64, device=dev).normal_(0.5, 0.05, generator=g2)
+        ll2 = (-0.91893853320467274178 - math.log(0.05) - 0.5 * ((x2 - 0.5) / 0.05) ** 2).sum(1)
+        lp2 = torch.zeros(N, dtype=torch.float64, device=dev)
+        torch.cuda.synchronize(dev)
+        for _ in range(2):
+            evidence.evidence_lebesgue_dev(x2.data_ptr(), ll2.data_ptr(), lp2.data_ptr(), N, Dd, n=64, eps=0.1, ctx=ctx)
+        tw = []
+        for _ in range(3):
+            sync_all(); t = time.perf_counter()
+            evidence.evidence_lebesgue_dev(x2.data_ptr(), ll2.data_ptr(), lp2.data_ptr(), N, Dd, n=64, eps=0.1, ctx=ctx)
+            ctx.sync(); tw.append(time.perf_counter() - t)
+        tt = torch.tensor([float(np.mean(tw))], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        if rank == 0:
+            out["weak"] = {"value": world * N / float(tt.item()), "unit": "evidence samples/s", "seconds": float(tt.item()),
+                           "scaling": "weak (one data set of N samples per rank, no data-path collective)"}
+        del x2, ll2, lp2
         torch.cuda.empty_cache()
     ctx.trim_pool()
     return out

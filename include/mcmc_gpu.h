@@ -83,6 +83,15 @@ int mg_ctx_last_kernel_stats(mg_ctx *ctx, char *name, int64_t name_cap,
  * MEASURED_PEAKS.json lacks (FP64 FMA TFLOP/s; streaming-store GB/s). */
 int mg_measure_fp64_tflops(mg_ctx *ctx, int reps, double *out_tflops);
 int mg_measure_store_gbs(mg_ctx *ctx, int64_t nbytes, int reps, double *out_gbs);
+/* FP64 tensor-core throughput (mma.sync m8n8k4.f64, DMMA) in TFLOP/s. */
+int mg_measure_dmma_tflops(mg_ctx *ctx, int reps, double *out_tflops);
+/* decision experiment for the north star's tensor-core clause: the quadratic
+ * form logc - 1/2 |L (x - mu)|^2 of M device points [D][M], D in {32, 64}, by
+ * variant 0 (one thread per point, the sampler plugin's FMA order) or 1 (one
+ * warp per 32 points on the FP64 tensor cores).  *ms: kernel time, best of reps. */
+int mg_debug_quadform(mg_ctx *ctx, int32_t variant, int32_t D, const double *mu,
+                      const double *Lpacked, double logc, const double *d_x,
+                      int64_t M, double *d_out, int32_t reps, double *ms);
 /* diagnostic: stable radix sort of n float64 keys on the device (the sort
  * under Kd_tree and Evidence); counts order / stability violations. */
 int mg_debug_sort_check(mg_ctx *ctx, const double *d_x, int64_t n, int64_t *violations);
@@ -300,6 +309,14 @@ int mg_kdtree_blob_size(const mg_kdtree *t, int64_t *nbytes);
 int mg_kdtree_blob_dev(const mg_kdtree *t, void **d_blob); /* borrowed */
 int mg_kdtree_from_blob_dev(mg_ctx *ctx, const void *d_blob, int64_t nbytes,
                             mg_kdtree **out);
+/* Interp.draw locates the cell of a STORED point by descent
+ * (interpolate_pdf.ml:114-119); that cell depends on the point only.  This
+ * locates it once for every stored point (N x (2 D + 2) doubles next to the
+ * tree, not inside the blob); leaf-level draws then gather one record instead
+ * of ~log2 N dependent node loads, with bit-identical results.
+ * mg_rjmcmc_array* enable it by themselves for trees of at most 8 dimensions
+ * (MCMC_GPU_DRAW_CACHE=0 turns that off). */
+int mg_kdtree_enable_draw_cache(mg_kdtree *t);
 /* Kd_tree.bounds_volume (kd_tree.ml:177-182) */
 double mg_bounds_volume(const double *low, const double *high, int32_t D);
 

@@ -561,8 +561,9 @@ extern "C" int mg_evidence_direct(mg_ctx *ctx, const double *pts, const double *
   return evidence_host(ctx, 1, pts, ll, lp, N, D, n, 0.0, out);
 }
 
-// bin/harmonic_evidence.ml:41-52: one CTA per bootstrap replicate.  Draw j of replicate b is lane j & 1 of
-// Philox block j >> 1 of stream (P_BOOT, b, 0) -- the sequence a sequential Random.int loop would consume.
+// bin/harmonic_evidence.ml:41-52: one CTA per bootstrap replicate.  Draw j of replicate b is draw j of stream
+// (P_BOOT, b, 0) -- the sequence a sequential Random.int loop would consume; a thread takes whole groups of 11 draws
+// (5 Philox blocks, rng.cuh).
 namespace mg {
 __global__ void inv_like_kernel(const double *__restrict__ ll, int64_t n, double *__restrict__ il) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
@@ -571,15 +572,13 @@ __global__ void inv_like_kernel(const double *__restrict__ ll, int64_t n, double
 __global__ void __launch_bounds__(EB)
 harmonic_bootstrap_kernel(const double *__restrict__ il, int64_t n, CallKey key, double *__restrict__ evs) {
   const uint64_t b = blockIdx.x;
-  const uint32_t c3 = (uint32_t)((b >> 32) & 0xFFFFu) | ((uint32_t)P_BOOT << 16);
   Comp acc;
-  const int64_t nblocks = (n + 1) / 2;
-  for (int64_t q = threadIdx.x; q < nblocks; q += EB) {
-    uint32_t w[4];
-    philox4x32_10((uint32_t)q, 0u, (uint32_t)b, c3, key.k0, key.k1, w);
-    const uint64_t l0 = ((uint64_t)w[0] << 32) | w[1], l1 = ((uint64_t)w[2] << 32) | w[3];
-    acc.add(il[__umul64hi(l0, (uint64_t)n)]);
-    if (2 * q + 1 < n) acc.add(il[__umul64hi(l1, (uint64_t)n)]);
+  const int64_t ngroups = (n + 10) / 11;
+  for (int64_t q = threadIdx.x; q < ngroups; q += EB) {
+    Rng r(key, P_BOOT, b, 0);
+    r.j = (uint32_t)(11 * q);                       // the cursor addresses draws: jump to this group
+    const int cnt = (int)((n - 11 * q < 11) ? n - 11 * q : 11);
+    for (int k = 0; k < cnt; ++k) acc.add(il[r.below((uint64_t)n)]);
   }
   const double t = block_reduce_comp<EB>(acc);
   if (threadIdx.x == 0) evs[b] = (double)n / t;
@@ -589,7 +588,7 @@ harmonic_bootstrap_kernel(const double *__restrict__ il, int64_t n, CallKey key,
 extern "C" int mg_evidence_harmonic_bootstrap(mg_ctx *ctx, const double *ll, int64_t N, int32_t nbstrap, double *out_evs) {
   if (!ctx) return MG_EINVAL;
   MG_REQUIRE(ctx, ll && out_evs && N >= 1 && nbstrap >= 1, "harmonic bootstrap: bad arguments");
-  MG_REQUIRE(ctx, (N + 1) / 2 < (1LL << 32), "harmonic bootstrap: too many samples");
+  MG_REQUIRE(ctx, N < (1LL << 31), "harmonic bootstrap: too many samples");
   MG_CUDA(ctx, cudaSetDevice(ctx->device));
   cudaStream_t s = ctx->stream;
   DevBuf<double> d_ll, d_il, d_evs;

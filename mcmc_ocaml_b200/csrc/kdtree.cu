@@ -335,6 +335,14 @@ int build_tree(mg_ctx *ctx, const double *d_pts, int64_t N, int D, const double 
   MG_REQUIRE(ctx, D >= 1 && D <= 64, "kd-tree: dim must be in 1..64");
   MG_REQUIRE(ctx, N < (1LL << 30), "kd-tree: too many points for int32 indices");
   if (min_split < 2) min_split = 2;
+  // MCMC_GPU_KD_BUILD=1 keeps the first builder (presorted index lists); the default is the second one (key columns
+  // moved level by level, subtrees finished in shared memory), which hands inputs it is not made for back to the first
+  static const int which = [] { const char *e = getenv("MCMC_GPU_KD_BUILD"); return e ? atoi(e) : 2; }();
+  if (which != 1) {
+    const int rc = build_tree_v2(ctx, d_pts, N, D, low, high, min_split, out);
+    if (rc != MG_V2_FALLBACK) return rc;
+    if (getenv("MCMC_GPU_DEBUG")) fprintf(stderr, "kd-tree: second builder handed the input back (ties / depth), first builder runs\n");
+  }
   // NaN coordinates are rejected (Pervasives.compare orders them, IEEE does not)
   DevBuf<int> d_flag;
   MG_CUDA(ctx, d_flag.alloc(1, s));
@@ -345,14 +353,6 @@ int build_tree(mg_ctx *ctx, const double *d_pts, int64_t N, int D, const double 
   MG_CUDA(ctx, cudaMemcpyAsync(&h_flag, d_flag.get(), sizeof(int), cudaMemcpyDeviceToHost, s));
   MG_CUDA(ctx, cudaStreamSynchronize(s));
   MG_REQUIRE(ctx, h_flag == 0, "kd-tree: NaN coordinate");
-  // MCMC_GPU_KD_BUILD=1 keeps the first builder (presorted index lists); the default is the second one (key columns
-  // moved level by level, subtrees finished in shared memory), which hands inputs it is not made for back to the first
-  static const int which = [] { const char *e = getenv("MCMC_GPU_KD_BUILD"); return e ? atoi(e) : 2; }();
-  if (which != 1) {
-    const int rc = build_tree_v2(ctx, d_pts, N, D, low, high, min_split, out);
-    if (rc != MG_V2_FALLBACK) return rc;
-    if (getenv("MCMC_GPU_DEBUG")) fprintf(stderr, "kd-tree: second builder handed the input back (ties / depth), first builder runs\n");
-  }
   return build_tree_v1(ctx, d_pts, N, D, low, high, min_split, out);
 }
 
@@ -549,6 +549,20 @@ __global__ void draw_kernel(KdView t, CallKey key, uint64_t draw_offset, int64_t
   for (int d = 0; d < t.D; ++d) out[i * t.D + d] = s.Q(d);
 }
 
+// the cell (box, count, node) that find_cell reaches from every stored point: KdView::dcache
+__global__ void draw_cache_kernel(KdView t, double *__restrict__ rec) {
+  extern __shared__ double smem[];
+  const KdScratch s = kd_scratch(smem, t.D);
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= t.N) return;
+  for (int d = 0; d < t.D; ++d) s.Q(d) = t.pts[k * t.D + d];
+  const int32_t id = kd_descend(t, s, 0);
+  double *o = rec + k * (2 * t.D + 2);
+  for (int d = 0; d < t.D; ++d) { o[d] = s.LO(d); o[t.D + d] = s.HI(d); }
+  o[2 * t.D] = (double)__ldg(t.count + id);
+  o[2 * t.D + 1] = (double)id;
+}
+
 static int query_block(int D) { return D <= 16 ? 128 : (D <= 32 ? 64 : 32); }
 
 template <class K>
@@ -587,7 +601,36 @@ extern "C" void mg_kdtree_destroy(mg_kdtree *t) {
   if (!t) return;
   if (t->ctx) { cudaSetDevice(t->ctx->device); cudaStreamSynchronize(t->ctx->stream); }
   if (t->owns_blob && t->d_blob) { if (t->ctx) cudaFreeAsync(t->d_blob, t->ctx->stream); else cudaFree(t->d_blob); }
+  if (t->d_draw_cache) { if (t->ctx) cudaFreeAsync(t->d_draw_cache, t->ctx->stream); else cudaFree(t->d_draw_cache); }
   delete t;
+}
+
+// Interp.draw picks a STORED point and locates its cell by descent (interpolate_pdf.ml:114-119).  That cell depends on
+// the point only, so it can be located once: this builds, for every stored point, the box / count / node the
+// descent reaches (N x (2 D + 2) doubles, outside the blob; after a broadcast every rank builds its own).  Draws at
+// leaf level (nstop = 0) then gather one record instead of walking ~log2 N dependent nodes; the values are the
+// descent's own, so draws and densities do not change by a bit.
+extern "C" int mg_kdtree_enable_draw_cache(mg_kdtree *t) {
+  if (!t || !t->ctx) return MG_EINVAL;
+  mg_ctx *ctx = t->ctx;
+  if (t->d_draw_cache) return MG_OK;
+  MG_CUDA(ctx, cudaSetDevice(ctx->device));
+  const int D = t->h.D;
+  const size_t bytes = (size_t)t->h.N * (2 * D + 2) * sizeof(double);
+  double *rec = nullptr;
+  cudaError_t e = cudaMallocAsync((void **)&rec, bytes, ctx->stream);
+  if (e != cudaSuccess) return set_err(ctx, MG_ENOMEM, "cuda: %s (draw cache of %zu bytes)", cudaGetErrorString(e), bytes);
+  const int block = query_block(D);
+  const size_t smem = kd_scratch_bytes(D, block);
+  int rc = prep_smem(ctx, draw_cache_kernel, smem);
+  if (rc) { cudaFreeAsync(rec, ctx->stream); return rc; }
+  draw_cache_kernel<<<(unsigned)((t->h.N + block - 1) / block), block, smem, ctx->stream>>>(t->view(), rec);
+  ctx->launches++;
+  e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  if (e != cudaSuccess) { cudaFreeAsync(rec, ctx->stream); return set_err(ctx, MG_ECUDA, "cuda: %s (draw cache)", cudaGetErrorString(e)); }
+  t->d_draw_cache = rec;
+  return MG_OK;
 }
 
 extern "C" int mg_kdtree_info(const mg_kdtree *t, int64_t *npoints, int32_t *dim, int64_t *nnodes, int32_t *nlevels) {

@@ -47,6 +47,10 @@ struct KdView {
   const double *pts;         // [N][D]
   int64_t N;
   int32_t D;
+  // optional: for every stored point the cell that find_cell reaches from it -- box low[D], high[D], object count,
+  // node id (2 D + 2 doubles per point), written by the same descent (mg_kdtree_enable_draw_cache).  Interp.draw
+  // then costs one gather instead of one dependent node load per level.
+  const double *dcache;
 };
 
 // Shared-memory scratch of one thread: q, lo, hi, each D doubles, laid out
@@ -134,6 +138,16 @@ __device__ __forceinline__ double kd_jump_prob(const KdView &t, const KdScratch 
 // written to s.Q(.).  Returns false where the reference raises.
 __device__ __forceinline__ bool kd_draw(const KdView &t, const KdScratch &s, int nstop, Rng &r, int32_t *node = nullptr) {
   const int64_t k = (int64_t)r.below((uint64_t)t.N);
+  if (t.dcache != nullptr && nstop == 0) {       // the cell of stored point k, located once by the same descent
+    const double *rec = t.dcache + k * (2 * t.D + 2);
+    for (int d = 0; d < t.D; ++d) {              // random_in_volume :80-86
+      const double lo = __ldg(rec + d), hi = __ldg(rec + t.D + d);
+      s.LO(d) = lo; s.HI(d) = hi;
+      s.Q(d) = lo + (hi - lo) * r.uniform();
+    }
+    if (node) *node = (int32_t)__ldg(rec + 2 * t.D + 1);
+    return true;
+  }
   const double *p = t.pts + k * t.D;
   for (int d = 0; d < t.D; ++d) s.Q(d) = __ldg(p + d);
   const int32_t id = kd_descend(t, s, nstop);
@@ -154,6 +168,7 @@ struct mg_kdtree {
   mg_ctx *ctx = nullptr;
   void *d_blob = nullptr;
   bool owns_blob = true;
+  double *d_draw_cache = nullptr;   // [N][2 D + 2], see KdView::dcache (not part of the blob: rebuilt per rank)
   mg::KdHeader h{};
   mg::KdView view() const {
     const char *b = (const char *)d_blob;
@@ -164,6 +179,7 @@ struct mg_kdtree {
     v.high = (const double *)(b + h.off_high);
     v.pts = (const double *)(b + h.off_pts);
     v.N = h.N; v.D = h.D;
+    v.dcache = d_draw_cache;
     return v;
   }
 };

@@ -67,25 +67,42 @@ __device__ __forceinline__ double ordered_to_f64(uint64_t k) {
   return __longlong_as_double((long long)b);
 }
 
+__device__ __forceinline__ uint64_t warp_min_u64(uint64_t v);
+__device__ __forceinline__ uint64_t warp_max_u64(uint64_t v);
+
 // ---- key columns ----------------------------------------------------------------------------------------------
 constexpr int V2_MK = 128;
+// Rows -> key columns through a shared-memory transpose; the same pass finds the root's bounds (bounds_of_objects of
+// level 0) and rejects NaN coordinates, so the data are read once for all three.
 __global__ void __launch_bounds__(256)
 v2_make_keys_kernel(const double *__restrict__ pts, int64_t N, int D, uint64_t *__restrict__ K, int32_t *__restrict__ perm,
-                    int32_t *__restrict__ seg) {
+                    int32_t *__restrict__ seg, uint64_t *__restrict__ root_lo, uint64_t *__restrict__ root_hi, int *__restrict__ nan_flag) {
   extern __shared__ double v2_mk_tile[];          // [V2_MK][DP], DP odd
+  __shared__ unsigned long long s_lo[64], s_hi[64];
   const int DP = D | 1;
+  if (threadIdx.x < 64) { s_lo[threadIdx.x] = ~0ull; s_hi[threadIdx.x] = 0ull; }
+  bool bad = false;
   for (int64_t i0 = (int64_t)blockIdx.x * V2_MK; i0 < N; i0 += (int64_t)gridDim.x * V2_MK) {
     const int cnt = (int)((N - i0 < V2_MK) ? N - i0 : V2_MK);
     const double *src = pts + i0 * D;
-    for (int k = threadIdx.x; k < cnt * D; k += 256) { const int r = k / D, c = k - r * D; v2_mk_tile[r * DP + c] = src[k]; }
     __syncthreads();
-    for (int k = threadIdx.x; k < D * V2_MK; k += 256) {
+    for (int k = threadIdx.x; k < cnt * D; k += 256) { const int r = k / D, c = k - r * D; const double v = src[k]; bad |= (v != v); v2_mk_tile[r * DP + c] = v; }
+    __syncthreads();
+    for (int k = threadIdx.x; k < D * V2_MK; k += 256) {      // a warp covers 32 consecutive points of ONE dimension
       const int d = k / V2_MK, r = k - d * V2_MK;
-      if (r < cnt) K[(int64_t)d * N + i0 + r] = f64_to_ordered(v2_mk_tile[r * DP + d]);
+      uint64_t key = 0ull;
+      if (r < cnt) { key = f64_to_ordered(v2_mk_tile[r * DP + d]); K[(int64_t)d * N + i0 + r] = key; }
+      const uint64_t mn = warp_min_u64(r < cnt ? key : ~0ull), mx = warp_max_u64(r < cnt ? key : 0ull);
+      if ((threadIdx.x & 31) == 0 && mn <= mx) { atomicMin(&s_lo[d], (unsigned long long)mn); atomicMax(&s_hi[d], (unsigned long long)mx); }
     }
     for (int r = threadIdx.x; r < cnt; r += 256) { perm[i0 + r] = (int32_t)(i0 + r); seg[i0 + r] = 0; }
-    __syncthreads();
   }
+  __syncthreads();
+  if (threadIdx.x < D && s_lo[threadIdx.x] <= s_hi[threadIdx.x]) {
+    atomicMin((unsigned long long *)root_lo + threadIdx.x, s_lo[threadIdx.x]);
+    atomicMax((unsigned long long *)root_hi + threadIdx.x, s_hi[threadIdx.x]);
+  }
+  if (bad) *nan_flag = 1;
 }
 
 __global__ void v2_init_kernel(V2Top t) {
@@ -971,7 +988,8 @@ int build_tree_v2(mg_ctx *ctx, const double *d_pts, int64_t N, int D, const doub
                   mg_kdtree **out) {
   cudaStream_t s = ctx->stream;
   // the largest subtree whose key columns fit the shared memory of one SM
-  const size_t smem_cap = 224 * 1024;
+  // (MCMC_GPU_KD_SMEM_KB caps the shared memory of a subtree CTA: ~110 lets two CTAs share an SM)
+  static const size_t smem_cap = [] { const char *e = getenv("MCMC_GPU_KD_SMEM_KB"); return (size_t)(e ? std::max(32, atoi(e)) : 224) * 1024; }();
   const int NMAX = v2_bottom_smem<2048, 1024>(D) <= smem_cap ? 2048 : v2_bottom_smem<1024, 1024>(D) <= smem_cap ? 1024
                    : v2_bottom_smem<512, 512>(D) <= smem_cap ? 512 : 256;
   if (N >= (1LL << 30)) return MG_V2_FALLBACK;
@@ -986,7 +1004,7 @@ int build_tree_v2(mg_ctx *ctx, const double *d_pts, int64_t N, int D, const doub
   DevBuf<int32_t> permA, permB, segA, segB, nb, ne, ndim, nleft, nspos, kth, below, nR, ebegin;
   DevBuf<double> nsplit;
   DevBuf<V2Sel> sel; DevBuf<uint32_t> hist; DevBuf<uint8_t> fix; DevBuf<V2Info> info;
-  DevBuf<unsigned long long> status; DevBuf<unsigned int> ticket;
+  DevBuf<unsigned long long> status; DevBuf<unsigned int> ticket; DevBuf<int> nan_flag;
   const int64_t ntiles = (N + V2_TILE - 1) / V2_TILE;
   MG_CUDA(ctx, KA.alloc((size_t)D * N, s)); MG_CUDA(ctx, KB.alloc((size_t)D * N, s));
   MG_CUDA(ctx, permA.alloc(N, s)); MG_CUDA(ctx, permB.alloc(N, s)); MG_CUDA(ctx, segA.alloc(N, s)); MG_CUDA(ctx, segB.alloc(N, s));
@@ -997,7 +1015,7 @@ int build_tree_v2(mg_ctx *ctx, const double *d_pts, int64_t N, int D, const doub
   MG_CUDA(ctx, sel.alloc(LC, s)); MG_CUDA(ctx, kth.alloc(LC, s)); MG_CUDA(ctx, below.alloc(LC, s)); MG_CUDA(ctx, hist.alloc((size_t)LC * 256, s));
   MG_CUDA(ctx, v.alloc(LC, s)); MG_CUDA(ctx, maxL.alloc(LC, s)); MG_CUDA(ctx, minR.alloc(LC, s)); MG_CUDA(ctx, fix.alloc(LC, s));
   MG_CUDA(ctx, nR.alloc(LC, s)); MG_CUDA(ctx, ebegin.alloc(LC, s)); MG_CUDA(ctx, info.alloc(1, s));
-  MG_CUDA(ctx, status.alloc((size_t)ntiles, s)); MG_CUDA(ctx, ticket.alloc(1, s));
+  MG_CUDA(ctx, status.alloc((size_t)ntiles, s)); MG_CUDA(ctx, ticket.alloc(1, s)); MG_CUDA(ctx, nan_flag.alloc(1, s));
   MG_CUDA(ctx, cudaMemsetAsync(hist.get(), 0, sizeof(uint32_t) * (size_t)LC * 256, s));
   V2Top t{N, D, min_split, LC, (int32_t)cap_top, info.get(), nb.get(), ne.get(), ndim.get(), nleft.get(), nspos.get(), nsplit.get(),
           lo.get(), hi.get(), sel.get(), kth.get(), below.get(), hist.get(), v.get(), maxL.get(), minR.get(), fix.get(), nR.get(), ebegin.get()};
@@ -1006,9 +1024,12 @@ int build_tree_v2(mg_ctx *ctx, const double *d_pts, int64_t N, int D, const doub
     const size_t mk_smem = (size_t)V2_MK * (D | 1) * sizeof(double);
     if (mk_smem > 48 * 1024) MG_CUDA(ctx, cudaFuncSetAttribute(v2_make_keys_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mk_smem));
     const int64_t gb = std::min<int64_t>((N + V2_MK - 1) / V2_MK, (int64_t)ctx->sm_count * 16);
-    v2_make_keys_kernel<<<(unsigned)gb, 256, mk_smem, s>>>(d_pts, N, D, KA.get(), permA.get(), segA.get());
-    MG_CHECK_LAUNCH(ctx);
     v2_init_kernel<<<1, 32, 0, s>>>(t);
+    MG_CHECK_LAUNCH(ctx);
+    v2_level_init_kernel<<<1, 64, 0, s>>>(t, 0, t.lo, t.hi);          // the root's bounds: filled by the key pass
+    MG_CHECK_LAUNCH(ctx);
+    MG_CUDA(ctx, cudaMemsetAsync(nan_flag.get(), 0, sizeof(int), s));
+    v2_make_keys_kernel<<<(unsigned)gb, 256, mk_smem, s>>>(d_pts, N, D, KA.get(), permA.get(), segA.get(), t.lo, t.hi, nan_flag.get());
     MG_CHECK_LAUNCH(ctx);
   }
   uint64_t *lo_next = lo2.get(), *hi_next = hi2.get();
@@ -1017,12 +1038,7 @@ int build_tree_v2(mg_ctx *ctx, const double *d_pts, int64_t N, int D, const doub
   auto run_level = [&](int L) -> int {
     const int64_t nodes_cap = std::min<int64_t>(LC, 1LL << std::min(L, 30));
     const unsigned gnode = (unsigned)((nodes_cap + 127) / 128);
-    if (L == 0) {    // deeper levels received their bounds from the scatter pass of their parents
-      v2_level_init_kernel<<<(unsigned)std::min<int64_t>((nodes_cap * D + 255) / 256, 4096), 256, 0, s>>>(t, L, t.lo, t.hi);
-      MG_CHECK_LAUNCH(ctx);
-      v2_bounds_kernel<<<gtile, V2_TB, 0, s>>>(t, L, Kin, sin, t.lo, t.hi);
-      MG_CHECK_LAUNCH(ctx);
-    }
+    // (the root's bounds came with the key pass, deeper levels received theirs from the scatter pass of their parents)
     v2_node_kernel<<<gnode, 128, 0, s>>>(t, L);
     MG_CHECK_LAUNCH(ctx);
     for (int pass = 0; pass < 8; ++pass) {
@@ -1056,8 +1072,13 @@ int build_tree_v2(mg_ctx *ctx, const double *d_pts, int64_t N, int D, const doub
   V2Info h_info;
   int Lh = L0;                                   // the hand-over level
   for (;;) {
+    int h_nan = 0;
     MG_CUDA(ctx, cudaMemcpyAsync(&h_info, info.get(), sizeof h_info, cudaMemcpyDeviceToHost, s));
+    MG_CUDA(ctx, cudaMemcpyAsync(&h_nan, nan_flag.get(), sizeof(int), cudaMemcpyDeviceToHost, s));
     MG_CUDA(ctx, cudaStreamSynchronize(s));
+    // NaN coordinates are rejected (Pervasives.compare orders them, IEEE does not); as keys they are ordinary
+    // integers, so the levels above ran to completion on them
+    MG_REQUIRE(ctx, h_nan == 0, "kd-tree: NaN coordinate");
     if (h_info.overflow) return MG_V2_FALLBACK;
     if (h_info.maxsize[Lh] <= NMAX) break;
     if (Lh >= L0 + V2_EXTRA) return MG_V2_FALLBACK;   // heavy ties: subtrees do not shrink -> first builder

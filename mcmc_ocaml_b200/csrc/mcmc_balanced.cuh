@@ -25,9 +25,28 @@
 // whole process): the warp writes MG_DEVERR_MH_QUEUE into the context's device error word and leaves; every other
 // waiter polls that word and leaves too, and the host reports MG_ECUDA for the call (common.cuh poll_device_error).
 #pragma once
+#include <cuda.h>   // CUtensorMap (the encoder itself is fetched from the driver at run time, mcmc_kernel.cuh)
+
 #include "mcmc_kernel_dev.cuh"
 
 namespace mg {
+
+// ---- recorded samples through the TMA ------------------------------------------------------------------------------
+// Recording a sample with plain stores costs ~45 instructions (12 STG.64 and their 64-bit address arithmetic) on a
+// kernel that is bound by instruction issue.  With kTma the warp instead parks its D + 2 fields in shared memory
+// (one STS.64 with an immediate offset per field) and, every kTmaSteps recorded samples, ONE elected lane hands the
+// [kTmaSteps][D + 2][32 chains] tile to the TMA as a 3-D bulk tensor store (cp.async.bulk.tensor.3d, UTMASTG in SASS)
+// into the [n][D + 2][C] block; the box is clipped by the hardware at the ragged last group.  The tile is written
+// again only ~kTmaSteps steps later, so the wait for the TMA to have READ it (wait_group.read) never stalls.
+constexpr int kTmaSteps = 4;
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap *tm, uint32_t smem_addr, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];"
+               :: "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(c2), "r"(smem_addr) : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void tma_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 #ifndef MG_MHB_MAXNREG
 #define MG_MHB_MAXNREG(D) MG_MH_MAXNREG(D)
@@ -66,10 +85,12 @@ static __global__ void mh_queue_init_kernel(MhQueue q) {
 // the chain's own slot-0 sample -- Stats.multi_mean / multi_std of the block without reading the block back
 // (the finishing kernel pools the chains with the parallel-variance formula, stats.cu).  The accumulators live in
 // registers (three warps per scheduler leave room for 168), the pivots in shared memory.
-template <class Like, class Prior, class Prop, int D, bool kMom>
+template <class Like, class Prior, class Prop, int D, bool kMom, bool kTma = false>
 __global__ void __maxnreg__(kMom ? MG_MHB_MOM_MAXNREG(D) : MG_MHB_MAXNREG(D))
-mh_balanced_kernel(const __grid_constant__ MhArgs<Like, Prior, Prop, D> a, const __grid_constant__ MhQueue q) {
+mh_balanced_kernel(const __grid_constant__ MhArgs<Like, Prior, Prop, D> a, const __grid_constant__ MhQueue q,
+                   const __grid_constant__ CUtensorMap tmap) {
   static_assert(MH_BLOCK == 32, "one warp per CTA");
+  __shared__ __align__(128) double s_tile[kTma ? kTmaSteps * (D + 2) * MH_BLOCK : 1];   // [step][field][lane]
   const int dd = Prop::kStaticDim ? D : a.d;
   const int F = dd + 2;
   const int64_t C = a.C;
@@ -154,8 +175,25 @@ mh_balanced_kernel(const __grid_constant__ MhArgs<Like, Prior, Prop, D> a, const
       m1[i] = m1[i] + dv;
       m2[i] = fma(dv, dv, m2[i]);
     };
+    int pend = 0;                       // samples parked in the tile
+    bool tile_in_flight = false;        // the TMA may still be reading the tile
+    int64_t tile_slot = 0;              // output slot of the tile's first sample
+    auto flush_tile = [&]() {           // kTmaSteps samples of 32 chains: one bulk tensor store by one lane
+      fence_proxy_async_smem();         // the generic-proxy writes of every lane, before the async proxy reads them
+      __syncwarp();
+      if (lane == 0) tma_store_3d(&tmap, (uint32_t)__cvta_generic_to_shared(s_tile), (int)(grp * MH_BLOCK), 0, (int)tile_slot);
+      tile_slot += kTmaSteps; pend = 0; tile_in_flight = true;
+    };
     auto record = [&](bool first) {
-      if (out) {
+      if (kTma && !first) {              // (the launcher selects kTma only with a sample block)
+        if (pend == 0 && tile_in_flight) { if (lane == 0) tma_wait_read(); __syncwarp(); tile_in_flight = false; }
+        double *tp = s_tile + (size_t)pend * F * MH_BLOCK + lane;
+#pragma unroll
+        for (int i = 0; i < D; ++i)
+          if (i < dd) tp[i * MH_BLOCK] = x[i];
+        tp[dd * MH_BLOCK] = ll; tp[(dd + 1) * MH_BLOCK] = lp;
+        if (++pend == kTmaSteps) flush_tile();
+      } else if (out) {
         store_sample<D>(out, pitch32, C, dd, x, ll, lp);
         out += sample_stride;
       }
@@ -185,6 +223,7 @@ mh_balanced_kernel(const __grid_constant__ MhArgs<Like, Prior, Prop, D> a, const
       const int64_t slot1 = (slot0 + q.seg_slots < a.n) ? slot0 + q.seg_slots : a.n;
       if (a.nbin == 0 && j == 0 && a.n > 0 && a.record_first) record(true);  // no burn-in: slot 0 is the start point
       if (out) out = a.samples + c + (slot0 - (a.record_first ? 0 : 1)) * sample_stride;
+      tile_slot = slot0 - (a.record_first ? 0 : 1);
       t = a.t0 + (uint64_t)(a.nbin + (slot0 - 1) * a.nskip);
       for (int64_t slot = slot0; slot < slot1; ++slot) {
         for (int64_t kk = 0; kk < a.nskip; ++kk, ++t) {
@@ -192,6 +231,21 @@ mh_balanced_kernel(const __grid_constant__ MhArgs<Like, Prior, Prop, D> a, const
           nacc += mh_step<Like, Prior, Prop, D>(a, sl, sp, sj, r, x, ll, lp);
         }
         record(false);
+      }
+      if (kTma) {
+        if (pend > 0) {                 // a ragged tail (fewer than kTmaSteps samples left in the segment): plain stores
+          __syncwarp();
+          if (live) {
+            double *o = a.samples + c + tile_slot * sample_stride;
+            for (int sft = 0; sft < pend; ++sft, o += sample_stride)
+              for (int i = 0; i < F; ++i) __stcs(o + (int64_t)i * C, s_tile[((size_t)sft * F + i) * MH_BLOCK + lane]);
+          }
+          __syncwarp();
+          pend = 0;
+        }
+        if (lane == 0) tma_wait_all();  // the group's next segment may run anywhere: its stores must follow these
+        __syncwarp();
+        tile_in_flight = false;
       }
     }
 

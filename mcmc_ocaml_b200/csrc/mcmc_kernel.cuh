@@ -21,6 +21,31 @@ namespace mg {
 constexpr int64_t kSegSteps = 128;
 static_assert(kDevErrMhQueue == MG_DEVERR_MH_QUEUE, "device error codes out of sync");
 
+// cuTensorMapEncodeTiled, fetched from the driver (no link-time dependency on libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static inline EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = [] {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) != cudaSuccess || qr != cudaDriverEntryPointSuccess) p = nullptr;
+    return (EncodeTiledFn)p;
+  }();
+  return fn;
+}
+// the [slots][F][C] float64 sample block as a 3-D tensor, box = [kTmaSteps][F][32 chains]
+static inline bool make_sample_tensor_map(CUtensorMap *tm, double *samples, int64_t slots, int F, int64_t C) {
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (!enc || !samples || slots < 1 || (C & 1) || ((uintptr_t)samples & 15) || C >= (1ll << 32) || slots >= (1ll << 31)) return false;
+  const cuuint64_t gdim[3] = {(cuuint64_t)C, (cuuint64_t)F, (cuuint64_t)slots};
+  const cuuint64_t gstride[2] = {(cuuint64_t)C * 8, (cuuint64_t)C * 8 * (cuuint64_t)F};
+  const cuuint32_t box[3] = {(cuuint32_t)MH_BLOCK, (cuuint32_t)F, (cuuint32_t)kTmaSteps};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, samples, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 template <class Like, class Prior, class Prop, int D>
 static int launch_mh(mg_ctx *ctx, const MhArgs<Like, Prior, Prop, D> &a) {
   const int64_t ngroups = (a.C + MH_BLOCK - 1) / MH_BLOCK;
@@ -35,8 +60,8 @@ static int launch_mh(mg_ctx *ctx, const MhArgs<Like, Prior, Prop, D> &a) {
     // own occupancy sizes the persistent grid
     const bool with_mom = ctx->mh_mom != nullptr && a.t0 == 0 && a.record_first && a.samples != nullptr;
     int occ = 0;
-    if (with_mom) MG_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, mh_balanced_kernel<Like, Prior, Prop, D, true>, MH_BLOCK, 0));
-    else MG_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, mh_balanced_kernel<Like, Prior, Prop, D, false>, MH_BLOCK, 0));
+    if (with_mom) MG_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, mh_balanced_kernel<Like, Prior, Prop, D, true, false>, MH_BLOCK, 0));
+    else MG_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, mh_balanced_kernel<Like, Prior, Prop, D, false, false>, MH_BLOCK, 0));
     int64_t grid = std::min<int64_t>((int64_t)std::max(occ, 1) * ctx->sm_count, (ngroups / nsched) * nsched);
     if (const char *e = getenv("MCMC_GPU_MH_GRID")) grid = std::max(1, atoi(e));
     if (grid != ngroups) {
@@ -78,18 +103,36 @@ static int launch_mh(mg_ctx *ctx, const MhArgs<Like, Prior, Prop, D> &a) {
     MG_CHECK_LAUNCH(ctx);
     // running moments of the recorded samples (requested through the context by mg_mcmc_array_resident): the
     // variant with the accumulators is a separate instantiation, the plain kernel does not pay for them
+    // Recorded samples leave through the TMA (one bulk tensor store per kTmaSteps samples of a warp) when the block's
+    // shape allows a tensor map (even C, compile-time dimension, a tile of at most 16 KB); plain stores otherwise.
+    // MCMC_GPU_MH_TMA=0 keeps the plain stores.
+    CUtensorMap tmap;
+    memset(&tmap, 0, sizeof tmap);
+    static const bool want_tma = [] { const char *e = getenv("MCMC_GPU_MH_TMA"); return e ? atoi(e) != 0 : true; }();
+    const int F = (Prop::kStaticDim ? D : a.d) + 2;
+    const int64_t slots = a.n - (a.record_first ? 0 : 1);
+    const bool use_tma = want_tma && Prop::kStaticDim && (D + 2) * kTmaSteps * MH_BLOCK * 8 <= 16 * 1024 && a.samples != nullptr &&
+                         make_sample_tensor_map(&tmap, a.samples, slots, F, a.C);
     time_begin(ctx);
-    kt_reset(ctx, with_mom ? (const void *)mh_balanced_kernel<Like, Prior, Prop, D, true>
-                           : (const void *)mh_balanced_kernel<Like, Prior, Prop, D, false>);
-    kt_start(ctx);
-    if (with_mom) {
-      MhArgs<Like, Prior, Prop, D> am = a;
-      am.mom = ctx->mh_mom;
-      mh_balanced_kernel<Like, Prior, Prop, D, true><<<(unsigned)grid, MH_BLOCK, 0, ctx->stream>>>(am, q);
-      ctx->mh_mom_done = true;
+    MhArgs<Like, Prior, Prop, D> am = a;
+    if (with_mom) { am.mom = ctx->mh_mom; ctx->mh_mom_done = true; }
+    const void *fn;
+#define MG_MHB_LAUNCH(MOM, TMA)                                                                         \
+    do {                                                                                                \
+      fn = (const void *)mh_balanced_kernel<Like, Prior, Prop, D, MOM, TMA>;                            \
+      kt_reset(ctx, fn); kt_start(ctx);                                                                 \
+      mh_balanced_kernel<Like, Prior, Prop, D, MOM, TMA><<<(unsigned)grid, MH_BLOCK, 0, ctx->stream>>>(am, q, tmap); \
+    } while (0)
+    if constexpr (Prop::kStaticDim && (D + 2) * kTmaSteps * MH_BLOCK * 8 <= 16 * 1024) {
+      if (with_mom && use_tma) MG_MHB_LAUNCH(true, true);
+      else if (with_mom) MG_MHB_LAUNCH(true, false);
+      else if (use_tma) MG_MHB_LAUNCH(false, true);
+      else MG_MHB_LAUNCH(false, false);
     } else {
-      mh_balanced_kernel<Like, Prior, Prop, D, false><<<(unsigned)grid, MH_BLOCK, 0, ctx->stream>>>(a, q);
+      if (with_mom) MG_MHB_LAUNCH(true, false);
+      else MG_MHB_LAUNCH(false, false);
     }
+#undef MG_MHB_LAUNCH
     kt_stop(ctx);
     MG_CHECK_LAUNCH(ctx);
     time_end(ctx);

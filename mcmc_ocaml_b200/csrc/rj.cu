@@ -87,7 +87,16 @@ extern "C" int mg_rjmcmc_array(mg_ctx *ctx, const mg_rj_model *A, const mg_rj_mo
     m.p = M[k]->p; m.log_p = log(M[k]->p);   // mcmc.ml:91, host libm like the reference
     m.into_p = nullptr;
     memset(&m.tree, 0, sizeof m.tree);
-    if (m.into_kind == MG_INTO_INTERP) m.tree = M[k]->into.tree->view();
+    if (m.into_kind == MG_INTO_INTERP) {
+      // leaf-level Interp.draw through the per-point cell records (kdtree.cu: mg_kdtree_enable_draw_cache)
+      static const bool want_cache = [] { const char *e = getenv("MCMC_GPU_DRAW_CACHE"); return e ? atoi(e) != 0 : true; }();
+      mg_kdtree *tr = const_cast<mg_kdtree *>(M[k]->into.tree);
+      if (want_cache && m.nstop == 0 && tr->h.D <= 8 && !tr->d_draw_cache && tr->ctx == ctx && C * (cfg->nbin + n * cfg->nskip) >= tr->h.N) {
+        if ((rc = mg_kdtree_enable_draw_cache(tr)) == MG_ENOMEM) rc = MG_OK;   // no room: descend as before
+        if (rc) return rc;
+      }
+      m.tree = M[k]->into.tree->view();
+    }
     else {
       MG_CUDA(ctx, upload(dinto[k], M[k]->into.params, (size_t)M[k]->into.nparams, s));
       m.into_p = dinto[k].get();

@@ -75,37 +75,53 @@ inline CallKey derive_key(uint64_t seed, uint64_t epoch) {
   return CallKey{w[0], w[1]};
 }
 
-// Sequential cursor over the draws of one (purpose, g, step).  In unrolled
-// code the cursor is a compile-time constant and the `(j & 1) == 0` tests fold.
+// Sequential cursor over the draws of one (purpose, g, step).  Draws come in groups of 11 from 5 Philox blocks
+// (oracle/og_rng.hpp has the specification): draws 0..9 of a group are the two 64-bit lanes of blocks 0..4 (low 20
+// bits of the first word : second word), draw 10 is assembled from the 12 top bits of the first words of blocks
+// 0..2, which the lane draws leave unused.  A 10-D proposal plus its accept test is one group: 5 blocks per step.
+// In unrolled code the cursor is a compile-time constant and the group arithmetic folds away.
 struct Rng {
   uint32_t k0, k1, c1, c2, c3;
   uint32_t w[4];
   uint32_t j;
+  uint32_t spA, spB, spC;   // spare bits of the group's blocks 0, 1, 2: (s0 << 12 | s1), (s2 << 12 | s3), s4
   const RoundKeys *rk;   // optional precomputed round keys (kernel argument block)
   __device__ __forceinline__ Rng(CallKey ck, uint32_t purpose, uint64_t g, uint64_t step, const RoundKeys *rk_ = nullptr)
       : k0(ck.k0), k1(ck.k1), c1((uint32_t)step), c2((uint32_t)g),
         c3((uint32_t)((g >> 32) & 0xFFFFu) | ((purpose & 0xFFu) << 16) |
            (uint32_t)(((step >> 32) & 0xFFu) << 24)),
-        j(0), rk(rk_) {}
+        j(0), spA(0), spB(0), spC(0), rk(rk_) {}
   __device__ __forceinline__ void gen(uint32_t blk) {
     if (rk) philox4x32_10_rk(blk, c1, c2, c3, *rk, w); else philox4x32_10(blk, c1, c2, c3, k0, k1, w);
   }
-  __device__ __forceinline__ uint64_t lane() {
-    if ((j & 1u) == 0u) gen(j >> 1);
-    const uint32_t a = (j & 1u) ? w[2] : w[0];
-    const uint32_t b = (j & 1u) ? w[3] : w[1];
+  // (high 20 bits, low 32 bits) of the next draw's 52 private bits
+  __device__ __forceinline__ void next52(uint32_t &hi20, uint32_t &lo32) {
+    const uint32_t m = j / 11u, i = j - 11u * m;
+    if (i < 10u) {
+      if ((i & 1u) == 0u) {
+        const uint32_t gi = i >> 1;
+        gen(5u * m + gi);
+        if (gi == 0u) spA = ((w[0] >> 20) << 12) | (w[2] >> 20);
+        else if (gi == 1u) spB = ((w[0] >> 20) << 12) | (w[2] >> 20);
+        else if (gi == 2u) spC = w[0] >> 20;
+      }
+      hi20 = ((i & 1u) ? w[2] : w[0]) & 0xFFFFFu;
+      lo32 = (i & 1u) ? w[3] : w[1];
+    } else {
+      hi20 = spA >> 4;
+      lo32 = (spA << 28) | (spB << 4) | (spC >> 8);
+    }
     ++j;
-    return ((uint64_t)a << 32) | b;
   }
-  // Random.float 1.0: 52 random mantissa bits, [0, 1).  The mantissa is the
-  // low 20 bits of the first word followed by the second word: one LOP3 to
-  // build the high half, the low half is the Philox word itself.
+  // the draw as a 64-bit word with its 52 bits on top (what Random.int multiplies)
+  __device__ __forceinline__ uint64_t lane() {
+    uint32_t h, l; next52(h, l);
+    return (((uint64_t)h << 32) | l) << 12;
+  }
+  // Random.float 1.0: 52 random mantissa bits, [0, 1)
   __device__ __forceinline__ double uniform12() {  // 1 + Random.float 1.0, in [1, 2)
-    if ((j & 1u) == 0u) gen(j >> 1);
-    const uint32_t a = (j & 1u) ? w[2] : w[0];
-    const uint32_t b = (j & 1u) ? w[3] : w[1];
-    ++j;
-    return __hiloint2double((int)((a & 0xFFFFFu) | 0x3FF00000u), (int)b);
+    uint32_t h, l; next52(h, l);
+    return __hiloint2double((int)(h | 0x3FF00000u), (int)l);
   }
   __device__ __forceinline__ double uniform() { return uniform12() - 1.0; }
   // Random.int n

@@ -12,11 +12,16 @@
 //   block      B(purpose, g, step, blk) = Philox4x32-10(
 //                  ctr = (blk, step_lo, g_lo,
 //                         g_hi16 | purpose << 16 | step_hi8 << 24), key = call key)
-//   draw j of (purpose, g, step) = the 64-bit lane  (w[2(j&1)] << 32 | w[2(j&1)+1])
-//                  of block j >> 1
-//   Random.float 1.0  ->  u52 = bits(0x3FF<<52 | lane & (2^52-1)) - 1.0   in [0,1)
-//                         (mantissa = low 20 bits of the first word : second word)
-//   Random.int n      ->  mulhi64(lane, n)
+//   draw j of (purpose, g, step): 52 private bits P.  Draws come in groups of 11 from 5 blocks (640 bits for
+//                  11 x 52 = 572): with m = j / 11, i = j % 11,
+//                    i < 10 : block 5m + i/2, words (a, b) = (w[2(i&1)], w[2(i&1)+1]),
+//                             P = (a & 0xFFFFF) << 32 | b          (low 20 bits of the first word : second word)
+//                    i = 10 : the 12 TOP bits of the first words that the ten draws above leave unused,
+//                             s0 = w0(5m) >> 20, s1 = w2(5m) >> 20, s2 = w0(5m+1) >> 20, s3 = w2(5m+1) >> 20,
+//                             s4 = w0(5m+2) >> 20:   P = s0<<40 | s1<<28 | s2<<16 | s3<<4 | s4>>8
+//                  (a 10-D proposal + accept test = 11 uniforms = 5 Philox blocks per Metropolis-Hastings step)
+//   Random.float 1.0  ->  u52 = bits(0x3FF<<52 | P) - 1.0   in [0,1)
+//   Random.int n      ->  mulhi64(P << 12, n)               (every draw uses its own 52 bits only)
 //
 // Philox4x32-10: Salmon et al., "Parallel random numbers: as easy as 1, 2, 3"
 // (SC'11); checked against the Random123 known-answer vectors in
@@ -75,21 +80,38 @@ struct Rng {
     ctr[3] = (uint32_t)((g >> 32) & 0xFFFFu) | ((purpose & 0xFFu) << 16) |
              (uint32_t)(((step >> 32) & 0xFFu) << 24);
   }
-  inline uint64_t lane() {
-    if ((j & 1u) == 0u) { ctr[0] = j >> 1; Philox::block(ctr, key, w); }
-    uint32_t a = w[2 * (j & 1u)], b = w[2 * (j & 1u) + 1];
+  uint32_t sp[5] = {0, 0, 0, 0, 0};  // spare top-12-bit pieces of the current group's first three blocks
+  // the 52 private bits of the next draw
+  inline uint64_t bits52() {
+    const uint32_t m = j / 11u, i = j % 11u;
+    uint64_t P;
+    if (i < 10u) {
+      if ((i & 1u) == 0u) {
+        const uint32_t gi = i >> 1;
+        ctr[0] = 5u * m + gi; Philox::block(ctr, key, w);
+        if (gi == 0u) { sp[0] = w[0] >> 20; sp[1] = w[2] >> 20; }
+        else if (gi == 1u) { sp[2] = w[0] >> 20; sp[3] = w[2] >> 20; }
+        else if (gi == 2u) { sp[4] = w[0] >> 20; }
+      }
+      const uint32_t a = w[2 * (i & 1u)], b = w[2 * (i & 1u) + 1];
+      P = ((uint64_t)(a & 0xFFFFFu) << 32) | b;
+    } else {
+      P = ((uint64_t)sp[0] << 40) | ((uint64_t)sp[1] << 28) | ((uint64_t)sp[2] << 16) | ((uint64_t)sp[3] << 4) | (uint64_t)(sp[4] >> 8);
+    }
     ++j;
-    return ((uint64_t)a << 32) | b;
+    return P;
   }
+  // the draw as a 64-bit word with its 52 bits on top (what Random.int multiplies)
+  inline uint64_t lane() { return bits52() << 12; }
   // Random.float 1.0
   inline double uniform() {
-    uint64_t bits = (0x3FFull << 52) | (lane() & 0xFFFFFFFFFFFFFull);
+    uint64_t bits = (0x3FFull << 52) | bits52();
     double d; std::memcpy(&d, &bits, 8);
     return d - 1.0;
   }
   // 1 + Random.float 1.0, in [1, 2): the raw mantissa pattern, no subtraction
   inline double uniform12() {
-    uint64_t bits = (0x3FFull << 52) | (lane() & 0xFFFFFFFFFFFFFull);
+    uint64_t bits = (0x3FFull << 52) | bits52();
     double d; std::memcpy(&d, &bits, 8);
     return d;
   }

@@ -77,14 +77,22 @@ int main(void) {
   CHECK(ctx, mg_rjmcmc_jump_counters(ctx, &jp_prop, &jp_acc));
   EXPECT(jp_prop > 0 && jp_acc > 0 && jp_acc <= jp_prop);
 
-  /* ---- Evidence on the unit-square chain: all three estimators ~ 1 (evidence_test.ml:52-81 style) ---------------- */
+  /* ---- Evidence on a chain of a normalised 2-D Gaussian in the unit box: all three estimators ~ 1
+   *      (evidence_test.ml:52-81: direct +- 0.5, Lebesgue +- 0.5; the harmonic mean is noisier) ---------------------- */
+  double gl[4] = {0.5, 0.5, 0.1, 0.1};
+  mg_logfn glike = {MG_FN_GAUSS_DIAG, D, 1.0, gl, 4};
+  double gwrap[6] = {0, 0, 1, 1, 0.3, 0.3};
+  mg_proposal gprop = {MG_PROP_WRAP, D, gwrap, 6};
+  double *s3 = malloc(sizeof(double) * C * n * (D + 2));
+  CHECK(ctx, mg_mcmc_array(ctx, &glike, &prior, &gprop, &cfg, x0, s3, NULL, NULL));
   const int64_t N = C * n;
-  double *ll = calloc(N, sizeof(double)), *lp = calloc(N, sizeof(double));
+  double *p3 = malloc(sizeof(double) * N * D), *ll = malloc(sizeof(double) * N), *lp = malloc(sizeof(double) * N);
+  for (int64_t i = 0; i < N; ++i) { p3[i * D] = s3[i * (D + 2)]; p3[i * D + 1] = s3[i * (D + 2) + 1]; ll[i] = s3[i * (D + 2) + 2]; lp[i] = s3[i * (D + 2) + 3]; }
   double zh = 0, zl = 0, zd = 0;
   CHECK(ctx, mg_evidence_harmonic_mean(ctx, ll, N, &zh));
-  CHECK(ctx, mg_evidence_lebesgue(ctx, p1, ll, lp, N, D, 64, 0.1, &zl));
-  CHECK(ctx, mg_evidence_direct(ctx, p1, ll, lp, N, D, 64, &zd));
-  EXPECT(zh == 1.0 && fabs(zl - 1.0) < 0.2 && fabs(zd - 1.0) < 0.2);
+  CHECK(ctx, mg_evidence_lebesgue(ctx, p3, ll, lp, N, D, 64, 0.1, &zl));
+  CHECK(ctx, mg_evidence_direct(ctx, p3, ll, lp, N, D, 64, &zd));
+  EXPECT(zh > 0.1 && zh < 3.0 && fabs(zl - 1.0) < 0.5 && fabs(zd - 1.0) < 0.5);
 
   /* ---- Stats ------------------------------------------------------------------------------------------------------- */
   double mean[2], sd[2];
@@ -126,7 +134,7 @@ int main(void) {
 
   mg_kdtree_destroy(t1); mg_kdtree_destroy(t2);
   mg_ctx_destroy(ctx);
-  free(s1); free(s2); free(p1); free(p2); free(model); free(ll); free(lp); free(g); free(npts); free(nll); free(nlp); free(nlw);
+  free(s1); free(s2); free(s3); free(p1); free(p2); free(p3); free(model); free(ll); free(lp); free(g); free(npts); free(nll); free(nlp); free(nlw);
   printf("ok: mcmc_array, Interp, rjmcmc_array (ratio %.3f), Evidence (%.3f %.3f %.3f), Stats, nested_evidence (Z = %.4f +- %.4f)\n",
          ratio, zh, zl, zd, exp(log_ev), err);
   return 0;

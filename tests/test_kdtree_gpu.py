@@ -212,3 +212,22 @@ def test_window_sort_ties(ctx, og, cluster, what):
     lo = pts.min(0) - 1.0
     hi = pts.max(0) + 1.0
     assert_same_tree(kd_tree.KdTree(pts, lo, hi, ctx=ctx), og.Tree(pts, lo, hi))
+
+
+@pytest.mark.parametrize("d", [1, 2, 4, 8])
+def test_draw_cache_changes_nothing(ctx, og, d):
+    """mg_kdtree_enable_draw_cache: the cell of every stored point located once (by the same descent); leaf-level
+    draws then gather a record instead of descending -- same draws, bit for bit, as before and as the oracle."""
+    rng = np.random.default_rng(100 + d)
+    pts = mh_like(rng, 20000, d, 0.2).clip(0.0, 1.0)
+    lo, hi = np.zeros(d), np.ones(d)
+    g = interpolate_pdf.InterpPdf(pts, lo, hi, ctx=ctx)
+    ctx.set_seed(55)
+    before = g.draw(30000)
+    ctx.check(ctx.lib.mg_kdtree_enable_draw_cache(g.tree.h))
+    ctx.set_seed(55)
+    after = g.draw(30000)
+    assert np.array_equal(before, after)
+    assert np.array_equal(after, og.Tree(pts, lo, hi).draw(55, 0, 30000))
+    ctx.set_seed(56)
+    assert np.array_equal(g.draw_high_level(64, 2000), og.Tree(pts, lo, hi).draw(56, 0, 2000, nstop=64))   # not cached: descends

@@ -289,3 +289,16 @@ def test_c_program_drives_the_abi():
     r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert r.stdout.startswith("ok:")
+
+
+def test_quadform_on_fp64_tensor_cores(ctx):
+    """The decision experiment of DESIGN.md (FP64 tensor cores for the high-D Gaussian quadratic form): the DMMA
+    variant agrees with the FMA variant to 1e-13 relative (a 4-term dot product inside mma.sync.m8n8k4.f64 is summed
+    in an unspecified order), the FMA variant IS the sampler plugin's arithmetic (identical to MG_FN_GAUSS_CORR)."""
+    import sys, os
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import dmma_decision
+    doc = dmma_decision.run(M=100_003, reps=1)
+    for c in doc["cases"]:
+        assert c["fma_identical_to_plugin"] and c["max_rel_diff_dmma_vs_fma"] < 1e-13
+    assert doc["fp64_dmma_tflops"] > 1.0

@@ -15,8 +15,29 @@ def test_uniform_range_and_moments(og):
     u, lanes = og.rng_stream(7, 0, 1, 3, 9, 200000)
     assert u.min() >= 0.0 and u.max() < 1.0
     assert abs(u.mean() - 0.5) < 5e-3 and abs(u.var() - 1 / 12) < 2e-3
-    # u52 = low 52 bits of the lane
-    assert np.array_equal(u, (lanes & np.uint64((1 << 52) - 1)).astype(np.float64) * 2.0 ** -52)
+    # every draw owns 52 bits; the lane carries them on top (what Random.int multiplies)
+    assert np.array_equal(u, (lanes >> np.uint64(12)).astype(np.float64) * 2.0 ** -52)
+    assert not np.any(lanes & np.uint64(0xFFF))
+
+
+def test_eleven_draws_per_five_blocks(og):
+    """The stream layout of oracle/og_rng.hpp: draws 0..9 of a group are the lanes of five Philox blocks, draw 10 is
+    assembled from the 12 top bits of the first words of blocks 0..2 (bits no other draw uses)."""
+    seed, epoch, purpose, g, step = 11, 3, 1, 123456789, 77
+    _, lanes = og.rng_stream(seed, epoch, purpose, g, step, 33)
+    key = og.philox([epoch & 0xFFFFFFFF, epoch >> 32, 0x6d636d63, 0], [seed & 0xFFFFFFFF, seed >> 32])[:2]
+    c3 = ((g >> 32) & 0xFFFF) | ((purpose & 0xFF) << 16) | (((step >> 32) & 0xFF) << 24)
+    for m in range(3):
+        blocks = [og.philox([5 * m + k, step & 0xFFFFFFFF, g & 0xFFFFFFFF, c3], key) for k in range(5)]
+        want = []
+        for k in range(5):
+            w = blocks[k]
+            want.append(((w[0] & 0xFFFFF) << 32) | w[1])
+            want.append(((w[2] & 0xFFFFF) << 32) | w[3])
+        s = [blocks[0][0] >> 20, blocks[0][2] >> 20, blocks[1][0] >> 20, blocks[1][2] >> 20, blocks[2][0] >> 20]
+        want.append((s[0] << 40) | (s[1] << 28) | (s[2] << 16) | (s[3] << 4) | (s[4] >> 8))
+        got = [int(x) >> 12 for x in lanes[11 * m:11 * m + 11]]
+        assert got == want
 
 
 def test_streams_are_distinct(og):
