@@ -385,6 +385,23 @@ int mg_rjmcmc_array(mg_ctx *ctx, const mg_rj_model *A, const mg_rj_model *B,
                     const mg_rjmcmc_cfg *cfg, const double *a0,
                     const double *b0, uint8_t *out_model, double *out_samples,
                     int64_t out_counts[2]);
+/* k-model reversible jump -- an EXTENSION: the reference's
+ * sampler is strictly two-model (type rjmcmc_value = A | B, mcmc.ml:83-87).
+ * Structure kept from make_rjmcmc_sampler / rjmcmc_array: the model prior p_k
+ * is part of the log prior (mcmc.ml:116-118,128), jump densities are
+ * log p_target + log q_into_target (mcmc.ml:103-112), the priors' sum is checked
+ * one-sidedly (mcmc.ml:90).  A step walks the priors cyclically from the current
+ * model with one uniform (stay with probability p_current, as mcmc.ml:92-102)
+ * and the initial model is uniform over the K (the fair coin of mcmc.ml:123).
+ * With nmodels = 2 the chains equal mg_rjmcmc_array's draw for draw.
+ * models: [nmodels]; starts: nmodels host pointers, starts[k] = [dim_k];
+ * out_model: uint8 [n][C] (model index) or NULL; out_samples: [n][Dmax+2][C] or
+ * NULL; out_counts: [nmodels] samples per model. */
+#define MG_RJ_MAX_MODELS 8
+int mg_rjmcmc_array_k(mg_ctx *ctx, const mg_rj_model *models, int32_t nmodels,
+                      const mg_rjmcmc_cfg *cfg, const double *const *starts,
+                      uint8_t *out_model, double *out_samples,
+                      int64_t *out_counts);
 /* Diagnostics of the last mg_rjmcmc_array call on this context: how many steps
  * proposed a jump into the other model (mcmc.ml:97,102) and how many of those
  * were accepted -- the mixing rate of the interpolated jumps. */

@@ -24,25 +24,60 @@ rj_ensemble_kernel(const __grid_constant__ RjArgs a) {
   rj_ensemble_body<DMAX>(a);
 }
 
+// the k-model kernel (mg_rjmcmc_array_k): same body over a table of up to MG_RJ_MAX_MODELS models
+template <int DMAX>
+__global__ void __maxnreg__(MG_RJ_MAXNREG(DMAX))
+rj_ensemble_k_kernel(const __grid_constant__ RjArgsT<MG_RJ_MAX_MODELS> a) {
+  rj_ensemble_body<DMAX, MG_RJ_MAX_MODELS>(a);
+}
+
 int jit_launch_rj(mg_ctx *ctx, const RjArgs &a, int Dm, unsigned grid, unsigned block, size_t smem);   // jit.cu
 
-}  // namespace mg
+template <int NM> static int rj_launch(mg_ctx *, const RjArgsT<NM> &, bool, int, unsigned, int, size_t, cudaStream_t);
+template <> int rj_launch<2>(mg_ctx *ctx, const RjArgsT<2> &a, bool any_user, int Dm, unsigned grid, int block, size_t smem,
+                             cudaStream_t s) {
+  if (any_user) return jit_launch_rj(ctx, a, Dm, grid, (unsigned)block, smem);
+#define MG_RJ_LAUNCH(DD)                                                                              \
+  do {                                                                                                \
+    if (smem > 48 * 1024)                                                                             \
+      MG_CUDA(ctx, cudaFuncSetAttribute(rj_ensemble_kernel<DD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    rj_ensemble_kernel<DD><<<grid, block, smem, s>>>(a);                                              \
+  } while (0)
+  if (Dm <= 2) MG_RJ_LAUNCH(2);
+  else if (Dm <= 4) MG_RJ_LAUNCH(4);
+  else if (Dm <= 8) MG_RJ_LAUNCH(8);
+  else if (Dm <= 16) MG_RJ_LAUNCH(16);
+  else if (Dm <= 32) MG_RJ_LAUNCH(32);
+  else MG_RJ_LAUNCH(64);
+#undef MG_RJ_LAUNCH
+  return MG_OK;
+}
+template <> int rj_launch<MG_RJ_MAX_MODELS>(mg_ctx *ctx, const RjArgsT<MG_RJ_MAX_MODELS> &a, bool any_user, int Dm, unsigned grid,
+                                            int block, size_t smem, cudaStream_t s) {
+  if (any_user) return set_err(ctx, MG_EINVAL, "rjmcmc_array_k: user-registered log-densities are supported by the two-model call only");
+#define MG_RJ_LAUNCH(DD)                                                                              \
+  do {                                                                                                \
+    if (smem > 48 * 1024)                                                                             \
+      MG_CUDA(ctx, cudaFuncSetAttribute(rj_ensemble_k_kernel<DD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    rj_ensemble_k_kernel<DD><<<grid, block, smem, s>>>(a);                                            \
+  } while (0)
+  if (Dm <= 4) MG_RJ_LAUNCH(4);
+  else if (Dm <= 8) MG_RJ_LAUNCH(8);
+  else if (Dm <= 16) MG_RJ_LAUNCH(16);
+  else if (Dm <= 32) MG_RJ_LAUNCH(32);
+  else MG_RJ_LAUNCH(64);
+#undef MG_RJ_LAUNCH
+  return MG_OK;
+}
 
-using namespace mg;
-
-extern "C" int mg_rjmcmc_array(mg_ctx *ctx, const mg_rj_model *A, const mg_rj_model *B, const mg_rjmcmc_cfg *cfg,
-                               const double *a0, const double *b0, uint8_t *out_model, double *out_samples,
-                               int64_t out_counts[2]) {
-  if (!ctx) return MG_EINVAL;
-  MG_REQUIRE(ctx, A && B && cfg && a0 && b0 && out_counts, "rjmcmc_array: null argument");
-  MG_REQUIRE(ctx, cfg->nchains >= 1 && cfg->nbin >= 0 && cfg->nskip >= 1 && cfg->n >= 0, "rjmcmc_array: bad nbin/nskip/n");
-  // mcmc.ml:90 assert(pa +. pb -. 1.0 < sqrt epsilon_float)  -- one-sided, as coded
-  if (!(A->p + B->p - 1.0 < sqrt(2.220446049250313e-16))) return set_err(ctx, MG_EFAIL, "Assert_failure mcmc.ml:90");
-  const mg_rj_model *M[2] = {A, B};
+// Mcmc.rjmcmc_array for K models; NM = 2 is the reference's two-model call, NM = MG_RJ_MAX_MODELS the extension.
+template <int NM>
+static int rj_run(mg_ctx *ctx, const mg_rj_model *const *M, int K, const mg_rjmcmc_cfg *cfg, const double *const *starts,
+                  uint8_t *out_model, double *out_samples, int64_t *out_counts) {
   int rc;
   int DT = 0, Dm = 0;
   bool any_user = false;      // a user-registered log-density: the kernel is compiled at run time with it inlined
-  for (int k = 0; k < 2; ++k) {
+  for (int k = 0; k < K; ++k) {
     const int D = M[k]->like.dim;
     MG_REQUIRE(ctx, D >= 1 && D <= 64, "rjmcmc_array: dim must be in 1..64");
     if ((rc = validate_logfn(ctx, &M[k]->like, D, "log_likelihood"))) return rc;
@@ -62,22 +97,22 @@ extern "C" int mg_rjmcmc_array(mg_ctx *ctx, const mg_rj_model *A, const mg_rj_mo
   cudaStream_t s = ctx->stream;
   const int64_t C = cfg->nchains, n = cfg->n;
   const int F = Dm + 2;
-  DevLogFn dl[2], dp[2]; DevProposal dj[2];
-  DevBuf<double> dinto[2], d_samples, d_t;
+  DevLogFn dl[NM], dp[NM]; DevProposal dj[NM];
+  DevBuf<double> dinto[NM], d_samples, d_t;
   DevBuf<uint8_t> d_model;
   DevBuf<unsigned long long> d_counts;
   DevBuf<double> d_start;
   DevBuf<int> d_fail;
-  RjArgs a{};
-  std::vector<double> h_start(128, 0.0);
-  for (int i = 0; i < A->like.dim; ++i) h_start[i] = a0[i];
-  for (int i = 0; i < B->like.dim; ++i) h_start[64 + i] = b0[i];
+  RjArgsT<NM> a{};
+  std::vector<double> h_start((size_t)64 * NM, 0.0);
+  for (int k = 0; k < K; ++k)
+    for (int i = 0; i < M[k]->like.dim; ++i) h_start[(size_t)64 * k + i] = starts[k][i];
   MG_CUDA(ctx, upload(d_start, h_start.data(), h_start.size(), s));
-  MG_CUDA(ctx, d_counts.alloc(8, s));
-  MG_CUDA(ctx, cudaMemsetAsync(d_counts.get(), 0, 8 * sizeof(unsigned long long), s));
+  MG_CUDA(ctx, d_counts.alloc(NM + 3, s));
+  MG_CUDA(ctx, cudaMemsetAsync(d_counts.get(), 0, (NM + 3) * sizeof(unsigned long long), s));
   MG_CUDA(ctx, d_fail.alloc(1, s));
   MG_CUDA(ctx, cudaMemsetAsync(d_fail.get(), 0, sizeof(int), s));
-  for (int k = 0; k < 2; ++k) {
+  for (int k = 0; k < K; ++k) {
     MG_CUDA(ctx, dl[k].upload_from(&M[k]->like, s));
     MG_CUDA(ctx, dp[k].upload_from(&M[k]->prior, s));
     MG_CUDA(ctx, dj[k].upload_from(&M[k]->prop, s));
@@ -106,46 +141,69 @@ extern "C" int mg_rjmcmc_array(mg_ctx *ctx, const mg_rj_model *A, const mg_rj_mo
   if (out_samples && n > 0) MG_CUDA(ctx, d_samples.alloc((size_t)n * F * C, s));
   a.C = C; a.nbin = cfg->nbin; a.nskip = cfg->nskip; a.n = n; a.chain_offset = cfg->chain_offset;
   a.key = next_key(ctx);
-  a.Dm = Dm; a.DT = DT;
+  a.Dm = Dm; a.DT = DT; a.K = K;
   a.out_model = d_model.get(); a.out_samples = d_samples.get();
   a.counts = d_counts.get(); a.start = d_start.get(); a.fail = d_fail.get();
   const int block = DT <= 32 ? 64 : 32;
   const size_t smem = kd_scratch_bytes(DT > 0 ? DT : 1, block);
   const unsigned grid = (unsigned)((C + block - 1) / block);
   time_begin(ctx);
-  if (any_user) {
-    if ((rc = jit_launch_rj(ctx, a, Dm, grid, (unsigned)block, smem))) return rc;
-  } else {
-#define MG_RJ_LAUNCH(DD)                                                                              \
-  do {                                                                                                \
-    if (smem > 48 * 1024)                                                                             \
-      MG_CUDA(ctx, cudaFuncSetAttribute(rj_ensemble_kernel<DD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    rj_ensemble_kernel<DD><<<grid, block, smem, s>>>(a);                                              \
-  } while (0)
-  if (Dm <= 2) MG_RJ_LAUNCH(2);
-  else if (Dm <= 4) MG_RJ_LAUNCH(4);
-  else if (Dm <= 8) MG_RJ_LAUNCH(8);
-  else if (Dm <= 16) MG_RJ_LAUNCH(16);
-  else if (Dm <= 32) MG_RJ_LAUNCH(32);
-  else MG_RJ_LAUNCH(64);
-#undef MG_RJ_LAUNCH
-  }
+  if ((rc = rj_launch<NM>(ctx, a, any_user, Dm, grid, block, smem, s))) return rc;
   MG_CHECK_LAUNCH(ctx);
   time_end(ctx);
   if (out_model && n > 0) MG_CUDA(ctx, cudaMemcpyAsync(out_model, d_model.get(), (size_t)n * C, cudaMemcpyDeviceToHost, s));
   if (out_samples && n > 0)
     MG_CUDA(ctx, cudaMemcpyAsync(out_samples, d_samples.get(), sizeof(double) * (size_t)n * F * C, cudaMemcpyDeviceToHost, s));
-  unsigned long long cnt[5];
+  unsigned long long cnt[NM + 3];
   int h_fail = 0;
   MG_CUDA(ctx, cudaMemcpyAsync(cnt, d_counts.get(), sizeof cnt, cudaMemcpyDeviceToHost, s));
   MG_CUDA(ctx, cudaMemcpyAsync(&h_fail, d_fail.get(), sizeof(int), cudaMemcpyDeviceToHost, s));
   MG_CUDA(ctx, cudaStreamSynchronize(s));
   if (h_fail) return set_err(ctx, MG_EFAIL, "draw: empty tree");   // interpolate_pdf.ml:117,124
-  out_counts[0] = (int64_t)cnt[0]; out_counts[1] = (int64_t)cnt[1];
+  for (int k = 0; k < K; ++k) out_counts[k] = (int64_t)cnt[k];
   const int64_t steps = C * (cfg->nbin + (n > 0 ? (n - 1) * cfg->nskip : 0));
-  ctx->naccept += (int64_t)cnt[2]; ctx->nreject += steps - (int64_t)cnt[2];
-  ctx->rj_cross[0] = (int64_t)cnt[3]; ctx->rj_cross[1] = (int64_t)cnt[4];
+  ctx->naccept += (int64_t)cnt[NM]; ctx->nreject += steps - (int64_t)cnt[NM];
+  ctx->rj_cross[0] = (int64_t)cnt[NM + 1]; ctx->rj_cross[1] = (int64_t)cnt[NM + 2];
   return MG_OK;
+}
+
+}  // namespace mg
+
+using namespace mg;
+
+extern "C" int mg_rjmcmc_array(mg_ctx *ctx, const mg_rj_model *A, const mg_rj_model *B, const mg_rjmcmc_cfg *cfg,
+                               const double *a0, const double *b0, uint8_t *out_model, double *out_samples,
+                               int64_t out_counts[2]) {
+  if (!ctx) return MG_EINVAL;
+  MG_REQUIRE(ctx, A && B && cfg && a0 && b0 && out_counts, "rjmcmc_array: null argument");
+  MG_REQUIRE(ctx, cfg->nchains >= 1 && cfg->nbin >= 0 && cfg->nskip >= 1 && cfg->n >= 0, "rjmcmc_array: bad nbin/nskip/n");
+  // mcmc.ml:90 assert(pa +. pb -. 1.0 < sqrt epsilon_float)  -- one-sided, as coded
+  if (!(A->p + B->p - 1.0 < sqrt(2.220446049250313e-16))) return set_err(ctx, MG_EFAIL, "Assert_failure mcmc.ml:90");
+  const mg_rj_model *M[2] = {A, B};
+  const double *starts[2] = {a0, b0};
+  return rj_run<2>(ctx, M, 2, cfg, starts, out_model, out_samples, out_counts);
+}
+
+// k-model reversible jump.  The reference's sampler is strictly two-model (rjmcmc_value = A | B,
+// mcmc.ml:83-87); this keeps its structure -- model prior p_k inside the log prior (:116-118, :128), jump densities
+// log p_target + log q_into_target (:103-112), the one-sided assertion on the priors' sum (:90) -- and lets a step
+// choose its target among K models (rj_kernel_dev.cuh: rj_pick_model).  With K = 2 the chains are those of
+// mg_rjmcmc_array, draw for draw.
+extern "C" int mg_rjmcmc_array_k(mg_ctx *ctx, const mg_rj_model *models, int32_t nmodels, const mg_rjmcmc_cfg *cfg,
+                                 const double *const *starts, uint8_t *out_model, double *out_samples, int64_t *out_counts) {
+  if (!ctx) return MG_EINVAL;
+  MG_REQUIRE(ctx, models && cfg && starts && out_counts, "rjmcmc_array_k: null argument");
+  MG_REQUIRE(ctx, nmodels >= 2 && nmodels <= MG_RJ_MAX_MODELS, "rjmcmc_array_k: 2..MG_RJ_MAX_MODELS models");
+  MG_REQUIRE(ctx, cfg->nchains >= 1 && cfg->nbin >= 0 && cfg->nskip >= 1 && cfg->n >= 0, "rjmcmc_array_k: bad nbin/nskip/n");
+  double psum = 0.0;
+  const mg_rj_model *M[MG_RJ_MAX_MODELS];
+  for (int k = 0; k < nmodels; ++k) {
+    MG_REQUIRE(ctx, starts[k] != nullptr, "rjmcmc_array_k: null start point");
+    MG_REQUIRE(ctx, models[k].p > 0.0, "rjmcmc_array_k: model priors must be positive");
+    psum = psum + models[k].p; M[k] = models + k;
+  }
+  if (!(psum - 1.0 < sqrt(2.220446049250313e-16))) return set_err(ctx, MG_EFAIL, "Assert_failure mcmc.ml:90 (sum of the model priors)");
+  return rj_run<MG_RJ_MAX_MODELS>(ctx, M, nmodels, cfg, starts, out_model, out_samples, out_counts);
 }
 
 extern "C" int mg_rjmcmc_jump_counters(const mg_ctx *ctx, int64_t *proposed, int64_t *accepted) {

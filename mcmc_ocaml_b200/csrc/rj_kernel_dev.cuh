@@ -16,18 +16,24 @@ struct RjModelDev {
   int32_t into_kind, nstop, D, pad;
 };
 
-struct RjArgs {
-  RjModelDev m[2];
+// NM = capacity of the model table.  NM = 2 is the reference's sum type (A | B, mcmc.ml:83-87) and the kernel of
+// mg_rjmcmc_array; NM = MG_RJ_MAX_MODELS serves mg_rjmcmc_array_k, the k-model extension, where
+// K <= NM models are live.
+template <int NM>
+struct RjArgsT {
+  RjModelDev m[NM];
   int64_t C, nbin, nskip, n;
   uint64_t chain_offset;
   CallKey key;
   int32_t Dm, DT;            // max model dim; scratch dim (max tree dim)
+  int32_t K, pad;            // live models (2 when NM == 2)
   uint8_t *out_model;        // [n][C] or null
   double *out_samples;       // [n][Dm+2][C] or null
-  unsigned long long *counts;  // [5]: #A, #B, #accepted, #cross-model proposals, #cross-model accepted
-  const double *start;         // [2][64]: the start points a0, b0
+  unsigned long long *counts;  // [NM + 3]: samples per model, then #accepted, #cross-model proposals, #cross-model accepted
+  const double *start;         // [NM][64]: the start points (a0, b0, ...)
   int *fail;
 };
+using RjArgs = RjArgsT<2>;
 
 // *lq / *lq_known: Interp.draw leaves the cell's box in the scratch.  When the drawn point lies strictly inside
 // it, Interp.jump_prob of that point descends to the same cell (at every ancestor the point is inside the child on
@@ -84,20 +90,43 @@ __device__ __forceinline__ double rj_log_into(const RjModelDev &m, const KdScrat
 #define MG_RJ_MAXNREG(DMAX) ((DMAX) <= 8 ? 64 : ((DMAX) <= 16 ? 96 : 255))
 #endif
 
-template <int DMAX>
-__device__ __forceinline__ void rj_ensemble_body(const RjArgs &a) {
+// Model choice of a step.  Two models: mcmc.ml:92-102 -- stay with probability p of the current model, else the
+// other one.  K models (extension): the same uniform walks the model priors cyclically from the current model
+// (current, current + 1, ..., mod K) and takes the first whose cumulative probability exceeds it, the last one taking
+// the remainder; with K = 2 that is the reference's rule, draw for draw.  The jump densities keep the reference's
+// form: log p_target + log q_into_target (mcmc.ml:103-112).
+template <int NM>
+__device__ __forceinline__ int rj_pick_model(const RjArgsT<NM> &a, int model, double u) {
+  if (NM == 2) return (u < a.m[model].p) ? model : 1 - model;
+  double cum = 0.0;
+  int j = model;
+  for (int k = 0; k < a.K - 1; ++k) {
+    cum = cum + a.m[j].p;
+    if (u < cum) return j;
+    j = (j + 1 == a.K) ? 0 : j + 1;
+  }
+  return j;
+}
+
+template <int DMAX, int NM = 2>
+__device__ __forceinline__ void rj_ensemble_body(const RjArgsT<NM> &a) {
   extern __shared__ double smem[];
   const KdScratch s = kd_scratch(smem, a.DT);
   const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const bool live = c < a.C;
-  unsigned na = 0, nb = 0, nacc = 0, ncross = 0, ncross_acc = 0;
+  unsigned nmod[NM];
+#pragma unroll
+  for (int k = 0; k < NM; ++k) nmod[k] = 0;
+  unsigned nacc = 0, ncross = 0, ncross_acc = 0;
   if (live) {
     const uint64_t g = a.chain_offset + (uint64_t)c;
     const int64_t C = a.C;
     const int F = a.Dm + 2;
-    // rjmcmc_array mcmc.ml:121-128: fair coin for the initial model (F5a)
+    // rjmcmc_array mcmc.ml:121-128: fair coin for the initial model (F5a); K models: uniform over the K
     Rng r0(a.key, P_RJ_INIT, g, 0);
-    int model = (r0.uniform() < 0.5) ? 0 : 1;
+    int model;
+    if (NM == 2) model = (r0.uniform() < 0.5) ? 0 : 1;
+    else { model = (int)(r0.uniform() * (double)a.K); if (model >= a.K) model = a.K - 1; }
     double x[DMAX], y[DMAX];
 #pragma unroll (DMAX <= 16 ? DMAX : 1)
     for (int i = 0; i < DMAX; ++i) x[i] = 0.0;
@@ -118,12 +147,10 @@ __device__ __forceinline__ void rj_ensemble_body(const RjArgs &a) {
       bool fwd_known = false;
       const double start_log_post = ll + lp;
       const RjModelDev &cm = a.m[model];
-      int pmodel;
-      if (r.uniform() < cm.p) {               // :94,99 stay in the model
-        pmodel = model;
+      const int pmodel = rj_pick_model<NM>(a, model, r.uniform());
+      if (pmodel == model) {                  // :94,99 stay in the model
         DynProp::propose<DMAX>(cm.prop, nullptr, r, x, y, cm.D);
       } else {                                // :97,102 jump into the other model
-        pmodel = 1 - model;
         if (!rj_draw_into<DMAX>(a.m[pmodel], s, r, y, &fwd_lq, &fwd_known)) { bad = true; return; }
       }
       const RjModelDev &pm = a.m[pmodel];
@@ -154,7 +181,8 @@ __device__ __forceinline__ void rj_ensemble_body(const RjArgs &a) {
       }
     };
     auto record = [&](int64_t smp) {
-      if (model == 0) ++na; else ++nb;
+#pragma unroll
+      for (int k = 0; k < NM; ++k) nmod[k] += (model == k) ? 1u : 0u;
       if (a.out_model) a.out_model[smp * C + c] = (uint8_t)model;
       if (a.out_samples) {
         double *o = a.out_samples + smp * (int64_t)F * C + c;
@@ -176,18 +204,18 @@ __device__ __forceinline__ void rj_ensemble_body(const RjArgs &a) {
   // rjmcmc_model_counts (mcmc.ml:141-149): warp-reduce, one atomic per warp
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) {
-    na += __shfl_down_sync(0xffffffffu, na, off);
-    nb += __shfl_down_sync(0xffffffffu, nb, off);
+#pragma unroll
+    for (int k = 0; k < NM; ++k) nmod[k] += __shfl_down_sync(0xffffffffu, nmod[k], off);
     nacc += __shfl_down_sync(0xffffffffu, nacc, off);
     ncross += __shfl_down_sync(0xffffffffu, ncross, off);
     ncross_acc += __shfl_down_sync(0xffffffffu, ncross_acc, off);
   }
   if ((threadIdx.x & 31) == 0) {
-    atomicAdd(a.counts + 0, (unsigned long long)na);
-    atomicAdd(a.counts + 1, (unsigned long long)nb);
-    atomicAdd(a.counts + 2, (unsigned long long)nacc);
-    atomicAdd(a.counts + 3, (unsigned long long)ncross);
-    atomicAdd(a.counts + 4, (unsigned long long)ncross_acc);
+#pragma unroll
+    for (int k = 0; k < NM; ++k) atomicAdd(a.counts + k, (unsigned long long)nmod[k]);
+    atomicAdd(a.counts + NM + 0, (unsigned long long)nacc);
+    atomicAdd(a.counts + NM + 1, (unsigned long long)ncross);
+    atomicAdd(a.counts + NM + 2, (unsigned long long)ncross_acc);
   }
 }
 
