@@ -408,6 +408,48 @@ int mg_rjmcmc_array_k(mg_ctx *ctx, const mg_rj_model *models, int32_t nmodels,
 int mg_rjmcmc_jump_counters(const mg_ctx *ctx, int64_t *proposed, int64_t *accepted);
 
 /* ------------------------------------------------------------------ */
+/* Ellipse (ellipse.ml) -- SURVEY.md 8f rank 4                          */
+/* ------------------------------------------------------------------ */
+typedef struct mg_ellipse_tree mg_ellipse_tree;
+
+/* Ellipse.enclosing_ellipse sf to_coord pts (ellipse.ml:98-103): centre =
+ * mean (:36-46), covariance (:48-66), eigen-system (:58-61, eigenvalues
+ * ascending as LAPACK returns them), axes = eigenvalue * sf^(1/D) * r_max
+ * (:83-86).  pts: host [N][D], D <= 32.  center[D], axes[D], orientation[D][D]
+ * with orientation[i][j] = component i of eigenvector j (Lacaml's z); the
+ * eigenvector sign, which LAPACK leaves open, is fixed here (largest
+ * component positive). */
+int mg_ellipse_enclosing(mg_ctx *ctx, const double *pts, int64_t N, int32_t D,
+                         double sf, double *center, double *axes,
+                         double *orientation);
+/* Ellipse.elliptical_range ell pt (ellipse.ml:63-73) of M host points q[M][D] */
+int mg_ellipse_range(mg_ctx *ctx, const double *center, const double *axes,
+                     const double *orientation, int32_t D, const double *q,
+                     int64_t M, double *out);
+/* Ellipse.ellipse_tree sf to_coord pts (ellipse.ml:150-173).  Nodes are
+ * numbered breadth first; a child with fewer than D + 1 points is Empty (-1).
+ * N < D + 1 is the reference's Assert_failure (MG_EINVAL); a node whose points
+ * all lie on one side of its centre makes the reference recurse forever and
+ * is MG_EFAIL here. */
+int mg_ellipse_tree_build(mg_ctx *ctx, const double *pts, int64_t N, int32_t D,
+                          double sf, mg_ellipse_tree **out);
+int mg_ellipse_tree_build_dev(mg_ctx *ctx, const double *d_pts, int64_t N,
+                              int32_t D, double sf, mg_ellipse_tree **out);
+void mg_ellipse_tree_destroy(mg_ellipse_tree *t);
+int mg_ellipse_tree_info(const mg_ellipse_tree *t, int64_t *npoints,
+                         int32_t *dim, int64_t *nnodes, int32_t *nlevels);
+/* Flat arrays of the tree (any pointer may be NULL): left / right child or -1
+ * (Empty); the node's points are perm[begin..end) -- as a set: the reference's
+ * `pts` field lists them in input order, i.e. sorted by id; `ellipse` =
+ * center[D], axes[D], orientation[D][D]; `circumcircle` (:159-167) =
+ * cc_center[D], cc_radius. */
+int mg_ellipse_tree_export(const mg_ellipse_tree *t, int32_t *left,
+                           int32_t *right, int32_t *begin, int32_t *end,
+                           int32_t *perm, double *center, double *axes,
+                           double *orientation, double *cc_center,
+                           double *cc_radius);
+
+/* ------------------------------------------------------------------ */
 /* Evidence + Stats                                                    */
 /* ------------------------------------------------------------------ */
 

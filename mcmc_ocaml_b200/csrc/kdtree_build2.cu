@@ -340,13 +340,18 @@ v2_pick_kernel(V2Top t, int L) {
   t.kth[k] = (int32_t)(kth - below);
   const int32_t below_tot = t.below[k] + (int32_t)below;
   t.below[k] = below_tot;
-  if (s.shift == 0) {                                       // all 64 bits decided: prefix is the order statistic
+  // The select is over as soon as the bin of the order statistic holds ONE key: the scatter only compares keys with
+  // the pivot, and a pivot that is alone in its bin is ordered against every other key by the bits decided so far
+  // (the split plane comes from max L / min R, which the scatter finds).  Otherwise all 64 bits are decided.
+  if (s.shift == 0 || cnt == 1u) {
     const int id = lv.lb + k;
     const int32_t b = t.nb[id], e = t.ne[id], n = e - b;
     int32_t cntL = below_tot + (int32_t)cnt;                // keys <= v   (List.partition (<= pvt), :168)
     uint8_t fix = 0;
     if (cntL == n) { cntL = below_tot; fix = 1; }           // adjust_for_empty_split :150-152: L = {k < max}
-    t.v[k] = s.prefix; t.fix[k] = fix; t.nR[k] = n - cntL; t.nspos[id] = b + cntL;
+    // undecided low bits: all ones for "key > v goes right", all zeros for "key >= v goes right" (the pivot itself)
+    const uint64_t low = (s.shift > 0 && !fix) ? ((1ull << s.shift) - 1ull) : 0ull;
+    t.v[k] = s.prefix | low; t.fix[k] = fix; t.nR[k] = n - cntL; t.nspos[id] = b + cntL;
     if (cntL <= 0 || cntL >= n) t.info->overflow = 1;       // cannot happen (lo != hi on the split dimension)
     s.shift = -1;
     atomicSub(&t.info->sel_active, 1);
@@ -639,7 +644,7 @@ v2_bottom_kernel(V2Bottom a) {
   uint16_t *ids = ids0, *idn = ids1, *cb = cb0, *ce = ce0, *nb_ = cb1, *ne_ = ce1;
   uint32_t *h = hist_all + warp * 256;
   uint64_t *cand = reinterpret_cast<uint64_t *>(h);      // the same 1 KB holds up to 32 candidate keys
-  int cur_n = 1, lbase = 0, l = 0;
+  int cur_n = 1, lbase = 0, l = 0, level_max = n;
   const int64_t gbase = 2 * (int64_t)b;
   constexpr int kLaneDimMax = 128;     // nodes up to this size: one lane per dimension walks the node's points
   constexpr int kTinyMax = 8;          // nodes up to this size: one thread per node
@@ -649,7 +654,10 @@ v2_bottom_kernel(V2Bottom a) {
     if (tid == 0) cnt[l] = cur_n;
     // Large nodes exist only while the level has few nodes (at most one per warp): their bounds are then computed by
     // ALL warps, one (node, dimension) pair at a time, instead of by the node's own warp alone.
-    const bool pair_mode = cur_n <= nwarps;
+    // (level_max estimates the level's largest node: without ties a child holds at most n / 2 + 1 of its parent's n
+    // points.  Once that is <= kLaneDimMax the pair pass would only skip its pairs; a node kept large by ties then gets
+    // its bounds from its own warp below -- slower, same result.)
+    const bool pair_mode = cur_n <= nwarps && level_max > kLaneDimMax;
     uint64_t pre_lo[2] = {~0ull, ~0ull}, pre_hi[2] = {0ull, 0ull};
     bool have_pre = false;
     if (pair_mode) {
@@ -906,7 +914,7 @@ v2_bottom_kernel(V2Bottom a) {
     }
     const int nsplit = carry;
     if (nsplit == 0) break;
-    lbase += cur_n; cur_n = 2 * nsplit; ++l;
+    lbase += cur_n; cur_n = 2 * nsplit; ++l; level_max = level_max / 2 + 1;
     if (l >= V2_MAXL) { if (tid == 0) *a.overflow = 1; --l; break; }
     { uint16_t *x = ids; ids = idn; idn = x; x = cb; cb = nb_; nb_ = x; x = ce; ce = ne_; ne_ = x; }
     __syncthreads();

@@ -186,6 +186,33 @@ def rjmcmc_array(n: int, A: RjModel, B: RjModel, a0, b0, *, nbin: int = 0, nskip
     return RjSamples(model, block, (int(counts[0]), int(counts[1])), (int(cp.value), int(ca.value)))
 
 
+def rjmcmc_array_k(n: int, models, starts, *, nbin: int = 0, nskip: int = 1, nchains: int = 1, chain_offset: int = 0,
+                   record_model: bool = True, record_samples: bool = False, ctx: Context | None = None) -> RjSamples:
+    """k-model reversible jump (``mg_rjmcmc_array_k``): an extension of ``Mcmc.rjmcmc_array`` -- the reference's sum
+    type is two-model (mcmc.ml:83-87).  ``models``: 2..8 ``RjModel``; ``starts``: one start point per model.  With two
+    models the chains are those of ``rjmcmc_array``.  ``counts`` has one entry per model."""
+    ctx = ctx or default_context()
+    K = len(models)
+    if K != len(starts):
+        raise _abi.InvalidArgument("rjmcmc_array_k: one start point per model")
+    dm = max(m.like.dim for m in models)
+    cfg = _abi.mg_rjmcmc_cfg(nchains, nbin, nskip, n, chain_offset, 0, 0)
+    model = np.empty((n, nchains), np.uint8) if record_model else None
+    block = np.empty((n, dm + 2, nchains)) if record_samples else None
+    counts = (C.c_int64 * K)()
+    arr = (_abi.mg_rj_model * K)(*[m.spec() for m in models])
+    st = [_abi.as_f64(x) for x in starts]
+    for m, x in zip(models, st):
+        if x.size != m.like.dim:
+            raise _abi.InvalidArgument("rjmcmc_array_k: start points must have the dimensions of their models")
+    sp = (_abi.c_double_p * K)(*[_abi.ptr(x) for x in st])
+    ctx.check(ctx.lib.mg_rjmcmc_array_k(ctx.h, arr, C.c_int32(K), C.byref(cfg), sp, _abi.ptr(model, _abi.c_uint8_p),
+                                        _abi.ptr(block), counts))
+    cp, ca = C.c_int64(), C.c_int64()
+    ctx.lib.mg_rjmcmc_jump_counters(ctx.h, C.byref(cp), C.byref(ca))
+    return RjSamples(model, block, tuple(int(c) for c in counts), (int(cp.value), int(ca.value)))
+
+
 def rjmcmc_model_counts(samples: RjSamples) -> tuple[int, int]:
     """``Mcmc.rjmcmc_model_counts`` (mcmc.ml:141-149)."""
     return samples.counts

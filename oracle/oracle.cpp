@@ -215,6 +215,92 @@ static int rj_chain(const CallKey &ck, const RjModel &A, const RjModel &B, const
   return bad ? 1 : 0;
 }
 
+// ---------------------------------------------------------------------------
+// k-model reversible jump: an EXTENSION, not a restatement (the reference's sampler is two-model, mcmc.ml:83-87).
+// It keeps make_rjmcmc_sampler's structure (mcmc.ml:89-119) over a table of K models and shares its specification
+// with the GPU kernel (include/mcmc_gpu.h: mg_rjmcmc_array_k): one uniform walks the model priors cyclically from the
+// current model, the last model taking the remainder; initial model uniform over the K; everything else as rj_chain.
+// With K = 2 the draws and decisions are rj_chain's.
+static int rj_chain_k(const CallKey &ck, const std::vector<RjModel> &Ms, const mg_rjmcmc_cfg &cfg,
+                      const double *const *starts, int64_t c, uint8_t *out_model, double *out_samples,
+                      int64_t *counts, int64_t *acc, double *margin, int64_t *cross) {
+  const int K = (int)Ms.size();
+  const int64_t C = cfg.nchains;
+  int Dm = 0; for (const auto &m : Ms) Dm = std::max(Dm, m.D);
+  const int F = Dm + 2;
+  tl_margin = HUGE_VAL;
+  int64_t ncross = 0, ncross_acc = 0;
+  const uint64_t g = cfg.chain_offset + (uint64_t)c;
+  std::vector<double> log_p(K);
+  for (int k = 0; k < K; ++k) log_p[k] = std::log(Ms[k].p);
+  Rng r0(ck, P_RJ_INIT, g, 0);
+  int m0;
+  if (K == 2) m0 = r0.uniform() < 0.5 ? 0 : 1;
+  else { m0 = (int)(r0.uniform() * (double)K); if (m0 >= K) m0 = K - 1; }
+  RjState cur{m0, std::vector<double>(Dm, 0.0)};
+  for (int i = 0; i < Ms[m0].D; ++i) cur.x[i] = starts[m0][i];
+  double ll = Ms[m0].like(cur.x.data());
+  double lp = Ms[m0].prior(cur.x.data()) + log_p[m0];
+  RjState prop{0, std::vector<double>(Dm, 0.0)};
+  int64_t nacc = 0, t = 0;
+  bool bad = false;
+  auto pick = [&](int model, double u) {
+    if (K == 2) return (u < Ms[model].p) ? model : 1 - model;
+    double cum = 0.0; int j = model;
+    for (int k = 0; k < K - 1; ++k) {
+      cum = cum + Ms[j].p;
+      if (u < cum) return j;
+      j = (j + 1 == K) ? 0 : j + 1;
+    }
+    return j;
+  };
+  auto step = [&]() {
+    Rng r(ck, P_RJ, g, (uint64_t)t);
+    double start_log_post = ll + lp;
+    const RjModel &cm = Ms[cur.model];
+    std::fill(prop.x.begin(), prop.x.end(), 0.0);
+    prop.model = pick(cur.model, r.uniform());
+    if (prop.model == cur.model) cm.prop.propose(r, cur.x.data(), prop.x.data());
+    else if (!Ms[prop.model].draw_into(r, cur.x.data(), prop.x.data())) bad = true;
+    const RjModel &pm = Ms[prop.model];
+    double proposed_like = pm.like(prop.x.data());
+    double proposed_prior = log_p[prop.model] + pm.prior(prop.x.data());
+    double proposed_log_posterior = proposed_like + proposed_prior;
+    auto ljp = [&](const RjState &x, const RjState &y) {
+      if (x.model == y.model) return log_p[y.model] + Ms[y.model].prop.log_q(x.x.data(), y.x.data());
+      return log_p[y.model] + Ms[y.model].log_into(x.x.data(), y.x.data());
+    };
+    double log_forward_jump = ljp(cur, prop), log_backward_jump = ljp(prop, cur);
+    double log_accept_prob = proposed_log_posterior - start_log_post + log_backward_jump - log_forward_jump;
+    const double log_u = std::log(r.uniform());
+    note_margin(log_u, log_accept_prob);
+    if (prop.model != cur.model) ++ncross;
+    if (log_u < log_accept_prob) {
+      if (prop.model != cur.model) ++ncross_acc;
+      cur.model = prop.model; cur.x = prop.x; ll = proposed_like; lp = proposed_prior; ++nacc;
+    }
+    ++t;
+  };
+  auto record = [&](int64_t s) {
+    counts[cur.model]++;
+    if (margin) { margin[s * C + c] = tl_margin; tl_margin = HUGE_VAL; }
+    if (out_model) out_model[s * C + c] = (uint8_t)cur.model;
+    if (out_samples) {
+      for (int f = 0; f < Dm; ++f) out_samples[(s * F + f) * C + c] = cur.x[f];
+      out_samples[(s * F + Dm) * C + c] = ll; out_samples[(s * F + Dm + 1) * C + c] = lp;
+    }
+  };
+  for (int64_t i = 0; i < cfg.nbin; ++i) step();
+  if (cfg.n > 0) record(0);
+  for (int64_t i = 1; i <= (cfg.n - 1) * cfg.nskip; ++i) {
+    step();
+    if (i % cfg.nskip == 0) record(i / cfg.nskip);
+  }
+  if (acc) *acc = nacc;
+  if (cross) { cross[0] = ncross; cross[1] = ncross_acc; }
+  return bad ? 1 : 0;
+}
+
 // ===========================================================================
 // evidence.ml
 // ===========================================================================
@@ -574,6 +660,36 @@ int og_rjmcmc_array(uint64_t seed, uint64_t epoch, const mg_rj_model *A, const m
                     double *out_samples, int64_t out_counts[2], int64_t *out_accept, int nthreads) {
   return og_rjmcmc_array_m(seed, epoch, A, B, cfg, a0, b0, out_model, out_samples, out_counts, out_accept, nthreads,
                            nullptr, nullptr);
+}
+
+// k-model extension (see rj_chain_k).  out_counts: [nmodels]; margin: [n][C] or null; out_cross: {proposed, accepted}
+int og_rjmcmc_array_k(uint64_t seed, uint64_t epoch, const mg_rj_model *models, int32_t nmodels,
+                      const mg_rjmcmc_cfg *cfg, const double *const *starts, uint8_t *out_model, double *out_samples,
+                      int64_t *out_counts, int64_t *out_accept, int nthreads, double *margin, int64_t *out_cross) {
+  OG_TRY
+  if (nmodels < 2 || nmodels > MG_RJ_MAX_MODELS) return fail(MG_EINVAL, "rjmcmc_array_k: 2..MG_RJ_MAX_MODELS models");
+  double psum = 0.0;
+  std::vector<RjModel> Ms;
+  for (int k = 0; k < nmodels; ++k) { psum = psum + models[k].p; Ms.emplace_back(models + k); }
+  if (!(psum - 1.0 < std::sqrt(2.220446049250313e-16))) return fail(MG_EFAIL, "Assert_failure mcmc.ml:90");
+  CallKey ck = derive_key(seed, epoch);
+  const int64_t C = cfg->nchains;
+  std::vector<int64_t> cnt((size_t)C * nmodels, 0), ac(C, 0), cr((size_t)C * 2, 0);
+  std::vector<int> bad(C, 0);
+  parallel_for(C, nthreads, [&](int64_t c) {
+    bad[c] = rj_chain_k(ck, Ms, *cfg, starts, c, out_model, out_samples, &cnt[(size_t)c * nmodels], &ac[c], margin, &cr[2 * c]);
+  });
+  for (int k = 0; k < nmodels; ++k) out_counts[k] = 0;
+  int64_t tacc = 0, c0 = 0, c1 = 0;
+  for (int64_t c = 0; c < C; ++c) {
+    for (int k = 0; k < nmodels; ++k) out_counts[k] += cnt[(size_t)c * nmodels + k];
+    tacc += ac[c]; c0 += cr[2 * c]; c1 += cr[2 * c + 1];
+    if (bad[c]) return fail(MG_EFAIL, "draw: empty tree");
+  }
+  if (out_accept) *out_accept = tacc;
+  if (out_cross) { out_cross[0] = c0; out_cross[1] = c1; }
+  return MG_OK;
+  OG_CATCH
 }
 
 // ---- kd-tree / interpolate ------------------------------------------------

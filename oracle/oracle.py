@@ -201,6 +201,28 @@ def rjmcmc_array(seed, epoch, n, A, B, a0, b0, *, nbin=0, nskip=1, nchains=1, ch
                 cross=(cross[0], cross[1]))
 
 
+def rjmcmc_array_k(seed, epoch, n, models, starts, *, nbin=0, nskip=1, nchains=1, chain_offset=0, nthreads=1,
+                   record_model=True, record_samples=False, margins=False):
+    """k-model extension (oracle.cpp: rj_chain_k).  models: list of rj_model(...) results."""
+    K = len(models)
+    arr = (_abi.mg_rj_model * K)(*[m for m, _ in models])
+    dm = max(m.like.dim for m, _ in models)
+    cfg = _abi.mg_rjmcmc_cfg(nchains, nbin, nskip, n, chain_offset, 0, 0)
+    model = np.empty((n, nchains), np.uint8) if record_model else None
+    samples = np.empty((n, dm + 2, nchains)) if record_samples else None
+    counts = (C.c_int64 * K)()
+    acc = C.c_int64()
+    st = [as_f64(x) for x in starts]
+    sp = (_abi.c_double_p * K)(*[ptr(x) for x in st])
+    mg = np.full((n, nchains), np.inf) if margins else None
+    cross = (C.c_int64 * 2)()
+    _check(lib().og_rjmcmc_array_k(U64(seed), U64(epoch), arr, C.c_int32(K), C.byref(cfg), sp,
+                                   ptr(model, _abi.c_uint8_p), ptr(samples), counts, C.byref(acc), C.c_int(nthreads),
+                                   ptr(mg), cross))
+    return dict(model=model, samples=samples, counts=tuple(counts), accept=acc.value, margins=mg,
+                cross=(cross[0], cross[1]))
+
+
 def evidence_harmonic_mean(ll):
     ll = as_f64(ll)
     out = (C.c_double * 2)()

@@ -62,3 +62,43 @@ def test_combine_jump_proposal(og):  # mcmc_test.ml:184-208
     out, _, _ = og.mcmc_array(7, 0, 4000, P.gauss_diag([0.0], [1.0]), P.zero(1), prop, [0.0], nskip=5, nchains=64, nthreads=8)
     x = out[:, 0, :].ravel()
     assert abs(x.mean()) < 0.05 and x.std(ddof=1) == pytest.approx(1.0, rel=2e-2)
+
+
+# ---- k-model reversible jump: an extension, specified in oracle.cpp: rj_chain_k ------------------
+
+def _three_gaussians(og):
+    """Three normalised 1-D Gaussians split differently between likelihood and prior: every model has evidence 1, so
+    the chain visits model k with its prior probability (the k-model form of mcmc_test.ml:114-148)."""
+    spec = [(0.31, 0.62, 0.5, 0.2), (0.77, 0.45, 0.3, 0.3), (-0.4, 0.8, 0.6, 0.5)]
+    ms = []
+    for mu, s, w, p in spec:
+        g = P.gauss_diag([mu], [s])
+        ms.append(og.rj_model(g.scaled(w), g.scaled(1.0 - w), P.indep_gauss_proposal([mu], [s]), p, into_gauss=([mu], [s])))
+    return ms, [[m] for m, _, _, _ in spec], [p for _, _, _, p in spec]
+
+
+def test_rjmcmc_k_with_two_models_is_the_two_model_sampler(og):
+    mu1, s1, mu2, s2 = 0.31, 0.62, 0.77, 0.45
+    g1, g2 = P.gauss_diag([mu1], [s1]), P.gauss_diag([mu2], [s2])
+    A = og.rj_model(g1.scaled(0.5), g1.scaled(0.5), P.indep_gauss_proposal([mu1], [s1]), 0.1, into_gauss=([mu1], [s1]))
+    B = og.rj_model(g2.scaled(0.3), g2.scaled(0.7), P.indep_gauss_proposal([mu2], [s2]), 0.9, into_gauss=([mu2], [s2]))
+    two = og.rjmcmc_array(11, 3, 200, A, B, [mu1], [mu2], nskip=3, nbin=7, nchains=32, nthreads=4, record_samples=True)
+    k = og.rjmcmc_array_k(11, 3, 200, [A, B], [[mu1], [mu2]], nskip=3, nbin=7, nchains=32, nthreads=4, record_samples=True)
+    assert np.array_equal(two["model"], k["model"]) and np.array_equal(two["samples"], k["samples"])
+    assert two["counts"] == k["counts"] and two["accept"] == k["accept"] and two["cross"] == k["cross"]
+
+
+def test_rjmcmc_k_three_models_recover_their_priors(og):
+    ms, starts, priors = _three_gaussians(og)
+    r = og.rjmcmc_array_k(4, 0, 2000, ms, starts, nskip=10, nchains=64, nthreads=8)
+    frac = np.array(r["counts"]) / sum(r["counts"])
+    assert sum(r["counts"]) == 2000 * 64
+    np.testing.assert_allclose(frac, priors, rtol=0.1)
+    assert r["model"].max() == 2 and r["cross"][0] > 0
+
+
+def test_rjmcmc_k_prior_sum_assertion(og):
+    ms, starts, _ = _three_gaussians(og)
+    ms[2] = (type(ms[2][0])(ms[2][0].like, ms[2][0].prior, ms[2][0].prop, ms[2][0].into, 0.6), ms[2][1])   # 0.2 + 0.3 + 0.6
+    with pytest.raises(Exception):
+        og.rjmcmc_array_k(4, 0, 10, ms, starts)

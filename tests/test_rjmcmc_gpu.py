@@ -149,3 +149,65 @@ def test_high_dimensional_interp_jumps_match_oracle(ctx, og, dA, dB, nstop):
     if frac == 0.0:
         assert g.counts == o["counts"] and g.cross == o["cross"]
     assert g.cross[0] > 0.4 * C * (n - 1) * 2          # half of the steps propose a jump into the other model
+
+
+# ---- k-model reversible jump (mg_rjmcmc_array_k): an extension, SURVEY 8f rank 3 -----------------------------------
+
+def test_k_model_call_with_two_models_equals_the_two_model_call(ctx):
+    prior, like1, like2, prop, p1, p2 = tophat_setup(ctx, None, nsamp=4000)
+    i1 = interpolate_pdf.InterpPdf(p1, [0, 0], [1, 1], ctx=ctx)
+    i2 = interpolate_pdf.InterpPdf(p2, [0, 0], [1, 1], ctx=ctx)
+    A = mcmc.RjModel(like1, prior, prop, 0.4, interp=i1)
+    B = mcmc.RjModel(like2, prior, prop, 0.6, interp=i2)
+    ctx.set_seed(501)
+    two = mcmc.rjmcmc_array(150, A, B, [0.5, 0.5], [0.5, 0.5], nskip=3, nbin=10, nchains=333, record_samples=True, ctx=ctx)
+    ctx.set_seed(501)
+    k = mcmc.rjmcmc_array_k(150, [A, B], [[0.5, 0.5], [0.5, 0.5]], nskip=3, nbin=10, nchains=333, record_samples=True, ctx=ctx)
+    assert np.array_equal(two.model, k.model) and np.array_equal(two.block, k.block)
+    assert two.counts == k.counts and two.cross == k.cross
+
+
+def test_three_models_match_oracle_and_known_evidence_ratios(ctx, og):
+    """Three top hats on the unit square (sides 1, 1/2, 1/4: evidences 1, 1/4, 1/16 under the unit-square prior) with
+    interpolated jumps into each, model priors (0.2, 0.3, 0.5): chain for chain against the oracle on the same Philox
+    stream, then the known answer -- time in model k proportional to p_k Z_k."""
+    prior = P.box([0, 0], [1, 1], 0.0)
+    boxes = [([0, 0], [1, 1]), ([0.25, 0.25], [0.75, 0.75]), ([0.375, 0.375], [0.625, 0.625])]
+    prop = P.wrap_proposal([0, 0], [1, 1], [0.5, 0.5])
+    pri = [0.2, 0.3, 0.5]
+    ctx.set_seed(1001)
+    gm, om = [], []
+    for (lo, hi), p in zip(boxes, pri):
+        like = P.box(lo, hi, 0.0)
+        pts = mcmc.mcmc_array(6000, like, prior, prop, [0.5, 0.5], nskip=50, ctx=ctx).values()
+        gm.append(mcmc.RjModel(like, prior, prop, p, interp=interpolate_pdf.InterpPdf(pts, [0, 0], [1, 1], ctx=ctx)))
+        om.append(og.rj_model(like, prior, prop, p, tree=og.Tree(pts, [0, 0], [1, 1])))
+    starts = [[0.5, 0.5]] * 3
+    ctx.set_seed(88)
+    g = mcmc.rjmcmc_array_k(200, gm, starts, nskip=3, nbin=10, nchains=256, record_samples=True, ctx=ctx)
+    o = og.rjmcmc_array_k(88, 0, 200, om, starts, nskip=3, nbin=10, nchains=256, nthreads=8, record_samples=True, margins=True)
+    frac = divergence_report(np.concatenate([g.block[:, :2, :], g.model[:, None, :].astype(float)], axis=1),
+                             np.concatenate([o["samples"][:, :2, :], o["model"][:, None, :].astype(float)], axis=1),
+                             o["margins"], "RJ three top hats")
+    assert frac <= 0.01
+    if frac == 0.0:
+        assert g.counts == o["counts"] and g.cross == o["cross"]
+    assert g.model.max() == 2
+    ctx.set_seed(89)
+    r = mcmc.rjmcmc_array_k(250, gm, starts, nskip=10, nbin=100, nchains=4096, record_model=False, ctx=ctx)
+    w = np.array(pri) * np.array([1.0, 0.25, 0.0625])
+    got = np.array(r.counts) / sum(r.counts)
+    np.testing.assert_allclose(got, w / w.sum(), rtol=0.05)
+    assert r.counts[0] / r.counts[1] == pytest.approx((0.2 * 1.0) / (0.3 * 0.25), rel=0.05)
+
+
+def test_k_model_arguments(ctx):
+    g = P.gauss_diag([0.0], [1.0])
+    mk = lambda p: mcmc.RjModel(g, P.zero(1), P.box_proposal([1.0]), p, into_gauss=([0.0], [1.0]))
+    with pytest.raises(Failure):                       # sum of the priors, as mcmc.ml:90
+        mcmc.rjmcmc_array_k(10, [mk(0.5), mk(0.4), mk(0.3)], [[0.0]] * 3, ctx=ctx)
+    from mcmc_ocaml_b200 import InvalidArgument
+    with pytest.raises(InvalidArgument):               # 2..MG_RJ_MAX_MODELS models
+        mcmc.rjmcmc_array_k(10, [mk(0.1)] * 9, [[0.0]] * 9, ctx=ctx)
+    r = mcmc.rjmcmc_array_k(50, [mk(0.125)] * 8, [[0.0]] * 8, nchains=512, ctx=ctx)
+    assert sum(r.counts) == 50 * 512 and min(r.counts) > 0.08 * 50 * 512   # eight equal models: about 1/8 each
