@@ -127,6 +127,11 @@ def load_library() -> C.CDLL:
     if hasattr(lib, "mg_kdtree_destroy"):
         lib.mg_kdtree_destroy.restype = None
         lib.mg_kdtree_destroy.argtypes = [C.c_void_p]
+    if hasattr(lib, "mg_ellipse_tree_destroy"):
+        lib.mg_ellipse_tree_destroy.restype = None
+        lib.mg_ellipse_tree_destroy.argtypes = [C.c_void_p]
+        lib.mg_ellipse_tree_info.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.mg_ellipse_tree_export.argtypes = [C.c_void_p] + [C.c_void_p] * 10
     _lib = lib
     return lib
 
