@@ -591,6 +591,17 @@ int mg_comm_allgather(mg_comm *comm, const void *send, void *recv, int64_t nbyte
  * *out: on the root `tree` itself, on the other ranks a new tree (destroy it). */
 int mg_kdtree_broadcast(mg_comm *comm, mg_kdtree *tree, int32_t root,
                         mg_kdtree **out);
+/* Kd_tree.tree_of_objects (kd_tree.ml:155-175) built by all ranks together
+ * (SURVEY.md 8f rank 3).  d_pts: the same N x D device rows on every rank.  Every
+ * rank builds the top log2(nranks) levels, rank r builds the subtree under node
+ * r of that level from its N / nranks rows, one ncclAllGather exchanges the
+ * subtrees; every rank receives the whole tree, bit-identical to
+ * mg_kdtree_build_dev on one GPU.  A rank count that is not a power of two,
+ * fewer than 4096 points per rank, min_split above N / nranks or ties that keep
+ * the top from being a complete tree make every rank build the tree alone. */
+int mg_kdtree_build_distributed(mg_comm *comm, const double *d_pts, int64_t N,
+                                int32_t D, const double *low, const double *high,
+                                int32_t min_split, mg_kdtree **out);
 /* Evidence.evidence_lebesgue / evidence_direct (evidence.ml:148-221) with the
  * kd-cells shared out: `root` holds the samples (device pointers; ignored on
  * the other ranks), does the global steps (sort, prefix cut, de-duplication,

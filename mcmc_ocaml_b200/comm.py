@@ -108,6 +108,16 @@ class Comm:
             return tree
         return KdTree(None, None, None, ctx=self.ctx, _handle=out)
 
+    def build_tree(self, pts_ptr: int, N: int, D: int, low, high, *, min_split: int = 2):
+        """``Kd_tree.tree_of_objects`` built by all ranks together (``mg_kdtree_build_distributed``): ``pts_ptr`` is the
+        same [N][D] device array on every rank; every rank receives the whole tree, bit-identical to the one-GPU build."""
+        from .kd_tree import KdTree
+        low, high = _abi.as_f64(low), _abi.as_f64(high)
+        out = C.c_void_p()
+        self.ctx.check(self.ctx.lib.mg_kdtree_build_distributed(self.h, C.c_void_p(pts_ptr), C.c_int64(N), C.c_int32(D),
+                                                                _abi.ptr(low), _abi.ptr(high), C.c_int32(min_split), C.byref(out)))
+        return KdTree(None, None, None, ctx=self.ctx, _handle=out)
+
     def _evidence(self, fn, root, pts_ptr, ll_ptr, lp_ptr, N, D, n, *extra):
         out = C.c_double()
         self.ctx.check(fn(self.h, C.c_int32(root), C.c_void_p(pts_ptr or 0), C.c_void_p(ll_ptr or 0), C.c_void_p(lp_ptr or 0),

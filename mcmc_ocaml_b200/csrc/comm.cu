@@ -9,6 +9,7 @@
 // NCCL is bound at run time (dlopen "libnccl.so.2"): the library has no link-time dependency on it, a process that
 // already carries an NCCL (torch) shares that copy, and without NCCL only these entry points fail (MG_EFAIL).
 #include <dlfcn.h>
+#include <time.h>
 #include <nccl.h>
 
 #include <algorithm>
@@ -339,5 +340,297 @@ extern "C" int mg_comm_pool_moments(mg_comm *c, int64_t n_local, const double *m
     if (out_mean) out_mean[i] = mean[i];
     if (out_std) out_std[i] = n > 1.0 ? sqrt(m2[i] / (n - 1.0)) : 0.0;
   }
+  return MG_OK;
+}
+
+// =====================================================================================================================
+// Distributed kd-tree build: Kd_tree.tree_of_objects (kd_tree.ml:155-175) with the
+// subtrees below level k = log2(ranks) built on different GPUs.
+//
+// Every rank holds the N points (replicated input: the posterior draws a model's interpolated jumps are made from).
+//   1. every rank builds the TOP of the tree, truncated where nodes fall below ~N / ranks points: k levels, 2^k leaves;
+//      the same arithmetic on the same data, so all ranks hold the same top and the same stable order of the points;
+//   2. rank r gathers the rows of leaf r in that order and builds the complete tree of those N / ranks points with
+//      the single-GPU builder -- the rule depends on a node's points and their order only, so this IS the subtree the
+//      single-GPU build hangs under node r;
+//   3. one ncclAllGather moves every rank's (nodes, count, begin, perm) sections; an unpack kernel gives the nodes
+//      their breadth-first numbers in the whole tree (level L of the whole tree = the ranks' levels L - k side by
+//      side, children adjacent) and maps the local point ids back through the top's order.
+// The result is bit-identical to mg_kdtree_build_dev on one GPU (tools/multi_gpu_check.py compares every array).
+// Inputs whose top does not come out as a complete k-level tree (ties that stop a node from splitting), fewer than
+// 4096 points per rank or a rank count that is not a power of two are built by every rank for itself.
+namespace mg {
+
+int build_tree(mg_ctx *ctx, const double *d_pts, int64_t N, int D, const double *low, const double *high, int min_split,
+               mg_kdtree **out);   // kdtree.cu
+
+constexpr int KDD_MAXL = 96;         // levels of a subtree
+constexpr int KDD_MAXR = 64;         // ranks
+
+// level table of a breadth-first tree with adjacent children: lb[l] = first node of level l, lb[nl] = nnodes
+__global__ void __launch_bounds__(1024) kdd_levels_kernel(const KdNode *__restrict__ nodes, int32_t nnodes, int32_t *__restrict__ lb,
+                                                          int32_t *__restrict__ nl) {
+  __shared__ int s_max;
+  int b = 0, e = 1, l = 0;
+  if (threadIdx.x == 0) lb[0] = 0;
+  while (b < e && l < KDD_MAXL) {
+    if (threadIdx.x == 0) s_max = -1;
+    __syncthreads();
+    int m = -1;
+    for (int i = b + threadIdx.x; i < e; i += blockDim.x) { const int lf = nodes[i].left; m = lf > m ? lf : m; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { const int x = __shfl_xor_sync(0xffffffffu, m, o); m = x > m ? x : m; }
+    if ((threadIdx.x & 31) == 0 && m >= 0) atomicMax(&s_max, m);
+    __syncthreads();
+    const int last = s_max;
+    ++l;
+    b = e; e = last >= 0 ? last + 2 : e;          // the last internal node's children end the next level
+    if (threadIdx.x == 0) lb[l] = b;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *nl = l;
+  (void)nnodes;
+}
+
+__global__ void kdd_gather_rows_kernel(const double *__restrict__ pts, const int32_t *__restrict__ perm, int64_t n, int D,
+                                       double *__restrict__ out) {
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n * D) return;
+  const int64_t i = k / D; const int j = (int)(k - i * D);
+  out[k] = pts[(int64_t)perm[i] * D + j];
+}
+
+struct KddTables {
+  int32_t lb[KDD_MAXR][KDD_MAXL + 1];   // per rank: first local node of every local level
+  int32_t goff[KDD_MAXR][KDD_MAXL + 1]; // per rank: nodes of lower ranks on the same level
+  int32_t gbase[KDD_MAXL + 2];          // whole tree: first node of level k + l
+  int32_t nl[KDD_MAXR], nn[KDD_MAXR], npts[KDD_MAXR], pbegin[KDD_MAXR];
+  int64_t off_count[KDD_MAXR], off_begin[KDD_MAXR], off_perm[KDD_MAXR];   // byte offsets inside a rank's chunk
+};
+
+__global__ void kdd_unpack_nodes_kernel(const KddTables *__restrict__ T, int r, const uint8_t *__restrict__ chunk,
+                                        KdNode *__restrict__ nodes, int32_t *__restrict__ count, int32_t *__restrict__ begin) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= T->nn[r]) return;
+  const int32_t *lb = T->lb[r];
+  int lo = 0, hi = T->nl[r];                     // level l with lb[l] <= i < lb[l + 1]
+  while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (lb[mid] <= i) lo = mid; else hi = mid; }
+  const int l = lo;
+  const int gid = T->gbase[l] + T->goff[r][l] + (i - lb[l]);
+  KdNode nd = reinterpret_cast<const KdNode *>(chunk)[i];
+  if (nd.left >= 0) nd.left = T->gbase[l + 1] + T->goff[r][l + 1] + (nd.left - lb[l + 1]);
+  nodes[gid] = nd;
+  count[gid] = reinterpret_cast<const int32_t *>(chunk + T->off_count[r])[i];
+  begin[gid] = T->pbegin[r] + reinterpret_cast<const int32_t *>(chunk + T->off_begin[r])[i];
+}
+
+__global__ void kdd_unpack_perm_kernel(const KddTables *__restrict__ T, int r, const uint8_t *__restrict__ chunk,
+                                       const int32_t *__restrict__ top_perm, int32_t *__restrict__ perm) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= T->npts[r]) return;
+  const int b = T->pbegin[r];
+  perm[b + j] = top_perm[b + reinterpret_cast<const int32_t *>(chunk + T->off_perm[r])[j]];
+}
+
+struct KdGuard { mg_kdtree *t = nullptr; ~KdGuard() { if (t) mg_kdtree_destroy(t); } };
+
+}  // namespace mg
+
+extern "C" int mg_kdtree_build_distributed(mg_comm *c, const double *d_pts, int64_t N, int32_t D, const double *low,
+                                           const double *high, int32_t min_split, mg_kdtree **out) {
+  if (!c) return MG_EINVAL;
+  mg_ctx *ctx = c->ctx;
+  MG_REQUIRE(ctx, d_pts && low && high && out, "kd-tree (distributed): null argument");
+  MG_CUDA(ctx, cudaSetDevice(ctx->device));
+  *out = nullptr;
+  if (min_split < 2) min_split = 2;
+  const int R = c->nranks;
+  int k = 0;
+  while ((1 << k) < R) ++k;
+  const int64_t ms_top = (N >> k) + 3;           // no node of level k reaches it, every node above does (without ties)
+  const bool shard = R > 1 && (1 << k) == R && R <= KDD_MAXR && N / R >= 4096 && (int64_t)min_split < ms_top && ms_top < (1LL << 31);
+  if (!shard) return build_tree(ctx, d_pts, N, D, low, high, min_split, out);
+  cudaStream_t s = ctx->stream;
+  int rc;
+  static const bool dbg = getenv("MCMC_GPU_DEBUG") != nullptr;
+  double t_prev = 0.0;
+  auto phase = [&](const char *name) {           // MCMC_GPU_DEBUG: wall time of the phases (adds synchronisation)
+    if (!dbg) return;
+    cudaStreamSynchronize(s);
+    timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts);
+    const double now = ts.tv_sec + 1e-9 * ts.tv_nsec;
+    uint64_t reserved = 0, used = 0;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, ctx->device) == cudaSuccess) {
+      cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &reserved);
+      cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used);
+    }
+    if (name) fprintf(stderr, "[kd-dist rank %d] %-10s %8.3f ms   pool reserved %.2f GB used %.2f GB\n", c->rank, name, 1e3 * (now - t_prev),
+                      1e-9 * reserved, 1e-9 * used);
+    t_prev = now;
+  };
+  phase(nullptr);
+  // The result's blob is allocated FIRST, for the largest possible node count (2 N): a caller that rebuilds trees
+  // gets the block of its previous tree back, where a late request for 2 GB in one piece makes the stream-ordered
+  // pool remap its fragments (measured: 15-180 ms).  Truncated trees (min_split > 16) are small next to that bound and
+  // get an exact blob at the end instead.
+  auto al = [](int64_t x) { return (x + 255) & ~255LL; };
+  auto layout = [&](KdHeader &h, int64_t node_cap) {
+    int64_t off = al(sizeof(KdHeader));
+    h.off_low = off; off = al(off + 8 * D);
+    h.off_high = off; off = al(off + 8 * D);
+    h.off_nodes = off; off = al(off + 16 * node_cap);
+    h.off_count = off; off = al(off + 4 * node_cap);
+    h.off_begin = off; off = al(off + 4 * node_cap);
+    h.off_perm = off; off = al(off + 4 * N);
+    h.off_pts = off; off = al(off + 8 * N * D);
+    h.nbytes = off;
+  };
+  KdGuard res;
+  const bool early = min_split <= 16;
+  if (early) {
+    res.t = new mg_kdtree;
+    res.t->ctx = ctx;
+    layout(res.t->h, 2 * N);
+    cudaError_t e = cudaMallocAsync(&res.t->d_blob, (size_t)res.t->h.nbytes, s);
+    if (e != cudaSuccess) { res.t->d_blob = nullptr; return set_err(ctx, MG_ENOMEM, "cuda: %s (kd-tree blob of %lld bytes)", cudaGetErrorString(e), (long long)res.t->h.nbytes); }
+  }
+  // ---- 1. the top, on every rank ---------------------------------------------------------------------------------------
+  KdGuard top, sub;
+  // (the top and the subtree are scaffolding: their blobs carry no copy of the points)
+  struct NoPts { mg_ctx *c; explicit NoPts(mg_ctx *c_) : c(c_) { c->kd_no_pts = true; } ~NoPts() { c->kd_no_pts = false; } };
+  { NoPts np(ctx); rc = build_tree(ctx, d_pts, N, D, low, high, (int)ms_top, &top.t); }
+  if (rc) return rc;
+  phase("top build");
+  const KdHeader &th = top.t->h;
+  const char *tb = (const char *)top.t->d_blob;
+  std::vector<KdNode> tnodes((size_t)th.nnodes);
+  std::vector<int32_t> tcount((size_t)th.nnodes), tbegin((size_t)th.nnodes);
+  bool complete = th.nnodes == 2 * (int64_t)R - 1;
+  if (complete) {
+    MG_CUDA(ctx, cudaMemcpyAsync(tnodes.data(), tb + th.off_nodes, sizeof(KdNode) * tnodes.size(), cudaMemcpyDeviceToHost, s));
+    MG_CUDA(ctx, cudaMemcpyAsync(tcount.data(), tb + th.off_count, 4 * tcount.size(), cudaMemcpyDeviceToHost, s));
+    MG_CUDA(ctx, cudaMemcpyAsync(tbegin.data(), tb + th.off_begin, 4 * tbegin.size(), cudaMemcpyDeviceToHost, s));
+    MG_CUDA(ctx, cudaStreamSynchronize(s));
+    for (int i = 0; i < R - 1; ++i) complete = complete && tnodes[i].left == 2 * i + 1;      // a complete binary top
+    for (int i = R - 1; i < 2 * R - 1; ++i) complete = complete && tnodes[i].left < 0 && tcount[i] >= 2;
+  }
+  phase("top d2h");
+  // every rank must take the same branch: the tops are identical, but agree explicitly
+  {
+    int64_t mine = complete ? 1 : 0;
+    std::vector<int64_t> all((size_t)R);
+    if ((rc = mg_comm_allgather(c, &mine, all.data(), sizeof mine))) return rc;
+    for (int r = 0; r < R; ++r) complete = complete && all[r] == 1;
+  }
+  if (!complete) return build_tree(ctx, d_pts, N, D, low, high, min_split, out);
+  phase("top");
+  // ---- 2. this rank's subtree -------------------------------------------------------------------------------------------
+  const int me = c->rank;
+  const int32_t my_b = tbegin[R - 1 + me], my_n = tcount[R - 1 + me];
+  const int32_t *top_perm = (const int32_t *)(tb + th.off_perm);
+  DevBuf<double> rows;
+  MG_CUDA(ctx, rows.alloc((size_t)my_n * D, s));
+  kdd_gather_rows_kernel<<<(unsigned)(((int64_t)my_n * D + 255) / 256), 256, 0, s>>>(d_pts, top_perm + my_b, my_n, D, rows.get());
+  MG_CHECK_LAUNCH(ctx);
+  phase("gather");
+  { NoPts np(ctx); rc = build_tree(ctx, rows.get(), my_n, D, low, high, min_split, &sub.t); }
+  if (rc) return rc;
+  phase("subtree");
+  const KdHeader &sh = sub.t->h;
+  const char *sb = (const char *)sub.t->d_blob;
+  struct Rec { int32_t nl, nn, npts, pbegin; int32_t lb[KDD_MAXL + 1]; int32_t bad; };
+  Rec mine{};
+  const std::vector<int32_t> &lvb = sub.t->level_begin;
+  if (lvb.size() >= 2 && lvb.size() <= (size_t)KDD_MAXL + 1) {     // the builder kept its level table
+    mine.nl = (int32_t)lvb.size() - 1;
+    for (size_t l = 0; l < lvb.size(); ++l) mine.lb[l] = lvb[l];
+  } else {                                                           // first builder: read the levels off the nodes
+    DevBuf<int32_t> d_lb, d_nl;
+    MG_CUDA(ctx, d_lb.alloc(KDD_MAXL + 1, s)); MG_CUDA(ctx, d_nl.alloc(1, s));
+    kdd_levels_kernel<<<1, 1024, 0, s>>>((const KdNode *)(sb + sh.off_nodes), (int32_t)sh.nnodes, d_lb.get(), d_nl.get());
+    MG_CHECK_LAUNCH(ctx);
+    MG_CUDA(ctx, cudaMemcpyAsync(mine.lb, d_lb.get(), sizeof mine.lb, cudaMemcpyDeviceToHost, s));
+    MG_CUDA(ctx, cudaMemcpyAsync(&mine.nl, d_nl.get(), sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    MG_CUDA(ctx, cudaStreamSynchronize(s));
+  }
+  phase("levels");
+  mine.nn = (int32_t)sh.nnodes; mine.npts = my_n; mine.pbegin = my_b;
+  mine.bad = (mine.nl >= KDD_MAXL || mine.lb[mine.nl] != mine.nn) ? 1 : 0;
+  std::vector<Rec> recs((size_t)R);
+  if ((rc = mg_comm_allgather(c, &mine, recs.data(), sizeof mine))) return rc;
+  phase("tables");
+  // ---- 3. numbering of the whole tree and the exchange -------------------------------------------------------------------
+  std::vector<KddTables> Tv(1);
+  KddTables &T = Tv[0];
+  memset(&T, 0, sizeof T);
+  int maxl = 0; int64_t chunk = 0;
+  for (int r = 0; r < R; ++r) {
+    const Rec &q = recs[r];
+    if (q.bad) return set_err(ctx, MG_EFAIL, "kd-tree (distributed): rank %d built a subtree deeper than %d levels", r, KDD_MAXL);
+    T.nl[r] = q.nl; T.nn[r] = q.nn; T.npts[r] = q.npts; T.pbegin[r] = q.pbegin;
+    memcpy(T.lb[r], q.lb, sizeof q.lb);
+    for (int l = q.nl + 1; l <= KDD_MAXL; ++l) T.lb[r][l] = q.nn;
+    maxl = std::max(maxl, (int)q.nl);
+    auto al = [](int64_t x) { return (x + 255) & ~255LL; };
+    T.off_count[r] = al(16LL * q.nn); T.off_begin[r] = al(T.off_count[r] + 4LL * q.nn); T.off_perm[r] = al(T.off_begin[r] + 4LL * q.nn);
+    chunk = std::max<int64_t>(chunk, al(T.off_perm[r] + 4LL * q.npts));
+  }
+  T.gbase[0] = R - 1;                               // level k of the whole tree starts after the 2^k - 1 nodes above it
+  for (int l = 0; l <= maxl; ++l) {
+    int64_t tot = 0;
+    for (int r = 0; r < R; ++r) { T.goff[r][l] = (int32_t)tot; tot += T.lb[r][l + 1] - T.lb[r][l]; }
+    T.gbase[l + 1] = T.gbase[l] + (int32_t)tot;
+  }
+  const int64_t nnodes = T.gbase[maxl];
+  MG_REQUIRE(ctx, nnodes <= 2 * N, "kd-tree (distributed): node count out of range");
+  DevBuf<uint8_t> sendb, recvb;
+  DevBuf<KddTables> d_T;
+  MG_CUDA(ctx, sendb.alloc((size_t)chunk, s)); MG_CUDA(ctx, recvb.alloc((size_t)chunk * R, s));
+  MG_CUDA(ctx, upload(d_T, &T, 1, s));
+  MG_CUDA(ctx, cudaMemcpyAsync(sendb.get(), sb + sh.off_nodes, 16 * (size_t)sh.nnodes, cudaMemcpyDeviceToDevice, s));
+  MG_CUDA(ctx, cudaMemcpyAsync(sendb.get() + T.off_count[me], sb + sh.off_count, 4 * (size_t)sh.nnodes, cudaMemcpyDeviceToDevice, s));
+  MG_CUDA(ctx, cudaMemcpyAsync(sendb.get() + T.off_begin[me], sb + sh.off_begin, 4 * (size_t)sh.nnodes, cudaMemcpyDeviceToDevice, s));
+  MG_CUDA(ctx, cudaMemcpyAsync(sendb.get() + T.off_perm[me], sb + sh.off_perm, 4 * (size_t)my_n, cudaMemcpyDeviceToDevice, s));
+  {
+    CollTimer tm(c);
+    if ((rc = comm_allgather_dev(c, sendb.get(), recvb.get(), (size_t)chunk))) return rc;
+    tm.stop();
+  }
+  phase("allgather");
+  // ---- the blob (layout of the single-GPU builders) -----------------------------------------------------------------------
+  if (!early) {
+    res.t = new mg_kdtree;
+    res.t->ctx = ctx;
+    layout(res.t->h, nnodes);
+    cudaError_t e = cudaMallocAsync(&res.t->d_blob, (size_t)res.t->h.nbytes, s);
+    if (e != cudaSuccess) { res.t->d_blob = nullptr; return set_err(ctx, MG_ENOMEM, "cuda: %s (kd-tree blob of %lld bytes)", cudaGetErrorString(e), (long long)res.t->h.nbytes); }
+  }
+  mg_kdtree *tr = res.t;
+  KdHeader &h = tr->h;
+  h.magic = KD_MAGIC; h.N = N; h.nnodes = nnodes; h.D = D; h.nlevels = k + maxl; h.min_split = min_split;
+  char *blob = (char *)tr->d_blob;
+  phase("blob alloc");
+  MG_CUDA(ctx, cudaMemcpyAsync(blob, &tr->h, sizeof(KdHeader), cudaMemcpyHostToDevice, s));
+  MG_CUDA(ctx, cudaMemcpyAsync(blob + h.off_low, low, 8 * D, cudaMemcpyHostToDevice, s));
+  MG_CUDA(ctx, cudaMemcpyAsync(blob + h.off_high, high, 8 * D, cudaMemcpyHostToDevice, s));
+  // the 2^k - 1 nodes above the subtrees: numbers, counts and positions are those of the top tree
+  MG_CUDA(ctx, cudaMemcpyAsync(blob + h.off_nodes, tb + th.off_nodes, 16 * (size_t)(R - 1), cudaMemcpyDeviceToDevice, s));
+  MG_CUDA(ctx, cudaMemcpyAsync(blob + h.off_count, tb + th.off_count, 4 * (size_t)(R - 1), cudaMemcpyDeviceToDevice, s));
+  MG_CUDA(ctx, cudaMemcpyAsync(blob + h.off_begin, tb + th.off_begin, 4 * (size_t)(R - 1), cudaMemcpyDeviceToDevice, s));
+  for (int r = 0; r < R; ++r) {
+    const uint8_t *ch = recvb.get() + (size_t)chunk * r;
+    kdd_unpack_nodes_kernel<<<(unsigned)((T.nn[r] + 255) / 256), 256, 0, s>>>(d_T.get(), r, ch, (KdNode *)(blob + h.off_nodes),
+                                                                              (int32_t *)(blob + h.off_count), (int32_t *)(blob + h.off_begin));
+    MG_CHECK_LAUNCH(ctx);
+    kdd_unpack_perm_kernel<<<(unsigned)((T.npts[r] + 255) / 256), 256, 0, s>>>(d_T.get(), r, ch, top_perm, (int32_t *)(blob + h.off_perm));
+    MG_CHECK_LAUNCH(ctx);
+  }
+  phase("unpack");
+  MG_CUDA(ctx, cudaMemcpyAsync(blob + h.off_pts, d_pts, 8 * (size_t)N * D, cudaMemcpyDeviceToDevice, s));
+  MG_CUDA(ctx, cudaStreamSynchronize(s));
+  phase("pts copy");
+  res.t = nullptr;
+  *out = tr;
   return MG_OK;
 }

@@ -40,6 +40,7 @@ struct mg_ctx {
   mg_nested_observer nest_observer = nullptr;   // Nested ?observer (nested.ml:123-125)
   void *nest_observer_user = nullptr;
   int *d_devflag = nullptr;        // device word set by a kernel whose bounded spin-wait ran out (MG_DEVERR_*)
+  bool kd_no_pts = false;          // internal (distributed build): the next kd-tree blob carries no copy of the points
   int sticky = MG_OK;              // a device-side failure that every later call reports until mg_ctx_clear_error
   std::string err;
 };

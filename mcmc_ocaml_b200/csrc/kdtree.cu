@@ -498,7 +498,8 @@ static int build_tree_v1(mg_ctx *ctx, const double *d_pts, int64_t N, int D, con
   h.off_count = off; off = align256(off + 4 * nnodes);
   h.off_begin = off; off = align256(off + 4 * nnodes);
   h.off_perm = off; off = align256(off + 4 * N);
-  h.off_pts = off; off = align256(off + 8 * N * D);
+  const bool with_pts = !ctx->kd_no_pts;
+  h.off_pts = off; off = align256(off + (with_pts ? 8 * N * D : 0));
   h.nbytes = off;
   mg_kdtree *t = new mg_kdtree;
   t->ctx = ctx; t->h = h;
@@ -514,7 +515,7 @@ static int build_tree_v1(mg_ctx *ctx, const double *d_pts, int64_t N, int D, con
                                                       (int32_t *)(blob + h.off_count), (int32_t *)(blob + h.off_begin));
   ctx->launches++;
   cudaMemcpyAsync(blob + h.off_perm, lin + (int64_t)D * N, 4 * N, cudaMemcpyDeviceToDevice, s);
-  cudaMemcpyAsync(blob + h.off_pts, d_pts, 8 * N * D, cudaMemcpyDeviceToDevice, s);
+  if (with_pts) cudaMemcpyAsync(blob + h.off_pts, d_pts, 8 * N * D, cudaMemcpyDeviceToDevice, s);
   time_end(ctx);
   e = cudaStreamSynchronize(s);
   if (e != cudaSuccess) { cudaFreeAsync(t->d_blob, s); delete t; return set_err(ctx, MG_ECUDA, "cuda: %s (kd-tree build)", cudaGetErrorString(e)); }

@@ -163,6 +163,7 @@ __device__ __forceinline__ bool kd_draw(const KdView &t, const KdScratch &s, int
 }  // namespace mg
 
 #ifndef __CUDACC_RTC__
+#include <vector>
 // host-side handle
 struct mg_kdtree {
   mg_ctx *ctx = nullptr;
@@ -170,6 +171,7 @@ struct mg_kdtree {
   bool owns_blob = true;
   double *d_draw_cache = nullptr;   // [N][2 D + 2], see KdView::dcache (not part of the blob: rebuilt per rank)
   mg::KdHeader h{};
+  std::vector<int32_t> level_begin;  // first node of every level and nnodes at the end, when the builder knows them (second builder)
   mg::KdView view() const {
     const char *b = (const char *)d_blob;
     mg::KdView v;

@@ -1076,9 +1076,16 @@ int build_tree_v2(mg_ctx *ctx, const double *d_pts, int64_t N, int D, const doub
     return MG_OK;
   };
   int rc;
-  for (int L = 0; L < L0; ++L) if ((rc = run_level(L))) return rc;
+  // A truncated build (min_split above the subtree size: Evidence with a large n, the top of a distributed build)
+  // stops splitting long before the hand-over level: without ties a node of level L holds at most (N >> L) + 2
+  // points (s' <= s / 2 + 1), so the level loop is cut where that falls below min_split and the read-back below
+  // decides the rest.
+  int Lrun = L0;
+  if (min_split > NMAX) { Lrun = 0; while (Lrun < L0 && (N >> Lrun) + 2 >= (int64_t)min_split) ++Lrun; }
+  for (int L = 0; L < Lrun; ++L) if ((rc = run_level(L))) return rc;
   V2Info h_info;
-  int Lh = L0;                                   // the hand-over level
+  int Lh = Lrun;                                 // the hand-over level
+  bool leaves_only = false;                      // no node of level Lh splits: the top phase has built the whole tree
   for (;;) {
     int h_nan = 0;
     MG_CUDA(ctx, cudaMemcpyAsync(&h_info, info.get(), sizeof h_info, cudaMemcpyDeviceToHost, s));
@@ -1088,13 +1095,22 @@ int build_tree_v2(mg_ctx *ctx, const double *d_pts, int64_t N, int D, const doub
     // integers, so the levels above ran to completion on them
     MG_REQUIRE(ctx, h_nan == 0, "kd-tree: NaN coordinate");
     if (h_info.overflow) return MG_V2_FALLBACK;
+    if (h_info.maxsize[Lh] < min_split && h_info.maxsize[Lh] > NMAX) { leaves_only = true; break; }
     if (h_info.maxsize[Lh] <= NMAX) break;
     if (Lh >= L0 + V2_EXTRA) return MG_V2_FALLBACK;   // heavy ties: subtrees do not shrink -> first builder
     if ((rc = run_level(Lh))) return rc;
     ++Lh;
   }
-  const int nsub = h_info.lvl[Lh].le - h_info.lvl[Lh].lb;
+  int nsub = h_info.lvl[Lh].le - h_info.lvl[Lh].lb;
   const int64_t nn_top = h_info.nnodes;
+  if (leaves_only) {                             // the nodes of level Lh are leaves: give them their fields, no bottom phase
+    if (nsub > 0) {
+      v2_node_kernel<<<(unsigned)((nsub + 127) / 128), 128, 0, s>>>(t, Lh);
+      MG_CHECK_LAUNCH(ctx);
+      h_info.nlevels = std::max(h_info.nlevels, Lh + 1);   // (counted by the children pass of a level, which did not run)
+    }
+    nsub = 0;
+  }
   // ---- bottom phase ----------------------------------------------------------------------------------------------
   DevBuf<int32_t> l_dim, l_child, l_begin, l_end, cnt, pre, depth, totals, perm_fin;
   DevBuf<double> l_split;
@@ -1143,10 +1159,15 @@ int build_tree_v2(mg_ctx *ctx, const double *d_pts, int64_t N, int D, const doub
   h.off_count = off; off = v2_align256(off + 4 * nnodes);
   h.off_begin = off; off = v2_align256(off + 4 * nnodes);
   h.off_perm = off; off = v2_align256(off + 4 * N);
-  h.off_pts = off; off = v2_align256(off + 8 * N * D);
+  const bool with_pts = !ctx->kd_no_pts;
+  h.off_pts = off; off = v2_align256(off + (with_pts ? 8 * N * D : 0));
   h.nbytes = off;
   mg_kdtree *tr = new mg_kdtree;
   tr->ctx = ctx; tr->h = h;
+  // first node of every level: the top levels as the level loop numbered them, the subtree levels from the scan
+  for (int L = 0; L <= Lh && L < nlevels; ++L) tr->level_begin.push_back(h_info.lvl[L].lb);
+  for (int l = 1; Lh + l < nlevels; ++l) tr->level_begin.push_back(lbase.base[l]);
+  tr->level_begin.push_back((int32_t)nnodes);
   cudaError_t e = cudaMallocAsync(&tr->d_blob, (size_t)h.nbytes, s);
   if (e != cudaSuccess) { delete tr; return set_err(ctx, MG_ENOMEM, "cuda: %s (kd-tree blob of %lld bytes)", cudaGetErrorString(e), (long long)h.nbytes); }
   char *blob = (char *)tr->d_blob;
@@ -1162,7 +1183,7 @@ int build_tree_v2(mg_ctx *ctx, const double *d_pts, int64_t N, int D, const doub
     ctx->launches++;
   }
   cudaMemcpyAsync(blob + h.off_perm, pin, 4 * N, cudaMemcpyDeviceToDevice, s);
-  cudaMemcpyAsync(blob + h.off_pts, d_pts, 8 * N * D, cudaMemcpyDeviceToDevice, s);
+  if (with_pts) cudaMemcpyAsync(blob + h.off_pts, d_pts, 8 * N * D, cudaMemcpyDeviceToDevice, s);
   time_end(ctx);
   e = cudaGetLastError();
   if (e == cudaSuccess) e = cudaStreamSynchronize(s);

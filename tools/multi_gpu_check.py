@@ -9,6 +9,8 @@ NCCL id and allocates the test data):
   3. harmonic mean over sharded samples (<= 2 ulp of the single-GPU value).
   4. MH ensemble sharded by global chain id, statistics pooled with mg_comm_pool_moments (1e-12 of the one-rank run).
   5. RJMCMC sharded (mg_rjmcmc_array_sharded): model counts equal to the one-rank run of all chains.
+  6. kd-tree built by all ranks together (mg_kdtree_build_distributed): every array equal to the single-GPU tree's on
+     every rank; both builds timed.
 Prints one JSON line on rank 0."""
 from __future__ import annotations
 
@@ -148,6 +150,35 @@ def main():
     ctx.set_seed(4711)
     r = comm.rjmcmc_array(51, A, B, a0, a0, nskip=4, nchains=20000)
     out["rj_counts_sharded"] = list(r.counts); out["rj_cross"] = list(r.cross)
+    # ---- 6. distributed kd-tree build (mg_kdtree_build_distributed) ---------------------
+    # every rank holds the rows; the top log2(world) levels are built everywhere, the subtrees one per rank, one
+    # all-gather; the result must equal the single-GPU tree array for array, on every rank
+    dpts = torch.from_numpy(pts).to(dev)
+    lo_, hi_ = np.zeros(Dm), np.ones(Dm)
+    for ms in (2, 64):
+        dt_d, dt_s = [], []
+        for rep in range(3):
+            comm.barrier(); torch.cuda.synchronize()
+            t = time.perf_counter()
+            td = comm.build_tree(dpts.data_ptr(), N, Dm, lo_, hi_, min_split=ms)
+            ctx.sync(); dt_d.append(time.perf_counter() - t)
+            if rep < 2:
+                td.close()
+        for rep in range(3):
+            comm.barrier(); torch.cuda.synchronize()
+            t = time.perf_counter()
+            ts = kd_tree.KdTree.from_device(dpts.data_ptr(), N, Dm, lo_, hi_, min_split=ms, ctx=ctx)
+            ctx.sync(); dt_s.append(time.perf_counter() - t)
+            if rep < 2:
+                ts.close()
+        ad, as_ = td.export(), ts.export()
+        same = all(np.array_equal(ad[k_], as_[k_]) for k_ in as_) and td.nnodes == ts.nnodes and td.nlevels == ts.nlevels
+        flags = comm.allgather(np.array([1.0 if same else 0.0]))
+        out[f"dist_build_ms{ms}"] = dict(identical_to_single_gpu_on_every_rank=bool(flags.min() == 1.0), nnodes=int(td.nnodes),
+                                         nlevels=int(td.nlevels), distributed_s=min(dt_d), single_gpu_s=min(dt_s),
+                                         speedup=min(dt_s) / min(dt_d))
+        td.close(); ts.close()
+    del dpts
     if rank == 0:
         ctx.set_seed(4711)
         r1 = mcmc.rjmcmc_array(51, A, B, a0, a0, nskip=4, nchains=20000, record_model=False, ctx=ctx)
@@ -156,7 +187,8 @@ def main():
         out["ok"] = bool(out["sharded_density_bit_exact"] and out["accept_equal"] and out["shard_chains_bit_exact"]
                          and out["ensemble_mean_err"] < 1e-12 and out["ensemble_std_err"] < 1e-12
                          and out["harmonic_sharded_rel_err"] < 1e-14 and out["evidence_identical_on_all_ranks"]
-                         and out["evidence_bit_identical_to_single_gpu"] and out["rj_counts_equal"])
+                         and out["evidence_bit_identical_to_single_gpu"] and out["rj_counts_equal"]
+                         and all(out[f"dist_build_ms{ms}"]["identical_to_single_gpu_on_every_rank"] for ms in (2, 64)))
         s_ = json.dumps(out)
         print(s_)
         if a.out:
