@@ -146,6 +146,30 @@ let rjmcmc_array ctx ?(nbin = 0) ?(nskip = 1) ?(nchains = 1) n (ma : rj_model) (
   (model, counts)
 let rjmcmc_evidence_ratio (na, nb) = float_of_int na /. float_of_int nb     (* mcmc.ml:151-153 *)
 
+(* k models (mg_rjmcmc_array_k): an extension, the reference's sum type is two-model (mcmc.ml:83-87); with two models
+   the chains are those of [rjmcmc_array].  Returns the model index of every recorded sample and the counts per model. *)
+external rjmcmc_array_k_raw :
+  ctx -> rj_model_raw array -> int -> int -> int -> int -> (float, float64_elt, c_layout) Array1.t array ->
+  (int, int8_unsigned_elt, c_layout) Array2.t -> int array
+  = "mcmcgpu_rjmcmc_array_k_bytecode" "mcmcgpu_rjmcmc_array_k_native"
+let rjmcmc_array_k ctx ?(nbin = 0) ?(nskip = 1) ?(nchains = 1) n (models : rj_model array) (starts : float array array) =
+  let model = Array2.create int8_unsigned c_layout n nchains in
+  let counts = rjmcmc_array_k_raw ctx (Array.map raw_of_model models) nbin nskip n nchains (Array.map ba1 starts) model in
+  (model, counts)
+
+(* Ellipse.enclosing_ellipse sf (fun x -> x) pts (ellipse.ml:98-103) *)
+type ellipse = { center : float array; axes : float array; orientation : float array array }
+external enclosing_ellipse_raw :
+  ctx -> float -> (float, float64_elt, c_layout) Array2.t -> (float, float64_elt, c_layout) Array1.t ->
+  (float, float64_elt, c_layout) Array1.t -> (float, float64_elt, c_layout) Array2.t -> unit
+  = "mcmcgpu_enclosing_ellipse_bytecode" "mcmcgpu_enclosing_ellipse"
+let enclosing_ellipse ctx sf (pts : float array array) =
+  let d = Array.length pts.(0) in
+  let c = Array1.create float64 c_layout d and a = Array1.create float64 c_layout d and o = Array2.create float64 c_layout d d in
+  enclosing_ellipse_raw ctx sf (Array2.of_array float64 c_layout pts) c a o;
+  { center = Array.init d (fun i -> c.{i}); axes = Array.init d (fun i -> a.{i});
+    orientation = Array.init d (fun i -> Array.init d (fun j -> o.{i, j})) }
+
 (* Stats.multi_mean / multi_std ?mean (stats.ml:58-87) *)
 let multi_mean ctx (xs : float array array) =
   let out = Array1.create float64 c_layout (Array.length xs.(0)) in

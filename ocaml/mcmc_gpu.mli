@@ -80,6 +80,16 @@ val rjmcmc_array :
 (** [rjmcmc_array ctx ?nbin ?nskip ?nchains n model_a model_b a b]: the model of every recorded sample ([n][nchains],
     0 = A) and [Mcmc.rjmcmc_model_counts].  Raises [Failure] where the reference's [assert] on the priors fails. *)
 val rjmcmc_evidence_ratio : int * int -> float
+val rjmcmc_array_k :
+  ctx -> ?nbin:int -> ?nskip:int -> ?nchains:int -> int -> rj_model array -> float array array ->
+  (int, int8_unsigned_elt, c_layout) Array2.t * int array
+(** k-model reversible jump (2..8 models): an extension -- the reference's sum type is two-model (mcmc.ml:83-87).
+    With two models the chains are those of [rjmcmc_array]. *)
+
+(** {2 Ellipse (ellipse.ml:21-24, 98-103)} *)
+type ellipse = { center : float array; axes : float array; orientation : float array array }
+val enclosing_ellipse : ctx -> float -> float array array -> ellipse
+(** [enclosing_ellipse ctx sf pts] = [Ellipse.enclosing_ellipse sf (fun x -> x) pts] *)
 
 (** {2 Stats (stats.mli:41-55)} *)
 val multi_mean : ctx -> float array array -> float array

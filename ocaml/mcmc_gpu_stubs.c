@@ -339,6 +339,60 @@ CAMLprim value mcmcgpu_rjmcmc_array_bytecode(value *a, int argn) {
   return mcmcgpu_rjmcmc_array_native(a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], a[8], a[9]);
 }
 
+/* k-model extension (mg_rjmcmc_array_k; the reference's sum type is two-model, mcmc.ml:83-87).
+ * external rjmcmc_array_k_raw : ctx -> raw_model array -> int -> int -> int -> int ->
+ *   (float, float64_elt, c_layout) Array1.t array -> (int, int8_unsigned_elt, c_layout) Array2.t -> int array */
+CAMLprim value mcmcgpu_rjmcmc_array_k_native(value ctx, value models, value nbin, value nskip, value n, value nchains,
+                                             value starts, value out_model) {
+  CAMLparam4(ctx, models, starts, out_model);
+  CAMLlocal1(r);
+  const int K = (int)Wosize_val(models);
+  mg_ctx *c = Ctx_val(ctx);
+  if (K < 2 || K > MG_RJ_MAX_MODELS || (int)Wosize_val(starts) != K) caml_invalid_argument("rjmcmc_array_k: 2..8 models, one start point each");
+  mg_rj_model M[MG_RJ_MAX_MODELS];
+  const double *st[MG_RJ_MAX_MODELS];
+  for (int k = 0; k < K; ++k) { M[k] = rj_of_value(Field(models, k)); st[k] = (const double *)Caml_ba_data_val(Field(starts, k)); }
+  mg_rjmcmc_cfg cfg;
+  memset(&cfg, 0, sizeof cfg);
+  cfg.nchains = Long_val(nchains); cfg.nbin = Long_val(nbin); cfg.nskip = Long_val(nskip); cfg.n = Long_val(n);
+  int64_t counts[MG_RJ_MAX_MODELS] = {0};
+  uint8_t *pm = (uint8_t *)Caml_ba_data_val(out_model);
+  caml_release_runtime_system();
+  int rc = mg_rjmcmc_array_k(c, M, K, &cfg, st, pm, NULL, counts);
+  caml_acquire_runtime_system();
+  check(c, rc);
+  r = caml_alloc_tuple(K);
+  for (int k = 0; k < K; ++k) Store_field(r, k, Val_long(counts[k]));
+  CAMLreturn(r);
+}
+CAMLprim value mcmcgpu_rjmcmc_array_k_bytecode(value *a, int argn) {
+  (void)argn;
+  return mcmcgpu_rjmcmc_array_k_native(a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7]);
+}
+
+/* ---- Ellipse.enclosing_ellipse sf to_coord pts (ellipse.ml:98-103), to_coord = identity ------------------
+ * external enclosing_ellipse_raw : ctx -> float -> (float, float64_elt, c_layout) Array2.t ->
+ *   (float, float64_elt, c_layout) Array1.t -> (float, float64_elt, c_layout) Array1.t ->
+ *   (float, float64_elt, c_layout) Array2.t -> unit        (center, axes, orientation are outputs) */
+CAMLprim value mcmcgpu_enclosing_ellipse(value ctx, value sf, value pts, value center, value axes, value ori) {
+  CAMLparam5(ctx, sf, pts, center, axes);
+  CAMLxparam1(ori);
+  mg_ctx *c = Ctx_val(ctx);
+  const int64_t N = Caml_ba_array_val(pts)->dim[0]; const int32_t D = (int32_t)Caml_ba_array_val(pts)->dim[1];
+  const double *pp = (const double *)Caml_ba_data_val(pts);
+  double *pc = (double *)Caml_ba_data_val(center), *pa = (double *)Caml_ba_data_val(axes), *po = (double *)Caml_ba_data_val(ori);
+  const double f = Double_val(sf);
+  caml_release_runtime_system();
+  int rc = mg_ellipse_enclosing(c, pp, N, D, f, pc, pa, po);
+  caml_acquire_runtime_system();
+  check(c, rc);
+  CAMLreturn(Val_unit);
+}
+CAMLprim value mcmcgpu_enclosing_ellipse_bytecode(value *a, int argn) {
+  (void)argn;
+  return mcmcgpu_enclosing_ellipse(a[0], a[1], a[2], a[3], a[4], a[5]);
+}
+
 /* ---- Nested.nested_evidence (nested.ml:122-146) ----------------------------
  * external nested_evidence : ctx -> logfn -> logfn -> lo -> hi -> epsrel:float -> nmcmc:int -> nlive:int ->
  *   mode_hopping_frac:float -> batch:int -> pts [cap][D] -> ll [cap] -> lp [cap] -> logw [cap] ->
