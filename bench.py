@@ -260,7 +260,7 @@ def leg_evidence(args, ctx, comm, dev, rank, world, peak):
     mean_s = float(tt.item())
     out.update({"value": N / mean_s, "unit": "evidence samples/s", "seconds": mean_s, "best_seconds": float(np.min(ts)),
                 "lebesgue_Z": z, "gpu_launches_per_call": int(launches),
-                "scaling": "strong (one data set; sort, prefix cut and tree on rank 0, kd-cells shared out)" if world > 1 else "n/a"})
+                "scaling": "strong (one data set: sort and prefix cut on rank 0, survivors broadcast, kd-tree built by all ranks together, kd-cells shared out)" if world > 1 else "n/a"})
     if rank == 0:
         # roofline of the dominant kernel: SURVEY.md 8d, one level of a row-permuting build moves (2*8*D + 16) N bytes
         per_launch = (2 * 8 * Dd + 16) * N

@@ -444,8 +444,9 @@ extern "C" int mg_evidence_direct_dev(mg_ctx *ctx, const double *d_pts, const do
 }
 
 // ---- the same over the GPUs of one box (evidence.ml:148-221) -----------------------------------------
-// The global steps (sort, prefix cut, de-duplication, tree of the survivors) run on `root`, which holds the samples;
-// the tree blob and the survivors' ll / lp are replicated with NCCL broadcasts; the tree's nodes are cut into
+// The global steps (sort, prefix cut, de-duplication) run on `root`, which holds the samples; the survivors' rows and
+// ll / lp are replicated with NCCL broadcasts; the tree over them is built by all ranks together
+// (mg_kdtree_build_distributed, bit-identical to the single-GPU tree); the tree's nodes are cut into
 // contiguous ranges, one per rank, each rank evaluates the cell terms of its range; the per-node terms are
 // all-gathered (ncclAllGather, in place) and every rank runs the SAME deterministic reduction over the complete
 // array -- the result is bit-identical on every rank and to the single-GPU call.
@@ -469,40 +470,44 @@ static int evidence_sharded(mg_comm *c, int which, int32_t root, const double *d
   cudaStream_t s = ctx->stream;
   int rc = MG_OK;
   Survivors sv;
-  double head[2] = {0.0, 0.0};        // {mean 1/L of the kept prefix, status of the root's preparation}
-  mg_kdtree *t_root = nullptr, *t = nullptr;
+  double head[3] = {0.0, 0.0, 0.0};   // {mean 1/L of the kept prefix, status of the root's preparation, survivors}
+  mg_kdtree *t = nullptr;
   if (rank == root) {
     double mean_il = 1.0;
     rc = which == 0 ? lebesgue_prepare(ctx, d_pts, d_ll, d_lp, N, D, n, eps, sv, &mean_il)
                     : direct_prepare(ctx, d_pts, d_ll, d_lp, N, D, n, sv);
-    if (rc == MG_OK) rc = survivors_tree(ctx, sv, D, n, &t_root);
-    head[0] = mean_il; head[1] = (double)rc;
+    head[0] = mean_il; head[1] = (double)rc; head[2] = (double)sv.K;
   }
   // the root's status travels first, so that a failure there ends the call on every rank instead of a hang
   DevBuf<double> d_head;
-  MG_CUDA(ctx, d_head.alloc(2, s));
+  MG_CUDA(ctx, d_head.alloc(3, s));
   if (rank == root) MG_CUDA(ctx, cudaMemcpyAsync(d_head.get(), head, sizeof head, cudaMemcpyHostToDevice, s));
   int rc2 = comm_broadcast_dev(c, d_head.get(), sizeof head, root);
-  if (rc2) { if (t_root) mg_kdtree_destroy(t_root); return rc2; }
+  if (rc2) return rc2;
   MG_CUDA(ctx, cudaMemcpyAsync(head, d_head.get(), sizeof head, cudaMemcpyDeviceToHost, s));
   MG_CUDA(ctx, cudaStreamSynchronize(s));
-  if (head[1] != 0.0) {
-    if (t_root) mg_kdtree_destroy(t_root);
+  if (head[1] != 0.0)
     return rank == root ? rc : set_err(ctx, (int)head[1], "evidence (sharded): the root rank failed to prepare the samples");
-  }
-  if ((rc = mg_kdtree_broadcast(c, t_root, root, &t))) { if (t_root) mg_kdtree_destroy(t_root); return rc; }
-  const int64_t K = t->h.N, nn = t->h.nnodes;
-  // survivors' ll and lp (the points travel inside the tree blob)
-  DevBuf<double> r_ll, r_lp;
-  const double *sll = sv.ll.get(), *slp = sv.lp.get();
+  // the survivors (rows, lp, and ll for the direct estimator) go to every rank; the tree over them is then built by
+  // all ranks together (mg_kdtree_build_distributed: top levels everywhere, one subtree per rank, one all-gather)
+  const int64_t K = (int64_t)head[2];
   if (rank != root) {
-    cudaError_t e = r_lp.alloc((size_t)K, s);
-    if (e == cudaSuccess && which == 1) e = r_ll.alloc((size_t)K, s);
-    if (e != cudaSuccess) { mg_kdtree_destroy(t); return set_err(ctx, MG_ENOMEM, "cuda: %s", cudaGetErrorString(e)); }
-    sll = r_ll.get(); slp = r_lp.get();
+    sv.K = K;
+    cudaError_t e = sv.pts.alloc((size_t)K * D, s);
+    if (e == cudaSuccess) e = sv.lp.alloc((size_t)K, s);
+    if (e == cudaSuccess && which == 1) e = sv.ll.alloc((size_t)K, s);
+    if (e != cudaSuccess) return set_err(ctx, MG_ENOMEM, "cuda: %s", cudaGetErrorString(e));
   }
-  rc = comm_broadcast_dev(c, (void *)slp, sizeof(double) * (size_t)K, root);
-  if (rc == MG_OK && which == 1) rc = comm_broadcast_dev(c, (void *)sll, sizeof(double) * (size_t)K, root);
+  rc = comm_broadcast_dev(c, sv.pts.get(), sizeof(double) * (size_t)K * D, root);
+  if (rc == MG_OK) rc = comm_broadcast_dev(c, sv.lp.get(), sizeof(double) * (size_t)K, root);
+  if (rc == MG_OK && which == 1) rc = comm_broadcast_dev(c, sv.ll.get(), sizeof(double) * (size_t)K, root);
+  if (rc) return rc;
+  {
+    std::vector<double> zeros(D, 0.0);            // the root box takes no part in the evidence (see survivors_tree)
+    if ((rc = mg_kdtree_build_distributed(c, sv.pts.get(), K, D, zeros.data(), zeros.data(), n < 2 ? 2 : n, &t))) return rc;
+  }
+  const int64_t nn = t->h.nnodes;
+  const double *sll = sv.ll.get(), *slp = sv.lp.get();
   // my range of nodes; slices of equal length so that the gathered slices ARE the node-ordered array
   const int64_t slice = (nn + R - 1) / R;
   const int64_t n0 = std::min<int64_t>(nn, (int64_t)rank * slice), n1 = std::min<int64_t>(nn, n0 + slice);
@@ -521,8 +526,7 @@ static int evidence_sharded(mg_comm *c, int which, int32_t root, const double *d
   if (rc == MG_OK) rc = comm_allgather_dev(c, terms.get() + (size_t)rank * slice, terms.get(), sizeof(double) * (size_t)slice);
   double total = 0.0;
   if (rc == MG_OK) rc = sum_terms(ctx, terms.get(), nn, &total);
-  if (t != t_root) mg_kdtree_destroy(t);
-  if (t_root) mg_kdtree_destroy(t_root);
+  mg_kdtree_destroy(t);
   if (rc) return rc;
   *out = which == 0 ? total / head[0] : total;
   return MG_OK;
