@@ -261,6 +261,25 @@ def leg_evidence(args, ctx, comm, dev, rank, world, peak):
     out.update({"value": N / mean_s, "unit": "evidence samples/s", "seconds": mean_s, "best_seconds": float(np.min(ts)),
                 "lebesgue_Z": z, "gpu_launches_per_call": int(launches),
                 "scaling": "strong (one data set: sort and prefix cut on rank 0, survivors broadcast, kd-tree built by all ranks together, kd-cells shared out)" if world > 1 else "n/a"})
+    if world > 1:
+        # the kd-tree of the same rows built by all ranks together (mg_kdtree_build_distributed): every rank holds the rows
+        g2 = torch.Generator(device=dev); g2.manual_seed(12345)
+        xr = x if rank == 0 else torch.empty((N, Dd), dtype=torch.float64, device=dev).normal_(0.5, 0.05, generator=g2)
+        torch.cuda.synchronize(dev)
+        lo_, hi_ = np.zeros(Dd), np.ones(Dd)
+        tb = []
+        for rep in range(4):
+            sync_all(); t = time.perf_counter()
+            trd = comm.build_tree(xr.data_ptr(), N, Dd, lo_, hi_)
+            ctx.sync(); tb.append(time.perf_counter() - t)
+            nn_, nl_ = trd.nnodes, trd.nlevels
+            trd.close()
+        tt2 = torch.tensor([float(np.min(tb[1:]))], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt2, op=dist.ReduceOp.MAX)
+        out["kdtree_distributed_build"] = {"seconds": float(tt2.item()), "points_per_s": N / float(tt2.item()), "nodes": int(nn_),
+                                           "levels": int(nl_), "note": "full tree (min_split 2) of the same rows, returned on every rank; "
+                                                                        "bit-identical to the one-GPU tree (tools/multi_gpu_check.py)"}
+        del xr
     if rank == 0:
         # roofline of the dominant kernel: SURVEY.md 8d, one level of a row-permuting build moves (2*8*D + 16) N bytes
         per_launch = (2 * 8 * Dd + 16) * N

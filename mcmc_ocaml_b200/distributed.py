@@ -123,3 +123,55 @@ def broadcast_tree(tree, src: int = 0, ctx=None):
         return tree
     torch.cuda.synchronize(dev)
     return KdTree.from_blob(buf.data_ptr(), n, ctx=ctx)
+
+
+# ---- distributed kd-tree build: the numbering rule of mg_kdtree_build_distributed (csrc/comm.cu) on the host -------------
+def tree_levels(left: np.ndarray) -> list[int]:
+    """First node of every level (and the node count at the end) of a breadth-first tree with adjacent children:
+    the next level ends two past the largest `left` of the level (``kdd_levels_kernel``)."""
+    lb, b, e = [0], 0, 1
+    while b < e:
+        last = int(left[b:e].max())
+        b, e = e, (last + 2 if last >= 0 else e)
+        lb.append(b)
+    return lb
+
+
+def graft_subtrees(top: dict, subs: list[dict]) -> dict:
+    """``top``: arrays of the tree truncated at 2^k leaves (a complete k-level tree); ``subs[r]``: arrays of the complete
+    tree over the rows of leaf r taken in the top's order.  Returns the arrays of the whole tree: level L >= k of the
+    whole tree is the ranks' levels L - k side by side, children adjacent; local point ids map back through the top's
+    order.  This is what the unpack kernels of ``mg_kdtree_build_distributed`` compute; ``tests/test_distributed_cpu.py``
+    checks it against the oracle's own whole tree."""
+    R = len(subs)
+    assert len(top["left"]) == 2 * R - 1, "the top must be a complete tree with one leaf per rank"
+    lbs = [tree_levels(s["left"]) for s in subs]
+    maxl = max(len(lb) - 1 for lb in lbs)
+    cnt = lambda r, l: (lbs[r][l + 1] - lbs[r][l]) if l + 1 < len(lbs[r]) else 0
+    gbase, goff = [R - 1], [[0] * (maxl + 1) for _ in range(R)]
+    for l in range(maxl + 1):
+        tot = 0
+        for r in range(R):
+            goff[r][l] = tot
+            tot += cnt(r, l)
+        gbase.append(gbase[-1] + tot)
+    nn = gbase[maxl]
+    out = {k: np.empty(nn, top[k].dtype) for k in ("split_dim", "split_val", "left", "begin", "end")}
+    for k in out:
+        out[k][:R - 1] = top[k][:R - 1]
+    perm = np.empty_like(top["perm"])
+    for r, s in enumerate(subs):
+        pb = int(top["begin"][R - 1 + r])
+        lb = lbs[r]
+        for l in range(len(lb) - 1):
+            i = np.arange(lb[l], lb[l + 1])
+            gid = gbase[l] + goff[r][l] + (i - lb[l])
+            lf = s["left"][i]
+            nxt = lb[l + 1]
+            out["left"][gid] = np.where(lf >= 0, gbase[l + 1] + (goff[r][l + 1] if l + 1 <= maxl else 0) + (lf - nxt), -1)
+            out["split_dim"][gid], out["split_val"][gid] = s["split_dim"][i], s["split_val"][i]
+            out["begin"][gid], out["end"][gid] = pb + s["begin"][i], pb + s["end"][i]
+        n_r = int(top["end"][R - 1 + r]) - pb
+        perm[pb:pb + n_r] = top["perm"][pb + s["perm"][:n_r]]
+    out["perm"] = perm
+    return out

@@ -78,3 +78,27 @@ def test_gloo_world2_gather_and_combine(tmp_path, monkeypatch):
         assert n == 1001 and acc == 30 and rej == 10 and ranks == [0.0, 1.0]
         np.testing.assert_allclose(mu, x.mean(0), rtol=1e-12)
         np.testing.assert_allclose(sd, x.std(0, ddof=1), rtol=1e-12)
+
+
+@pytest.mark.parametrize("n,d,ranks,min_split", [(20000, 3, 2, 2), (30011, 5, 4, 2), (16384, 2, 8, 2), (50000, 4, 4, 64)])
+def test_distributed_build_rule_reproduces_the_whole_tree(n, d, ranks, min_split):
+    """The numbering rule of mg_kdtree_build_distributed (D.graft_subtrees mirrors csrc/comm.cu) on oracle trees: the
+    top truncated at (N >> k) + 3, one complete subtree per leaf built from the leaf's rows in the top's order, grafted
+    -> every array of the oracle's own whole tree, bit for bit."""
+    from oracle import oracle as og
+    rng = np.random.default_rng(n + ranks)
+    pts = rng.normal(0.5, 0.1, (n, d))
+    lo, hi = np.zeros(d) - 5, np.ones(d) + 5
+    k = ranks.bit_length() - 1
+    whole = og.Tree(pts, lo, hi, min_split=min_split).export()
+    top = og.Tree(pts, lo, hi, min_split=(n >> k) + 3).export()
+    assert len(top["left"]) == 2 * ranks - 1 and np.all(top["left"][:ranks - 1] == 2 * np.arange(ranks - 1) + 1)
+    subs = []
+    for r in range(ranks):
+        b, e = top["begin"][ranks - 1 + r], top["end"][ranks - 1 + r]
+        rows = np.ascontiguousarray(pts[top["perm"][b:e]])
+        subs.append(og.Tree(rows, lo, hi, min_split=min_split).export())
+    got = D.graft_subtrees(top, subs)
+    for key in whole:
+        assert np.array_equal(got[key], whole[key]), key
+    assert D.tree_levels(whole["left"])[-1] == len(whole["left"])
