@@ -126,7 +126,8 @@ static int rj_run(mg_ctx *ctx, const mg_rj_model *const *M, int K, const mg_rjmc
       // leaf-level Interp.draw through the per-point cell records (kdtree.cu: mg_kdtree_enable_draw_cache)
       static const bool want_cache = [] { const char *e = getenv("MCMC_GPU_DRAW_CACHE"); return e ? atoi(e) != 0 : true; }();
       mg_kdtree *tr = const_cast<mg_kdtree *>(M[k]->into.tree);
-      if (want_cache && m.nstop == 0 && tr->h.D <= 8 && !tr->d_draw_cache && tr->ctx == ctx && C * (cfg->nbin + n * cfg->nskip) >= tr->h.N) {
+      static const int cache_maxd = [] { const char *e = getenv("MCMC_GPU_DRAW_CACHE_MAXD"); return e ? atoi(e) : 8; }();
+      if (want_cache && m.nstop == 0 && tr->h.D <= cache_maxd && !tr->d_draw_cache && tr->ctx == ctx && C * (cfg->nbin + n * cfg->nskip) >= tr->h.N) {
         if ((rc = mg_kdtree_enable_draw_cache(tr)) == MG_ENOMEM) rc = MG_OK;   // no room: descend as before
         if (rc) return rc;
       }
