@@ -48,8 +48,11 @@ __device__ __forceinline__ void tma_wait_read() { asm volatile("cp.async.bulk.wa
 __device__ __forceinline__ void tma_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// Register cap of the balanced kernel: its grid holds exactly three one-warp CTAs per scheduler, which leaves room for
+// 170 registers; tools/mh_maxnreg_sweep.sh (D = 10, ms per pass on one box): 128: 15.49, 136: 15.33, 144: 15.21,
+// 152: 15.26-15.40, 160: 15.03-15.19, 168: 15.24-15.33.
 #ifndef MG_MHB_MAXNREG
-#define MG_MHB_MAXNREG(D) MG_MH_MAXNREG(D)
+#define MG_MHB_MAXNREG(D) ((D) <= 10 ? 160 : MG_MH_MAXNREG(D))
 #endif
 #ifndef MG_MHB_MOM_MAXNREG
 #define MG_MHB_MOM_MAXNREG(D) ((D) <= 10 ? 168 : 255)

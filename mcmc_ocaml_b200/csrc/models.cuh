@@ -114,6 +114,13 @@ __device__ __forceinline__ double2 lds2(const double *p) {
                : "r"((unsigned)__cvta_generic_to_shared(p)));
   return v;
 }
+// non-volatile form: the compiler may keep the pair in registers across steps (loop-invariant); used for the few
+// parameters the register budget has room for (experiment switches MG_EXP_REG_PROP / MG_EXP_REG_MU)
+__device__ __forceinline__ double2 lds2_hoistable(const double *p) {
+  double2 v;
+  asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"((unsigned)__cvta_generic_to_shared(p)));
+  return v;
+}
 __device__ __forceinline__ double lds1(const double *p) {
   double v;
   asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"((unsigned)__cvta_generic_to_shared(p)));
@@ -155,7 +162,11 @@ struct GaussCorr {
     double z[D];
 #pragma unroll
     for (int j = 0; j < D; j += 2) {
+#ifdef MG_EXP_REG_MU
+      const double2 m = lds2_hoistable(s + j);
+#else
       const double2 m = lds2(s + j);
+#endif
       z[j] = x[j] - m.x;
       if (j + 1 < D) z[j + 1] = x[j + 1] - m.y;
     }
@@ -195,7 +206,11 @@ struct BoxProp {
     static_assert(DD == D, "BoxProp: dimension mismatch");
 #pragma unroll
     for (int i = 0; i < D; ++i) {
+#ifdef MG_EXP_REG_PROP
+      const double2 cw = lds2_hoistable(s + 2 * i);
+#else
       const double2 cw = lds2(s + 2 * i);
+#endif
       y[i] = x[i] + fma(cw.y, r.uniform12(), cw.x);
     }
   }
