@@ -542,7 +542,8 @@ extern "C" int mg_kdtree_build_distributed(mg_comm *c, const double *d_pts, int6
   struct Rec { int32_t nl, nn, npts, pbegin; int32_t lb[KDD_MAXL + 1]; int32_t bad; };
   Rec mine{};
   const std::vector<int32_t> &lvb = sub.t->level_begin;
-  if (lvb.size() >= 2 && lvb.size() <= (size_t)KDD_MAXL + 1) {     // the builder kept its level table
+  static const bool force_kernel = getenv("MCMC_GPU_KDD_LEVELS_KERNEL") != nullptr;   // tests: take the first builder's path
+  if (!force_kernel && lvb.size() >= 2 && lvb.size() <= (size_t)KDD_MAXL + 1) {     // the builder kept its level table
     mine.nl = (int32_t)lvb.size() - 1;
     for (size_t l = 0; l < lvb.size(); ++l) mine.lb[l] = lvb[l];
   } else {                                                           // first builder: read the levels off the nodes

@@ -1128,7 +1128,11 @@ int build_tree_v2(mg_ctx *ctx, const double *d_pts, int64_t N, int D, const doub
     MG_CUDA(ctx, cudaMemcpyAsync(pout, pin, sizeof(int32_t) * N, cudaMemcpyDeviceToDevice, s));   // positions outside the subtrees
     a = V2Bottom{N, D, min_split, Lh, info.get(), nb.get(), ne.get(), Kin, pin, pout, l_dim.get(), l_child.get(), l_begin.get(),
                  l_end.get(), l_split.get(), cnt.get(), depth.get(), b_over.get()};
-    rc = NMAX == 2048 ? v2_launch_bottom<2048, 1024>(ctx, a, nsub, D) : NMAX == 1024 ? v2_launch_bottom<1024, 1024>(ctx, a, nsub, D)
+    // MCMC_GPU_KD_BT: threads of a 1024-point subtree CTA (experiment; tools/kd_bottom_sweep.sh)
+    static const int bt1024 = [] { const char *e = getenv("MCMC_GPU_KD_BT"); return e ? atoi(e) : 1024; }();
+    rc = NMAX == 2048 ? v2_launch_bottom<2048, 1024>(ctx, a, nsub, D)
+         : NMAX == 1024 ? (bt1024 == 256 ? v2_launch_bottom<1024, 256>(ctx, a, nsub, D) : bt1024 == 512 ? v2_launch_bottom<1024, 512>(ctx, a, nsub, D)
+                                         : v2_launch_bottom<1024, 1024>(ctx, a, nsub, D))
          : NMAX == 512 ? v2_launch_bottom<512, 512>(ctx, a, nsub, D) : v2_launch_bottom<256, 256>(ctx, a, nsub, D);
     if (rc) return rc;
     v2_level_scan_kernel<<<V2_MAXL, 1024, 0, s>>>(cnt.get(), pre.get(), nsub, totals.get());
