@@ -225,6 +225,22 @@ def test_balanced_kernel_bit_exact(ctx, og, D, nbin, nskip, n):
     assert np.array_equal(got.accept, acc) and np.array_equal(got.reject, rej)
 
 
+@pytest.mark.parametrize("segments", [1, 3, 7])
+def test_samples_leave_in_segments_while_the_sampler_runs(ctx, og, monkeypatch, segments):
+    """mg_mcmc_array cuts a run into segments and copies segment k's slice of the sample block to the host on the
+    second stream while segment k + 1 computes (MCMC_GPU_D2H_SEGMENTS; blocks below MCMC_GPU_D2H_MIN_MB go out in one
+    piece).  Chains and counters must not depend on the number of segments: bit-identical to the oracle."""
+    monkeypatch.setenv("MCMC_GPU_D2H_SEGMENTS", str(segments))
+    monkeypatch.setenv("MCMC_GPU_D2H_MIN_MB", "0")
+    mu, like, prior, prop = corr_model(10)
+    C, n, nbin, nskip = 3000 + 13, 23, 11, 5
+    ctx.set_seed(0xD2A)
+    got = mcmc.mcmc_array(n, like, prior, prop, mu, nchains=C, nbin=nbin, nskip=nskip, ctx=ctx)
+    want, acc, rej = og.mcmc_array(0xD2A, 0, n, like, prior, prop, mu, nchains=C, nbin=nbin, nskip=nskip, nthreads=8)
+    assert np.array_equal(got.block, want)
+    assert np.array_equal(got.accept, acc) and np.array_equal(got.reject, rej)
+
+
 def test_resident_call_running_moments(ctx, og):
     """Above one warp per scheduler the resident call takes Stats.multi_mean / multi_std from per-chain running
     moments kept by the balanced sampler (pivot = each chain's slot-0 sample, pooled with the parallel-variance
