@@ -610,6 +610,7 @@ def main():
     del samples, state
     torch.cuda.empty_cache()
     ctx.trim_pool()
+    ctx.reserve_pool()
     if not args.no_evidence:
         try:
             ev = leg_evidence(args, ctx, comm, dev, rank, world, peak)

@@ -64,6 +64,11 @@ int mg_ctx_sync(mg_ctx *ctx);
  * cached there between calls; this returns the cached memory to the driver
  * (for processes that share the GPU with another allocator). */
 int mg_ctx_trim_pool(mg_ctx *ctx);
+/* The opposite: make the pool hold at least nbytes in ONE piece (a pool grown
+ * request by request answers some 1-2 GB requests by remapping its fragments,
+ * 15-180 ms).  mg_ctx_create reserves 12 GB when the device has 48 GB free
+ * (MCMC_GPU_POOL_RESERVE_GB overrides, 0 = none); call this after a trim. */
+int mg_ctx_reserve_pool(mg_ctx *ctx, int64_t nbytes);
 /* Mcmc.reset_counters / Mcmc.get_counters (mcmc.ml:30-35). */
 int mg_reset_counters(mg_ctx *ctx);
 int mg_get_counters(mg_ctx *ctx, int64_t *naccept, int64_t *nreject);

@@ -68,6 +68,11 @@ class Context:
         """Hand the library's cached temporaries (stream-ordered pool) back to the driver."""
         self.check(self.lib.mg_ctx_trim_pool(self.h))
 
+    def reserve_pool(self, gigabytes: float = 12.0):
+        """Make the pool hold at least this much in one piece (``mg_ctx_reserve_pool``; done once by ``mg_ctx_create``,
+        to be repeated after ``trim_pool``)."""
+        self.check(self.lib.mg_ctx_reserve_pool(self.h, C.c_int64(int(gigabytes * (1 << 30)))))
+
     @property
     def launch_count(self) -> int:
         return int(self.lib.mg_ctx_launch_count(self.h))

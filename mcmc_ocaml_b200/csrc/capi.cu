@@ -7,6 +7,24 @@ using namespace mg;
 
 extern "C" int mg_abi_version(void) { return MG_ABI_VERSION; }
 
+// Make sure the device's stream-ordered pool holds at least `nbytes` in one piece (allocate, free: it stays cached).
+extern "C" int mg_ctx_reserve_pool(mg_ctx *ctx, int64_t nbytes) {
+  if (!ctx) return MG_EINVAL;
+  if (nbytes <= 0) return MG_OK;
+  cudaSetDevice(ctx->device);
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, ctx->device) != cudaSuccess) { cudaGetLastError(); return MG_OK; }
+  uint64_t have = 0;
+  cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &have);
+  if ((int64_t)have >= nbytes) return MG_OK;
+  void *p = nullptr;
+  if (cudaMallocAsync(&p, (size_t)nbytes, ctx->stream) == cudaSuccess) {
+    cudaFreeAsync(p, ctx->stream);
+    cudaStreamSynchronize(ctx->stream);
+  } else cudaGetLastError();                        // not enough memory for a reserve: the pool grows on demand instead
+  return MG_OK;
+}
+
 extern "C" int mg_ctx_create(int device, uint64_t seed, mg_ctx **out) {
   if (!out) return MG_EINVAL;
   *out = nullptr;
@@ -31,6 +49,18 @@ extern "C" int mg_ctx_create(int device, uint64_t seed, mg_ctx **out) {
   if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
     uint64_t thr = ~0ull;
     cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    // The pool is given one large piece up front (allocated and freed again: it stays cached).  The calls of this
+    // library ask for temporaries of 1-2 GB in varying order; a pool that grew request by request answers some of them
+    // by remapping its fragments -- measured on mg_evidence_lebesgue with host buffers at 1e7 x 20: 58-195 ms per call
+    // without the reserve, 58.7-60 ms with 12 GB (profiles/r02_summary.md).  Default: 12 GB when the device has at
+    // least 48 GB free; MCMC_GPU_POOL_RESERVE_GB overrides (0 = none); mg_ctx_trim_pool hands it back.
+    {
+      double gb = 12.0;
+      size_t free_b = 0, total_b = 0;
+      if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess || free_b < (48ull << 30)) gb = 0.0;
+      if (const char *e = getenv("MCMC_GPU_POOL_RESERVE_GB")) gb = atof(e);
+      if (gb > 0.0) mg_ctx_reserve_pool(ctx, (int64_t)(gb * 1073741824.0));
+    }
   }
   *out = ctx;
   return MG_OK;

@@ -161,6 +161,10 @@ extern "C" int mg_mcmc_array(mg_ctx *ctx, const mg_logfn *like, const mg_logfn *
       const char *e = getenv("MCMC_GPU_D2H_SEGMENTS");
       const int want = e ? atoi(e) : 8;
       nseg = want < 1 ? 1 : (want > 64 ? 64 : want);
+      // a segment keeps at least 1,024 steps (the balanced sampler wants >= 512 per launch), unless the tests ask
+      const int64_t by_steps = (n - 1) * cfg->nskip / 1024;
+      if (!getenv("MCMC_GPU_D2H_MIN_MB") && nseg > by_steps) nseg = by_steps < 1 ? 1 : (int)by_steps;
+      if (nseg > n - 1) nseg = (int)(n - 1);
     }
   }
   if (nseg > 1) {
