@@ -302,3 +302,17 @@ def test_quadform_on_fp64_tensor_cores(ctx):
     for c in doc["cases"]:
         assert c["fma_identical_to_plugin"] and c["max_rel_diff_dmma_vs_fma"] < 1e-13
     assert doc["fp64_dmma_tflops"] > 1.0
+
+
+def test_pool_trim_and_reserve(ctx):
+    """mg_ctx_trim_pool hands the cached temporaries back, mg_ctx_reserve_pool makes the pool hold one large piece again;
+    results do not depend on either."""
+    rng = np.random.default_rng(3)
+    ll = rng.normal(-3.0, 1.0, 100_000)
+    z0 = evidence.evidence_harmonic_mean(ll=ll, ctx=ctx)
+    ctx.trim_pool()
+    assert evidence.evidence_harmonic_mean(ll=ll, ctx=ctx) == z0
+    ctx.reserve_pool(1.0)
+    ctx.reserve_pool(0.0)                      # nothing to do
+    assert evidence.evidence_harmonic_mean(ll=ll, ctx=ctx) == z0
+    ctx.reserve_pool()                         # back to the default for the tests that follow
