@@ -307,6 +307,7 @@ def test_quadform_on_fp64_tensor_cores(ctx):
 def test_pool_trim_and_reserve(ctx):
     """mg_ctx_trim_pool hands the cached temporaries back, mg_ctx_reserve_pool makes the pool hold one large piece again;
     results do not depend on either."""
+    from mcmc_ocaml_b200 import evidence
     rng = np.random.default_rng(3)
     ll = rng.normal(-3.0, 1.0, 100_000)
     z0 = evidence.evidence_harmonic_mean(ll=ll, ctx=ctx)
