@@ -475,6 +475,7 @@ extern "C" int mg_kdtree_build_distributed(mg_comm *c, const double *d_pts, int6
   // pool remap its fragments (measured: 15-180 ms).  Truncated trees (min_split > 16) are small next to that bound and
   // get an exact blob at the end instead.
   auto al = [](int64_t x) { return (x + 255) & ~255LL; };
+  const bool result_with_pts = !ctx->kd_no_pts;    // (internal callers that keep the rows themselves)
   auto layout = [&](KdHeader &h, int64_t node_cap) {
     int64_t off = al(sizeof(KdHeader));
     h.off_low = off; off = al(off + 8 * D);
@@ -483,7 +484,7 @@ extern "C" int mg_kdtree_build_distributed(mg_comm *c, const double *d_pts, int6
     h.off_count = off; off = al(off + 4 * node_cap);
     h.off_begin = off; off = al(off + 4 * node_cap);
     h.off_perm = off; off = al(off + 4 * N);
-    h.off_pts = off; off = al(off + 8 * N * D);
+    h.off_pts = off; off = al(off + (result_with_pts ? 8 * N * D : 0));
     h.nbytes = off;
   };
   KdGuard res;
@@ -498,7 +499,7 @@ extern "C" int mg_kdtree_build_distributed(mg_comm *c, const double *d_pts, int6
   // ---- 1. the top, on every rank ---------------------------------------------------------------------------------------
   KdGuard top, sub;
   // (the top and the subtree are scaffolding: their blobs carry no copy of the points)
-  struct NoPts { mg_ctx *c; explicit NoPts(mg_ctx *c_) : c(c_) { c->kd_no_pts = true; } ~NoPts() { c->kd_no_pts = false; } };
+  struct NoPts { mg_ctx *c; bool was; explicit NoPts(mg_ctx *c_) : c(c_), was(c_->kd_no_pts) { c->kd_no_pts = true; } ~NoPts() { c->kd_no_pts = was; } };
   { NoPts np(ctx); rc = build_tree(ctx, d_pts, N, D, low, high, (int)ms_top, &top.t); }
   if (rc) return rc;
   phase("top build");
@@ -628,7 +629,7 @@ extern "C" int mg_kdtree_build_distributed(mg_comm *c, const double *d_pts, int6
     MG_CHECK_LAUNCH(ctx);
   }
   phase("unpack");
-  MG_CUDA(ctx, cudaMemcpyAsync(blob + h.off_pts, d_pts, 8 * (size_t)N * D, cudaMemcpyDeviceToDevice, s));
+  if (result_with_pts) MG_CUDA(ctx, cudaMemcpyAsync(blob + h.off_pts, d_pts, 8 * (size_t)N * D, cudaMemcpyDeviceToDevice, s));
   MG_CUDA(ctx, cudaStreamSynchronize(s));
   phase("pts copy");
   res.t = nullptr;

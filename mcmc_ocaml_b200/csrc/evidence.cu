@@ -227,7 +227,7 @@ static int compact_reversed(mg_ctx *ctx, const double *d_pts, const double *d_ll
 
 // per-cell terms of the nodes [node0, node1) of a tree that was not split below nmax objects
 template <int MODE>
-int cell_terms_range(mg_ctx *ctx, const mg_kdtree *t, const double *sll, const double *slp, int nmax, int64_t node0,
+int cell_terms_range(mg_ctx *ctx, const mg_kdtree *t, const double *spts, const double *sll, const double *slp, int nmax, int64_t node0,
                      int64_t node1, double *d_terms, unsigned long long *d_ncells) {
   if (node1 <= node0) return MG_OK;
   cudaStream_t s = ctx->stream;
@@ -237,12 +237,12 @@ int cell_terms_range(mg_ctx *ctx, const mg_kdtree *t, const double *sll, const d
   if (smem > 48 * 1024) MG_CUDA(ctx, cudaFuncSetAttribute(cell_terms_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   cell_terms_kernel<MODE><<<g, EB, smem, s>>>((const KdNode *)(blob + t->h.off_nodes), (const int32_t *)(blob + t->h.off_count),
                                               (const int32_t *)(blob + t->h.off_begin), (const int32_t *)(blob + t->h.off_perm),
-                                              (const double *)(blob + t->h.off_pts), sll, slp, node0, node1, t->h.D, nmax, d_terms, d_ncells);
+                                              spts, sll, slp, node0, node1, t->h.D, nmax, d_terms, d_ncells);
   MG_CHECK_LAUNCH(ctx);
   return MG_OK;
 }
-template int cell_terms_range<0>(mg_ctx *, const mg_kdtree *, const double *, const double *, int, int64_t, int64_t, double *, unsigned long long *);
-template int cell_terms_range<1>(mg_ctx *, const mg_kdtree *, const double *, const double *, int, int64_t, int64_t, double *, unsigned long long *);
+template int cell_terms_range<0>(mg_ctx *, const mg_kdtree *, const double *, const double *, const double *, int, int64_t, int64_t, double *, unsigned long long *);
+template int cell_terms_range<1>(mg_ctx *, const mg_kdtree *, const double *, const double *, const double *, int, int64_t, int64_t, double *, unsigned long long *);
 
 // the sum of the terms of all nodes, in node order: one deterministic compensated reduction (fixed grid for a given
 // node count), the same on every rank and for every way the terms were produced
@@ -255,7 +255,11 @@ static int survivors_tree(mg_ctx *ctx, const Survivors &sv, int D, int nmax, mg_
   std::vector<double> zeros(D, 0.0);
   // The root box (bounds_of_objects, evidence.ml:164,206) does not influence
   // any split nor the tight per-cell volumes, so it is not computed.
-  return build_tree(ctx, sv.pts.get(), sv.K, D, zeros.data(), zeros.data(), nmax < 2 ? 2 : nmax, t);
+  // (the tree is scaffolding here: the cell terms read the survivors' own rows, so the blob carries no copy of them)
+  ctx->kd_no_pts = true;
+  const int rc = build_tree(ctx, sv.pts.get(), sv.K, D, zeros.data(), zeros.data(), nmax < 2 ? 2 : nmax, t);
+  ctx->kd_no_pts = false;
+  return rc;
 }
 
 // tree of the survivors and the sum of the per-cell terms
@@ -272,7 +276,7 @@ static int integrate_cells(mg_ctx *ctx, const Survivors &sv, int D, int nmax, do
   if (e == cudaSuccess) e = ncells.alloc(1, s);
   if (e == cudaSuccess) e = cudaMemsetAsync(ncells.get(), 0, 8, s);
   if (e != cudaSuccess) { mg_kdtree_destroy(t); return set_err(ctx, MG_ECUDA, "cuda: %s", cudaGetErrorString(e)); }
-  rc = cell_terms_range<MODE>(ctx, t, sv.ll.get(), sv.lp.get(), nmax, 0, nn, terms.get(), ncells.get());
+  rc = cell_terms_range<MODE>(ctx, t, sv.pts.get(), sv.ll.get(), sv.lp.get(), nmax, 0, nn, terms.get(), ncells.get());
   if (rc == MG_OK) rc = sum_terms(ctx, terms.get(), nn, out);
   unsigned long long nc = 0;
   if (rc == MG_OK && ncells_out) {
@@ -504,7 +508,10 @@ static int evidence_sharded(mg_comm *c, int which, int32_t root, const double *d
   if (rc) return rc;
   {
     std::vector<double> zeros(D, 0.0);            // the root box takes no part in the evidence (see survivors_tree)
-    if ((rc = mg_kdtree_build_distributed(c, sv.pts.get(), K, D, zeros.data(), zeros.data(), n < 2 ? 2 : n, &t))) return rc;
+    ctx->kd_no_pts = true;                        // the cell terms read the survivors' rows, not a copy inside the blob
+    rc = mg_kdtree_build_distributed(c, sv.pts.get(), K, D, zeros.data(), zeros.data(), n < 2 ? 2 : n, &t);
+    ctx->kd_no_pts = false;
+    if (rc) return rc;
   }
   const int64_t nn = t->h.nnodes;
   const double *sll = sv.ll.get(), *slp = sv.lp.get();
@@ -521,8 +528,8 @@ static int evidence_sharded(mg_comm *c, int which, int32_t root, const double *d
     if (e != cudaSuccess) rc = set_err(ctx, MG_ENOMEM, "cuda: %s", cudaGetErrorString(e));
   }
   if (rc == MG_OK)
-    rc = which == 0 ? cell_terms_range<0>(ctx, t, sll, slp, n, n0, n1, terms.get(), ncells.get())
-                    : cell_terms_range<1>(ctx, t, sll, slp, n, n0, n1, terms.get(), ncells.get());
+    rc = which == 0 ? cell_terms_range<0>(ctx, t, sv.pts.get(), sll, slp, n, n0, n1, terms.get(), ncells.get())
+                    : cell_terms_range<1>(ctx, t, sv.pts.get(), sll, slp, n, n0, n1, terms.get(), ncells.get());
   if (rc == MG_OK) rc = comm_allgather_dev(c, terms.get() + (size_t)rank * slice, terms.get(), sizeof(double) * (size_t)slice);
   double total = 0.0;
   if (rc == MG_OK) rc = sum_terms(ctx, terms.get(), nn, &total);
