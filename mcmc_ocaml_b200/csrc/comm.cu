@@ -501,13 +501,16 @@ extern "C" int mg_kdtree_build_distributed(mg_comm *c, const double *d_pts, int6
   // (the top and the subtree are scaffolding: their blobs carry no copy of the points)
   struct NoPts { mg_ctx *c; bool was; explicit NoPts(mg_ctx *c_) : c(c_), was(c_->kd_no_pts) { c->kd_no_pts = true; } ~NoPts() { c->kd_no_pts = was; } };
   { NoPts np(ctx); rc = build_tree(ctx, d_pts, N, D, low, high, (int)ms_top, &top.t); }
-  if (rc) return rc;
+  // A rank that fails here still takes part in the agreement below (as "not complete"): every rank then builds alone
+  // and the failing rank reports its own error, instead of the others waiting in a collective for ever.
+  const int rc_top = rc;
   phase("top build");
-  const KdHeader &th = top.t->h;
-  const char *tb = (const char *)top.t->d_blob;
+  static const KdHeader no_header{};
+  const KdHeader &th = rc_top == MG_OK ? top.t->h : no_header;
+  const char *tb = rc_top == MG_OK ? (const char *)top.t->d_blob : nullptr;
   std::vector<KdNode> tnodes((size_t)th.nnodes);
   std::vector<int32_t> tcount((size_t)th.nnodes), tbegin((size_t)th.nnodes);
-  bool complete = th.nnodes == 2 * (int64_t)R - 1;
+  bool complete = rc_top == MG_OK && th.nnodes == 2 * (int64_t)R - 1;
   if (complete) {
     MG_CUDA(ctx, cudaMemcpyAsync(tnodes.data(), tb + th.off_nodes, sizeof(KdNode) * tnodes.size(), cudaMemcpyDeviceToHost, s));
     MG_CUDA(ctx, cudaMemcpyAsync(tcount.data(), tb + th.off_count, 4 * tcount.size(), cudaMemcpyDeviceToHost, s));
@@ -524,7 +527,7 @@ extern "C" int mg_kdtree_build_distributed(mg_comm *c, const double *d_pts, int6
     if ((rc = mg_comm_allgather(c, &mine, all.data(), sizeof mine))) return rc;
     for (int r = 0; r < R; ++r) complete = complete && all[r] == 1;
   }
-  if (!complete) return build_tree(ctx, d_pts, N, D, low, high, min_split, out);
+  if (!complete) return rc_top != MG_OK ? rc_top : build_tree(ctx, d_pts, N, D, low, high, min_split, out);
   phase("top");
   // ---- 2. this rank's subtree -------------------------------------------------------------------------------------------
   const int me = c->rank;
@@ -536,15 +539,18 @@ extern "C" int mg_kdtree_build_distributed(mg_comm *c, const double *d_pts, int6
   MG_CHECK_LAUNCH(ctx);
   phase("gather");
   { NoPts np(ctx); rc = build_tree(ctx, rows.get(), my_n, D, low, high, min_split, &sub.t); }
-  if (rc) return rc;
+  const int rc_sub = rc;                         // a failure travels in the record below, so that no rank is left waiting
   phase("subtree");
-  const KdHeader &sh = sub.t->h;
-  const char *sb = (const char *)sub.t->d_blob;
+  const KdHeader &sh = rc_sub == MG_OK ? sub.t->h : no_header;
+  const char *sb = rc_sub == MG_OK ? (const char *)sub.t->d_blob : nullptr;
   struct Rec { int32_t nl, nn, npts, pbegin; int32_t lb[KDD_MAXL + 1]; int32_t bad; };
   Rec mine{};
-  const std::vector<int32_t> &lvb = sub.t->level_begin;
+  static const std::vector<int32_t> no_levels;
+  const std::vector<int32_t> &lvb = rc_sub == MG_OK ? sub.t->level_begin : no_levels;
   static const bool force_kernel = getenv("MCMC_GPU_KDD_LEVELS_KERNEL") != nullptr;   // tests: take the first builder's path
-  if (!force_kernel && lvb.size() >= 2 && lvb.size() <= (size_t)KDD_MAXL + 1) {     // the builder kept its level table
+  if (rc_sub != MG_OK) {
+    mine.nl = 0;
+  } else if (!force_kernel && lvb.size() >= 2 && lvb.size() <= (size_t)KDD_MAXL + 1) {     // the builder kept its level table
     mine.nl = (int32_t)lvb.size() - 1;
     for (size_t l = 0; l < lvb.size(); ++l) mine.lb[l] = lvb[l];
   } else {                                                           // first builder: read the levels off the nodes
@@ -558,7 +564,7 @@ extern "C" int mg_kdtree_build_distributed(mg_comm *c, const double *d_pts, int6
   }
   phase("levels");
   mine.nn = (int32_t)sh.nnodes; mine.npts = my_n; mine.pbegin = my_b;
-  mine.bad = (mine.nl >= KDD_MAXL || mine.lb[mine.nl] != mine.nn) ? 1 : 0;
+  mine.bad = rc_sub != MG_OK ? 2 : ((mine.nl >= KDD_MAXL || mine.lb[mine.nl] != mine.nn) ? 1 : 0);
   std::vector<Rec> recs((size_t)R);
   if ((rc = mg_comm_allgather(c, &mine, recs.data(), sizeof mine))) return rc;
   phase("tables");
@@ -569,6 +575,7 @@ extern "C" int mg_kdtree_build_distributed(mg_comm *c, const double *d_pts, int6
   int maxl = 0; int64_t chunk = 0;
   for (int r = 0; r < R; ++r) {
     const Rec &q = recs[r];
+    if (q.bad == 2) return (r == c->rank) ? rc_sub : set_err(ctx, MG_EFAIL, "kd-tree (distributed): rank %d failed to build its subtree", r);
     if (q.bad) return set_err(ctx, MG_EFAIL, "kd-tree (distributed): rank %d built a subtree deeper than %d levels", r, KDD_MAXL);
     T.nl[r] = q.nl; T.nn[r] = q.nn; T.npts[r] = q.npts; T.pbegin[r] = q.pbegin;
     memcpy(T.lb[r], q.lb, sizeof q.lb);
