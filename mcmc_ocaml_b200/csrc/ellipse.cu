@@ -41,7 +41,9 @@ constexpr int EL_TB = 256;        // threads per CTA
 constexpr int EL_CH = 128;        // rows per shared-memory chunk
 constexpr int EL_DMAX = 32;
 constexpr int EL_ACC = 3;         // accumulators per thread: ceil(D (D + 1) / 2 / 256) at D = 32
-constexpr int EL_SMAX = 64;       // slices per node
+constexpr int EL_SMAX = 592;      // slices per node (four CTAs per SM when a level has one node)
+constexpr int EL_SMALL = 1024;    // a node of at most this many doubles (points x D) is finished by ONE warp (el_small_kernel)
+constexpr int EL_SWARPS = 4;      // warps (nodes) per CTA of that kernel
 
 struct ElNodes {                  // growing node table (device)
   int32_t *left, *right, *begin, *end;
@@ -59,11 +61,14 @@ __device__ __forceinline__ void el_slice(int b, int e, int s, int S, int *sb, in
   *se = b + (int)(n * (s + 1) / S);
 }
 
+__device__ __forceinline__ bool el_is_small(const ElNodes &nd, int node, int D) { return (nd.end[node] - nd.begin[node]) * D <= EL_SMALL; }
+
 // ---- Ellipse.center (:36-46): per-(node, slice) column sums --------------------------------------------------------------
 __global__ void __launch_bounds__(EL_TB)
 el_mean_partial_kernel(const double *__restrict__ rows, int D, ElNodes nd, int lb, int S, double *__restrict__ part) {
   extern __shared__ double el_sm[];                 // [EL_CH][D] then [G][D]
   const int node = lb + blockIdx.x, s = blockIdx.y;
+  if (el_is_small(nd, node, D)) return;             // finished by el_small_kernel
   int sb, se;
   el_slice(nd.begin[node], nd.end[node], s, S, &sb, &se);
   const int G = EL_TB / D;                          // row groups: thread (g, j) sums rows g, g + G, ... of column j
@@ -94,6 +99,7 @@ __global__ void el_mean_finish_kernel(int D, ElNodes nd, int lb, int nn, int S, 
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= nn * D) return;
   const int r = k / D, j = k - r * D, node = lb + r;
+  if (el_is_small(nd, node, D)) return;
   double t = 0.0;
   for (int s = 0; s < S; ++s) t = t + part[((int64_t)r * S + s) * D + j];
   nd.center[(int64_t)node * D + j] = t / (double)(nd.end[node] - nd.begin[node]);
@@ -106,6 +112,7 @@ el_cov_partial_kernel(const double *__restrict__ rows, int D, ElNodes nd, int lb
   __shared__ double mu[EL_DMAX];
   __shared__ unsigned char pj[EL_DMAX * (EL_DMAX + 1) / 2], pk[EL_DMAX * (EL_DMAX + 1) / 2];
   const int node = lb + blockIdx.x, s = blockIdx.y;
+  if (el_is_small(nd, node, D)) return;
   const int P = el_pairs(D);
   if (threadIdx.x < D) mu[threadIdx.x] = nd.center[(int64_t)node * D + threadIdx.x];
   for (int q = threadIdx.x; q < P; q += EL_TB) {     // pair q -> (j, k), row-major upper triangle
@@ -148,24 +155,8 @@ el_cov_partial_kernel(const double *__restrict__ rows, int D, ElNodes nd, int lb
   }
 }
 
-// ---- Ellipse.eigensystem (:58-61): cyclic Jacobi, one warp per node -------------------------------------------------------
-// Output like LAPACK's syevr through Lacaml: eigenvalues ascending, ori[i][j] = component i of eigenvector j.
-__global__ void __launch_bounds__(32)
-el_eigen_kernel(int D, ElNodes nd, int lb, int S, const double *__restrict__ part) {
-  extern __shared__ double el_sm[];                 // A[D][D+1], V[D][D+1], w[D]
-  const int r = blockIdx.x, node = lb + r, lane = threadIdx.x;
-  const int P = el_pairs(D), LD = D + 1;
-  double *A = el_sm, *V = A + D * LD, *w = V + D * LD;
-  const double nf = (double)(nd.end[node] - nd.begin[node]);
-  for (int q = lane; q < P; q += 32) {
-    int j = 0, rem = q;
-    while (rem >= D - j) { rem -= D - j; ++j; }
-    const int k = j + rem;
-    double t = 0.0;
-    for (int s = 0; s < S; ++s) t = t + part[((int64_t)r * S + s) * P + q];
-    t = t / nf;
-    A[j * LD + k] = t; A[k * LD + j] = t;
-  }
+// cyclic Jacobi on the symmetric matrix A (leading dimension LD) by one warp; V receives the eigenvectors (columns)
+__device__ __forceinline__ void el_jacobi_warp(double *A, double *V, int D, int LD, int lane) {
   for (int q = lane; q < D * D; q += 32) { const int i = q / D, j = q - i * D; V[i * LD + j] = (i == j) ? 1.0 : 0.0; }
   __syncwarp();
   for (int sweep = 0; sweep < 60; ++sweep) {
@@ -198,7 +189,11 @@ el_eigen_kernel(int D, ElNodes nd, int lb, int S, const double *__restrict__ par
         __syncwarp();
       }
   }
-  // ascending order (ties by index), sign: the component of largest magnitude (first on ties) is positive
+}
+// ascending order (ties by index), sign: the component of largest magnitude (first on ties) is positive; written to the
+// node table and, when given, to a shared-memory copy (ev_s[D], ori_s[D][D])
+__device__ __forceinline__ void el_eigen_store(const double *A, const double *V, double *w, int D, int LD, int lane, const ElNodes &nd,
+                                               int node, double *ev_s, double *ori_s) {
   if (lane < D) w[lane] = A[lane * LD + lane];
   __syncwarp();
   if (lane < D) {
@@ -208,8 +203,37 @@ el_eigen_kernel(int D, ElNodes nd, int lb, int S, const double *__restrict__ par
     double big = 0.0; double sgn = 1.0;
     for (int i = 0; i < D; ++i) { const double v = V[i * LD + lane]; if (fabs(v) > big) { big = fabs(v); sgn = v < 0.0 ? -1.0 : 1.0; } }
     nd.evals[(int64_t)node * D + rank] = me;
-    for (int i = 0; i < D; ++i) nd.ori[((int64_t)node * D + i) * D + rank] = sgn * V[i * LD + lane];
+    if (ev_s) ev_s[rank] = me;
+    for (int i = 0; i < D; ++i) {
+      const double v = sgn * V[i * LD + lane];
+      nd.ori[((int64_t)node * D + i) * D + rank] = v;
+      if (ori_s) ori_s[i * D + rank] = v;
+    }
   }
+  __syncwarp();
+}
+
+// ---- Ellipse.eigensystem (:58-61): cyclic Jacobi, one warp per node -------------------------------------------------------
+// Output like LAPACK's syevr through Lacaml: eigenvalues ascending, ori[i][j] = component i of eigenvector j.
+__global__ void __launch_bounds__(32)
+el_eigen_kernel(int D, ElNodes nd, int lb, int S, const double *__restrict__ part) {
+  extern __shared__ double el_sm[];                 // A[D][D+1], V[D][D+1], w[D]
+  const int r = blockIdx.x, node = lb + r, lane = threadIdx.x;
+  if (el_is_small(nd, node, D)) return;
+  const int P = el_pairs(D), LD = D + 1;
+  double *A = el_sm, *V = A + D * LD, *w = V + D * LD;
+  const double nf = (double)(nd.end[node] - nd.begin[node]);
+  for (int q = lane; q < P; q += 32) {
+    int j = 0, rem = q;
+    while (rem >= D - j) { rem -= D - j; ++j; }
+    const int k = j + rem;
+    double t = 0.0;
+    for (int s = 0; s < S; ++s) t = t + part[((int64_t)r * S + s) * P + q];
+    t = t / nf;
+    A[j * LD + k] = t; A[k * LD + j] = t;
+  }
+  el_jacobi_warp(A, V, D, LD, lane);
+  el_eigen_store(A, V, w, D, LD, lane, nd, node, nullptr, nullptr);
 }
 
 // ---- Ellipse.elliptical_range (:63-73) -------------------------------------------------------------------------------------
@@ -229,6 +253,7 @@ el_range_partial_kernel(const double *__restrict__ rows, int D, ElNodes nd, int 
   extern __shared__ double el_sm[];                 // c[D], a[D], ori[D][D], then the chunk [EL_CH][D]
   __shared__ double wmax[EL_TB / 32];
   const int node = lb + blockIdx.x, s = blockIdx.y;
+  if (el_is_small(nd, node, D)) return;
   double *c = el_sm, *a = c + D, *ori = a + D, *chunk = ori + D * D;
   for (int k = threadIdx.x; k < D; k += EL_TB) { c[k] = nd.center[(int64_t)node * D + k]; a[k] = nd.evals[(int64_t)node * D + k]; }
   for (int k = threadIdx.x; k < D * D; k += EL_TB) ori[k] = nd.ori[(int64_t)node * D * D + k];
@@ -258,6 +283,7 @@ __global__ void el_rescale_kernel(int D, ElNodes nd, int lb, int nn, int S, cons
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= nn) return;
   const int node = lb + r;
+  if (el_is_small(nd, node, D)) return;
   double rmax = neg_inf_d();
   for (int s = 0; s < S; ++s) { const double x = part[(int64_t)r * S + s]; rmax = x > rmax ? x : rmax; }
   int imax = -1; double amax = neg_inf_d();
@@ -267,6 +293,83 @@ __global__ void el_rescale_kernel(int D, ElNodes nd, int lb, int nn, int S, cons
     if (a > amax) { amax = a; imax = j; }
   }
   nd.split[node] = imax;
+}
+
+// ---- small nodes: enclosing_ellipse (:98-103) of a node of at most EL_SMALL doubles by ONE warp -----------------------------
+// The deep levels of the tree hold most of its nodes (D + 1 .. a few dozen points each); a CTA per (node, slice) and
+// five launches per node are wasteful there.  One warp stages the node's rows in shared memory and does centre,
+// covariance, eigen-system, largest elliptical range and the rescaling in one go (same formulas; sums in a fixed order).
+__global__ void __launch_bounds__(32 * EL_SWARPS)
+el_small_kernel(const double *__restrict__ rows, int D, ElNodes nd, int lb, int nn, double dim_sf) {
+  extern __shared__ double el_sm[];
+  const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+  const int r = blockIdx.x * EL_SWARPS + wrp;
+  if (r >= nn) return;
+  const int node = lb + r;
+  const int b = nd.begin[node], n = nd.end[node] - b;
+  if (n * D > EL_SMALL) return;                     // the (node, slice) kernels take it
+  const int LD = D + 1, P = el_pairs(D);
+  double *base = el_sm + (size_t)wrp * (EL_SMALL + 2 * D * LD + 4 * D + D * D + 64);
+  double *pt = base, *A = pt + EL_SMALL, *V = A + D * LD, *w = V + D * LD, *mu = w + D, *ev = mu + D, *ori = ev + D, *red = ori + D * D;
+  const double *src = rows + (int64_t)b * D;
+  for (int k = lane; k < n * D; k += 32) pt[k] = src[k];
+  __syncwarp();
+  const double nf = (double)n;
+  // centre (:36-46): lane (g, j) sums rows g, g + G, ... of column j; groups combined in order
+  {
+    const int G = 32 / D;                           // D <= 32: at least one group
+    const int g = lane / D, j = lane - g * D;
+    const bool worker = g < G;
+    double acc = 0.0;
+    if (worker) for (int i = g; i < n; i += G) acc = acc + pt[i * D + j];
+    if (worker) red[g * D + j] = acc;
+    __syncwarp();
+    if (lane < D) {
+      double t = 0.0;
+      for (int gg = 0; gg < G; ++gg) t = t + red[gg * D + lane];
+      t = t / nf;
+      mu[lane] = t; nd.center[(int64_t)node * D + lane] = t;
+    }
+    __syncwarp();
+  }
+  for (int k = lane; k < n * D; k += 32) pt[k] = pt[k] - mu[k % D];    // centred rows
+  __syncwarp();
+  // covariance (:48-66): one pair (j <= k) per lane and round, rows in order
+  for (int q = lane; q < P; q += 32) {
+    int j = 0, rem = q;
+    while (rem >= D - j) { rem -= D - j; ++j; }
+    const int k = j + rem;
+    double t = 0.0;
+    for (int i = 0; i < n; ++i) t = t + pt[i * D + j] * pt[i * D + k];
+    t = t / nf;
+    A[j * LD + k] = t; A[k * LD + j] = t;
+  }
+  __syncwarp();
+  el_jacobi_warp(A, V, D, LD, lane);
+  el_eigen_store(A, V, w, D, LD, lane, nd, node, ev, ori);
+  // largest elliptical range (:75-81) of the centred rows against the unscaled ellipse, then rescale_ellipse (:83-86)
+  double m = neg_inf_d();
+  for (int i = lane; i < n; i += 32) {
+    double rr = 0.0;
+    for (int j = 0; j < D; ++j) {
+      double d = 0.0;
+      for (int k = 0; k < D; ++k) d = d + pt[i * D + k] * ori[k * D + j];
+      rr = rr + d * d / ev[j];
+    }
+    rr = rr + 0.0;
+    m = rr > m ? rr : m;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { const double x = __shfl_xor_sync(0xffffffffu, m, o); m = x > m ? x : m; }
+  if (lane == 0) {
+    int imax = -1; double amax = neg_inf_d();
+    for (int j = 0; j < D; ++j) {
+      const double a = ev[j] * dim_sf * m;
+      nd.axes[(int64_t)node * D + j] = a;
+      if (a > amax) { amax = a; imax = j; }
+    }
+    nd.split[node] = imax;
+  }
 }
 
 // ---- the partition of a level (:151-156) ---------------------------------------------------------------------------------------
@@ -296,6 +399,8 @@ __global__ void el_children_count_kernel(int D, ElNodes nd, int lb, int nn, cons
   if (nL == e - b || nR == e - b) *stuck = 1;        // the reference would recurse on the same points forever
   has[2 * r] = nL >= D + 1 ? 1 : 0;
   has[2 * r + 1] = nR >= D + 1 ? 1 : 0;
+  const int big = (nL >= D + 1 && nL > nR) ? nL : (nR >= D + 1 ? nR : (nL >= D + 1 ? nL : 0));
+  if (big > 0) atomicMax(stuck + 1, big);            // the largest node of the next level
 }
 __global__ void el_children_make_kernel(ElNodes nd, int lb, int nn, int next_base, const int32_t *__restrict__ lscan,
                                         const int32_t *__restrict__ has, const int32_t *__restrict__ hscan) {
@@ -419,8 +524,17 @@ static int el_reserve(mg_ctx *ctx, ElTable &t, int64_t used, int64_t want, int D
 }
 
 // enclosing_ellipse (:98-103) of every node of a level: centre, covariance, eigen-system, rescaling
-static int el_level_ellipses(mg_ctx *ctx, const double *rows, int D, const ElTable &t, int lb, int nn, double sf, DevBuf<double> &part) {
+static int el_level_ellipses(mg_ctx *ctx, const double *rows, int D, const ElTable &t, int lb, int nn, double sf, DevBuf<double> &part,
+                             int64_t max_points) {
   cudaStream_t s = ctx->stream;
+  const double dim_sf = pow(sf, 1.0 / (double)D);              // :85, host libm like the reference
+  {
+    const size_t sm_small = sizeof(double) * (size_t)EL_SWARPS * (EL_SMALL + 2 * D * (D + 1) + 4 * D + D * D + 64);
+    if (sm_small > 48 * 1024) MG_CUDA(ctx, cudaFuncSetAttribute(el_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_small));
+    el_small_kernel<<<(unsigned)((nn + EL_SWARPS - 1) / EL_SWARPS), 32 * EL_SWARPS, sm_small, s>>>(rows, D, t.view(), lb, nn, dim_sf);
+    MG_CHECK_LAUNCH(ctx);
+    if (max_points * D <= EL_SMALL) return MG_OK;             // every node of the level was a small one
+  }
   const int P = D * (D + 1) / 2;
   const int S = (int)std::max<int64_t>(1, std::min<int64_t>(EL_SMAX, (4 * (int64_t)ctx->sm_count + nn - 1) / nn));
   const size_t need = (size_t)nn * S * std::max(P, D);
@@ -443,7 +557,6 @@ static int el_level_ellipses(mg_ctx *ctx, const double *rows, int D, const ElTab
   MG_CHECK_LAUNCH(ctx);
   el_range_partial_kernel<<<grid, EL_TB, sm_rng, s>>>(rows, D, nd, lb, S, part.get());
   MG_CHECK_LAUNCH(ctx);
-  const double dim_sf = pow(sf, 1.0 / (double)D);              // :85, host libm like the reference
   el_rescale_kernel<<<(unsigned)((nn + 255) / 256), 256, 0, s>>>(D, nd, lb, nn, S, part.get(), dim_sf);
   MG_CHECK_LAUNCH(ctx);
   return MG_OK;
@@ -477,7 +590,7 @@ extern "C" int mg_ellipse_enclosing(mg_ctx *ctx, const double *pts, int64_t N, i
   const int32_t be[2] = {0, (int32_t)N};
   MG_CUDA(ctx, cudaMemcpyAsync(t.begin.get(), &be[0], sizeof(int32_t), cudaMemcpyHostToDevice, s));
   MG_CUDA(ctx, cudaMemcpyAsync(t.end.get(), &be[1], sizeof(int32_t), cudaMemcpyHostToDevice, s));
-  if ((rc = el_level_ellipses(ctx, rows.get(), D, t, 0, 1, sf, part))) return rc;
+  if ((rc = el_level_ellipses(ctx, rows.get(), D, t, 0, 1, sf, part, N))) return rc;
   MG_CUDA(ctx, cudaMemcpyAsync(center, t.center.get(), sizeof(double) * D, cudaMemcpyDeviceToHost, s));
   MG_CUDA(ctx, cudaMemcpyAsync(axes, t.axes.get(), sizeof(double) * D, cudaMemcpyDeviceToHost, s));
   MG_CUDA(ctx, cudaMemcpyAsync(orientation, t.ori.get(), sizeof(double) * D * D, cudaMemcpyDeviceToHost, s));
@@ -524,8 +637,8 @@ static int ellipse_tree_build(mg_ctx *ctx, const double *pts, bool on_device, in
   MG_CUDA(ctx, segA.alloc((size_t)N, s)); MG_CUDA(ctx, segB.alloc((size_t)N, s));
   MG_CUDA(ctx, flag.alloc((size_t)N + 1, s)); MG_CUDA(ctx, lscan.alloc((size_t)N + 1, s));
   MG_CUDA(ctx, tmp.alloc((size_t)scan_tmp_elems(N + 1, 1), s));
-  MG_CUDA(ctx, htot.alloc(1, s)); MG_CUDA(ctx, stuck.alloc(1, s));
-  MG_CUDA(ctx, cudaMemsetAsync(stuck.get(), 0, sizeof(int), s));
+  MG_CUDA(ctx, htot.alloc(1, s)); MG_CUDA(ctx, stuck.alloc(2, s));   // [0] a node cannot be split, [1] largest node of the next level
+  MG_CUDA(ctx, cudaMemsetAsync(stuck.get(), 0, 2 * sizeof(int), s));
   el_iota_kernel<<<(unsigned)((N + 255) / 256), 256, 0, s>>>(permA.get(), segA.get(), N);
   MG_CHECK_LAUNCH(ctx);
   ElTable t;
@@ -536,13 +649,13 @@ static int ellipse_tree_build(mg_ctx *ctx, const double *pts, bool on_device, in
   double *rin = rowsA.get(), *rout = rowsB.get();
   int32_t *pin = permA.get(), *pout = permB.get(), *sin = segA.get(), *sout = segB.get();
   std::vector<std::pair<int64_t, int64_t>> levels;       // [lb, le) of every level
-  int64_t lb = 0, le = 1;
+  int64_t lb = 0, le = 1, level_max = N;
   while (le > lb) {
     const int64_t nn = le - lb;
     MG_REQUIRE(ctx, levels.size() < 4096, "ellipse_tree: more than 4096 levels");
     levels.push_back({lb, le});
     if ((rc = el_reserve(ctx, t, le, le + 2 * nn, D, s))) return rc;
-    if ((rc = el_level_ellipses(ctx, rin, D, t, (int)lb, (int)nn, sf, part))) return rc;
+    if ((rc = el_level_ellipses(ctx, rin, D, t, (int)lb, (int)nn, sf, part, level_max))) return rc;
     ElNodes nd = t.view();
     el_flag_kernel<<<(unsigned)((N + 1 + 255) / 256), 256, 0, s>>>(rin, N, D, nd, sin, (int)lb, (int)le, flag.get());
     MG_CHECK_LAUNCH(ctx);
@@ -558,10 +671,13 @@ static int ellipse_tree_build(mg_ctx *ctx, const double *pts, bool on_device, in
     MG_CHECK_LAUNCH(ctx);
     el_scatter_kernel<<<(unsigned)((N + 255) / 256), 256, 0, s>>>(rin, rout, pin, pout, sin, sout, N, D, nd, (int)lb, (int)le, lscan.get(), flag.get());
     MG_CHECK_LAUNCH(ctx);
-    int32_t nchild = 0; int h_stuck = 0;
+    int32_t nchild = 0; int h_st[2] = {0, 0};
     MG_CUDA(ctx, cudaMemcpyAsync(&nchild, htot.get(), sizeof(int32_t), cudaMemcpyDeviceToHost, s));
-    MG_CUDA(ctx, cudaMemcpyAsync(&h_stuck, stuck.get(), sizeof(int), cudaMemcpyDeviceToHost, s));
+    MG_CUDA(ctx, cudaMemcpyAsync(h_st, stuck.get(), sizeof h_st, cudaMemcpyDeviceToHost, s));
+    MG_CUDA(ctx, cudaMemsetAsync(stuck.get() + 1, 0, sizeof(int), s));
     MG_CUDA(ctx, cudaStreamSynchronize(s));
+    const int h_stuck = h_st[0];
+    level_max = h_st[1];
     if (h_stuck) return set_err(ctx, MG_EFAIL, "ellipse_tree: all points of a node lie on one side of its centre (the reference recurses forever, ellipse.ml:153-158)");
     std::swap(rin, rout); std::swap(pin, pout); std::swap(sin, sout);
     lb = le; le = le + nchild;
