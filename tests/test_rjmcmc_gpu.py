@@ -211,3 +211,35 @@ def test_k_model_arguments(ctx):
         mcmc.rjmcmc_array_k(10, [mk(0.1)] * 9, [[0.0]] * 9, ctx=ctx)
     r = mcmc.rjmcmc_array_k(50, [mk(0.125)] * 8, [[0.0]] * 8, nchains=512, ctx=ctx)
     assert sum(r.counts) == 50 * 512 and min(r.counts) > 0.08 * 50 * 512   # eight equal models: about 1/8 each
+
+
+def test_four_models_of_different_dimensions_match_oracle(ctx, og):
+    """k-model sampler across dimensions: isotropic Gaussian posteriors of 2, 3, 5 and 8 dimensions (evidences 1, 1/2,
+    1/4, 1/8 through the prior's density), interpolated jumps at leaf level and through the *_high_level forms, unequal
+    model priors.  Chain for chain against the oracle's rj_chain_k on the same Philox stream."""
+    import math
+    s, ntree = 0.05, 60_000
+    dims, pri, nstops = (2, 3, 5, 8), (0.1, 0.2, 0.3, 0.4), (0, 0, 32, 0)
+    rng = np.random.default_rng(2468)
+    gm, om, starts = [], [], []
+    for k, d in enumerate(dims):
+        pts = rng.normal(0.5, s, (ntree, d)).clip(0.0, 1.0)
+        lo, hi = np.zeros(d), np.ones(d)
+        like = P.gauss_diag(np.full(d, 0.5), np.full(d, s))
+        prior = P.box(lo, hi, -k * math.log(2.0))
+        prop = P.wrap_proposal(lo, hi, np.full(d, 2.0 * s / math.sqrt(d)))
+        gm.append(mcmc.RjModel(like, prior, prop, pri[k], interp=interpolate_pdf.InterpPdf(pts, lo, hi, ctx=ctx), nstop=nstops[k]))
+        om.append(og.rj_model(like, prior, prop, pri[k], tree=og.Tree(pts, lo, hi), nstop=nstops[k]))
+        starts.append(np.full(d, 0.5))
+    C, n = 384, 100
+    ctx.set_seed(1357)
+    g = mcmc.rjmcmc_array_k(n, gm, starts, nskip=2, nbin=5, nchains=C, record_samples=True, ctx=ctx)
+    o = og.rjmcmc_array_k(1357, 0, n, om, starts, nskip=2, nbin=5, nchains=C, nthreads=8, record_samples=True, margins=True)
+    Dm = max(dims)
+    frac = divergence_report(np.concatenate([g.block[:, :Dm, :], g.model[:, None, :].astype(float)], axis=1),
+                             np.concatenate([o["samples"][:, :Dm, :], o["model"][:, None, :].astype(float)], axis=1),
+                             o["margins"], "RJ four models (2,3,5,8)-D")
+    assert frac <= 0.01
+    if frac == 0.0:
+        assert g.counts == o["counts"] and g.cross == o["cross"]
+    assert set(np.unique(g.model)) == {0, 1, 2, 3} and g.cross[1] > 0
