@@ -212,3 +212,42 @@ let posterior_samples ctx n (pts : float array array) (log_wts : float array) =
   let idx = Array1.create int64 c_layout n in
   posterior_indices_raw ctx lw idx;
   Array.init n (fun i -> pts.(Int64.to_int idx.{i}))
+
+
+(* Several GPUs: one OCaml process per GPU.  Rank 0 makes the 128-byte NCCL id ([Comm.unique_id]) and hands it to the other
+   ranks (a file, a socket, MPI ...); every rank then creates its communicator.  All functions below are collective. *)
+module Comm = struct
+  type comm
+  type id = (int, int8_unsigned_elt, c_layout) Array1.t
+  external unique_id_raw : id -> unit = "mcmcgpu_comm_unique_id"
+  external create : ctx -> int -> int -> id -> comm = "mcmcgpu_comm_create"
+  external interp_broadcast_raw : ctx -> comm -> tree option -> int -> tree = "mcmcgpu_interp_broadcast"
+  external interp_make_distributed_raw :
+    ctx -> comm -> (float, float64_elt, c_layout) Array2.t -> (float, float64_elt, c_layout) Array1.t ->
+    (float, float64_elt, c_layout) Array1.t -> tree = "mcmcgpu_interp_make_distributed"
+  external evidence_lebesgue_sharded_raw :
+    ctx -> comm -> int -> (float, float64_elt, c_layout) Array2.t -> (float, float64_elt, c_layout) Array1.t ->
+    (float, float64_elt, c_layout) Array1.t -> int -> float -> float
+    = "mcmcgpu_evidence_lebesgue_sharded_bytecode" "mcmcgpu_evidence_lebesgue_sharded_native"
+  external rjmcmc_array_sharded_raw :
+    ctx -> comm -> rj_model_raw -> rj_model_raw -> int -> int -> int -> int -> (float, float64_elt, c_layout) Array1.t ->
+    (float, float64_elt, c_layout) Array1.t -> int * int
+    = "mcmcgpu_rjmcmc_array_sharded_bytecode" "mcmcgpu_rjmcmc_array_sharded_native"
+  let unique_id () = let id = Array1.create int8_unsigned c_layout 128 in unique_id_raw id; id
+  (* Interp.make on [root], replicated on every rank by one broadcast *)
+  let interp_broadcast ctx comm ?(root = 0) ~dim (ip : Interp.interp_pdf option) =
+    let t = interp_broadcast_raw ctx comm (match ip with Some i -> Some i.Interp.tree | None -> None) root in
+    { Interp.tree = t; dim }
+  (* Interp.make by all ranks together; every rank passes the same points *)
+  let interp_make_distributed ctx comm (pts : float array array) low high =
+    { Interp.tree = interp_make_distributed_raw ctx comm (Array2.of_array float64 c_layout pts) (ba1 low) (ba1 high);
+      dim = Array.length low }
+  (* Evidence.evidence_lebesgue ?n ?eps of the samples held by [root] (the other ranks pass [||]) *)
+  let evidence_lebesgue ctx comm ?(root = 0) ?(n = 64) ?(eps = 0.1) (pts : float array array) (ll : float array) (lp : float array) =
+    let d = if Array.length pts > 0 then Array.length pts.(0) else 1 in
+    let p = if Array.length pts > 0 then Array2.of_array float64 c_layout pts else Array2.create float64 c_layout 0 d in
+    evidence_lebesgue_sharded_raw ctx comm root p (ba1 ll) (ba1 lp) n eps
+  (* Mcmc.rjmcmc_array over all ranks: the model counts of the whole ensemble *)
+  let rjmcmc_array ctx comm ?(nbin = 0) ?(nskip = 1) ?(nchains = 1) n (ma : rj_model) (mb : rj_model) a0 b0 =
+    rjmcmc_array_sharded_raw ctx comm (raw_of_model ma) (raw_of_model mb) nbin nskip n nchains (ba1 a0) (ba1 b0)
+end

@@ -112,3 +112,21 @@ val draw_cauchy : ctx -> float -> float -> int -> float array
 
 (** [Nested.posterior_samples n output] (nested.ml:167-178) given the points and their log weights. *)
 val posterior_samples : ctx -> int -> float array array -> float array -> float array array
+
+
+(** {2 Several GPUs} one OCaml process per GPU; rank 0 makes the NCCL id and hands it to the others; every function is
+    collective.  Results do not depend on the number of ranks (global chain ids; evidences bit-identical to one GPU). *)
+module Comm : sig
+  type comm
+  type id = (int, int8_unsigned_elt, c_layout) Array1.t
+  val unique_id : unit -> id
+  val create : ctx -> int -> int -> id -> comm
+  (** [create ctx nranks rank id] *)
+  val interp_broadcast : ctx -> comm -> ?root:int -> dim:int -> Interp.interp_pdf option -> Interp.interp_pdf
+  (** the root passes [Some tree], the other ranks [None]; [dim] is the tree's dimension (known to every rank) *)
+  val interp_make_distributed : ctx -> comm -> float array array -> float array -> float array -> Interp.interp_pdf
+  val evidence_lebesgue :
+    ctx -> comm -> ?root:int -> ?n:int -> ?eps:float -> float array array -> float array -> float array -> float
+  val rjmcmc_array :
+    ctx -> comm -> ?nbin:int -> ?nskip:int -> ?nchains:int -> int -> rj_model -> rj_model -> float array -> float array -> int * int
+end

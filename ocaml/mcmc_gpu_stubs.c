@@ -432,3 +432,153 @@ CAMLprim value mcmcgpu_nested_evidence_bytecode(value *a, int argn) {
 CAMLprim value mcmcgpu_log_total_error_estimate(value log_ev, value log_dev, value nlive) {
   return caml_copy_double(mg_nested_log_total_error(Double_val(log_ev), Double_val(log_dev), Int_val(nlive)));
 }
+
+/* ---- several GPUs: one OCaml process per GPU, one communicator per context (mg_comm_*, NCCL inside the library) ---------
+ * The 128-byte NCCL id is made by rank 0 (comm_unique_id) and handed to the other ranks by the host program (a file, a
+ * socket, MPI ...); it travels as a (int, int8_unsigned_elt, c_layout) Array1.t of length 128. */
+typedef struct { mg_comm *comm; ctx_box *box; } comm_box;
+#define Commbox_val(v) ((comm_box *)Data_custom_val(v))
+#define Comm_val(v) (Commbox_val(v)->comm)
+static void comm_finalize(value v) {
+  comm_box *b = Commbox_val(v);
+  if (b->comm) { mg_comm_destroy(b->comm); b->comm = NULL; }
+  box_release(b->box); b->box = NULL;
+}
+static struct custom_operations comm_ops = {"mcmc_gpu.comm", comm_finalize, custom_compare_default, custom_hash_default,
+                                            custom_serialize_default, custom_deserialize_default,
+                                            custom_compare_ext_default, custom_fixed_length_default};
+/* external comm_unique_id : (int, int8_unsigned_elt, c_layout) Array1.t -> unit */
+CAMLprim value mcmcgpu_comm_unique_id(value id) {
+  CAMLparam1(id);
+  if (Caml_ba_array_val(id)->dim[0] != MG_COMM_ID_BYTES) caml_invalid_argument("comm_unique_id: the id holds 128 bytes");
+  if (mg_comm_get_unique_id((uint8_t *)Caml_ba_data_val(id)) != MG_OK) caml_failwith("nccl: cannot create a unique id");
+  CAMLreturn(Val_unit);
+}
+/* external comm_create : ctx -> int -> int -> (int, int8_unsigned_elt, c_layout) Array1.t -> comm   (nranks, rank, id) */
+CAMLprim value mcmcgpu_comm_create(value ctx, value nranks, value rank, value id) {
+  CAMLparam4(ctx, nranks, rank, id);
+  CAMLlocal1(v);
+  mg_ctx *c = Ctx_val(ctx);
+  mg_comm *cm = NULL;
+  const uint8_t *pid = (const uint8_t *)Caml_ba_data_val(id);
+  const int n = Int_val(nranks), r = Int_val(rank);
+  caml_release_runtime_system();                 /* ncclCommInitRank waits for the other ranks */
+  int rc = mg_comm_create(c, n, r, pid, &cm);
+  caml_acquire_runtime_system();
+  check(c, rc);
+  v = caml_alloc_custom(&comm_ops, sizeof(comm_box), 0, 1);
+  Commbox_val(v)->comm = cm; Commbox_val(v)->box = Box_val(ctx); Box_val(ctx)->refs++;
+  CAMLreturn(v);
+}
+static value wrap_tree(value ctx, mg_kdtree *t) {
+  CAMLparam1(ctx);
+  CAMLlocal1(v);
+  v = caml_alloc_custom(&tree_ops, sizeof(tree_box), 0, 1);
+  Treebox_val(v)->tree = t; Treebox_val(v)->box = Box_val(ctx); Box_val(ctx)->refs++;
+  CAMLreturn(v);
+}
+/* Interp.make on `root`, the tree replicated on every rank (one ncclBroadcast of the blob).
+ * external interp_broadcast : ctx -> comm -> interp_tree option -> int -> interp_tree */
+CAMLprim value mcmcgpu_interp_broadcast(value ctx, value comm, value tree_opt, value root) {
+  CAMLparam4(ctx, comm, tree_opt, root);
+  mg_ctx *c = Ctx_val(ctx);
+  mg_kdtree *mine = Is_block(tree_opt) ? Tree_val(Field(tree_opt, 0)) : NULL, *out = NULL;
+  mg_comm *cm = Comm_val(comm);
+  const int r = Int_val(root);
+  caml_release_runtime_system();
+  int rc = mg_kdtree_broadcast(cm, mine, r, &out);
+  caml_acquire_runtime_system();
+  check(c, rc);
+  if (out == mine && Is_block(tree_opt)) CAMLreturn(Field(tree_opt, 0));   /* the root keeps its own tree */
+  CAMLreturn(wrap_tree(ctx, out));
+}
+/* Interp.make by all ranks together (every rank passes the same points): mg_kdtree_build_distributed.
+ * external interp_make_distributed : ctx -> comm -> pts -> low -> high -> interp_tree */
+CAMLprim value mcmcgpu_interp_make_distributed(value ctx, value comm, value pts, value low, value high) {
+  CAMLparam5(ctx, comm, pts, low, high);
+  mg_ctx *c = Ctx_val(ctx);
+  mg_comm *cm = Comm_val(comm);
+  struct caml_ba_array *b = Caml_ba_array_val(pts);
+  const int64_t N = b->dim[0]; const int32_t D = (int32_t)b->dim[1];
+  const double *pp = (const double *)Caml_ba_data_val(pts), *pl = (const double *)Caml_ba_data_val(low),
+               *ph = (const double *)Caml_ba_data_val(high);
+  mg_kdtree *t = NULL;
+  void *d_pts = NULL;
+  caml_release_runtime_system();
+  int rc = mg_malloc_device(c, (int64_t)sizeof(double) * N * D, &d_pts);
+  if (rc == MG_OK) rc = mg_memcpy_h2d(c, d_pts, pp, (int64_t)sizeof(double) * N * D);
+  if (rc == MG_OK) rc = mg_kdtree_build_distributed(cm, (const double *)d_pts, N, D, pl, ph, 2, &t);
+  if (d_pts) mg_free_device(c, d_pts);
+  caml_acquire_runtime_system();
+  check(c, rc);
+  CAMLreturn(wrap_tree(ctx, t));
+}
+/* Evidence.evidence_lebesgue ?n ?eps with the kd-tree built by all ranks and the cells shared out; the samples live on
+ * `root` (the other ranks pass empty arrays).  Every rank receives the same value.
+ * external evidence_lebesgue_sharded : ctx -> comm -> int -> pts -> ll -> lp -> int -> float -> float */
+CAMLprim value mcmcgpu_evidence_lebesgue_sharded_native(value ctx, value comm, value root, value pts, value ll, value lp,
+                                                        value n, value eps) {
+  CAMLparam5(ctx, comm, root, pts, ll);
+  CAMLxparam3(lp, n, eps);
+  mg_ctx *c = Ctx_val(ctx);
+  mg_comm *cm = Comm_val(comm);
+  const int r = Int_val(root), nn = Int_val(n);
+  const double e = Double_val(eps);
+  const int is_root = mg_comm_rank(cm) == r;
+  struct caml_ba_array *b = Caml_ba_array_val(pts);
+  const int64_t N = b->dim[0]; const int32_t D = (int32_t)b->dim[1];
+  const double *pp = (const double *)Caml_ba_data_val(pts), *pll = (const double *)Caml_ba_data_val(ll),
+               *plp = (const double *)Caml_ba_data_val(lp);
+  void *dp = NULL, *dl = NULL, *dq = NULL;
+  double z = 0.0;
+  caml_release_runtime_system();
+  int rc = MG_OK;
+  if (is_root) {
+    rc = mg_malloc_device(c, (int64_t)sizeof(double) * N * D, &dp);
+    if (rc == MG_OK) rc = mg_malloc_device(c, (int64_t)sizeof(double) * N, &dl);
+    if (rc == MG_OK) rc = mg_malloc_device(c, (int64_t)sizeof(double) * N, &dq);
+    if (rc == MG_OK) rc = mg_memcpy_h2d(c, dp, pp, (int64_t)sizeof(double) * N * D);
+    if (rc == MG_OK) rc = mg_memcpy_h2d(c, dl, pll, (int64_t)sizeof(double) * N);
+    if (rc == MG_OK) rc = mg_memcpy_h2d(c, dq, plp, (int64_t)sizeof(double) * N);
+  }
+  /* (a root that failed above still enters the collective: the library broadcasts its status first) */
+  int rc2 = mg_evidence_lebesgue_sharded(cm, r, rc == MG_OK ? (const double *)dp : NULL, (const double *)dl, (const double *)dq, N, D, nn, e, &z);
+  if (dp) mg_free_device(c, dp);
+  if (dl) mg_free_device(c, dl);
+  if (dq) mg_free_device(c, dq);
+  caml_acquire_runtime_system();
+  check(c, rc != MG_OK ? rc : rc2);
+  CAMLreturn(caml_copy_double(z));
+}
+CAMLprim value mcmcgpu_evidence_lebesgue_sharded_bytecode(value *a, int argn) {
+  (void)argn;
+  return mcmcgpu_evidence_lebesgue_sharded_native(a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7]);
+}
+/* Mcmc.rjmcmc_array with the chains cut into one range per rank (global chain ids: results do not depend on the number
+ * of ranks); returns the counts of ALL ranks.
+ * external rjmcmc_array_sharded_raw : ctx -> comm -> rj_model_raw -> rj_model_raw -> int -> int -> int -> int -> a0 -> b0 -> int * int */
+CAMLprim value mcmcgpu_rjmcmc_array_sharded_native(value ctx, value comm, value ma, value mb, value nbin, value nskip,
+                                                   value n, value nchains, value a0, value b0) {
+  CAMLparam5(ctx, comm, ma, mb, a0);
+  CAMLxparam1(b0);
+  CAMLlocal1(r);
+  mg_rj_model A = rj_of_value(ma), B = rj_of_value(mb);
+  mg_rjmcmc_cfg cfg;
+  memset(&cfg, 0, sizeof cfg);
+  cfg.nchains = Long_val(nchains); cfg.nbin = Long_val(nbin); cfg.nskip = Long_val(nskip); cfg.n = Long_val(n);
+  int64_t counts[2] = {0, 0}, sb = 0, sc = 0;
+  mg_ctx *c = Ctx_val(ctx);
+  mg_comm *cm = Comm_val(comm);
+  const double *pa = (const double *)Caml_ba_data_val(a0), *pb = (const double *)Caml_ba_data_val(b0);
+  caml_release_runtime_system();
+  int rc = mg_rjmcmc_array_sharded(cm, &A, &B, &cfg, pa, pb, NULL, NULL, counts, &sb, &sc);
+  caml_acquire_runtime_system();
+  check(c, rc);
+  r = caml_alloc_tuple(2);
+  Store_field(r, 0, Val_long(counts[0])); Store_field(r, 1, Val_long(counts[1]));
+  CAMLreturn(r);
+}
+CAMLprim value mcmcgpu_rjmcmc_array_sharded_bytecode(value *a, int argn) {
+  (void)argn;
+  return mcmcgpu_rjmcmc_array_sharded_native(a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], a[8], a[9]);
+}
