@@ -51,7 +51,10 @@ struct V2Info {
   int32_t sel_active;               // nodes of the current level whose select is still running
   int32_t overflow;                 // a capacity was exceeded
 };
-struct V2Sel { uint64_t prefix; int32_t shift; int32_t dim; };   // shift < 0: no (more) select work
+// shift: position of the next 8-bit digit (< 0: no (more) select work); dim: split dimension in the low byte, and in the
+// second byte the lowest key bit already decided (64: none) -- digits start at the highest bit in which the node's keys
+// differ, not at a byte boundary, so the first pass already resolves eight bits
+struct V2Sel { uint64_t prefix; int32_t shift; int32_t dim; };
 
 struct V2Top {
   int64_t N; int D, min_split; int32_t LC, cap;
@@ -250,8 +253,10 @@ __global__ void v2_node_kernel(V2Top t, int L) {
   if (sd >= 0) {
     const uint64_t l = t.lo[(int64_t)k * t.D + sd], h = t.hi[(int64_t)k * t.D + sd];
     const int top = 63 - __clzll((long long)(l ^ h));      // highest differing bit (l != h here)
-    s.shift = (top >> 3) << 3;
-    s.prefix = (s.shift >= 56) ? 0ull : (l >> (s.shift + 8)) << (s.shift + 8);
+    const int df = top + 1;                                // bits df .. 63 are shared by all keys of the node
+    s.shift = top >= 7 ? top - 7 : 0;
+    s.prefix = df >= 64 ? 0ull : (l >> df) << df;
+    s.dim = sd | (df << 8);
     atomicAdd(&t.info->sel_active, 1);
   }
   t.sel[k] = s;
@@ -281,8 +286,9 @@ v2_hist_kernel(V2Top t, int L, const uint64_t *__restrict__ K, const int32_t *__
     id -= lv.lb;
     const V2Sel s = t.sel[id];
     if (s.shift < 0) continue;
-    const uint64_t key = K[(int64_t)s.dim * t.N + p];
-    if (s.shift < 56 && ((key ^ s.prefix) >> (s.shift + 8)) != 0ull) continue;
+    const uint64_t key = K[(int64_t)(s.dim & 255) * t.N + p];
+    const int df = s.dim >> 8;
+    if (df < 64 && ((key ^ s.prefix) >> df) != 0ull) continue;
     nd[k] = id; bin[k] = (uint32_t)(key >> s.shift) & 255u;
     mymin = id < mymin ? id : mymin;
   }
@@ -356,7 +362,8 @@ v2_pick_kernel(V2Top t, int L) {
     s.shift = -1;
     atomicSub(&t.info->sel_active, 1);
   } else {
-    s.shift -= 8;
+    s.dim = (s.dim & 255) | (s.shift << 8);                 // decided down to this digit; the last digit may overlap it
+    s.shift = s.shift >= 8 ? s.shift - 8 : 0;
   }
   t.sel[k] = s;
 }
