@@ -102,3 +102,20 @@ def test_rjmcmc_k_prior_sum_assertion(og):
     ms[2] = (type(ms[2][0])(ms[2][0].like, ms[2][0].prior, ms[2][0].prop, ms[2][0].into, 0.6), ms[2][1])   # 0.2 + 0.3 + 0.6
     with pytest.raises(Exception):
         og.rjmcmc_array_k(4, 0, 10, ms, starts)
+
+
+def test_rjmcmc_k_three_top_hats_known_evidence_ratios(og):
+    """The k-model form of mcmc_test.ml:150-182: top hats of side 1, 1/2, 1/4 on the unit square (evidences 1, 1/4, 1/16),
+    interpolated jumps into each, model priors (0.2, 0.3, 0.5): time in model k is proportional to p_k Z_k."""
+    prior = P.box([0, 0], [1, 1], 0.0)
+    boxes = [([0, 0], [1, 1]), ([0.25, 0.25], [0.75, 0.75]), ([0.375, 0.375], [0.625, 0.625])]
+    prop = P.wrap_proposal([0, 0], [1, 1], [0.5, 0.5])
+    pri = [0.2, 0.3, 0.5]
+    ms = []
+    for k, ((lo, hi), p) in enumerate(zip(boxes, pri)):
+        like = P.box(lo, hi, 0.0)
+        s, _, _ = og.mcmc_array(5, k, 6000, like, prior, prop, [0.5, 0.5], nskip=20)
+        ms.append(og.rj_model(like, prior, prop, p, tree=og.Tree(np.ascontiguousarray(s[:, :2, 0]), [0, 0], [1, 1])))
+    r = og.rjmcmc_array_k(6, 0, 3000, ms, [[0.5, 0.5]] * 3, nskip=10, nbin=100, nchains=64, nthreads=8, record_model=False)
+    w = np.array(pri) * np.array([1.0, 0.25, 0.0625])
+    np.testing.assert_allclose(np.array(r["counts"]) / sum(r["counts"]), w / w.sum(), rtol=0.08)
