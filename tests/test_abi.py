@@ -120,3 +120,40 @@ def test_plugin_translation_unit_compiles_with_nvrtc():
     log = ctypes.create_string_buffer(n.value)
     nv.nvrtcGetProgramLog(prog, log)
     assert rc == 0, log.value.decode()[:2000]
+
+
+def test_ocaml_externals_have_the_arity_of_their_stubs():
+    """Without an OCaml compiler the one mistake a reader is likely to miss is an `external` whose number of arguments
+    differs from its C stub's: count the arrows of every external's type (outside parentheses) against the `value`
+    parameters of the native stub; externals with more than five arguments must name a bytecode stub first."""
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(_abi.__file__)))
+    c_text = open(os.path.join(root, "ocaml", "mcmc_gpu_stubs.c")).read()
+    ml = open(os.path.join(root, "ocaml", "mcmc_gpu.ml")).read()
+    prims = {m.group(1): len(re.findall(r"\bvalue\s+\w+", m.group(2)))
+             for m in re.finditer(r"CAMLprim\s+value\s+(\w+)\s*\(([^)]*)\)", c_text)}
+    checked = 0
+    for m in re.finditer(r"external\s+(\w+)\s*:\s*(.*?)=\s*((?:\"\w+\"\s*)+)", ml, re.S):
+        name, typ, stubs = m.group(1), m.group(2), re.findall(r'"(\w+)"', m.group(3))
+        depth, arrows, i = 0, 0, 0
+        while i < len(typ):                       # arrows at nesting depth 0 = arguments
+            ch = typ[i]
+            if ch in "([":
+                depth += 1
+            elif ch in ")]":
+                depth -= 1
+            elif typ.startswith("->", i) and depth == 0:
+                arrows += 1
+                i += 1
+            i += 1
+        native = stubs[-1]
+        assert native in prims, (name, native)
+        assert prims[native] == arrows, f"external {name}: {arrows} arguments, stub {native} takes {prims[native]}"
+        if arrows > 5:
+            assert len(stubs) == 2 and stubs[0].endswith("_bytecode"), f"external {name} needs a bytecode stub"
+            assert prims[stubs[0]] == 1 or "value *" in c_text[c_text.index(stubs[0]):c_text.index(stubs[0]) + 80], stubs[0]
+        else:
+            assert len(stubs) == 1, f"external {name}: {arrows} arguments need no bytecode stub"
+        checked += 1
+    assert checked >= 20
