@@ -26,6 +26,7 @@ def main():
     ap.add_argument("--seeds", type=int, default=6)
     ap.add_argument("--out", default=None)
     ap.add_argument("--quick", action="store_true", help="small sizes (test of the script itself)")
+    ap.add_argument("--same-nlive", type=int, default=0, help="like for like: K = 1 against K = 64 at nlive = 1000 with this many seeds each (only these cases)")
     a = ap.parse_args()
     import numpy as np
     from scipy import integrate, special
@@ -40,10 +41,12 @@ def main():
     cases = [(1000, 1), (100_000, 1024), (100_000, 8192)]
     if a.quick:
         cases = [(200, 1), (4000, 64), (4000, 512)]
+    if a.same_nlive > 0:
+        cases = [(1000, 1), (1000, 64)]
     doc = {"dim": D, "log_ev_analytic": logZ, "nmcmc": 1000, "epsrel": 0.01, "cases": []}
     for nlive, K in cases:
         rows = []
-        for seed in range(min(a.seeds, 3) if K == 1 else a.seeds):
+        for seed in range(a.same_nlive if a.same_nlive > 0 else (min(a.seeds, 3) if K == 1 else a.seeds)):
             ctx = Context(0, 1000 + seed)
             t = time.perf_counter()
             res = nested.nested_evidence(like, prior, np.full(D, -6.0), np.full(D, 6.0), nlive=nlive, nmcmc=1000, batch=K,
