@@ -6,23 +6,26 @@
 //
 //   top phase (level-synchronous, nodes larger than NMAX points).  The points live as D key columns
 //   K[d][position] (order-preserving uint64 keys) in the current node order.  Per level:
-//     bounds    per-node min / max of every column                        (bounds_of_objects :96-110)
+//     bounds    per-node min / max of every column: the root's come with the key pass, the children's are found by
+//               the scatter pass of their parent                          (bounds_of_objects :96-110)
 //     node      first strictly largest spread -> split dimension          (longest_dim :120-130), leaves (:157-160)
-//     select    the n/2-th order statistic of the split column by MSB-first radix select on the keys, starting
-//               below the bytes that the node's min and max share          (find_ith :69-86 -- its RESULT)
+//     select    the n/2-th order statistic of the split column by MSB-first radix select on the keys: 8-bit digits
+//               from the highest bit in which the node's keys differ, over as soon as the order statistic is alone in
+//               its bin (the scatter only compares keys with it)           (find_ith :69-86 -- its RESULT)
 //     scatter   stable partition (<= pivot | > pivot, or < max | >= max after adjust_for_empty_split :144-153) of
 //               all D columns + the index column by one chained scan with decoupled look-back; the same pass
-//               finds max L / min R for the split plane 0.5 (max L + min R)  (:113,170-172)
+//               finds max L / min R for the split plane 0.5 (max L + min R)  (:113,170-172) and the children's bounds
 //   Traffic per level ~ (2 * 8 D + 16) N bytes for the scatter -- SURVEY.md 8d's figure for a row-permuting build --
-//   plus 8 D N for the bounds and <= 8 x 12 N for the select.
+//   plus 3-4 x 12 N for the select.  A truncated build stops the level loop where no node can split any more.
 //
-//   bottom phase (one CTA per subtree of <= NMAX points, everything in shared memory).  Each column of the subtree
-//   is sorted in shared memory (bitonic) and replaced by dense 16-bit ranks; the rest of the subtree is integer work
-//   on ranks, one warp per node: bounds = min / max rank, order statistic = binary search on the rank, stable
-//   partition of the 16-bit local ids by ballots.  Real values are fetched only for the spread comparison and the
-//   split plane.  Nodes are written with subtree-local numbers; a scan over (subtree, level) node counts turns them
+//   bottom phase (one CTA per subtree of <= NMAX points).  The subtree's raw key columns live in shared memory and are
+//   never moved: nodes are ranges of a 16-bit local-id list.  One warp per node (all warps for the bounds of a level's
+//   few large nodes, one lane per dimension for nodes of <= 128 points, one thread per node of <= 8 points): bounds,
+//   split dimension, radix select on the split column finished by ranking <= 32 candidates, stable partition of the
+//   ids by ballots.  Nodes are written with subtree-local numbers; a scan over (subtree, level) node counts turns them
 //   into the breadth-first numbers of the whole tree (children adjacent), which is the numbering of the first
-//   builder and of the oracle.
+//   builder and of the oracle.  The builder keeps the first node of every level (mg_kdtree::level_begin) for the
+//   distributed build (comm.cu).
 //
 // Inputs on which the top phase cannot reach subtrees of <= NMAX points within its level budget (heavy ties), or
 // whose subtrees are deeper than the local level budget, return MG_V2_FALLBACK and take the first builder.
