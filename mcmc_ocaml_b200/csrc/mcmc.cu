@@ -5,11 +5,14 @@
 //
 // HBM layout.  state: [D+2][C] (coordinates, ll, lp), samples: [n][D+2][C].
 // Thread c of a warp owns chain c, so every store of a field is one fully
-// coalesced 256-byte warp transaction; the sample block is written once with
-// streaming (evict-first) stores and never read by this kernel.
+// coalesced 256-byte warp transaction; the sample block is written once --
+// through the TMA ([4 steps][D+2][32 chains] tiles, mcmc_balanced.cuh) by the
+// balanced sampler, with streaming stores by the static-mapping kernel -- and
+// never read by this kernel.
 // Roofline: the only mandatory traffic is the recorded sample,
 // 8 (D+2) / nskip bytes per chain-step; at nskip = 1 and D = 10
-// that is 96 B/step against ~170 FP64 instructions + 6 Philox blocks per step.
+// that is 96 B/step against ~100 FP64 instructions + 5 Philox blocks per step
+// (474 warp instructions in all: the step is bound by instruction issue).
 #include "mcmc_kernel.cuh"
 
 #include <cstdlib>

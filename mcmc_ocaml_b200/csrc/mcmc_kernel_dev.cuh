@@ -95,7 +95,8 @@ __device__ __forceinline__ int mh_step(const MhArgs<Like, Prior, Prop, D> &a, co
 
 // kStaticDim: the run-time dimension equals D (static plugins), so every
 // `i < d` guard folds away.  Register budget: 65,536 chains need 13.8 warps
-// per SM to be resident at once; the register file is split per scheduler (16K each), so <= 128 registers keep 4 warps on each.
+// per SM to be resident at once; the register file is split per scheduler (16K each), so <= 128 registers keep 4 warps on each
+// (the balanced sampler holds exactly 3 per scheduler and takes 160, mcmc_balanced.cuh).
 template <class Like, class Prior, class Prop, int D>
 __device__ __forceinline__ void mh_ensemble_body(const MhArgs<Like, Prior, Prop, D> &a) {
   int64_t c = (int64_t)blockIdx.x * MH_BLOCK + threadIdx.x;
