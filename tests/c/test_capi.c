@@ -6,6 +6,7 @@
  *   mcmcgpu_evidence_*          -> mg_evidence_harmonic_mean / _lebesgue / _direct
  *   mcmcgpu_nested_evidence_native -> mg_nested_evidence, mg_nested_log_total_error, mg_nested_posterior_indices
  *   mcmcgpu_stats_*             -> mg_stats_multi_mean / _multi_std / mg_stats_draw
+ *   mcmcgpu_rjmcmc_array_k_native -> mg_rjmcmc_array_k;  mcmcgpu_enclosing_ellipse -> mg_ellipse_*
  * and checks the reference's known answers (test/mcmc_test.ml:150-182 ratio 4, test/nested_test.ml:23-39 evidence 1).
  * Built by __graft_entry__.build() with gcc; run on the GPU box by tests/test_abi.py::test_c_program. */
 #include <math.h>
@@ -125,6 +126,73 @@ int main(void) {
   CHECK(ctx, mg_nested_posterior_indices(ctx, nlw, np, 1000, idx));
   double pm = 0; for (int i = 0; i < 1000; ++i) { EXPECT(idx[i] >= 0 && idx[i] < np); pm += npts[idx[i] * D]; }
   EXPECT(fabs(pm / 1000 - 0.5) < 0.02);
+
+  /* ---- mcmcgpu_rjmcmc_array_k_native -> mg_rjmcmc_array_k: with two models it is the two-model call, draw for draw;
+   *      three top hats (side 1, 1/2, 1/4: evidences 1, 1/4, 1/16), priors 0.2 / 0.3 / 0.5: time in model k ~ p_k Z_k ------ */
+  {
+    A.p = 0.5; B.p = 0.5;
+    mg_rj_model two[2] = {A, B};
+    const double *st2[2] = {x0, x0};
+    int64_t c2[2] = {0, 0};
+    CHECK(ctx, mg_ctx_set_seed(ctx, 77ull));
+    CHECK(ctx, mg_rjmcmc_array(ctx, &A, &B, &rcfg, x0, x0, NULL, NULL, counts));
+    CHECK(ctx, mg_ctx_set_seed(ctx, 77ull));
+    CHECK(ctx, mg_rjmcmc_array_k(ctx, two, 2, &rcfg, st2, NULL, NULL, c2));
+    EXPECT(c2[0] == counts[0] && c2[1] == counts[1]);
+    double box3[5] = {0.375, 0.375, 0.625, 0.625, 0.0};
+    mg_logfn like3 = {MG_FN_BOX_CLOSED, D, 1.0, box3, 5};
+    double *s4 = malloc(sizeof(double) * C * n * (D + 2)), *p4 = malloc(sizeof(double) * C * n * D);
+    CHECK(ctx, mg_mcmc_array(ctx, &like3, &prior, &prop, &cfg, x0, s4, NULL, NULL));
+    for (int64_t i = 0; i < C * n; ++i) for (int d = 0; d < D; ++d) p4[i * D + d] = s4[i * (D + 2) + d];
+    mg_kdtree *t3 = NULL;
+    CHECK(ctx, mg_kdtree_build(ctx, p4, C * n, D, lo, hi, 2, &t3));
+    mg_rj_model three[3] = {A, B, B};
+    three[2].like = like3; three[2].into.tree = t3;
+    three[0].p = 0.2; three[1].p = 0.3; three[2].p = 0.5;
+    const double *st3[3] = {x0, x0, x0};
+    int64_t c3[3] = {0, 0, 0};
+    CHECK(ctx, mg_rjmcmc_array_k(ctx, three, 3, &rcfg, st3, NULL, NULL, c3));
+    const double w0 = 0.2, w1 = 0.3 * 0.25, w2 = 0.5 * 0.0625, tot = (double)(c3[0] + c3[1] + c3[2]);
+    EXPECT(c3[0] + c3[1] + c3[2] == rcfg.n * rcfg.nchains);
+    EXPECT(fabs(c3[0] / tot - w0 / (w0 + w1 + w2)) < 0.02 && fabs(c3[1] / tot - w1 / (w0 + w1 + w2)) < 0.02 &&
+           fabs(c3[2] / tot - w2 / (w0 + w1 + w2)) < 0.02);
+    mg_kdtree_destroy(t3); free(s4); free(p4);
+  }
+
+  /* ---- mcmcgpu_enclosing_ellipse -> mg_ellipse_enclosing, mg_ellipse_range, mg_ellipse_tree_* (ellipse_test.ml:73-84:
+   *      every point of the cloud lies inside enclosing_ellipse 2.0) ---------------------------------------------------- */
+  {
+    double cen[2], axes[2], ori[4], *rr = malloc(sizeof(double) * N);
+    /* (the chains on the unit square accept every proposal, so no point repeats -- except slot 0 of every chain, the
+     *  shared start point: a node of identical points makes the reference recurse forever and this library return
+     *  MG_EFAIL, checked below; the cloud handed to the tree leaves those rows out) */
+    double *p5 = malloc(sizeof(double) * N * D); int64_t N5 = 0;
+    for (int64_t i = 0; i < N; ++i) if (i % n != 0) { p5[N5 * D] = p1[i * D]; p5[N5 * D + 1] = p1[i * D + 1]; ++N5; }
+    CHECK(ctx, mg_ellipse_enclosing(ctx, p1, N, D, 2.0, cen, axes, ori));
+    CHECK(ctx, mg_ellipse_range(ctx, cen, axes, ori, D, p1, N, rr));
+    double rmax = 0; for (int64_t i = 0; i < N; ++i) { EXPECT(rr[i] < 1.0); rmax = rr[i] > rmax ? rr[i] : rmax; }
+    EXPECT(fabs(rmax - 1.0 / sqrt(2.0)) < 1e-9 && fabs(cen[0] - 0.5) < 0.02 && axes[0] <= axes[1]);
+    mg_ellipse_tree *et = NULL;
+    EXPECT(mg_ellipse_tree_build(ctx, p1, N, D, 2.0, &et) == MG_EFAIL && et == NULL);   /* four copies of the start point */
+    CHECK(ctx, mg_ellipse_tree_build(ctx, p5, N5, D, 2.0, &et));
+    int64_t enp = 0, enn = 0; int32_t ed = 0, enl = 0;
+    CHECK(ctx, mg_ellipse_tree_info(et, &enp, &ed, &enn, &enl));
+    EXPECT(enp == N5 && ed == D && enn >= 1 && enl >= 1);
+    int32_t *el = malloc(4 * enn), *er = malloc(4 * enn), *eb = malloc(4 * enn), *ee = malloc(4 * enn);
+    CHECK(ctx, mg_ellipse_tree_export(et, el, er, eb, ee, NULL, NULL, NULL, NULL, NULL, NULL));
+    EXPECT(eb[0] == 0 && ee[0] == N5);
+    for (int64_t k = 0; k < enn; ++k) EXPECT(ee[k] - eb[k] >= D + 1 && el[k] < enn && er[k] < enn);
+    mg_ellipse_tree_destroy(et); free(el); free(er); free(eb); free(ee); free(rr); free(p5);
+  }
+
+  /* ---- the pool: trim, reserve, same results ----------------------------------------------------------------------------- */
+  {
+    double zh2 = 0;
+    CHECK(ctx, mg_ctx_trim_pool(ctx));
+    CHECK(ctx, mg_ctx_reserve_pool(ctx, (int64_t)1 << 30));
+    CHECK(ctx, mg_evidence_harmonic_mean(ctx, ll, N, &zh2));
+    EXPECT(zh2 == zh);
+  }
 
   /* ---- errors map as the stubs expect: MG_EINVAL <-> Invalid_argument, message available ---------------------------- */
   mg_mcmc_cfg bad = cfg; bad.nskip = 0;

@@ -276,8 +276,10 @@ def test_blob_validation_rejects_corrupt_headers(ctx):
 
 def test_c_program_drives_the_abi():
     """tests/c/test_capi.c: the call sequences of ocaml/mcmc_gpu_stubs.c (mg_mcmc_array, Interp, mg_rjmcmc_array,
-    Evidence, Stats, mg_nested_evidence) from plain C, no Python between the program and libmcmcgpu.so; checks the
-    reference's known answers (ratio 4.0 +- 0.1, nested evidence 1 within 2x its error)."""
+    Evidence, Stats, mg_nested_evidence, mg_rjmcmc_array_k, mg_ellipse_*, the pool calls) from plain C, no Python between
+    the program and libmcmcgpu.so; checks the reference's known answers (ratio 4.0 +- 0.1, nested evidence 1 within 2x
+    its error, every point inside its enclosing ellipse) and that two models through the k-model call equal the
+    two-model call."""
     import os
     import subprocess
     here = os.path.dirname(os.path.abspath(__file__))
