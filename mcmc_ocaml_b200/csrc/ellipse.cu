@@ -61,7 +61,7 @@ __device__ __forceinline__ void el_slice(int b, int e, int s, int S, int *sb, in
   *se = b + (int)(n * (s + 1) / S);
 }
 
-__device__ __forceinline__ bool el_is_small(const ElNodes &nd, int node, int D) { return (nd.end[node] - nd.begin[node]) * D <= EL_SMALL; }
+__device__ __forceinline__ bool el_is_small(const ElNodes &nd, int node, int D) { return (long long)(nd.end[node] - nd.begin[node]) * D <= EL_SMALL; }
 
 // ---- Ellipse.center (:36-46): per-(node, slice) column sums --------------------------------------------------------------
 __global__ void __launch_bounds__(EL_TB)
@@ -307,7 +307,7 @@ el_small_kernel(const double *__restrict__ rows, int D, ElNodes nd, int lb, int 
   if (r >= nn) return;
   const int node = lb + r;
   const int b = nd.begin[node], n = nd.end[node] - b;
-  if (n * D > EL_SMALL) return;                     // the (node, slice) kernels take it
+  if ((long long)n * D > EL_SMALL) return;          // the (node, slice) kernels take it
   const int LD = D + 1, P = el_pairs(D);
   double *base = el_sm + (size_t)wrp * (EL_SMALL + 2 * D * LD + 4 * D + D * D + 64);
   double *pt = base, *A = pt + EL_SMALL, *V = A + D * LD, *w = V + D * LD, *mu = w + D, *ev = mu + D, *ori = ev + D, *red = ori + D * D;
