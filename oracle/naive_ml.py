@@ -417,3 +417,71 @@ def flatten_bfs(tree, index_of):
             out_perm[b + len(l[0]):b + len(objs)] = [index_of(o) for o in r[0]]
         lvl_b, lvl_e = lvl_e, len(nodes)
     return dict(split_dim=sd, split_val=sv, left=left, begin=begin, end=end, perm=out_perm)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# nested.ml:81-120, 148-165 and stats.ml:240-248, transcribed statement by statement (scalar Python floats are IEEE
+# doubles; math.exp / log / log1p are the C library's, as OCaml's are).  Independent of oracle.cpp: compared exactly.
+def log_sum_logs(a, b):
+    """stats.ml:240-248"""
+    import math
+    if a == -math.inf and b == -math.inf:
+        return -math.inf
+    if b > a:
+        return log_sum_logs(b, a)
+    r = math.exp(b - a)
+    return a + math.log1p(r)
+
+
+def evidence_error_and_weights(nlive, ll):
+    """nested.ml:81-120: ll = log-likelihoods of all points in ascending order.  Returns (log_ev, log_dev, wts)."""
+    import math
+    vol_fraction = 1.0 / float(nlive)
+    log_vol_fraction = math.log(vol_fraction)
+    log_reduction_frac = math.log1p(-vol_fraction)
+    log_half = -0.69314718055994530942
+    n = len(ll)
+    wts = [-math.inf] * n
+    low, high = -math.inf, -math.inf
+    ilive = n - nlive
+    for i in range(0, ilive):
+        logli, logli1 = ll[i], ll[i + 1]
+        log_dv = log_vol_fraction + (float(i) * log_reduction_frac)
+        log_dlow, log_dhigh = log_dv + logli, log_dv + logli1
+        low = log_sum_logs(low, log_dlow)
+        high = log_sum_logs(high, log_dhigh)
+        wts[i] = log_sum_logs(wts[i], log_half + log_dlow)
+        wts[i + 1] = log_sum_logs(wts[i + 1], log_half + log_dhigh)
+    log_dv = log_vol_fraction + (float(ilive - 1) * log_reduction_frac)
+    for i in range(ilive, n):
+        logli1, logli = ll[i - 1], ll[i]
+        log_dlow, log_dhigh = log_dv + logli1, log_dv + logli
+        low = log_sum_logs(low, log_dlow)
+        high = log_sum_logs(high, log_dhigh)
+        wts[i - 1] = log_sum_logs(wts[i - 1], log_half + log_dlow)
+        wts[i] = log_sum_logs(wts[i], log_half + log_dhigh)
+    log_ev = log_half + log_sum_logs(low, high)
+    log_dev = high + math.log1p(-(math.exp(low - high)))
+    wts = [w - log_ev for w in wts]
+    return log_ev, log_dev, wts
+
+
+def log_total_error_estimate(log_ev, log_dev, nlive):
+    """nested.ml:148-150"""
+    import math
+    log_rel_error2 = -(math.log(float(nlive)))
+    return 0.5 * log_sum_logs(2.0 * log_dev, log_rel_error2 + 2.0 * log_ev)
+
+
+def weight_binary_search_index(x, running_sums):
+    """nested.ml:152-165"""
+    if x <= running_sums[0]:
+        return 0
+    ilow, ihigh = 0, len(running_sums) - 1
+    while ihigh - ilow > 1:
+        imid = (ilow + ihigh) // 2
+        if x <= running_sums[imid]:
+            ihigh = imid
+        else:
+            ilow = imid
+    return ihigh

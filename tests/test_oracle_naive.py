@@ -129,3 +129,22 @@ def test_bounds_volume_and_reference_structure(og):
 
     check(tree)
     assert kd.bounds_volume([0.0, -1.0, 0.5], [1.0, 2.0, 0.75]) == og.bounds_volume([0.0, -1.0, 0.5], [1.0, 2.0, 0.75])
+
+
+@pytest.mark.parametrize("n,nlive,seed", [(60, 10, 1), (5000, 1000, 2), (2001, 2000, 3), (350, 7, 4)])
+def test_nested_weights_identical(og, n, nlive, seed):
+    """nested.ml:81-120 / 148-150 transcribed statement by statement in Python against oracle.cpp (the reference-order
+    scan, K = 1): log evidence, its error and every log weight bit for bit."""
+    rng = np.random.default_rng(seed)
+    ll = np.sort(rng.normal(-20.0, 8.0, n))
+    ll[n // 3] = ll[n // 3 + 1]                                   # a tie
+    lev, ldev, lw = og.nested_weights(ll, nlive)
+    nev, ndev, nw = nv.evidence_error_and_weights(nlive, [float(v) for v in ll])
+    assert lev == nev and ldev == ndev
+    assert np.array_equal(lw, np.array(nw))
+    assert og.nested_log_total_error(lev, ldev, nlive) == nv.log_total_error_estimate(nev, ndev, nlive)
+    # weight_binary_search_index (nested.ml:152-165) on the running sums of the weights
+    sums = np.cumsum(np.exp(lw))
+    for x in (0.0, float(sums[0]), 0.3, 0.999999, 1.5):
+        i = nv.weight_binary_search_index(x, [float(v) for v in sums])
+        assert 0 <= i < n and (i == 0 or sums[i - 1] < x or i == n - 1) and (x <= sums[i] or i == n - 1)
